@@ -1,0 +1,769 @@
+// api.cu -- the C ABI of libicnf_b200.so (include/icnf_b200.h): handle, buffers,
+// host<->device staging, kernel-family dispatch, and the two small reduction
+// kernels (loss mean, partial-gradient sum).  No CPU fallback lives here: every
+// entry point either launches CUDA kernels or returns an error code.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "family.h"
+
+namespace icnf {
+
+std::vector<const Family*>& tiny_registry() {
+    static std::vector<const Family*> reg;
+    return reg;
+}
+const Family* generic_family();  // generic.cu
+
+// ---------------------------------------------------------------- small kernels
+// dtheta[p] = sum over partial rows, fixed order (bit-reproducible)
+__global__ void reduce_grad_kernel(const float* __restrict__ partial, int nrows, int np, float* __restrict__ out) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int r = 0;
+    for (; r + 3 < nrows; r += 4) {
+        s0 += partial[(size_t)r * np + p];
+        s1 += partial[(size_t)(r + 1) * np + p];
+        s2 += partial[(size_t)(r + 2) * np + p];
+        s3 += partial[(size_t)(r + 3) * np + p];
+    }
+    for (; r < nrows; ++r) s0 += partial[(size_t)r * np + p];
+    out[p] = (s0 + s1) + (s2 + s3);
+}
+
+// out[0] = scale * sum(x[0..n)) with a fixed reduction tree; single CTA, double accumulation
+__global__ void sum_kernel(const float* __restrict__ x, long long n, float scale, float* __restrict__ out) {
+    __shared__ double sh[32];
+    double acc = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) acc += (double)x[i];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += sh[i];
+        out[0] = (float)(t * (double)scale);
+    }
+}
+
+// FP32 FMA-pipe microbenchmark (the roofline denominator of the narrow-MLP kernels, which
+// MEASURED_PEAKS.json does not carry): 16 independent FFMA chains per thread.
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
+    float x[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = (float)(threadIdx.x + i) * 1e-3f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], a, b);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += x[i];
+    if (s == 123.456f) out[0] = s;   // never true; keeps the chain alive
+}
+
+}  // namespace icnf
+
+using namespace icnf;
+
+// ---------------------------------------------------------------- handle
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+}  // namespace
+
+struct icnf_handle {
+    icnf_config cfg;
+    const Family* fam = nullptr;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<float> theta_host;
+    bool have_params = false;
+    DevBuf theta_dev, in, eps, ys, out0, out1, out2, wu0, wu1, wk0, wk1, partials, ckpt, steps, stats, gpartial,
+        lossterm, scalar, dtheta, dxs;
+    DevStats* stats_host = nullptr;  // pinned
+    float* scalar_host = nullptr;    // pinned
+    long long launches = 0;
+    bool profiling = false;
+    cudaEvent_t prof_ev[4][2] = {};
+    bool prof_used[4] = {false, false, false, false};
+    std::string err;
+    // slot: 0 forward solve (or rhs), 1 loss sum, 2 backward, 3 gradient reduce
+    void prof_begin(int slot, cudaStream_t st) {
+        if (!profiling) return;
+        if (!prof_ev[slot][0]) { cudaEventCreate(&prof_ev[slot][0]); cudaEventCreate(&prof_ev[slot][1]); }
+        cudaEventRecord(prof_ev[slot][0], st);
+    }
+    void prof_end(int slot, cudaStream_t st) {
+        if (!profiling) return;
+        cudaEventRecord(prof_ev[slot][1], st);
+        prof_used[slot] = true;
+    }
+
+    int D() const { return cfg.nvars + cfg.naug; }
+    int S() const { return D() + 3; }
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+    int cuda_fail(cudaError_t e, const char* what) {
+        return fail(ICNF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    }
+};
+
+#define CK(h, call)                                                  \
+    do {                                                             \
+        cudaError_t e__ = (call);                                    \
+        if (e__ != cudaSuccess) return (h)->cuda_fail(e__, #call);   \
+    } while (0)
+
+namespace {
+
+Controller make_controller(const icnf_solver* s) {
+    Controller c;
+    c.reltol = (s && s->reltol > 0) ? s->reltol : 1e-4f;
+    c.abstol = (s && s->abstol > 0) ? s->abstol : 1e-4f;
+    c.beta1 = (s && s->beta1 > 0) ? s->beta1 : 7.0f / 50.0f;
+    c.beta2 = (s && s->beta2 > 0) ? s->beta2 : 2.0f / 25.0f;
+    c.gamma = (s && s->gamma > 0) ? s->gamma : 0.9f;
+    c.qmin = (s && s->qmin > 0) ? s->qmin : 0.2f;
+    c.qmax = (s && s->qmax > 0) ? s->qmax : 10.0f;
+    c.qsteady_min = (s && s->qsteady_min > 0) ? s->qsteady_min : 1.0f;
+    c.qsteady_max = (s && s->qsteady_max > 0) ? s->qsteady_max : 1.2f;
+    c.qoldinit = (s && s->qoldinit > 0) ? s->qoldinit : 1e-4f;
+    c.max_steps = (s && s->max_steps > 0) ? s->max_steps : 100000;
+    return c;
+}
+
+struct ModeFlags {
+    bool exact;
+    int reg_e, reg_n, reg_a;
+};
+ModeFlags mode_flags(const icnf_config& c, int mode) {
+    ModeFlags f;
+    f.exact = (mode == ICNF_TEST);
+    const bool reg = (mode == ICNF_TRAIN_REG);
+    f.reg_e = reg && c.lambda1 != 0.0f;
+    f.reg_n = reg && c.lambda2 != 0.0f;
+    f.reg_a = reg && c.lambda3 != 0.0f && c.naug != 0;
+    return f;
+}
+
+int validate_common(icnf_handle* h, int mode, int64_t B) {
+    if (!h) return ICNF_ERR_INVALID;
+    if (!h->have_params) return h->fail(ICNF_ERR_INVALID, "icnf_set_params has not been called");
+    if (mode < ICNF_TEST || mode > ICNF_TRAIN_NOREG) return h->fail(ICNF_ERR_INVALID, "bad mode %d", mode);
+    if (B < 0) return h->fail(ICNF_ERR_INVALID, "negative batch");
+    CK(h, cudaSetDevice(h->device));
+    return ICNF_OK;
+}
+
+// Number of fixed steps for |t1 - t0| at step dt (last step clipped to land on t1).
+int fixed_steps(float t0, float t1, float dt) {
+    double span = std::fabs((double)t1 - (double)t0);
+    if (span == 0.0) return 0;
+    return (int)std::ceil(span / (double)dt - 1e-6);
+}
+
+struct SolveRequest {
+    int mode;
+    const icnf_solver* sol;
+    float t0, t1;
+    const float* in;
+    int in_kind;
+    const icnf_noise* noise;
+    const float* eps;
+    const float* ys;
+    float *out_u, *out_logp, *out_regs, *out_x, *out_lossterm;
+    bool want_ckpt;
+    int64_t B;
+};
+
+// Enqueue one solve on `st`.  All pointers are device pointers.  Statistics land in
+// h->stats (device).
+int enqueue_solve(icnf_handle* h, const SolveRequest& r, cudaStream_t st) {
+    const icnf_config& c = h->cfg;
+    const ModeFlags mf = mode_flags(c, r.mode);
+    const int D = h->D(), S = h->S();
+    const bool adaptive = r.sol ? (r.sol->adaptive != 0) : true;
+    int eps_kind = r.noise ? r.noise->kind : ICNF_EPS_SUPPLIED;
+    if (r.mode != ICNF_TEST && eps_kind == ICNF_EPS_SUPPLIED && !r.eps)
+        return h->fail(ICNF_ERR_INVALID, "mode needs a Hutchinson probe: pass eps or a noise kind");
+    if (eps_kind < ICNF_EPS_SUPPLIED || eps_kind > ICNF_EPS_RADEMACHER) return h->fail(ICNF_ERR_INVALID, "bad noise kind");
+    if (c.ncond && !r.ys) return h->fail(ICNF_ERR_INVALID, "conditioned flow needs ys");
+    if (!adaptive && !(r.sol && r.sol->dt > 0)) return h->fail(ICNF_ERR_INVALID, "fixed-step solve needs dt > 0");
+
+    SolveArgs a;
+    memset(&a, 0, sizeof a);
+    a.theta = h->theta_dev.as<float>();
+    a.in = r.in; a.eps = r.eps; a.ys = r.ys;
+    a.out_u = r.out_u; a.out_logp = r.out_logp; a.out_regs = r.out_regs; a.out_x = r.out_x;
+    a.out_lossterm = r.out_lossterm;
+    a.B = r.B;
+    a.sample_offset = r.noise ? r.noise->sample_offset : 0;
+    a.seed = r.noise ? r.noise->seed : 0;
+    a.in_kind = r.in_kind; a.eps_kind = eps_kind; a.mode = r.mode;
+    a.reg_e = mf.reg_e; a.reg_n = mf.reg_n; a.reg_a = mf.reg_a; a.squared = c.reg_squared;
+    a.lam1 = c.lambda1; a.lam2 = c.lambda2; a.lam3 = c.lambda3;
+    a.t0 = r.t0; a.t1 = r.t1;
+    a.ctl = make_controller(r.sol);
+    CK(h, h->stats.reserve(sizeof(DevStats)));
+    a.stats = h->stats.as<DevStats>();
+
+    if (r.B == 0) {
+        CK(h, cudaMemsetAsync(a.stats, 0, sizeof(DevStats), st));
+        return ICNF_OK;
+    }
+    if (!adaptive) {
+        a.nsteps = fixed_steps(r.t0, r.t1, r.sol->dt);
+        a.dt = r.sol->dt;
+        if (r.want_ckpt) {
+            a.max_ckpt_steps = a.nsteps;
+            CK(h, h->ckpt.reserve(sizeof(float) * (size_t)(a.nsteps + 1) * r.B * D));
+            CK(h, h->steps.reserve(sizeof(StepRec) * (size_t)(a.nsteps + 1)));
+            a.ckpt = h->ckpt.as<float>();
+            a.steps = h->steps.as<StepRec>();
+        }
+        h->prof_begin(0, st);
+        cudaError_t e = h->fam->solve_fixed(h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st);
+        h->prof_end(0, st);
+        if (e != cudaSuccess) return h->cuda_fail(e, "solve_fixed launch");
+        h->launches++;
+        return ICNF_OK;
+    }
+    // adaptive: cooperative persistent kernel
+    const int grid_cap = h->fam->adaptive_max_grid(mf.exact, h->sm_count);
+    if (grid_cap <= 0) return h->fail(ICNF_ERR_UNSUPPORTED, "adaptive kernel cannot be made resident on this device");
+    const long long need = (r.B + 127) / 128;
+    const int grid = (int)std::max(1LL, std::min<long long>(need, grid_cap));
+    a.dt = (r.sol && r.sol->dt > 0) ? r.sol->dt : 0.0f;
+    const size_t sb = sizeof(float) * (size_t)S * r.B;
+    CK(h, h->wu0.reserve(sb));
+    CK(h, h->wu1.reserve(sb));
+    CK(h, h->wk0.reserve(sb));
+    CK(h, h->wk1.reserve(sb));
+    CK(h, h->partials.reserve(sizeof(double) * 2 * (size_t)grid_cap));
+    a.wu[0] = h->wu0.as<float>(); a.wu[1] = h->wu1.as<float>();
+    a.wk[0] = h->wk0.as<float>(); a.wk[1] = h->wk1.as<float>();
+    a.partials = h->partials.as<double>();
+    if (r.want_ckpt) {
+        a.max_ckpt_steps = std::min(a.ctl.max_steps, 256);
+        CK(h, h->ckpt.reserve(sizeof(float) * (size_t)(a.max_ckpt_steps + 1) * r.B * D));
+        CK(h, h->steps.reserve(sizeof(StepRec) * (size_t)(a.max_ckpt_steps + 1)));
+        a.ckpt = h->ckpt.as<float>();
+        a.steps = h->steps.as<StepRec>();
+    }
+    h->prof_begin(0, st);
+    cudaError_t e = h->fam->solve_adaptive(h->theta_host.data(), a, c.nvars, mf.exact, grid, st);
+    h->prof_end(0, st);
+    if (e != cudaSuccess) return h->cuda_fail(e, "solve_adaptive launch");
+    h->launches++;
+    return ICNF_OK;
+}
+
+int finish_stats(icnf_handle* h, icnf_stats* stats, cudaStream_t st) {
+    CK(h, cudaMemcpyAsync(h->stats_host, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    if (stats) {
+        stats->naccept = h->stats_host->naccept;
+        stats->nreject = h->stats_host->nreject;
+        stats->nf = h->stats_host->nf;
+        stats->status = h->stats_host->status;
+        stats->t_final = h->stats_host->t_final;
+        stats->dt_last = h->stats_host->dt_last;
+    }
+    const int s = h->stats_host->status;
+    if (s != ICNF_OK) {
+        const char* why = s == ICNF_ERR_MAX_STEPS ? "max_steps reached"
+                          : s == ICNF_ERR_DT_UNDERFLOW ? "step size underflow"
+                          : s == ICNF_ERR_NONFINITE ? "non-finite error estimate" : "device loop failed";
+        return h->fail(s, "tsit5: %s (t = %g, accepted %d, rejected %d)", why, (double)h->stats_host->t_final,
+                       h->stats_host->naccept, h->stats_host->nreject);
+    }
+    return ICNF_OK;
+}
+
+// _dev entry points run on the caller's stream; NULL is the legacy default stream (what
+// torch.cuda.current_stream() is unless the caller changed it), so results are ordered with
+// the caller's own work on that stream.
+cudaStream_t pick_stream(icnf_handle*, void* stream) { return (cudaStream_t)stream; }
+
+int upload(icnf_handle* h, DevBuf& buf, const float* src, size_t n, cudaStream_t st, const float** out) {
+    *out = nullptr;
+    if (!src || n == 0) return ICNF_OK;
+    CK(h, buf.reserve(n * sizeof(float)));
+    CK(h, cudaMemcpyAsync(buf.p, src, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    *out = buf.as<float>();
+    return ICNF_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- lifetime
+extern "C" {
+
+const char* icnf_version(void) { return "icnf_b200 0.1.0 (sm_100a)"; }
+
+int icnf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int icnf_create(const icnf_config* cfg, icnf_handle** out) {
+    if (out) *out = nullptr;
+    if (!cfg || !out) { g_create_error = "null argument"; return ICNF_ERR_INVALID; }
+    if (cfg->abi_version != ICNF_ABI_VERSION) { g_create_error = "abi_version mismatch"; return ICNF_ERR_INVALID; }
+    const int D = cfg->nvars + cfg->naug;
+    if (cfg->nvars < 1 || cfg->naug < 0 || cfg->ncond < 0 || cfg->n_layers < 1 || cfg->n_layers > ICNF_MAX_LAYERS) {
+        g_create_error = "bad dimensions";
+        return ICNF_ERR_INVALID;
+    }
+    const int n_in = D + (cfg->autonomous ? 0 : 1) + cfg->ncond;
+    if (cfg->sizes[0] != n_in || cfg->sizes[cfg->n_layers] != D) {
+        g_create_error = "sizes[0] must be nvars+naug+!autonomous+ncond and sizes[n_layers] must be nvars+naug";
+        return ICNF_ERR_INVALID;
+    }
+    for (int l = 0; l <= cfg->n_layers; ++l)
+        if (cfg->sizes[l] < 1) { g_create_error = "layer size < 1"; return ICNF_ERR_INVALID; }
+    if (cfg->activation < ICNF_ACT_SOFTPLUS || cfg->activation > ICNF_ACT_IDENTITY) {
+        g_create_error = "unknown activation";
+        return ICNF_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        g_create_error = std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return ICNF_ERR_NO_DEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "device ordinal out of range"; return ICNF_ERR_INVALID; }
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return ICNF_ERR_CUDA; }
+
+    icnf_handle* h = new (std::nothrow) icnf_handle();
+    if (!h) { g_create_error = "out of memory"; return ICNF_ERR_INVALID; }
+    h->cfg = *cfg;
+    h->device = cfg->device;
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+
+    NetShape shape;
+    memset(&shape, 0, sizeof shape);
+    shape.act = cfg->activation; shape.D = D; shape.C = cfg->ncond; shape.NL = cfg->n_layers;
+    for (int l = 0; l <= cfg->n_layers; ++l) shape.n[l] = cfg->sizes[l];
+    if (cfg->precision == ICNF_FP32) {
+        for (const Family* f : tiny_registry())
+            if (f->shape == shape) { h->fam = f; break; }
+    }
+    if (!h->fam) h->fam = generic_family();
+    if (!h->fam) {
+        g_create_error = "no kernel family serves this network shape in this build";
+        delete h;
+        return ICNF_ERR_UNSUPPORTED;
+    }
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&h->stats_host, sizeof(DevStats))) != cudaSuccess ||
+        (e = cudaMallocHost((void**)&h->scalar_host, 4 * sizeof(float))) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        icnf_destroy(h);
+        return ICNF_ERR_CUDA;
+    }
+    *out = h;
+    return ICNF_OK;
+}
+
+void icnf_destroy(icnf_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    DevBuf* bufs[] = {&h->theta_dev, &h->in, &h->eps, &h->ys, &h->out0, &h->out1, &h->out2, &h->wu0, &h->wu1, &h->wk0,
+                      &h->wk1, &h->partials, &h->ckpt, &h->steps, &h->stats, &h->gpartial, &h->lossterm, &h->scalar,
+                      &h->dtheta, &h->dxs};
+    for (DevBuf* b : bufs) b->release();
+    if (h->stats_host) cudaFreeHost(h->stats_host);
+    if (h->scalar_host) cudaFreeHost(h->scalar_host);
+    for (auto& pr : h->prof_ev)
+        for (cudaEvent_t ev : pr)
+            if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+const char* icnf_last_error(const icnf_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int64_t icnf_n_params(const icnf_handle* h) {
+    if (!h) return 0;
+    int64_t n = 0;
+    for (int l = 0; l < h->cfg.n_layers; ++l) n += (int64_t)h->cfg.sizes[l] * h->cfg.sizes[l + 1] + h->cfg.sizes[l + 1];
+    return n;
+}
+int32_t icnf_n_state(const icnf_handle* h) { return h ? h->S() : 0; }
+const char* icnf_kernel_family(const icnf_handle* h) { return (h && h->fam) ? h->fam->name : ""; }
+int64_t icnf_launch_count(const icnf_handle* h) { return h ? h->launches : 0; }
+
+int icnf_set_profiling(icnf_handle* h, int enabled) {
+    if (!h) return ICNF_ERR_INVALID;
+    h->profiling = enabled != 0;
+    for (bool& u : h->prof_used) u = false;
+    return ICNF_OK;
+}
+
+int icnf_kernel_times(icnf_handle* h, float* ms4) {
+    if (!h || !ms4) return ICNF_ERR_INVALID;
+    CK(h, cudaSetDevice(h->device));
+    for (int s = 0; s < 4; ++s) {
+        ms4[s] = -1.0f;
+        if (!h->prof_used[s]) continue;
+        CK(h, cudaEventSynchronize(h->prof_ev[s][1]));
+        CK(h, cudaEventElapsedTime(&ms4[s], h->prof_ev[s][0], h->prof_ev[s][1]));
+    }
+    return ICNF_OK;
+}
+
+int icnf_measure_fp32_peak(int device, float* tflops) {
+    if (!tflops) return ICNF_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return ICNF_ERR_NO_DEVICE;
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    float* d = nullptr;
+    if (cudaMalloc(&d, 16) != cudaSuccess) return ICNF_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int iters = 4096, grid = sms * 8;
+    float best = 0.f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fma_peak_kernel<<<grid, 256>>>(d, iters, 0.999f, 1e-3f);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return ICNF_ERR_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 16 * 8 * (double)iters * 256.0 * grid;
+        if (rep > 0) best = fmaxf(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *tflops = best;
+    return ICNF_OK;
+}
+
+int icnf_set_params(icnf_handle* h, const float* theta, int64_t n) {
+    if (!h || !theta) return ICNF_ERR_INVALID;
+    if (n != icnf_n_params(h)) return h->fail(ICNF_ERR_INVALID, "theta has %lld entries, network has %lld", (long long)n, (long long)icnf_n_params(h));
+    CK(h, cudaSetDevice(h->device));
+    h->theta_host.assign(theta, theta + n);
+    CK(h, h->theta_dev.reserve(sizeof(float) * n));
+    CK(h, cudaMemcpyAsync(h->theta_dev.p, h->theta_host.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    h->have_params = true;
+    return ICNF_OK;
+}
+
+int icnf_set_params_dev(icnf_handle* h, const float* theta, int64_t n, void* stream) {
+    if (!h || !theta) return ICNF_ERR_INVALID;
+    if (n != icnf_n_params(h)) return h->fail(ICNF_ERR_INVALID, "theta has %lld entries, network has %lld", (long long)n, (long long)icnf_n_params(h));
+    CK(h, cudaSetDevice(h->device));
+    cudaStream_t st = pick_stream(h, stream);
+    h->theta_host.resize(n);
+    CK(h, h->theta_dev.reserve(sizeof(float) * n));
+    CK(h, cudaMemcpyAsync(h->theta_dev.p, theta, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+    // the tiny family passes the weights as a kernel parameter, so it needs them on the host
+    CK(h, cudaMemcpyAsync(h->theta_host.data(), theta, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    CK(h, cudaStreamSynchronize(st));
+    h->have_params = true;
+    return ICNF_OK;
+}
+
+// ---------------------------------------------------------------- S1
+int icnf_rhs_dev(icnf_handle* h, int mode, float t, const float* u, const float* eps, const float* ys, float* du,
+                 int64_t B, void* stream) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!u || !du) return h->fail(ICNF_ERR_INVALID, "null u/du");
+    if (mode != ICNF_TEST && !eps) return h->fail(ICNF_ERR_INVALID, "TrainMode RHS needs eps");
+    if (h->cfg.ncond && !ys) return h->fail(ICNF_ERR_INVALID, "conditioned flow needs ys");
+    if (B == 0) return ICNF_OK;
+    const ModeFlags mf = mode_flags(h->cfg, mode);
+    RhsArgs a;
+    memset(&a, 0, sizeof a);
+    a.theta = h->theta_dev.as<float>();
+    a.u = u; a.eps = eps; a.ys = ys; a.du = du; a.B = B;
+    a.mode = mode; a.reg_e = mf.reg_e; a.reg_n = mf.reg_n; a.squared = h->cfg.reg_squared; a.t = t;
+    cudaError_t e = h->fam->rhs(h->theta_host.data(), a, mf.exact, h->sm_count, pick_stream(h, stream));
+    if (e != cudaSuccess) return h->cuda_fail(e, "rhs launch");
+    h->launches++;
+    return ICNF_OK;
+}
+
+int icnf_rhs(icnf_handle* h, int mode, float t, const float* u, const float* eps, const float* ys, float* du, int64_t B) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!u || !du) return h->fail(ICNF_ERR_INVALID, "null u/du");
+    const int D = h->D(), S = h->S();
+    const float *du_, *de_, *dy_;
+    if ((rc = upload(h, h->in, u, (size_t)S * B, h->stream, &du_))) return rc;
+    if ((rc = upload(h, h->eps, mode == ICNF_TEST ? nullptr : eps, (size_t)D * B, h->stream, &de_))) return rc;
+    if ((rc = upload(h, h->ys, ys, (size_t)h->cfg.ncond * B, h->stream, &dy_))) return rc;
+    CK(h, h->out0.reserve(sizeof(float) * (size_t)S * B + 4));
+    if ((rc = icnf_rhs_dev(h, mode, t, du_, de_, dy_, h->out0.as<float>(), B, h->stream))) return rc;
+    if (B) CK(h, cudaMemcpyAsync(du, h->out0.p, sizeof(float) * (size_t)S * B, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    return ICNF_OK;
+}
+
+// ---------------------------------------------------------------- S2
+int icnf_solve_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* u0,
+                   const icnf_noise* noise, const float* eps, const float* ys, float* u_final, icnf_stats* stats,
+                   int64_t B, void* stream) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!u0 || !u_final) return h->fail(ICNF_ERR_INVALID, "null u0/u_final");
+    cudaStream_t st = pick_stream(h, stream);
+    SolveRequest r{mode, sol, t0, t1, u0, IN_U0, noise, eps, ys, u_final, nullptr, nullptr, nullptr, nullptr, false, B};
+    if ((rc = enqueue_solve(h, r, st))) return rc;
+    if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
+    return ICNF_OK;
+}
+
+int icnf_solve(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* u0,
+               const icnf_noise* noise, const float* eps, const float* ys, float* u_final, icnf_stats* stats, int64_t B) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!u0 || !u_final) return h->fail(ICNF_ERR_INVALID, "null u0/u_final");
+    const int D = h->D(), S = h->S();
+    const float *d_in, *d_eps, *d_ys;
+    if ((rc = upload(h, h->in, u0, (size_t)S * B, h->stream, &d_in))) return rc;
+    if ((rc = upload(h, h->eps, mode == ICNF_TEST ? nullptr : eps, (size_t)D * B, h->stream, &d_eps))) return rc;
+    if ((rc = upload(h, h->ys, ys, (size_t)h->cfg.ncond * B, h->stream, &d_ys))) return rc;
+    CK(h, h->out0.reserve(sizeof(float) * (size_t)S * B + 4));
+    SolveRequest r{mode, sol, t0, t1, B ? d_in : u0, IN_U0, noise, d_eps, d_ys, h->out0.as<float>(), nullptr, nullptr,
+                   nullptr, nullptr, false, B};
+    if ((rc = enqueue_solve(h, r, h->stream))) return rc;
+    if (B) CK(h, cudaMemcpyAsync(u_final, h->out0.p, sizeof(float) * (size_t)S * B, cudaMemcpyDeviceToHost, h->stream));
+    return finish_stats(h, stats, h->stream);
+}
+
+int icnf_inference_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+                       const icnf_noise* noise, const float* eps, const float* ys, float* logp, float* regs,
+                       icnf_stats* stats, int64_t B, void* stream) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!xs || !logp) return h->fail(ICNF_ERR_INVALID, "null xs/logp");
+    cudaStream_t st = pick_stream(h, stream);
+    SolveRequest r{mode, sol, t0, t1, xs, IN_XS, noise, eps, ys, nullptr, logp, regs, nullptr, nullptr, false, B};
+    if ((rc = enqueue_solve(h, r, st))) return rc;
+    if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
+    return ICNF_OK;
+}
+
+int icnf_inference(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+                   const icnf_noise* noise, const float* eps, const float* ys, float* logp, float* regs,
+                   icnf_stats* stats, int64_t B) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!xs || !logp) return h->fail(ICNF_ERR_INVALID, "null xs/logp");
+    const int D = h->D();
+    const float *d_in, *d_eps, *d_ys;
+    if ((rc = upload(h, h->in, xs, (size_t)h->cfg.nvars * B, h->stream, &d_in))) return rc;
+    if ((rc = upload(h, h->eps, mode == ICNF_TEST ? nullptr : eps, (size_t)D * B, h->stream, &d_eps))) return rc;
+    if ((rc = upload(h, h->ys, ys, (size_t)h->cfg.ncond * B, h->stream, &d_ys))) return rc;
+    CK(h, h->out0.reserve(sizeof(float) * (size_t)B + 4));
+    CK(h, h->out1.reserve(sizeof(float) * 3 * (size_t)B + 4));
+    SolveRequest r{mode, sol, t0, t1, B ? d_in : xs, IN_XS, noise, d_eps, d_ys, nullptr, h->out0.as<float>(),
+                   regs ? h->out1.as<float>() : nullptr, nullptr, nullptr, false, B};
+    if ((rc = enqueue_solve(h, r, h->stream))) return rc;
+    if (B) {
+        CK(h, cudaMemcpyAsync(logp, h->out0.p, sizeof(float) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+        if (regs) CK(h, cudaMemcpyAsync(regs, h->out1.p, sizeof(float) * 3 * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+    }
+    return finish_stats(h, stats, h->stream);
+}
+
+int icnf_generate_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* z0,
+                      const icnf_noise* noise, const float* eps, const float* ys, float* xs_out, icnf_stats* stats,
+                      int64_t n, void* stream) {
+    int rc = validate_common(h, mode, n);
+    if (rc) return rc;
+    if (!xs_out) return h->fail(ICNF_ERR_INVALID, "null xs_out");
+    if (!z0 && !noise) return h->fail(ICNF_ERR_INVALID, "generate needs z0 or a noise seed to draw it");
+    cudaStream_t st = pick_stream(h, stream);
+    // reverse(steer_tspan(...)), base_icnf.jl:372: integrate t1 -> t0
+    SolveRequest r{mode, sol, t1, t0, z0, z0 ? IN_Z0 : IN_Z0_DRAW, noise, eps, ys, nullptr, nullptr, nullptr, xs_out,
+                   nullptr, false, n};
+    if ((rc = enqueue_solve(h, r, st))) return rc;
+    if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
+    return ICNF_OK;
+}
+
+int icnf_generate(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* z0,
+                  const icnf_noise* noise, const float* eps, const float* ys, float* xs_out, icnf_stats* stats, int64_t n) {
+    int rc = validate_common(h, mode, n);
+    if (rc) return rc;
+    if (!xs_out) return h->fail(ICNF_ERR_INVALID, "null xs_out");
+    if (!z0 && !noise) return h->fail(ICNF_ERR_INVALID, "generate needs z0 or a noise seed to draw it");
+    const int D = h->D();
+    const float *d_in, *d_eps, *d_ys;
+    if ((rc = upload(h, h->in, z0, (size_t)D * n, h->stream, &d_in))) return rc;
+    if ((rc = upload(h, h->eps, mode == ICNF_TEST ? nullptr : eps, (size_t)D * n, h->stream, &d_eps))) return rc;
+    if ((rc = upload(h, h->ys, ys, (size_t)h->cfg.ncond * n, h->stream, &d_ys))) return rc;
+    CK(h, h->out0.reserve(sizeof(float) * (size_t)h->cfg.nvars * n + 4));
+    SolveRequest r{mode, sol, t1, t0, d_in, (z0 && n) ? IN_Z0 : IN_Z0_DRAW, noise, d_eps, d_ys, nullptr, nullptr, nullptr,
+                   h->out0.as<float>(), nullptr, false, n};
+    if ((rc = enqueue_solve(h, r, h->stream))) return rc;
+    if (n) CK(h, cudaMemcpyAsync(xs_out, h->out0.p, sizeof(float) * (size_t)h->cfg.nvars * n, cudaMemcpyDeviceToHost, h->stream));
+    return finish_stats(h, stats, h->stream);
+}
+
+// ---------------------------------------------------------------- S3
+// loss (and gradient) with all pointers on the device; loss/dtheta/dxs/stats device or null
+static int loss_grad_device(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+                            const icnf_noise* noise, const float* eps, const float* ys, float* loss, float* dtheta,
+                            float* dxs, int64_t B, int64_t global_batch, cudaStream_t st) {
+    if (B <= 0) return h->fail(ICNF_ERR_INVALID, "loss needs at least one sample");
+    const int64_t denom = global_batch > 0 ? global_batch : B;
+    const bool want_grad = dtheta != nullptr || dxs != nullptr;
+    CK(h, h->lossterm.reserve(sizeof(float) * (size_t)B));
+    SolveRequest r{mode, sol, t0, t1, xs, IN_XS, noise, eps, ys, nullptr, nullptr, nullptr, nullptr,
+                   h->lossterm.as<float>(), want_grad, B};
+    int rc = enqueue_solve(h, r, st);
+    if (rc) return rc;
+    if (loss) {
+        h->prof_begin(1, st);
+        sum_kernel<<<1, 1024, 0, st>>>(h->lossterm.as<float>(), (long long)B, 1.0f / (float)denom, loss);
+        h->prof_end(1, st);
+        CK(h, cudaGetLastError());
+        h->launches++;
+    }
+    if (!want_grad) return ICNF_OK;
+    const ModeFlags mf = mode_flags(h->cfg, mode);
+    const int np = (int)icnf_n_params(h);
+    const int grid = h->fam->backward_grid(mf.exact, h->sm_count, B);
+    const int nrows = grid * h->fam->backward_partials_per_block;
+    CK(h, h->gpartial.reserve(sizeof(float) * (size_t)nrows * np));
+    BackwardArgs b;
+    memset(&b, 0, sizeof b);
+    b.theta = h->theta_dev.as<float>();
+    b.ckpt = h->ckpt.as<float>();
+    b.steps = h->steps.as<StepRec>();
+    b.stats = h->stats.as<DevStats>();
+    b.eps = eps; b.ys = ys;
+    b.gpartial = h->gpartial.as<float>();
+    b.dxs = dxs;
+    b.B = B;
+    b.sample_offset = noise ? noise->sample_offset : 0;
+    b.seed = noise ? noise->seed : 0;
+    b.eps_kind = noise ? noise->kind : ICNF_EPS_SUPPLIED;
+    b.mode = mode; b.reg_e = mf.reg_e; b.reg_n = mf.reg_n; b.reg_a = mf.reg_a; b.squared = h->cfg.reg_squared;
+    b.lam1 = h->cfg.lambda1; b.lam2 = h->cfg.lambda2; b.lam3 = h->cfg.lambda3;
+    b.inv_denominator = 1.0f / (float)denom;
+    b.nvars = h->cfg.nvars;
+    h->prof_begin(2, st);
+    cudaError_t e = h->fam->backward(h->theta_host.data(), b, mf.exact, grid, st);
+    h->prof_end(2, st);
+    if (e != cudaSuccess) return h->cuda_fail(e, "backward launch");
+    h->launches++;
+    if (dtheta) {
+        h->prof_begin(3, st);
+        reduce_grad_kernel<<<(np + 127) / 128, 128, 0, st>>>(h->gpartial.as<float>(), nrows, np, dtheta);
+        h->prof_end(3, st);
+        CK(h, cudaGetLastError());
+        h->launches++;
+    }
+    return ICNF_OK;
+}
+
+int icnf_loss_grad_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+                       const icnf_noise* noise, const float* eps, const float* ys, float* loss, float* dtheta, float* dxs,
+                       icnf_stats* stats, int64_t B, int64_t global_batch, void* stream) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!xs) return h->fail(ICNF_ERR_INVALID, "null xs");
+    cudaStream_t st = pick_stream(h, stream);
+    if ((rc = loss_grad_device(h, mode, sol, t0, t1, xs, noise, eps, ys, loss, dtheta, dxs, B, global_batch, st))) return rc;
+    if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
+    return ICNF_OK;
+}
+
+static int loss_grad_host(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+                          const icnf_noise* noise, const float* eps, const float* ys, float* loss, float* dtheta,
+                          float* dxs, icnf_stats* stats, int64_t B, int64_t global_batch) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!xs || !loss) return h->fail(ICNF_ERR_INVALID, "null xs/loss");
+    const int D = h->D();
+    const int np = (int)icnf_n_params(h);
+    const float *d_in, *d_eps, *d_ys;
+    if ((rc = upload(h, h->in, xs, (size_t)h->cfg.nvars * B, h->stream, &d_in))) return rc;
+    if ((rc = upload(h, h->eps, mode == ICNF_TEST ? nullptr : eps, (size_t)D * B, h->stream, &d_eps))) return rc;
+    if ((rc = upload(h, h->ys, ys, (size_t)h->cfg.ncond * B, h->stream, &d_ys))) return rc;
+    CK(h, h->scalar.reserve(4 * sizeof(float)));
+    if (dtheta) CK(h, h->dtheta.reserve(sizeof(float) * (size_t)np));
+    if (dxs) CK(h, h->dxs.reserve(sizeof(float) * (size_t)h->cfg.nvars * B));
+    if ((rc = loss_grad_device(h, mode, sol, t0, t1, d_in, noise, d_eps, d_ys, h->scalar.as<float>(),
+                               dtheta ? h->dtheta.as<float>() : nullptr, dxs ? h->dxs.as<float>() : nullptr, B,
+                               global_batch, h->stream)))
+        return rc;
+    CK(h, cudaMemcpyAsync(h->scalar_host, h->scalar.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (dtheta) CK(h, cudaMemcpyAsync(dtheta, h->dtheta.p, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+    if (dxs) CK(h, cudaMemcpyAsync(dxs, h->dxs.p, sizeof(float) * (size_t)h->cfg.nvars * B, cudaMemcpyDeviceToHost, h->stream));
+    rc = finish_stats(h, stats, h->stream);
+    *loss = h->scalar_host[0];
+    return rc;
+}
+
+int icnf_loss(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+              const icnf_noise* noise, const float* eps, const float* ys, float* loss, icnf_stats* stats, int64_t B,
+              int64_t global_batch) {
+    return loss_grad_host(h, mode, sol, t0, t1, xs, noise, eps, ys, loss, nullptr, nullptr, stats, B, global_batch);
+}
+
+int icnf_loss_grad(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+                   const icnf_noise* noise, const float* eps, const float* ys, float* loss, float* dtheta, float* dxs,
+                   icnf_stats* stats, int64_t B, int64_t global_batch) {
+    if (h && !dtheta) return h->fail(ICNF_ERR_INVALID, "null dtheta");
+    return loss_grad_host(h, mode, sol, t0, t1, xs, noise, eps, ys, loss, dtheta, dxs, stats, B, global_batch);
+}
+
+}  // extern "C"

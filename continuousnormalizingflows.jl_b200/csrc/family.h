@@ -1,0 +1,46 @@
+// family.h -- host-side interface between the C ABI (api.cu) and a kernel family.
+// A family is a set of launchers specialised for one network shape ("tiny":
+// compile-time shapes, one thread per sample) or for any shape ("generic").
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace icnf {
+
+struct NetShape {
+    int act, D, C, NL;
+    int n[ICNF_MAX_LAYERS + 1];
+    bool operator==(const NetShape& o) const {
+        if (act != o.act || D != o.D || C != o.C || NL != o.NL) return false;
+        for (int l = 0; l <= NL; ++l)
+            if (n[l] != o.n[l]) return false;
+        return true;
+    }
+};
+
+struct Family {
+    const char* name;
+    NetShape shape;          // for tiny entries: the exact shape served
+    int n_params;
+    // `theta_host` is the HOST copy of the parameters (tiny kernels take the weights as a
+    // kernel parameter; the generic family reads a.theta on the device and ignores it).
+    // launchers return the CUDA error of the launch; `exact` selects the TestMode trace
+    cudaError_t (*rhs)(const float* theta_host, const RhsArgs& a, bool exact, int sm_count, cudaStream_t st);
+    cudaError_t (*solve_fixed)(const float* theta_host, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st);
+    cudaError_t (*solve_adaptive)(const float* theta_host, const SolveArgs& a, int nvars, bool exact, int grid, cudaStream_t st);
+    // largest cooperative grid for the adaptive kernel on this device (0 = unsupported)
+    int (*adaptive_max_grid)(bool exact, int sm_count);
+    cudaError_t (*backward)(const float* theta_host, const BackwardArgs& a, bool exact, int grid, cudaStream_t st);
+    int (*backward_grid)(bool exact, int sm_count, long long B);
+    int backward_partials_per_block;  // gradient partial rows written per CTA
+};
+
+std::vector<const Family*>& tiny_registry();
+struct TinyRegistrar {
+    explicit TinyRegistrar(const Family* f) { tiny_registry().push_back(f); }
+};
+
+}  // namespace icnf

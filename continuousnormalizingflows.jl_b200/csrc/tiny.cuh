@@ -1,0 +1,968 @@
+// tiny.cuh -- "tiny" kernel family: one thread integrates one sample.
+//
+// For narrow MLPs (every width <= 32: configs 1 and 2 of BASELINE.json, the
+// reference's own test/benchmark shapes) the whole augmented state, the layer
+// activations and the VJP chain of one sample fit in one thread's registers.
+// Layer sizes are template parameters, every loop over units is fully unrolled,
+// the weights are a __grid_constant__ kernel parameter (constant bank, fed to the FMA pipe
+// through uniform registers), and a solve is
+// ONE kernel launch: stage combination, error norm, accept/reject and the
+// log-density readout never leave the device.
+//
+// What it computes (reference, paths relative to the reference root):
+//   rhs_eval       augmented_f, src/core/icnf.jl:297-316 (TestMode, exact trace) and
+//                  :517-536 (TrainMode, Hutchinson VJP) with icnf_jacobian,
+//                  src/core/utils.jl:35-54 / :150-159, reg_z / reg_j icnf.jl:184-251,
+//                  network input [z; t; ys] (src/layers/cond_layer.jl)
+//   solve kernels  base_sol, src/core/base_icnf.jl:134-140 (Tsit5 instead of the
+//                  third-party VCABM default: BASELINE.json north_star)
+//                  fused with inference_prob :247-296 (u0 build, eps draw),
+//                  inference_sol :158-172, reg_z_aug :106-132, generate_sol :185-194
+//   backward       gradient of loss (src/core/icnf.jl:628-649) that the reference
+//                  obtains from Zygote + SciMLSensitivity (icnf.jl:90-99)
+#pragma once
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace icnf {
+namespace tiny {
+
+namespace cg = cooperative_groups;
+
+constexpr int NT = 128;  // threads per CTA
+
+__constant__ float c_a[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0.161f, 0, 0, 0, 0, 0},
+    {-0.008480655492356989f, 0.335480655492357f, 0, 0, 0, 0},
+    {2.8971530571054935f, -6.359448489975075f, 4.3622954328695815f, 0, 0, 0},
+    {5.325864828439257f, -11.748883564062828f, 7.4955393428898365f, -0.09249506636175525f, 0, 0},
+    {5.86145544294642f, -12.92096931784711f, 8.159367898576159f, -0.071584973281401f, -0.028269050394068383f, 0},
+    {0.09646076681806523f, 0.01f, 0.4798896504144996f, 1.379008574103742f, -3.290069515436081f, 2.324710524099774f}};
+__constant__ float c_c[7] = {0.0f, 0.161f, 0.327f, 0.9f, 0.9800255409045097f, 1.0f, 1.0f};
+__constant__ float c_bt[7] = {-0.00178001105222577714f, -0.0008164344596567469f, 0.007880878010261995f,
+                              -0.1447110071732629f, 0.5823571654525552f, -0.45808210592918697f,
+                              0.015151515151515152f};
+
+// ------------------------------------------------------------------ network shape
+template <int ACT_, int D_, int C_, int NL_, int N0, int N1, int N2 = 0, int N3 = 0, int N4 = 0>
+struct Net {
+    static constexpr int ACT = ACT_, D = D_, C = C_, NL = NL_;
+    __host__ __device__ static constexpr int n(int l) { return l == 0 ? N0 : l == 1 ? N1 : l == 2 ? N2 : l == 3 ? N3 : N4; }
+    static constexpr int TIN = N0 - D_ - C_;
+    static_assert(TIN == 0 || TIN == 1, "n_in = D' + !autonomous + ncond");
+    static_assert(NL_ >= 1 && NL_ <= 4, "1..4 layers");
+    static_assert(n(NL_) == D_, "n_out = D'");
+    static constexpr int S = D_ + 3;
+    __host__ __device__ static constexpr int nmax() {
+        int m = 0;
+        for (int l = 0; l <= NL; ++l) m = n(l) > m ? n(l) : m;
+        return m;
+    }
+    static constexpr int NMAX = nmax();
+    // padded shared-memory layout: W_l column k at woff(l) + k * ld(l), bias at boff(l)
+    __host__ __device__ static constexpr int ld(int l) { return (n(l + 1) + 3) & ~3; }
+    __host__ __device__ static constexpr int woff(int l) {
+        int o = 0;
+        for (int i = 0; i < l; ++i) o += ld(i) * n(i) + ld(i);
+        return o;
+    }
+    __host__ __device__ static constexpr int boff(int l) { return woff(l) + ld(l) * n(l); }
+    static constexpr int WPAD = woff(NL_);
+    // native (ComponentArray) offsets
+    __host__ __device__ static constexpr int toff(int l) {
+        int o = 0;
+        for (int i = 0; i < l; ++i) o += n(i) * n(i + 1) + n(i + 1);
+        return o;
+    }
+    static constexpr int NP = toff(NL_);
+    // gradient accumulators: layer l owns nent(l) = W_l entries + b_l entries, in chunks of 32
+    __host__ __device__ static constexpr int nent(int l) { return n(l) * n(l + 1) + n(l + 1); }
+    __host__ __device__ static constexpr int nchunk(int l) { return (nent(l) + 31) / 32; }
+    __host__ __device__ static constexpr int choff(int l) {
+        int o = 0;
+        for (int i = 0; i < l; ++i) o += nchunk(i);
+        return o;
+    }
+    static constexpr int NCHUNK = choff(NL_);
+    // inputs of layer l that carry a z-derivative: only the first D' of layer 0
+    __host__ __device__ static constexpr int kz(int l) { return l == 0 ? D_ : n(l); }
+};
+
+// Weights travel as a __grid_constant__ kernel parameter: they live in constant bank 0,
+// reach the FMA pipe through uniform registers (LDCU.128 + FFMA R, R, UR, R) and cost no
+// vector registers, no shared memory and no LSU traffic.
+template <class N>
+struct WBlock {
+    float v[N::WPAD];
+};
+#define WREF(N, sw, l, j, k) (sw).v[N::woff(l) + (k) * N::ld(l) + (j)]
+#define BREF(N, sw, l, j) (sw).v[N::boff(l) + (j)]
+
+// activations of one sample: h[l] = output of layer l (post-activation, linear for the
+// last layer), d[l] = sigma'(a_l) for hidden layers
+template <class N>
+struct Acts {
+    float h[N::NL][N::NMAX];
+    float d[N::NL][N::NMAX];
+};
+
+template <class N>
+__device__ __forceinline__ void forward(const WBlock<N>& sw, const float (&x)[N::n(0)], Acts<N>& A) {
+    static_for<0, N::NL>([&](auto lc) __attribute__((always_inline)) {
+        constexpr int l = decltype(lc)::value;
+        constexpr int nin = N::n(l), nout = N::n(l + 1);
+        float acc[nout];
+#pragma unroll
+        for (int j = 0; j < nout; ++j) acc[j] = BREF(N, sw, l, j);
+#pragma unroll
+        for (int k = 0; k < nin; ++k) {
+            float hk;
+            if constexpr (l == 0) hk = x[k];
+            else hk = A.h[l - 1][k];
+#pragma unroll
+            for (int j = 0; j < nout; ++j) acc[j] = fmaf(WREF(N, sw, l, j, k), hk, acc[j]);
+        }
+        if constexpr (l < N::NL - 1) {
+#pragma unroll
+            for (int j = 0; j < nout; ++j) act_eval<N::ACT>(acc[j], A.h[l][j], A.d[l][j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < nout; ++j) A.h[l][j] = acc[j];
+        }
+    });
+}
+
+// VJP chain of one probe: g[l] = cotangent at the pre-activation of layer l,
+// v[l] = cotangent at the output of hidden layer l, q = probe' J (first D' inputs).
+template <class N>
+struct Chain {
+    float g[N::NL][N::NMAX];
+    float v[N::NL][N::NMAX];
+};
+
+template <class N>
+__device__ __forceinline__ void vjp_chain(const WBlock<N>& sw, const Acts<N>& A, const float (&probe)[N::D],
+                                          Chain<N>& Cn, float (&q)[N::D]) {
+#pragma unroll
+    for (int j = 0; j < N::D; ++j) Cn.g[N::NL - 1][j] = probe[j];
+    static_rfor<N::NL>([&](auto lc) __attribute__((always_inline)) {
+        constexpr int l = decltype(lc)::value;
+        constexpr int nout = N::n(l + 1), kk = N::kz(l);
+#pragma unroll
+        for (int k = 0; k < kk; ++k) {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < nout; ++j) s = fmaf(WREF(N, sw, l, j, k), Cn.g[l][j], s);
+            if constexpr (l > 0) {
+                Cn.v[l - 1][k] = s;
+                Cn.g[l - 1][k] = s * A.d[l - 1][k];
+            } else {
+                q[k] = s;
+            }
+        }
+    });
+}
+
+__device__ __forceinline__ float vec_norm(float ss, int squared) { return squared ? ss : sqrtf(ss); }
+
+// One right-hand-side evaluation for one sample.  x = [z; t; ys] must be filled by
+// the caller.  Outputs kz = zdot (D'), kl = -trace (exact or Hutchinson), kE, kn.
+template <class N, bool EXACT>
+__device__ __forceinline__ void rhs_eval(const WBlock<N>& sw, const float (&x)[N::n(0)], const float (&eps)[N::D],
+                                         int reg_e, int reg_n, int squared, float (&kz)[N::D], float& kl,
+                                         float& kE, float& kn) {
+    Acts<N> A;
+    forward<N>(sw, x, A);
+#pragma unroll
+    for (int j = 0; j < N::D; ++j) kz[j] = A.h[N::NL - 1][j];
+    if constexpr (EXACT) {
+        // exact trace by D' one-hot pullbacks (utils.jl:35-54); the one-hot probe is a
+        // compile-time constant so the first chain link folds to a weight row
+        float tr = 0.0f;
+        static_for<0, N::D>([&](auto pc) __attribute__((always_inline)) {
+            constexpr int p = decltype(pc)::value;
+            float probe[N::D], q[N::D];
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) probe[j] = (j == p) ? 1.0f : 0.0f;
+            Chain<N> Cn;
+            vjp_chain<N>(sw, A, probe, Cn, q);
+            tr += q[p];
+        });
+        kl = -tr;
+        kE = 0.0f;
+        kn = 0.0f;
+    } else {
+        Chain<N> Cn;
+        float q[N::D];
+        vjp_chain<N>(sw, A, eps, Cn, q);
+        float s = 0.0f, qq = 0.0f, zz = 0.0f;
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) {
+            s = fmaf(q[j], eps[j], s);
+            qq = fmaf(q[j], q[j], qq);
+            zz = fmaf(kz[j], kz[j], zz);
+        }
+        kl = -s;
+        kE = reg_e ? vec_norm(zz, squared) : 0.0f;
+        kn = reg_n ? vec_norm(qq, squared) : 0.0f;
+    }
+}
+
+// ------------------------------------------------------------------ per-sample I/O
+template <class N>
+struct Sample {
+    float eps[N::D];
+    float x[N::n(0)];  // network input; x[0..D') is rewritten per stage, x[D'] = t, then ys
+};
+
+template <class N>
+__device__ __forceinline__ void load_sample_consts(const SolveArgs& a, int64_t b, Sample<N>& sm) {
+    if (a.mode != ICNF_TEST) {
+        if (a.eps_kind == ICNF_EPS_SUPPLIED) {
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) sm.eps[j] = __ldg(a.eps + b * N::D + j);
+        } else {
+#pragma unroll
+            for (int blk = 0; blk < (N::D + 3) / 4; ++blk) {
+                float o[4];
+                philox_draw4(a.eps_kind, a.seed, PHILOX_STREAM_EPS, a.sample_offset + b, blk, o);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (blk * 4 + r < N::D) sm.eps[blk * 4 + r] = o[r];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) sm.eps[j] = 0.0f;
+    }
+#pragma unroll
+    for (int c = 0; c < N::C; ++c) sm.x[N::D + N::TIN + c] = __ldg(a.ys + b * N::C + c);
+}
+
+// initial state of sample b: z (D'), l, E, n
+template <class N>
+__device__ __forceinline__ void load_state(const SolveArgs& a, int64_t b, int nvars, float (&z)[N::D], float& l,
+                                           float& E, float& n) {
+    l = 0.0f; E = 0.0f; n = 0.0f;
+    if (a.in_kind == IN_U0) {
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) z[j] = __ldg(a.in + b * N::S + j);
+        l = __ldg(a.in + b * N::S + N::D);
+        E = __ldg(a.in + b * N::S + N::D + 1);
+        n = __ldg(a.in + b * N::S + N::D + 2);
+    } else if (a.in_kind == IN_XS) {
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) z[j] = (j < nvars) ? __ldg(a.in + b * nvars + j) : 0.0f;
+    } else if (a.in_kind == IN_Z0) {
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) z[j] = __ldg(a.in + b * N::D + j);
+    } else {
+#pragma unroll
+        for (int blk = 0; blk < (N::D + 3) / 4; ++blk) {
+            float o[4];
+            philox_draw4(ICNF_EPS_GAUSSIAN, a.seed, PHILOX_STREAM_BASE, a.sample_offset + b, blk, o);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (blk * 4 + r < N::D) z[blk * 4 + r] = o[r];
+        }
+    }
+}
+
+// readout of the final state: inference_sol + reg_z_aug + generate_sol + per-sample loss
+template <class N>
+__device__ __forceinline__ void write_outputs(const SolveArgs& a, int64_t b, int nvars, const float (&z)[N::D],
+                                              float l, float E, float n) {
+    if (a.out_u) {
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) a.out_u[b * N::S + j] = z[j];
+        a.out_u[b * N::S + N::D] = l;
+        a.out_u[b * N::S + N::D + 1] = E;
+        a.out_u[b * N::S + N::D + 2] = n;
+    }
+    if (a.out_x) {
+#pragma unroll
+        for (int j = 0; j < N::D; ++j)
+            if (j < nvars) a.out_x[b * nvars + j] = z[j];
+    }
+    if (a.out_logp || a.out_regs || a.out_lossterm) {
+        float zz = 0.0f, za = 0.0f;
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) {
+            zz = fmaf(z[j], z[j], zz);
+            if (j >= nvars) za = fmaf(z[j], z[j], za);
+        }
+        float logp = -0.91893853320467274178f * (float)N::D - 0.5f * zz - l;
+        float Aa = a.reg_a ? vec_norm(za, a.squared) : 0.0f;
+        if (a.out_logp) a.out_logp[b] = logp;
+        if (a.out_regs) {
+            a.out_regs[b * 3 + 0] = E;
+            a.out_regs[b * 3 + 1] = n;
+            a.out_regs[b * 3 + 2] = Aa;
+        }
+        if (a.out_lossterm) a.out_lossterm[b] = -logp + a.lam1 * E + a.lam2 * n + a.lam3 * Aa;
+    }
+}
+
+// stage-derivative storage in shared memory: K(i)[r] for stage i, row r, this thread
+struct StageMem {
+    float* base;
+    __device__ __forceinline__ float& at(int idx) { return base[idx * NT + threadIdx.x]; }
+};
+
+// ------------------------------------------------------------------ S1: one RHS
+template <class N, bool EXACT>
+__global__ void __launch_bounds__(NT) rhs_kernel(const __grid_constant__ WBlock<N> sw, RhsArgs a) {
+    for (int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * NT) {
+        float x[N::n(0)], eps[N::D];
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) {
+            x[j] = __ldg(a.u + b * N::S + j);
+            eps[j] = (!EXACT && a.eps) ? __ldg(a.eps + b * N::D + j) : 0.0f;
+        }
+        if constexpr (N::TIN) x[N::D] = a.t;
+#pragma unroll
+        for (int c = 0; c < N::C; ++c) x[N::D + N::TIN + c] = __ldg(a.ys + b * N::C + c);
+        float kz[N::D], kl, kE, kn;
+        rhs_eval<N, EXACT>(sw, x, eps, a.reg_e, a.reg_n, a.squared, kz, kl, kE, kn);
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) a.du[b * N::S + j] = kz[j];
+        a.du[b * N::S + N::D] = kl;
+        a.du[b * N::S + N::D + 1] = kE;
+        a.du[b * N::S + N::D + 2] = kn;
+    }
+}
+
+// ------------------------------------------------------------------ S2: fixed-step solve
+// Each thread integrates its samples through all steps; no cross-thread traffic.
+template <class N, bool EXACT>
+__global__ void __launch_bounds__(NT) solve_fixed_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
+    extern __shared__ __align__(16) float smem[];
+    StageMem K{smem};
+    const float tdir = (a.t1 >= a.t0) ? 1.0f : -1.0f;
+    const float span = fabsf(a.t1 - a.t0);
+    for (int64_t b = (int64_t)blockIdx.x * NT + threadIdx.x; b < a.B; b += (int64_t)gridDim.x * NT) {
+        Sample<N> sm;
+        load_sample_consts<N>(a, b, sm);
+        float z[N::D], l, E, n;
+        load_state<N>(a, b, nvars, z, l, E, n);
+        if (a.ckpt) {
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) a.ckpt[b * N::D + j] = z[j];
+        }
+        for (int step = 0; step < a.nsteps; ++step) {
+            const float tb = fminf(span, step * a.dt);
+            const float hmag = fminf(a.dt, span - tb);
+            const float h = tdir * hmag;
+            const float t = a.t0 + tdir * tb;
+            float zs[N::D], sl = 0.0f, sE = 0.0f, sn = 0.0f;
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) zs[j] = 0.0f;
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) sm.x[j] = z[j];
+                for (int jj = 0; jj < i; ++jj) {
+                    const float c = h * c_a[i][jj];
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) sm.x[j] = fmaf(c, K.at(jj * N::D + j), sm.x[j]);
+                }
+                if constexpr (N::TIN) sm.x[N::D] = fmaf(c_c[i], h, t);
+                float kz[N::D], kl, kE, kn;
+                rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kl, kE, kn);
+                const float bi = c_a[6][i];
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) {
+                    K.at(i * N::D + j) = kz[j];
+                    zs[j] = fmaf(bi, kz[j], zs[j]);
+                }
+                sl = fmaf(bi, kl, sl);
+                sE = fmaf(bi, kE, sE);
+                sn = fmaf(bi, kn, sn);
+            }
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) z[j] = fmaf(h, zs[j], z[j]);
+            l = fmaf(h, sl, l);
+            E = fmaf(h, sE, E);
+            n = fmaf(h, sn, n);
+            if (a.ckpt) {
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) a.ckpt[((int64_t)(step + 1) * a.B + b) * N::D + j] = z[j];
+            }
+        }
+        write_outputs<N>(a, b, nvars, z, l, E, n);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        if (a.steps) {
+            for (int step = 0; step < a.nsteps; ++step) {
+                const float tb = fminf(span, step * a.dt);
+                a.steps[step].t = a.t0 + tdir * tb;
+                a.steps[step].dt = tdir * fminf(a.dt, span - tb);
+            }
+        }
+        if (a.stats) {
+            a.stats->naccept = a.nsteps;
+            a.stats->nreject = 0;
+            a.stats->nf = 6 * a.nsteps;
+            a.stats->status = ICNF_OK;
+            a.stats->t_final = a.t1;
+            a.stats->dt_last = a.nsteps ? tdir * fminf(a.dt, span - fminf(span, (a.nsteps - 1) * a.dt)) : 0.0f;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ S2: adaptive solve
+// Cooperative persistent kernel.  One dt for the whole batch: the scaled error is
+// reduced over all S*B entries (per-CTA partial sums in a fixed order, so the
+// result is bit-reproducible), then every thread runs the same PI controller.
+struct GridReducer {
+    cg::grid_group grid;
+    double* partials;  // [2][gridDim.x]
+    double* sred;      // shared, >= NT/32 + 1
+    int parity;
+    __device__ double sum(double local) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        double v = warp_sum(local);
+        if (lane == 0) sred[w] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.0;
+            for (int i = 0; i < NT / 32; ++i) s += sred[i];
+            partials[(size_t)parity * gridDim.x + blockIdx.x] = s;
+        }
+        __threadfence();
+        grid.sync();
+        double acc = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += NT) acc += __ldcg(partials + (size_t)parity * gridDim.x + i);
+        acc = warp_sum(acc);
+        __syncthreads();
+        if (lane == 0) sred[w] = acc;
+        __syncthreads();
+        double tot = 0.0;
+        for (int i = 0; i < NT / 32; ++i) tot += sred[i];
+        __syncthreads();
+        parity ^= 1;
+        return tot;
+    }
+};
+
+template <class N, bool EXACT>
+__global__ void __launch_bounds__(NT) solve_adaptive_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
+    extern __shared__ __align__(16) float smem[];
+    StageMem K{smem};
+    __shared__ double sred[NT / 32 + 1];
+    GridReducer red{cg::this_grid(), a.partials, sred, 0};
+
+    const float tdir = (a.t1 >= a.t0) ? 1.0f : -1.0f;
+    const float span = fabsf(a.t1 - a.t0);
+    const int64_t stride = (int64_t)gridDim.x * NT;
+    const int64_t b0 = (int64_t)blockIdx.x * NT + threadIdx.x;
+    const Controller ctl = a.ctl;
+    const double inv_count = 1.0 / ((double)a.B * (double)N::S);
+    int cur = 0;
+    int nacc = 0, nrej = 0, nf = 0, status = ICNF_OK;
+    float t = a.t0;
+
+    // ---- init: u0, k1 = f(u0, t0), and the norms of the automatic initial step
+    double d0s = 0.0, d1s = 0.0;
+    for (int64_t b = b0; b < a.B; b += stride) {
+        Sample<N> sm;
+        load_sample_consts<N>(a, b, sm);
+        float z[N::D], l, E, n;
+        load_state<N>(a, b, nvars, z, l, E, n);
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) sm.x[j] = z[j];
+        if constexpr (N::TIN) sm.x[N::D] = t;
+        float kz[N::D], kl, kE, kn;
+        rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kl, kE, kn);
+        float* u = a.wu[0] + b * N::S;
+        float* k = a.wk[0] + b * N::S;
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) {
+            u[j] = z[j];
+            k[j] = kz[j];
+            float sk = ctl.abstol + fabsf(z[j]) * ctl.reltol;
+            d0s += (double)((z[j] / sk) * (z[j] / sk));
+            d1s += (double)((kz[j] / sk) * (kz[j] / sk));
+        }
+        u[N::D] = l; u[N::D + 1] = E; u[N::D + 2] = n;
+        k[N::D] = kl; k[N::D + 1] = kE; k[N::D + 2] = kn;
+        const float ex[3] = {l, E, n}, kx[3] = {kl, kE, kn};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            float sk = ctl.abstol + fabsf(ex[r]) * ctl.reltol;
+            d0s += (double)((ex[r] / sk) * (ex[r] / sk));
+            d1s += (double)((kx[r] / sk) * (kx[r] / sk));
+        }
+        if (a.ckpt) {
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) a.ckpt[b * N::D + j] = z[j];
+        }
+    }
+    nf = 1;
+    float dt;
+    if (a.dt > 0.0f) {
+        dt = fminf(a.dt, span);
+    } else {
+        // Hairer-Wanner starting step as OrdinaryDiffEq applies it
+        const float d0 = (float)sqrt(red.sum(d0s) * inv_count);
+        const float d1 = (float)sqrt(red.sum(d1s) * inv_count);
+        float dt0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+        dt0 = fminf(dt0, span);
+        double d2s = 0.0;
+        for (int64_t b = b0; b < a.B; b += stride) {
+            Sample<N> sm;
+            load_sample_consts<N>(a, b, sm);
+            const float* u = a.wu[0] + b * N::S;
+            const float* k = a.wk[0] + b * N::S;
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) sm.x[j] = fmaf(tdir * dt0, k[j], u[j]);
+            if constexpr (N::TIN) sm.x[N::D] = t + tdir * dt0;
+            float kz[N::D], kl, kE, kn;
+            rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kl, kE, kn);
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) {
+                float sk = ctl.abstol + fabsf(u[j]) * ctl.reltol;
+                float df = (kz[j] - k[j]) / sk;
+                d2s += (double)(df * df);
+            }
+            const float kx[3] = {kl, kE, kn};
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float sk = ctl.abstol + fabsf(u[N::D + r]) * ctl.reltol;
+                float df = (kx[r] - k[N::D + r]) / sk;
+                d2s += (double)(df * df);
+            }
+        }
+        nf += 1;
+        const float d2 = (float)sqrt(red.sum(d2s) * inv_count) / dt0;
+        const float dm = fmaxf(d1, d2);
+        float dt1 = (dm <= 1e-15f) ? fmaxf(1e-6f, dt0 * 1e-3f) : exp10f(-(2.0f + log10f(dm)) / 6.0f);
+        dt = fminf(fminf(100.0f * dt0, dt1), span);
+    }
+
+    // ---- step loop
+    float qold = ctl.qoldinit;
+    float dt_last = 0.0f;
+    int attempts = 0;
+    while (true) {
+        const float remaining = fabsf(a.t1 - t);
+        if (remaining <= 1e-7f * fmaxf(1.0f, fabsf(a.t1))) break;
+        const bool last = dt >= remaining * (1.0f - 1e-6f);
+        const float hmag = last ? remaining : dt;
+        const float h = tdir * hmag;
+        if (!(hmag > 0.0f) || t + h == t) { status = ICNF_ERR_DT_UNDERFLOW; break; }
+        if (++attempts > ctl.max_steps || (a.ckpt && nacc >= a.max_ckpt_steps)) { status = ICNF_ERR_MAX_STEPS; break; }
+
+        double es = 0.0;
+        for (int64_t b = b0; b < a.B; b += stride) {
+            Sample<N> sm;
+            load_sample_consts<N>(a, b, sm);
+            const float* u = a.wu[cur] + b * N::S;
+            const float* k1 = a.wk[cur] + b * N::S;
+            float z[N::D], zs[N::D], ze[N::D];
+            float ux[3], sx[3], exs[3];
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) {
+                z[j] = u[j];
+                float kk = k1[j];
+                K.at(j) = kk;
+                zs[j] = c_a[6][0] * kk;
+                ze[j] = c_bt[0] * kk;
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                ux[r] = u[N::D + r];
+                float kk = k1[N::D + r];
+                sx[r] = c_a[6][0] * kk;
+                exs[r] = c_bt[0] * kk;
+            }
+            for (int i = 1; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) sm.x[j] = z[j];
+                for (int jj = 0; jj < i; ++jj) {
+                    const float c = h * c_a[i][jj];
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) sm.x[j] = fmaf(c, K.at(jj * N::D + j), sm.x[j]);
+                }
+                if constexpr (N::TIN) sm.x[N::D] = fmaf(c_c[i], h, t);
+                float kz[N::D], kx[3];
+                rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kx[0], kx[1], kx[2]);
+                const float bi = c_a[6][i], bti = c_bt[i];
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) {
+                    K.at(i * N::D + j) = kz[j];
+                    zs[j] = fmaf(bi, kz[j], zs[j]);
+                    ze[j] = fmaf(bti, kz[j], ze[j]);
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    sx[r] = fmaf(bi, kx[r], sx[r]);
+                    exs[r] = fmaf(bti, kx[r], exs[r]);
+                }
+            }
+            // u_new and the FSAL stage k7 = f(u_new, t + h)
+            float zn[N::D], un[3];
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) { zn[j] = fmaf(h, zs[j], z[j]); sm.x[j] = zn[j]; }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) un[r] = fmaf(h, sx[r], ux[r]);
+            if constexpr (N::TIN) sm.x[N::D] = last ? a.t1 : t + h;
+            float k7[N::D], k7x[3];
+            rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, k7, k7x[0], k7x[1], k7x[2]);
+            float* uo = a.wu[cur ^ 1] + b * N::S;
+            float* ko = a.wk[cur ^ 1] + b * N::S;
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) {
+                float e = h * fmaf(c_bt[6], k7[j], ze[j]);
+                float sk = ctl.abstol + fmaxf(fabsf(z[j]), fabsf(zn[j])) * ctl.reltol;
+                float r = e / sk;
+                es += (double)(r * r);
+                uo[j] = zn[j];
+                ko[j] = k7[j];
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float e = h * fmaf(c_bt[6], k7x[r], exs[r]);
+                float sk = ctl.abstol + fmaxf(fabsf(ux[r]), fabsf(un[r])) * ctl.reltol;
+                float q = e / sk;
+                es += (double)(q * q);
+                uo[N::D + r] = un[r];
+                ko[N::D + r] = k7x[r];
+            }
+            if (a.ckpt) {
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) a.ckpt[((int64_t)(nacc + 1) * a.B + b) * N::D + j] = zn[j];
+            }
+        }
+        nf += 6;
+        const float eest = (float)sqrt(red.sum(es) * inv_count);
+        if (!isfinite(eest)) { status = ICNF_ERR_NONFINITE; break; }
+        const float q11 = eest > 0.0f ? powf(eest, ctl.beta1) : 0.0f;
+        float q = q11 / powf(qold, ctl.beta2);
+        q = fmaxf(1.0f / ctl.qmax, fminf(1.0f / ctl.qmin, q / ctl.gamma));
+        if (eest <= 1.0f) {
+            if (a.steps && blockIdx.x == 0 && threadIdx.x == 0) { a.steps[nacc].t = t; a.steps[nacc].dt = h; }
+            nacc++;
+            dt_last = h;
+            t = last ? a.t1 : t + h;
+            cur ^= 1;
+            if (q >= ctl.qsteady_min && q <= ctl.qsteady_max) q = 1.0f;
+            qold = fmaxf(eest, ctl.qoldinit);
+            dt = hmag / q;
+        } else {
+            nrej++;
+            dt = hmag / fminf(1.0f / ctl.qmin, q11 / ctl.gamma);
+        }
+    }
+
+    // ---- readout
+    for (int64_t b = b0; b < a.B; b += stride) {
+        const float* u = a.wu[cur] + b * N::S;
+        float z[N::D];
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) z[j] = u[j];
+        write_outputs<N>(a, b, nvars, z, u[N::D], u[N::D + 1], u[N::D + 2]);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
+        a.stats->naccept = nacc;
+        a.stats->nreject = nrej;
+        a.stats->nf = nf;
+        a.stats->status = status;
+        a.stats->t_final = t;
+        a.stats->dt_last = dt_last;
+    }
+}
+
+// ------------------------------------------------------------------ S3: backward
+// Warp-transposed reduction: every lane contributes v[0..31]; on return lane L
+// holds sum over lanes of v[L] in v[0].  31 shuffles for 32 sums.
+__device__ __forceinline__ float transposed_reduce32(float (&v)[32]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            float send = up ? v[i] : v[i + half];
+            float keep = up ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+// Reverse of one RHS evaluation at stage input x (= [Z; t; ys]) for one sample:
+// cotangents zb (on zdot), cl (on ldot), cE, cn (on the two norms) ->
+// sbar = cotangent on Z, and the parameter gradient accumulated into gacc
+// (lane L of chunk c owns entry 32 c + L of that layer's [vec(W); b]).
+template <class N, bool EXACT>
+__device__ __forceinline__ void rhs_reverse(const WBlock<N>& sw, const float (&x)[N::n(0)], const float (&eps)[N::D],
+                                            const float (&zb_in)[N::D], float cl, float cE, float cn,
+                                            int squared, float (&sbar)[N::D], float (&gacc)[N::NCHUNK]) {
+    Acts<N> A;
+    forward<N>(sw, x, A);
+    float zb[N::D];
+#pragma unroll
+    for (int j = 0; j < N::D; ++j) zb[j] = zb_in[j];
+    if (!EXACT && cE != 0.0f) {
+        float zz = 0.0f;
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) zz = fmaf(A.h[N::NL - 1][j], A.h[N::NL - 1][j], zz);
+        // d|z|/dz = z/|z| (0 at 0, the ChainRules convention); d|z|^2/dz = 2 z
+        float s = squared ? 2.0f * cE : (zz > 0.0f ? cE * rsqrtf(zz) : 0.0f);
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) zb[j] = fmaf(s, A.h[N::NL - 1][j], zb[j]);
+    }
+    // extra pre-activation cotangents from the second-order terms
+    float aex[N::NL][N::NMAX];
+#pragma unroll
+    for (int l = 0; l < N::NL; ++l)
+#pragma unroll
+        for (int j = 0; j < N::NMAX; ++j) aex[l][j] = 0.0f;
+
+    constexpr int NPROBE = EXACT ? N::D : 1;
+    static_for<0, NPROBE>([&](auto pc) __attribute__((always_inline)) {
+        constexpr int p = decltype(pc)::value;
+        float probe[N::D], q[N::D], qb[N::D];
+#pragma unroll
+        for (int j = 0; j < N::D; ++j) probe[j] = EXACT ? ((j == p) ? 1.0f : 0.0f) : eps[j];
+        Chain<N> Cn;
+        vjp_chain<N>(sw, A, probe, Cn, q);
+        if constexpr (EXACT) {
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) qb[j] = (j == p) ? -cl : 0.0f;
+        } else {
+            float qq = 0.0f;
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) qq = fmaf(q[j], q[j], qq);
+            float s = (cn != 0.0f) ? (squared ? 2.0f * cn : (qq > 0.0f ? cn * rsqrtf(qq) : 0.0f)) : 0.0f;
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) qb[j] = fmaf(s, q[j], -cl * eps[j]);
+        }
+        // tangent pass w_0 = qb, r_l = W_l w_l, w_{l+1} = r_l .* d_l; the weight gradient of
+        // the chain is g_l w_l' and is reduced across the warp layer by layer
+        float w[N::NMAX];
+#pragma unroll
+        for (int k = 0; k < N::D; ++k) w[k] = qb[k];
+        static_for<0, N::NL>([&](auto lc) __attribute__((always_inline)) {
+            constexpr int l = decltype(lc)::value;
+            constexpr int nin = N::n(l), nout = N::n(l + 1), kk = N::kz(l);
+            // gradient contribution g_l[j] * w[k], k < kk
+            static_for<0, N::nchunk(l)>([&](auto cc) __attribute__((always_inline)) {
+                constexpr int c = decltype(cc)::value;
+                float v[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int e = c * 32 + i;
+                    const int k = e / nout, j = e - k * nout;
+                    v[i] = (e < nin * nout && k < kk) ? Cn.g[l][j] * w[k < kk ? k : 0] : 0.0f;
+                }
+                // chunks that only hold zeros (inputs without a z-derivative, biases) are skipped
+                if constexpr (c * 32 < kk * nout) gacc[N::choff(l) + c] += transposed_reduce32(v);
+            });
+            if constexpr (l < N::NL - 1) {
+                float wn[N::NMAX];
+#pragma unroll
+                for (int j = 0; j < nout; ++j) {
+                    float r = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < kk; ++k) r = fmaf(WREF(N, sw, l, j, k), w[k], r);
+                    wn[j] = r * A.d[l][j];
+                    aex[l][j] = fmaf(r * Cn.v[l][j], act_dd<N::ACT>(A.h[l][j], A.d[l][j]), aex[l][j]);
+                }
+#pragma unroll
+                for (int j = 0; j < nout; ++j) w[j] = wn[j];
+            }
+        });
+    });
+
+    // ordinary backprop with output cotangent zb and the extra terms
+    float ab[N::NMAX];
+#pragma unroll
+    for (int j = 0; j < N::D; ++j) ab[j] = zb[j];
+    static_rfor<N::NL>([&](auto lc) __attribute__((always_inline)) {
+        constexpr int l = decltype(lc)::value;
+        constexpr int nin = N::n(l), nout = N::n(l + 1), kk = N::kz(l);
+        static_for<0, N::nchunk(l)>([&](auto cc) __attribute__((always_inline)) {
+            constexpr int c = decltype(cc)::value;
+            float v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const int e = c * 32 + i;
+                const int k = e / nout, j = e - k * nout;
+                float hin;
+                if constexpr (l == 0) hin = x[k < nin ? k : 0];
+                else hin = A.h[l - 1][k < nin ? k : 0];
+                if (e < nin * nout) v[i] = ab[j] * hin;
+                else if (e < nin * nout + nout) v[i] = ab[e - nin * nout];
+                else v[i] = 0.0f;
+            }
+            gacc[N::choff(l) + c] += transposed_reduce32(v);
+        });
+        float hb[N::NMAX];
+#pragma unroll
+        for (int k = 0; k < kk; ++k) {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < nout; ++j) s = fmaf(WREF(N, sw, l, j, k), ab[j], s);
+            hb[k] = s;
+        }
+        if constexpr (l > 0) {
+#pragma unroll
+            for (int k = 0; k < kk; ++k) ab[k] = fmaf(hb[k], A.d[l - 1][k], aex[l - 1][k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < N::D; ++k) sbar[k] = hb[k];
+        }
+    });
+}
+
+// forward-only network evaluation (zdot), used to rebuild the stage inputs
+template <class N>
+__device__ __forceinline__ void zdot_eval(const WBlock<N>& sw, const float (&x)[N::n(0)], float (&kz)[N::D]) {
+    Acts<N> A;
+    forward<N>(sw, x, A);
+#pragma unroll
+    for (int j = 0; j < N::D; ++j) kz[j] = A.h[N::NL - 1][j];
+}
+
+template <class N, bool EXACT>
+__global__ void __launch_bounds__(NT) backward_kernel(const __grid_constant__ WBlock<N> sw, BackwardArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    StageMem Z{smem};                  // stage inputs Z_i, 6 x D'
+    StageMem KB{smem + 6 * N::D * NT};  // stage cotangents Kbar_i, 6 x D'
+    const int nsteps = a.stats->naccept;
+    float gacc[N::NCHUNK];
+#pragma unroll
+    for (int c = 0; c < N::NCHUNK; ++c) gacc[c] = 0.0f;
+
+    const int64_t stride = (int64_t)gridDim.x * NT;
+    const int64_t nloop = (a.B + stride - 1) / stride;
+    for (int64_t it = 0; it < nloop; ++it) {
+        const int64_t braw = it * stride + (int64_t)blockIdx.x * NT + threadIdx.x;
+        const bool valid = braw < a.B;
+        const int64_t b = valid ? braw : a.B - 1;
+        const float wgt = valid ? a.inv_denominator : 0.0f;
+
+        float eps[N::D], x[N::n(0)];
+        if (a.mode != ICNF_TEST) {
+            if (a.eps_kind == ICNF_EPS_SUPPLIED) {
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) eps[j] = __ldg(a.eps + b * N::D + j);
+            } else {
+#pragma unroll
+                for (int blk = 0; blk < (N::D + 3) / 4; ++blk) {
+                    float o[4];
+                    philox_draw4(a.eps_kind, a.seed, PHILOX_STREAM_EPS, a.sample_offset + b, blk, o);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        if (blk * 4 + r < N::D) eps[blk * 4 + r] = o[r];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) eps[j] = 0.0f;
+        }
+#pragma unroll
+        for (int c = 0; c < N::C; ++c) x[N::D + N::TIN + c] = __ldg(a.ys + b * N::C + c);
+
+        // cotangent of the loss on the final state (inference_sol + loss):
+        //   L_b = (1/B) [ D'/2 log 2pi + |z|^2/2 + dlogp + l1 E + l2 n + l3 |z_aug| ]
+        float zbar[N::D];
+        {
+            const float* zf = a.ckpt + ((int64_t)nsteps * a.B + b) * N::D;
+            float za = 0.0f;
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) {
+                zbar[j] = zf[j];
+                if (j >= a.nvars) za = fmaf(zf[j], zf[j], za);
+            }
+            if (a.reg_a) {
+                float s = a.squared ? 2.0f * a.lam3 : (za > 0.0f ? a.lam3 * rsqrtf(za) : 0.0f);
+#pragma unroll
+                for (int j = 0; j < N::D; ++j)
+                    if (j >= a.nvars) zbar[j] = fmaf(s, zf[j], zbar[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < N::D; ++j) zbar[j] *= wgt;
+        }
+        const float lbar = wgt;
+        const float Ebar = a.reg_e ? a.lam1 * wgt : 0.0f;
+        const float nbar = a.reg_n ? a.lam2 * wgt : 0.0f;
+
+        for (int step = nsteps - 1; step >= 0; --step) {
+            const float t = a.steps[step].t, h = a.steps[step].dt;
+            float z[N::D];
+            {
+                const float* zc = a.ckpt + ((int64_t)step * a.B + b) * N::D;
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) z[j] = zc[j];
+            }
+            // rebuild the stage inputs Z_1..Z_6 (needs zdot of stages 1..5 only); KB
+            // temporarily holds those stage derivatives
+            for (int i = 0; i < 6; ++i) {
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) x[j] = z[j];
+                for (int jj = 0; jj < i; ++jj) {
+                    const float c = h * c_a[i][jj];
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) x[j] = fmaf(c, KB.at(jj * N::D + j), x[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) Z.at(i * N::D + j) = x[j];
+                if (i < 5) {
+                    if constexpr (N::TIN) x[N::D] = fmaf(c_c[i], h, t);
+                    float kz[N::D];
+                    zdot_eval<N>(sw, x, kz);
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) KB.at(i * N::D + j) = kz[j];
+                }
+            }
+            // Kbar_i = h b_i zbar_{n+1}
+            for (int i = 0; i < 6; ++i) {
+                const float c = h * c_a[6][i];
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) KB.at(i * N::D + j) = c * zbar[j];
+            }
+            for (int i = 5; i >= 0; --i) {
+                float kb[N::D], sbar[N::D];
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) {
+                    x[j] = Z.at(i * N::D + j);
+                    kb[j] = KB.at(i * N::D + j);
+                }
+                if constexpr (N::TIN) x[N::D] = fmaf(c_c[i], h, t);
+                const float hb = h * c_a[6][i];
+                rhs_reverse<N, EXACT>(sw, x, eps, kb, hb * lbar, hb * Ebar, hb * nbar, a.squared, sbar, gacc);
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) zbar[j] += sbar[j];
+                for (int jj = 0; jj < i; ++jj) {
+                    const float c = h * c_a[i][jj];
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) KB.at(jj * N::D + j) = fmaf(c, sbar[j], KB.at(jj * N::D + j));
+                }
+            }
+        }
+        if (a.dxs && valid) {
+#pragma unroll
+            for (int j = 0; j < N::D; ++j)
+                if (j < a.nvars) a.dxs[b * a.nvars + j] = zbar[j];
+        }
+    }
+    // per-warp partial gradient, native ComponentArray order
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
+    float* gp = a.gpartial + gw * N::NP;
+    static_for<0, N::NL>([&](auto lc) __attribute__((always_inline)) {
+        constexpr int l = decltype(lc)::value;
+#pragma unroll
+        for (int c = 0; c < N::nchunk(l); ++c) {
+            const int e = c * 32 + lane;
+            if (e < N::nent(l)) gp[N::toff(l) + e] = gacc[N::choff(l) + c];
+        }
+    });
+}
+
+}  // namespace tiny
+}  // namespace icnf

@@ -1,0 +1,117 @@
+// tiny_launch.cuh -- host launchers for one instantiation of the tiny family and
+// the macro that registers it with the dispatcher in api.cu.
+#pragma once
+#include <algorithm>
+
+#include "family.h"
+#include "tiny.cuh"
+
+namespace icnf {
+namespace tiny {
+
+template <class N>
+struct Launch {
+    static constexpr size_t smem_rhs = 0;
+    static constexpr size_t smem_solve = sizeof(float) * (6 * N::D * NT);
+    static constexpr size_t smem_bwd = sizeof(float) * (12 * N::D * NT);
+    static_assert(sizeof(WBlock<N>) + sizeof(SolveArgs) + 16 <= 32764, "weights must fit the kernel parameter space");
+
+    // theta (host, native ComponentArray order) -> padded parameter block
+    static void pack(const float* theta, WBlock<N>& w) {
+        for (int i = 0; i < N::WPAD; ++i) w.v[i] = 0.0f;
+        for (int l = 0; l < N::NL; ++l) {
+            const int nin = N::n(l), nout = N::n(l + 1);
+            for (int k = 0; k < nin; ++k)
+                for (int j = 0; j < nout; ++j) w.v[N::woff(l) + k * N::ld(l) + j] = theta[N::toff(l) + k * nout + j];
+            for (int j = 0; j < nout; ++j) w.v[N::boff(l) + j] = theta[N::toff(l) + nin * nout + j];
+        }
+    }
+
+    template <class K>
+    static cudaError_t prep(K kernel, size_t smem) {
+        return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    }
+    template <class K>
+    static int occupancy(K kernel, size_t smem) {
+        int nb = 0;
+        if (prep(kernel, smem) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, NT, smem) != cudaSuccess) return 0;
+        return nb;
+    }
+    static int grid_for(long long B, int per_sm, int sm_count) {
+        long long need = (B + NT - 1) / NT;
+        long long cap = (long long)std::max(per_sm, 1) * sm_count;
+        return (int)std::max(1LL, std::min(need, cap));
+    }
+
+    static cudaError_t rhs(const float* theta, const RhsArgs& a, bool exact, int sm_count, cudaStream_t st) {
+        auto k = exact ? rhs_kernel<N, true> : rhs_kernel<N, false>;
+        int grid = grid_for(a.B, occupancy(k, smem_rhs), sm_count);
+        WBlock<N> w;
+        pack(theta, w);
+        k<<<grid, NT, smem_rhs, st>>>(w, a);
+        return cudaGetLastError();
+    }
+    static cudaError_t solve_fixed(const float* theta, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st) {
+        auto k = exact ? solve_fixed_kernel<N, true> : solve_fixed_kernel<N, false>;
+        int grid = grid_for(a.B, occupancy(k, smem_solve), sm_count);
+        WBlock<N> w;
+        pack(theta, w);
+        k<<<grid, NT, smem_solve, st>>>(w, a, nvars);
+        return cudaGetLastError();
+    }
+    static int adaptive_max_grid(bool exact, int sm_count) {
+        auto k = exact ? solve_adaptive_kernel<N, true> : solve_adaptive_kernel<N, false>;
+        return occupancy(k, smem_solve) * sm_count;
+    }
+    static cudaError_t solve_adaptive(const float* theta, const SolveArgs& a, int nvars, bool exact, int grid, cudaStream_t st) {
+        auto k = exact ? solve_adaptive_kernel<N, true> : solve_adaptive_kernel<N, false>;
+        cudaError_t e = prep(k, smem_solve);
+        if (e != cudaSuccess) return e;
+        SolveArgs aa = a;
+        int nv = nvars;
+        WBlock<N> w;
+        pack(theta, w);
+        void* args[] = {(void*)&w, (void*)&aa, (void*)&nv};
+        return cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(NT), args, smem_solve, st);
+    }
+    static int backward_grid(bool exact, int sm_count, long long B) {
+        auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
+        return grid_for(B, occupancy(k, smem_bwd), sm_count);
+    }
+    static cudaError_t backward(const float* theta, const BackwardArgs& a, bool exact, int grid, cudaStream_t st) {
+        auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
+        cudaError_t e = prep(k, smem_bwd);
+        if (e != cudaSuccess) return e;
+        WBlock<N> w;
+        pack(theta, w);
+        k<<<grid, NT, smem_bwd, st>>>(w, a);
+        return cudaGetLastError();
+    }
+    static Family make() {
+        Family f{};
+        f.name = "tiny";
+        f.shape.act = N::ACT; f.shape.D = N::D; f.shape.C = N::C; f.shape.NL = N::NL;
+        for (int l = 0; l <= N::NL; ++l) f.shape.n[l] = N::n(l);
+        f.n_params = N::NP;
+        f.rhs = &rhs;
+        f.solve_fixed = &solve_fixed;
+        f.solve_adaptive = &solve_adaptive;
+        f.adaptive_max_grid = &adaptive_max_grid;
+        f.backward = &backward;
+        f.backward_grid = &backward_grid;
+        f.backward_partials_per_block = NT / 32;
+        return f;
+    }
+};
+
+}  // namespace tiny
+}  // namespace icnf
+
+#define ICNF_TINY_CAT2(a, b) a##b
+#define ICNF_TINY_CAT(a, b) ICNF_TINY_CAT2(a, b)
+// ICNF_REGISTER_TINY(act, D', ncond, n_layers, n0, n1, ...)
+#define ICNF_REGISTER_TINY(...)                                                                       \
+    static const icnf::Family ICNF_TINY_CAT(s_family_, __LINE__) =                                    \
+        icnf::tiny::Launch<icnf::tiny::Net<__VA_ARGS__>>::make();                                     \
+    static icnf::TinyRegistrar ICNF_TINY_CAT(s_registrar_, __LINE__)(&ICNF_TINY_CAT(s_family_, __LINE__));

@@ -1,0 +1,243 @@
+/*
+ * icnf_b200.h -- C ABI of libicnf_b200.so
+ *
+ * A B200-native (sm_100a) implementation of the data-parallel hot path of
+ * ContinuousNormalizingFlows.jl: the batched augmented ODE right-hand side of
+ * ICNF / RNODE / FFJORD / CondICNF, the Tsit5 loop that integrates it, the
+ * log-density / sample / loss readouts and the training gradient.
+ *
+ * The reference has no FFI for this path (it is pure Julia; the extension
+ * mechanism is multiple dispatch on the ICNF type parameters).  Each entry point
+ * below names the reference method it stands behind; a Julia maintainer binds it
+ * with `ccall` from a method specialised on a new `B200MatrixMode <: MatrixMode`
+ * (see INTEGRATION.md and continuousnormalizingflows.jl_b200/julia/B200Mode.jl).
+ * All citations are relative to the reference checkout's root.
+ *
+ * Data layout (exactly Julia's): Float32, column-major.  An `R x B` matrix is B
+ * contiguous records of R floats (one record per sample).  `theta` is
+ * `ComponentArrays.getdata(ps)`: [vec(W1); b1; vec(W2); b2; ...] with W_l
+ * column-major n_l x n_{l-1} (src/exts/mlj_ext/core_icnf.jl:35).
+ *
+ * Ownership: the caller owns every buffer passed in and keeps it alive for the
+ * duration of the call; the library owns all device memory behind the opaque
+ * handle.  Entry points without the `_dev` suffix take HOST pointers and copy
+ * in/out internally (they return when the result is in the caller's buffer);
+ * `_dev` entry points take DEVICE pointers on the handle's device, enqueue on
+ * the given CUDA stream (a `cudaStream_t` passed as `void*`, NULL = the legacy
+ * default stream) and do not synchronise; their `loss`, `dtheta`, `dxs` and
+ * `stats` arguments are DEVICE pointers too (`stats` receives an icnf_stats
+ * record asynchronously; its `status` field carries the device loop's verdict).
+ *
+ * Errors: every function returns an `icnf_status`; no C++ exception crosses the
+ * ABI; `icnf_last_error` returns a message.  There is NO CPU fallback: without a
+ * usable CUDA device `icnf_create` returns ICNF_ERR_NO_DEVICE.
+ *
+ * Threading: a handle is used by one thread at a time; distinct handles are
+ * independent.  One process per GPU for multi-GPU use; the batch is sharded by
+ * columns; `icnf_noise.sample_offset` and `global_batch` tell the library where
+ * this shard sits in the global batch.
+ */
+#ifndef ICNF_B200_H
+#define ICNF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define ICNF_API __attribute__((visibility("default")))
+#else
+#define ICNF_API
+#endif
+
+#define ICNF_MAX_LAYERS 8
+#define ICNF_ABI_VERSION 1
+
+typedef enum icnf_status {
+    ICNF_OK = 0,
+    ICNF_ERR_INVALID = 1,       /* bad argument / inconsistent config            */
+    ICNF_ERR_CUDA = 2,          /* CUDA runtime error (message has the detail)   */
+    ICNF_ERR_MAX_STEPS = 3,     /* adaptive loop hit max_steps                   */
+    ICNF_ERR_DT_UNDERFLOW = 4,  /* step size underflow                           */
+    ICNF_ERR_NONFINITE = 5,     /* NaN/Inf in the error estimate or state        */
+    ICNF_ERR_NO_DEVICE = 6,     /* no CUDA device: there is no CPU fallback      */
+    ICNF_ERR_UNSUPPORTED = 7    /* valid request this build has no kernel for    */
+} icnf_status;
+
+/* src/core/types.jl:1-7 -- TestMode, TrainMode{true}, TrainMode{false}.
+ * TEST uses the exact Jacobian trace (src/core/icnf.jl:297-316); both TRAIN modes
+ * use one Hutchinson probe (src/core/icnf.jl:517-536); the regularisers E, n, A
+ * are non-zero only for TRAIN_REG (src/core/icnf.jl:184-251, base_icnf.jl:106-132). */
+typedef enum icnf_mode { ICNF_TEST = 0, ICNF_TRAIN_REG = 1, ICNF_TRAIN_NOREG = 2 } icnf_mode;
+
+typedef enum icnf_activation {
+    ICNF_ACT_SOFTPLUS = 0,      /* NNlib.softplus, the reference default (icnf.jl:68-69) */
+    ICNF_ACT_TANH = 1,
+    ICNF_ACT_SIGMOID = 2,
+    ICNF_ACT_IDENTITY = 3
+} icnf_activation;
+
+typedef enum icnf_eps_kind {
+    ICNF_EPS_SUPPLIED = 0,      /* caller passes the D' x B probe matrix (parity mode)   */
+    ICNF_EPS_GAUSSIAN = 1,      /* N(0,I): the reference default epsdist (icnf.jl:80-83) */
+    ICNF_EPS_RADEMACHER = 2     /* +-1, drawn in-kernel with Philox4x32-10               */
+} icnf_eps_kind;
+
+typedef enum icnf_precision {
+    ICNF_FP32 = 0,              /* fp32 FMA path (parity path, every width)              */
+    ICNF_BF16_TC = 1            /* bf16 tcgen05 tensor-core RHS for wide MLPs            */
+} icnf_precision;
+
+/* Mirror of the `ICNF` struct and keyword constructor (src/core/icnf.jl:16-141).
+ * Booleans the reference lifts into type parameters (icnf.jl:105-115) are derived
+ * here: CONDITIONED = ncond != 0, AUGMENTED = naug != 0, NORM_Z = lambda1 != 0,
+ * NORM_J = lambda2 != 0, NORM_Z_AUG = lambda3 != 0.  The network is the Lux
+ * Chain of Dense layers of icnf.jl:67-71: sizes[0] = n_in = nvars + naug +
+ * !autonomous + ncond (icnf.jl:64), sizes[n_layers] = nvars + naug; every layer
+ * but the last applies `activation`. */
+typedef struct icnf_config {
+    int32_t abi_version;        /* ICNF_ABI_VERSION */
+    int32_t nvars;
+    int32_t naug;
+    int32_t ncond;
+    int32_t autonomous;         /* 0: time is appended to the network input (icnf.jl:147-153) */
+    int32_t n_layers;
+    int32_t sizes[ICNF_MAX_LAYERS + 1];
+    int32_t activation;         /* icnf_activation */
+    float lambda1, lambda2, lambda3;   /* icnf.jl:73-75 */
+    int32_t reg_squared;        /* 0 = un-squared norms as the reference (icnf.jl:198,244); 1 = RNODE-paper squares */
+    int32_t precision;          /* icnf_precision */
+    int32_t device;             /* CUDA ordinal */
+} icnf_config;
+
+/* The part of `sol_kwargs` (src/core/icnf.jl:84-102) this path consumes, for the
+ * Tsit5 stepper.  Zero in a controller field selects OrdinaryDiffEq's default. */
+typedef struct icnf_solver {
+    int32_t adaptive;           /* 1: PI-controlled steps, error norm over the whole S x B state */
+    float dt;                   /* fixed step, or initial step (0 = automatic) when adaptive */
+    float reltol, abstol;       /* icnf.jl:87-88 (1e-4) */
+    int32_t max_steps;          /* 0 = 100000; the reference's maxiters is typemax(Int) (icnf.jl:86) */
+    float beta1, beta2, gamma, qmin, qmax, qsteady_min, qsteady_max, qoldinit;
+} icnf_solver;
+
+/* Hutchinson probe / base sample source.  `sample_offset` is the global column
+ * index of this shard's first sample so that a sharded batch draws the same
+ * numbers as the unsharded one. */
+typedef struct icnf_noise {
+    int32_t kind;               /* icnf_eps_kind */
+    uint64_t seed;
+    int64_t sample_offset;
+} icnf_noise;
+
+typedef struct icnf_stats {
+    int32_t naccept, nreject, nf;   /* accepted / rejected steps, RHS evaluations */
+    int32_t status;                 /* icnf_status of the device loop */
+    float t_final, dt_last;
+} icnf_stats;
+
+typedef struct icnf_handle icnf_handle;
+
+/* -- lifetime --------------------------------------------------------------- */
+ICNF_API const char* icnf_version(void);
+ICNF_API int icnf_device_count(void);
+/* `ICNF(; ...)` constructor, src/core/icnf.jl:53-141 */
+ICNF_API int icnf_create(const icnf_config* cfg, icnf_handle** out);
+ICNF_API void icnf_destroy(icnf_handle* h);
+/* message of the last failure on this handle (or of the last failed icnf_create when h == NULL) */
+ICNF_API const char* icnf_last_error(const icnf_handle* h);
+ICNF_API int64_t icnf_n_params(const icnf_handle* h);
+ICNF_API int32_t icnf_n_state(const icnf_handle* h);        /* S = nvars + naug + 3 (icnf.jl:143-145) */
+/* name of the kernel family that serves this config ("tiny", "generic", "tc") */
+ICNF_API const char* icnf_kernel_family(const icnf_handle* h);
+
+/* `ps` of every reference call (ComponentArray data, host or device pointer) */
+ICNF_API int icnf_set_params(icnf_handle* h, const float* theta, int64_t n);
+ICNF_API int icnf_set_params_dev(icnf_handle* h, const float* theta, int64_t n, void* stream);
+
+/* -- S1: one RHS evaluation ------------------------------------------------- */
+/* `augmented_f(du, u, p, t, icnf, mode, nn, st, eps)`, src/core/icnf.jl:297-339
+ * (TestMode) and :517-559 (TrainMode, VJP).  u, du: S x B; eps: D' x B (ignored
+ * for ICNF_TEST); ys: ncond x B or NULL. */
+ICNF_API int icnf_rhs(icnf_handle* h, int mode, float t, const float* u, const float* eps,
+             const float* ys, float* du, int64_t B);
+ICNF_API int icnf_rhs_dev(icnf_handle* h, int mode, float t, const float* u, const float* eps,
+                 const float* ys, float* du, int64_t B, void* stream);
+
+/* -- S2: one whole solve ---------------------------------------------------- */
+/* `base_sol(icnf, prob)`, src/core/base_icnf.jl:134-140: integrates u0 from t0
+ * to t1 (t1 < t0 runs backwards, as generate does) and returns u(t1) only
+ * (save_everystep = false, icnf.jl:85).  eps may be NULL when noise->kind is not
+ * SUPPLIED or mode is ICNF_TEST. */
+ICNF_API int icnf_solve(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+               const float* u0, const icnf_noise* noise, const float* eps, const float* ys,
+               float* u_final, icnf_stats* stats, int64_t B);
+ICNF_API int icnf_solve_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                   const float* u0, const icnf_noise* noise, const float* eps, const float* ys,
+                   float* u_final, icnf_stats* stats, int64_t B, void* stream);
+
+/* `inference(icnf, mode, xs, [ys,] ps, st)`, src/core/base_icnf.jl:406-424 =
+ * inference_prob (:247-296) + base_sol + inference_sol (:158-172) fused: builds
+ * u0 = [xs; 0], solves t0 -> t1, returns logp (B) and regs = [E; n; A] (3 x B).
+ * regs may be NULL. */
+ICNF_API int icnf_inference(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                   const float* xs, const icnf_noise* noise, const float* eps, const float* ys,
+                   float* logp, float* regs, icnf_stats* stats, int64_t B);
+ICNF_API int icnf_inference_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                       const float* xs, const icnf_noise* noise, const float* eps, const float* ys,
+                       float* logp, float* regs, icnf_stats* stats, int64_t B, void* stream);
+
+/* `generate(icnf, mode, [ys,] ps, st, n)`, src/core/base_icnf.jl:351-404 +
+ * generate_sol (:185-194): z0 ~ basedist (D' x n; pass NULL to draw N(0,I)
+ * in-kernel from noise->seed), integrates t1 -> t0, returns rows 1:nvars
+ * (nvars x n).  Pass the span in inference order (t0 < t1); the reversal is done
+ * here as the reference does (`reverse(steer_tspan(...))`, :372). */
+ICNF_API int icnf_generate(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                  const float* z0, const icnf_noise* noise, const float* eps, const float* ys,
+                  float* xs_out, icnf_stats* stats, int64_t n);
+ICNF_API int icnf_generate_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                      const float* z0, const icnf_noise* noise, const float* eps, const float* ys,
+                      float* xs_out, icnf_stats* stats, int64_t n, void* stream);
+
+/* -- S3: loss and its gradient ---------------------------------------------- */
+/* `loss(icnf, mode, xs, [ys,] ps, st)`, src/core/icnf.jl:628-649:
+ * mean_b(-logp + l1 E + l2 n + l3 A).  `global_batch` is the mean's denominator
+ * (0 = B); a shard of a larger batch passes the global size so that the shards'
+ * losses and gradients SUM to the unsharded result. */
+ICNF_API int icnf_loss(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+              const float* xs, const icnf_noise* noise, const float* eps, const float* ys,
+              float* loss, icnf_stats* stats, int64_t B, int64_t global_batch);
+/* Gradient of the above w.r.t. theta (and xs when dxs != NULL): what Zygote +
+ * SciMLSensitivity produce for the reference (sensealg at src/core/icnf.jl:90-99;
+ * exercised at test/ci_tests/smoke_tests.jl:132-133).  Computed by reverse-mode
+ * differentiation of the discrete Tsit5 steps actually taken (step sizes held
+ * constant), in one fused backward kernel. */
+ICNF_API int icnf_loss_grad(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                   const float* xs, const icnf_noise* noise, const float* eps, const float* ys,
+                   float* loss, float* dtheta, float* dxs, icnf_stats* stats,
+                   int64_t B, int64_t global_batch);
+ICNF_API int icnf_loss_grad_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                       const float* xs, const icnf_noise* noise, const float* eps, const float* ys,
+                       float* loss, float* dtheta, float* dxs, icnf_stats* stats,
+                       int64_t B, int64_t global_batch, void* stream);
+
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+ICNF_API int64_t icnf_launch_count(const icnf_handle* h);
+
+
+/* -- measurement support (bench.py) ------------------------------------------ */
+/* When enabled, CUDA events are recorded on the launching stream around every
+ * kernel of the next calls; icnf_kernel_times returns the device time in ms of the
+ * last {forward solve or rhs, loss sum, backward, gradient reduce} launches
+ * (-1 where a kernel did not run).  Off by default: no events, no overhead. */
+ICNF_API int icnf_set_profiling(icnf_handle* h, int enabled);
+ICNF_API int icnf_kernel_times(icnf_handle* h, float* ms4);
+/* FP32 FMA-pipe throughput of `device` from an FFMA-chain microbenchmark, in
+ * TFLOP/s: the roofline denominator of the narrow-MLP kernels. */
+ICNF_API int icnf_measure_fp32_peak(int device, float* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ICNF_B200_H */
