@@ -55,7 +55,8 @@ class Stats(C.Structure):
 
 
 LIB_NAME = "libicnf_b200.so"
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
+# ICNF_B200_LIB points at an alternative build of the same library (tuning sweeps)
+LIB_PATH = os.environ.get("ICNF_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), LIB_NAME)
 
 # every symbol include/icnf_b200.h declares: (name, restype, argtypes)
 _P = C.c_void_p

@@ -24,20 +24,33 @@ std::vector<const Family*>& tiny_registry() {
 const Family* generic_family();  // generic.cu
 
 // ---------------------------------------------------------------- small kernels
-// dtheta[p] = sum over partial rows, fixed order (bit-reproducible)
-__global__ void reduce_grad_kernel(const float* __restrict__ partial, int nrows, int np, float* __restrict__ out) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= np) return;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-    int r = 0;
-    for (; r + 3 < nrows; r += 4) {
-        s0 += partial[(size_t)r * np + p];
-        s1 += partial[(size_t)(r + 1) * np + p];
-        s2 += partial[(size_t)(r + 2) * np + p];
-        s3 += partial[(size_t)(r + 3) * np + p];
+// dtheta[p] = sum over partial rows, fixed order (bit-reproducible).  One CTA per 32
+// parameters: 8 warps each sum a contiguous slice of the rows (coalesced across p), then
+// the 8 partial sums are added in order.
+__global__ void __launch_bounds__(256) reduce_grad_kernel(const float* __restrict__ partial, int nrows, int np,
+                                                        float* __restrict__ out) {
+    __shared__ float sh[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int p = blockIdx.x * 32 + lane;
+    const int per = (nrows + 7) / 8;
+    const int r0 = w * per, r1 = min(nrows, r0 + per);
+    float s0 = 0.f, s1 = 0.f;
+    if (p < np) {
+        int r = r0;
+        for (; r + 1 < r1; r += 2) {
+            s0 += partial[(size_t)r * np + p];
+            s1 += partial[(size_t)(r + 1) * np + p];
+        }
+        if (r < r1) s0 += partial[(size_t)r * np + p];
     }
-    for (; r < nrows; ++r) s0 += partial[(size_t)r * np + p];
-    out[p] = (s0 + s1) + (s2 + s3);
+    sh[w][lane] = s0 + s1;
+    __syncthreads();
+    if (w == 0 && p < np) {
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += sh[i][lane];
+        out[p] = s;
+    }
 }
 
 // out[0] = scale * sum(x[0..n)) with a fixed reduction tree; single CTA, double accumulation
@@ -706,7 +719,7 @@ static int loss_grad_device(icnf_handle* h, int mode, const icnf_solver* sol, fl
     h->launches++;
     if (dtheta) {
         h->prof_begin(3, st);
-        reduce_grad_kernel<<<(np + 127) / 128, 128, 0, st>>>(h->gpartial.as<float>(), nrows, np, dtheta);
+        reduce_grad_kernel<<<(np + 31) / 32, 256, 0, st>>>(h->gpartial.as<float>(), nrows, np, dtheta);
         h->prof_end(3, st);
         CK(h, cudaGetLastError());
         h->launches++;

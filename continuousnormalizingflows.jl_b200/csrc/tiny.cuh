@@ -31,6 +31,14 @@ namespace tiny {
 namespace cg = cooperative_groups;
 
 constexpr int NT = 128;  // threads per CTA
+// minimum resident CTAs per SM the compiler must allow for (caps registers per thread);
+// values chosen from the sweep recorded in profiles/ (scripts/sweep_tiny_bounds.sh)
+#ifndef ICNF_TINY_MINB_FWD
+#define ICNF_TINY_MINB_FWD 1
+#endif
+#ifndef ICNF_TINY_MINB_BWD
+#define ICNF_TINY_MINB_BWD 1
+#endif
 
 __constant__ float c_a[7][6] = {
     {0, 0, 0, 0, 0, 0},
@@ -69,7 +77,16 @@ struct Net {
         return o;
     }
     __host__ __device__ static constexpr int boff(int l) { return woff(l) + ld(l) * n(l); }
-    static constexpr int WPAD = woff(NL_);
+    static constexpr int WA = woff(NL_);   // size of layout A
+    // layout B (for W' products): W_l row j (inputs 0..kz(l)) at wtoff(l) + j * ldt(l)
+    __host__ __device__ static constexpr int ldt(int l) { return ((l == 0 ? D_ : n(l)) + 3) & ~3; }
+    __host__ __device__ static constexpr int wtoff(int l) {
+        int o = WA;
+        for (int i = 0; i < l; ++i) o += ldt(i) * n(i + 1);
+        return o;
+    }
+    static constexpr int WPAD = wtoff(NL_);
+    static constexpr int NP2 = (nmax() + 1) / 2;   // packed pairs per activation vector
     // native (ComponentArray) offsets
     __host__ __device__ static constexpr int toff(int l) {
         int o = 0;
@@ -99,37 +116,59 @@ struct WBlock {
 };
 #define WREF(N, sw, l, j, k) (sw).v[N::woff(l) + (k) * N::ld(l) + (j)]
 #define BREF(N, sw, l, j) (sw).v[N::boff(l) + (j)]
+#define WTREF(N, sw, l, j, k) (sw).v[N::wtoff(l) + (j) * N::ldt(l) + (k)]
+// adjacent pairs as packed FFMA2 operands (both layouts are padded to multiples of 4 and
+// zero-filled, so a pair never straddles into foreign data)
+#define WPAIR(N, sw, l, jp, k) make_float2(WREF(N, sw, l, 2 * (jp), k), WREF(N, sw, l, 2 * (jp) + 1, k))
+#define BPAIR(N, sw, l, jp) make_float2(BREF(N, sw, l, 2 * (jp)), BREF(N, sw, l, 2 * (jp) + 1))
+#define WTPAIR(N, sw, l, j, kp) make_float2(WTREF(N, sw, l, j, 2 * (kp)), WTREF(N, sw, l, j, 2 * (kp) + 1))
+// element k of a vector stored as packed pairs (k is a compile-time constant after unrolling)
+#define EL(a, k) ((((k) & 1) != 0) ? (a)[(k) >> 1].y : (a)[(k) >> 1].x)
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+
+// Blackwell packed FP32: every mat-vec below issues FFMA2 (fma.rn.f32x2), two FMAs per
+// instruction, with the weight pair coming straight from a uniform register
+// (FFMA2 R, R.F32, UR.F32x2, R in SASS).  Vectors over units are stored as float2 pairs.
+template <int ACT>
+__device__ __forceinline__ void act_eval2(float2 a, float2& h, float2& d) {
+    act_eval<ACT>(a.x, h.x, d.x);
+    act_eval<ACT>(a.y, h.y, d.y);
+}
+template <int ACT>
+__device__ __forceinline__ float2 act_dd2(float2 h, float2 d) {
+    return make_float2(act_dd<ACT>(h.x, d.x), act_dd<ACT>(h.y, d.y));
+}
 
 // activations of one sample: h[l] = output of layer l (post-activation, linear for the
 // last layer), d[l] = sigma'(a_l) for hidden layers
 template <class N>
 struct Acts {
-    float h[N::NL][N::NMAX];
-    float d[N::NL][N::NMAX];
+    float2 h[N::NL][N::NP2];
+    float2 d[N::NL][N::NP2];
 };
 
 template <class N>
 __device__ __forceinline__ void forward(const WBlock<N>& sw, const float (&x)[N::n(0)], Acts<N>& A) {
     static_for<0, N::NL>([&](auto lc) __attribute__((always_inline)) {
         constexpr int l = decltype(lc)::value;
-        constexpr int nin = N::n(l), nout = N::n(l + 1);
-        float acc[nout];
-#pragma unroll
-        for (int j = 0; j < nout; ++j) acc[j] = BREF(N, sw, l, j);
+        constexpr int nin = N::n(l), nout = N::n(l + 1), np = (nout + 1) / 2;
+        float2 acc[np];
 #pragma unroll
         for (int k = 0; k < nin; ++k) {
             float hk;
             if constexpr (l == 0) hk = x[k];
-            else hk = A.h[l - 1][k];
+            else hk = EL(A.h[l - 1], k);
 #pragma unroll
-            for (int j = 0; j < nout; ++j) acc[j] = fmaf(WREF(N, sw, l, j, k), hk, acc[j]);
+            for (int jp = 0; jp < np; ++jp) {
+                if (k == 0) acc[jp] = __fmul2_rn(WPAIR(N, sw, l, jp, k), bc2(hk));
+                else acc[jp] = __ffma2_rn(WPAIR(N, sw, l, jp, k), bc2(hk), acc[jp]);
+            }
         }
-        if constexpr (l < N::NL - 1) {
 #pragma unroll
-            for (int j = 0; j < nout; ++j) act_eval<N::ACT>(acc[j], A.h[l][j], A.d[l][j]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < nout; ++j) A.h[l][j] = acc[j];
+        for (int jp = 0; jp < np; ++jp) {
+            acc[jp] = __fadd2_rn(acc[jp], BPAIR(N, sw, l, jp));
+            if constexpr (l < N::NL - 1) act_eval2<N::ACT>(acc[jp], A.h[l][jp], A.d[l][jp]);
+            else A.h[l][jp] = acc[jp];
         }
     });
 }
@@ -138,29 +177,46 @@ __device__ __forceinline__ void forward(const WBlock<N>& sw, const float (&x)[N:
 // v[l] = cotangent at the output of hidden layer l, q = probe' J (first D' inputs).
 template <class N>
 struct Chain {
-    float g[N::NL][N::NMAX];
-    float v[N::NL][N::NMAX];
+    float2 g[N::NL][N::NP2];
+    float2 v[N::NL][N::NP2];
 };
+
+// s[kp] = sum_j W_l[j, (2kp, 2kp+1)] * gin[j]   (W_l' gin restricted to the first kz(l) inputs)
+template <class N, int l>
+__device__ __forceinline__ void wt_matvec(const WBlock<N>& sw, const float2 (&gin)[N::NP2],
+                                          float2 (&s)[N::NP2]) {
+    constexpr int nout = N::n(l + 1), kp = (N::kz(l) + 1) / 2;
+#pragma unroll
+    for (int j = 0; j < nout; ++j) {
+        const float gj = EL(gin, j);
+#pragma unroll
+        for (int c = 0; c < kp; ++c) {
+            if (j == 0) s[c] = __fmul2_rn(WTPAIR(N, sw, l, j, c), bc2(gj));
+            else s[c] = __ffma2_rn(WTPAIR(N, sw, l, j, c), bc2(gj), s[c]);
+        }
+    }
+}
 
 template <class N>
 __device__ __forceinline__ void vjp_chain(const WBlock<N>& sw, const Acts<N>& A, const float (&probe)[N::D],
                                           Chain<N>& Cn, float (&q)[N::D]) {
 #pragma unroll
-    for (int j = 0; j < N::D; ++j) Cn.g[N::NL - 1][j] = probe[j];
+    for (int jp = 0; jp < (N::D + 1) / 2; ++jp)
+        Cn.g[N::NL - 1][jp] = make_float2(probe[2 * jp], (2 * jp + 1 < N::D) ? probe[2 * jp + 1] : 0.0f);
     static_rfor<N::NL>([&](auto lc) __attribute__((always_inline)) {
         constexpr int l = decltype(lc)::value;
-        constexpr int nout = N::n(l + 1), kk = N::kz(l);
+        constexpr int kp = (N::kz(l) + 1) / 2;
+        float2 s[N::NP2];
+        wt_matvec<N, l>(sw, Cn.g[l], s);
+        if constexpr (l > 0) {
 #pragma unroll
-        for (int k = 0; k < kk; ++k) {
-            float s = 0.0f;
-#pragma unroll
-            for (int j = 0; j < nout; ++j) s = fmaf(WREF(N, sw, l, j, k), Cn.g[l][j], s);
-            if constexpr (l > 0) {
-                Cn.v[l - 1][k] = s;
-                Cn.g[l - 1][k] = s * A.d[l - 1][k];
-            } else {
-                q[k] = s;
+            for (int c = 0; c < kp; ++c) {
+                Cn.v[l - 1][c] = s[c];
+                Cn.g[l - 1][c] = __fmul2_rn(s[c], A.d[l - 1][c]);
             }
+        } else {
+#pragma unroll
+            for (int k = 0; k < N::D; ++k) q[k] = EL(s, k);
         }
     });
 }
@@ -176,7 +232,7 @@ __device__ __forceinline__ void rhs_eval(const WBlock<N>& sw, const float (&x)[N
     Acts<N> A;
     forward<N>(sw, x, A);
 #pragma unroll
-    for (int j = 0; j < N::D; ++j) kz[j] = A.h[N::NL - 1][j];
+    for (int j = 0; j < N::D; ++j) kz[j] = EL(A.h[N::NL - 1], j);
     if constexpr (EXACT) {
         // exact trace by D' one-hot pullbacks (utils.jl:35-54); the one-hot probe is a
         // compile-time constant so the first chain link folds to a weight row
@@ -337,7 +393,7 @@ __global__ void __launch_bounds__(NT) rhs_kernel(const __grid_constant__ WBlock<
 // ------------------------------------------------------------------ S2: fixed-step solve
 // Each thread integrates its samples through all steps; no cross-thread traffic.
 template <class N, bool EXACT>
-__global__ void __launch_bounds__(NT) solve_fixed_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
+__global__ void __launch_bounds__(NT, ICNF_TINY_MINB_FWD) solve_fixed_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
     extern __shared__ __align__(16) float smem[];
     StageMem K{smem};
     const float tdir = (a.t1 >= a.t0) ? 1.0f : -1.0f;
@@ -447,7 +503,7 @@ struct GridReducer {
 };
 
 template <class N, bool EXACT>
-__global__ void __launch_bounds__(NT) solve_adaptive_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
+__global__ void __launch_bounds__(NT, ICNF_TINY_MINB_FWD) solve_adaptive_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
     extern __shared__ __align__(16) float smem[];
     StageMem K{smem};
     __shared__ double sred[NT / 32 + 1];
@@ -696,6 +752,12 @@ __device__ __forceinline__ float transposed_reduce32(float (&v)[32]) {
 // cotangents zb (on zdot), cl (on ldot), cE, cn (on the two norms) ->
 // sbar = cotangent on Z, and the parameter gradient accumulated into gacc
 // (lane L of chunk c owns entry 32 c + L of that layer's [vec(W); b]).
+//
+// Derivation (SURVEY Appendix B notation, g_L = probe):
+//   chain     v_{l-1} = W_l' g_l,  g_{l-1} = v_{l-1} .* d_{l-1},  q = v_0[1:D']
+//   tangent   w_0 = qbar, r_l = W_l w_{l-1}, w_l = r_l .* d_l, extra abar_l = r_l .* v_l .* sigma''(a_l)
+//   backprop  abar_L = zbar, hbar_{l-1} = W_l' abar_l, abar_{l-1} = hbar_{l-1} .* d_{l-1} + extra
+//   gradient  dW_l = abar_l h_{l-1}' + g_l w_{l-1}',  db_l = abar_l
 template <class N, bool EXACT>
 __device__ __forceinline__ void rhs_reverse(const WBlock<N>& sw, const float (&x)[N::n(0)], const float (&eps)[N::D],
                                             const float (&zb_in)[N::D], float cl, float cE, float cn,
@@ -708,26 +770,28 @@ __device__ __forceinline__ void rhs_reverse(const WBlock<N>& sw, const float (&x
     if (!EXACT && cE != 0.0f) {
         float zz = 0.0f;
 #pragma unroll
-        for (int j = 0; j < N::D; ++j) zz = fmaf(A.h[N::NL - 1][j], A.h[N::NL - 1][j], zz);
+        for (int j = 0; j < N::D; ++j) zz = fmaf(EL(A.h[N::NL - 1], j), EL(A.h[N::NL - 1], j), zz);
         // d|z|/dz = z/|z| (0 at 0, the ChainRules convention); d|z|^2/dz = 2 z
         float s = squared ? 2.0f * cE : (zz > 0.0f ? cE * rsqrtf(zz) : 0.0f);
 #pragma unroll
-        for (int j = 0; j < N::D; ++j) zb[j] = fmaf(s, A.h[N::NL - 1][j], zb[j]);
+        for (int j = 0; j < N::D; ++j) zb[j] = fmaf(s, EL(A.h[N::NL - 1], j), zb[j]);
     }
     // extra pre-activation cotangents from the second-order terms
-    float aex[N::NL][N::NMAX];
+    float2 aex[N::NL][N::NP2];
 #pragma unroll
     for (int l = 0; l < N::NL; ++l)
 #pragma unroll
-        for (int j = 0; j < N::NMAX; ++j) aex[l][j] = 0.0f;
+        for (int j = 0; j < N::NP2; ++j) aex[l][j] = make_float2(0.0f, 0.0f);
 
     constexpr int NPROBE = EXACT ? N::D : 1;
+    constexpr bool MERGE = (NPROBE == 1);   // one probe: its g w' term rides in the backprop reduction
+    Chain<N> Cn;
+    float2 wv[N::NL][N::NP2];               // tangent vectors w_l (input side of layer l)
     static_for<0, NPROBE>([&](auto pc) __attribute__((always_inline)) {
         constexpr int p = decltype(pc)::value;
         float probe[N::D], q[N::D], qb[N::D];
 #pragma unroll
         for (int j = 0; j < N::D; ++j) probe[j] = EXACT ? ((j == p) ? 1.0f : 0.0f) : eps[j];
-        Chain<N> Cn;
         vjp_chain<N>(sw, A, probe, Cn, q);
         if constexpr (EXACT) {
 #pragma unroll
@@ -740,50 +804,55 @@ __device__ __forceinline__ void rhs_reverse(const WBlock<N>& sw, const float (&x
 #pragma unroll
             for (int j = 0; j < N::D; ++j) qb[j] = fmaf(s, q[j], -cl * eps[j]);
         }
-        // tangent pass w_0 = qb, r_l = W_l w_l, w_{l+1} = r_l .* d_l; the weight gradient of
-        // the chain is g_l w_l' and is reduced across the warp layer by layer
-        float w[N::NMAX];
 #pragma unroll
-        for (int k = 0; k < N::D; ++k) w[k] = qb[k];
+        for (int c = 0; c < (N::D + 1) / 2; ++c)
+            wv[0][c] = make_float2(qb[2 * c], (2 * c + 1 < N::D) ? qb[2 * c + 1] : 0.0f);
         static_for<0, N::NL>([&](auto lc) __attribute__((always_inline)) {
             constexpr int l = decltype(lc)::value;
-            constexpr int nin = N::n(l), nout = N::n(l + 1), kk = N::kz(l);
-            // gradient contribution g_l[j] * w[k], k < kk
-            static_for<0, N::nchunk(l)>([&](auto cc) __attribute__((always_inline)) {
-                constexpr int c = decltype(cc)::value;
-                float v[32];
+            constexpr int nin = N::n(l), nout = N::n(l + 1), kk = N::kz(l), np = (nout + 1) / 2;
+            if constexpr (!MERGE) {
+                // several probes (exact trace): reduce each probe's g_l w_l' separately
+                static_for<0, N::nchunk(l)>([&](auto cc) __attribute__((always_inline)) {
+                    constexpr int c = decltype(cc)::value;
+                    if constexpr (c * 32 < kk * nout) {
+                        float v[32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int e = c * 32 + i;
-                    const int k = e / nout, j = e - k * nout;
-                    v[i] = (e < nin * nout && k < kk) ? Cn.g[l][j] * w[k < kk ? k : 0] : 0.0f;
-                }
-                // chunks that only hold zeros (inputs without a z-derivative, biases) are skipped
-                if constexpr (c * 32 < kk * nout) gacc[N::choff(l) + c] += transposed_reduce32(v);
-            });
+                        for (int i = 0; i < 32; ++i) {
+                            const int e = c * 32 + i;
+                            const int k = e / nout, j = e - k * nout;
+                            v[i] = (e < nin * nout && k < kk) ? EL(Cn.g[l], j) * EL(wv[l], (k < kk ? k : 0)) : 0.0f;
+                        }
+                        gacc[N::choff(l) + c] += transposed_reduce32(v);
+                    }
+                });
+            }
             if constexpr (l < N::NL - 1) {
-                float wn[N::NMAX];
+                float2 r[np];
 #pragma unroll
-                for (int j = 0; j < nout; ++j) {
-                    float r = 0.0f;
+                for (int k = 0; k < kk; ++k) {
+                    const float wk = EL(wv[l], k);
 #pragma unroll
-                    for (int k = 0; k < kk; ++k) r = fmaf(WREF(N, sw, l, j, k), w[k], r);
-                    wn[j] = r * A.d[l][j];
-                    aex[l][j] = fmaf(r * Cn.v[l][j], act_dd<N::ACT>(A.h[l][j], A.d[l][j]), aex[l][j]);
+                    for (int jp = 0; jp < np; ++jp) {
+                        if (k == 0) r[jp] = __fmul2_rn(WPAIR(N, sw, l, jp, k), bc2(wk));
+                        else r[jp] = __ffma2_rn(WPAIR(N, sw, l, jp, k), bc2(wk), r[jp]);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < nout; ++j) w[j] = wn[j];
+                for (int jp = 0; jp < np; ++jp) {
+                    wv[l + 1][jp] = __fmul2_rn(r[jp], A.d[l][jp]);
+                    aex[l][jp] = __ffma2_rn(__fmul2_rn(r[jp], Cn.v[l][jp]), act_dd2<N::ACT>(A.h[l][jp], A.d[l][jp]), aex[l][jp]);
+                }
             }
         });
     });
 
     // ordinary backprop with output cotangent zb and the extra terms
-    float ab[N::NMAX];
+    float2 ab[N::NP2];
 #pragma unroll
-    for (int j = 0; j < N::D; ++j) ab[j] = zb[j];
+    for (int c = 0; c < (N::D + 1) / 2; ++c) ab[c] = make_float2(zb[2 * c], (2 * c + 1 < N::D) ? zb[2 * c + 1] : 0.0f);
     static_rfor<N::NL>([&](auto lc) __attribute__((always_inline)) {
         constexpr int l = decltype(lc)::value;
-        constexpr int nin = N::n(l), nout = N::n(l + 1), kk = N::kz(l);
+        constexpr int nin = N::n(l), nout = N::n(l + 1), kk = N::kz(l), kp = (kk + 1) / 2;
         static_for<0, N::nchunk(l)>([&](auto cc) __attribute__((always_inline)) {
             constexpr int c = decltype(cc)::value;
             float v[32];
@@ -791,29 +860,29 @@ __device__ __forceinline__ void rhs_reverse(const WBlock<N>& sw, const float (&x
             for (int i = 0; i < 32; ++i) {
                 const int e = c * 32 + i;
                 const int k = e / nout, j = e - k * nout;
-                float hin;
-                if constexpr (l == 0) hin = x[k < nin ? k : 0];
-                else hin = A.h[l - 1][k < nin ? k : 0];
-                if (e < nin * nout) v[i] = ab[j] * hin;
-                else if (e < nin * nout + nout) v[i] = ab[e - nin * nout];
-                else v[i] = 0.0f;
+                if (e < nin * nout) {
+                    float hin;
+                    if constexpr (l == 0) hin = x[k < nin ? k : 0];
+                    else hin = EL(A.h[l - 1], (k < nin ? k : 0));
+                    float t = EL(ab, j) * hin;
+                    if (MERGE && k < kk) t = fmaf(EL(Cn.g[l], j), EL(wv[l], (k < kk ? k : 0)), t);
+                    v[i] = t;
+                } else if (e < nin * nout + nout) {
+                    v[i] = EL(ab, (e - nin * nout < nout ? e - nin * nout : 0));
+                } else {
+                    v[i] = 0.0f;
+                }
             }
             gacc[N::choff(l) + c] += transposed_reduce32(v);
         });
-        float hb[N::NMAX];
-#pragma unroll
-        for (int k = 0; k < kk; ++k) {
-            float s = 0.0f;
-#pragma unroll
-            for (int j = 0; j < nout; ++j) s = fmaf(WREF(N, sw, l, j, k), ab[j], s);
-            hb[k] = s;
-        }
+        float2 hb[N::NP2];
+        wt_matvec<N, l>(sw, ab, hb);
         if constexpr (l > 0) {
 #pragma unroll
-            for (int k = 0; k < kk; ++k) ab[k] = fmaf(hb[k], A.d[l - 1][k], aex[l - 1][k]);
+            for (int c = 0; c < kp; ++c) ab[c] = __ffma2_rn(hb[c], A.d[l - 1][c], aex[l - 1][c]);
         } else {
 #pragma unroll
-            for (int k = 0; k < N::D; ++k) sbar[k] = hb[k];
+            for (int k = 0; k < N::D; ++k) sbar[k] = EL(hb, k);
         }
     });
 }
@@ -824,11 +893,11 @@ __device__ __forceinline__ void zdot_eval(const WBlock<N>& sw, const float (&x)[
     Acts<N> A;
     forward<N>(sw, x, A);
 #pragma unroll
-    for (int j = 0; j < N::D; ++j) kz[j] = A.h[N::NL - 1][j];
+    for (int j = 0; j < N::D; ++j) kz[j] = EL(A.h[N::NL - 1], j);
 }
 
 template <class N, bool EXACT>
-__global__ void __launch_bounds__(NT) backward_kernel(const __grid_constant__ WBlock<N> sw, BackwardArgs a) {
+__global__ void __launch_bounds__(NT, ICNF_TINY_MINB_BWD) backward_kernel(const __grid_constant__ WBlock<N> sw, BackwardArgs a) {
     extern __shared__ __align__(16) float smem[];
     StageMem Z{smem};                  // stage inputs Z_i, 6 x D'
     StageMem KB{smem + 6 * N::D * NT};  // stage cotangents Kbar_i, 6 x D'
@@ -950,18 +1019,27 @@ __global__ void __launch_bounds__(NT) backward_kernel(const __grid_constant__ WB
                 if (j < a.nvars) a.dxs[b * a.nvars + j] = zbar[j];
         }
     }
-    // per-warp partial gradient, native ComponentArray order
-    const int lane = threadIdx.x & 31;
-    const int64_t gw = (int64_t)blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-    float* gp = a.gpartial + gw * N::NP;
+    // per-CTA partial gradient in native ComponentArray order: the 4 warps' accumulators are
+    // summed through shared memory (reusing the stage buffers) in a fixed order
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float* sg = smem;   // [NT/32][NP]
     static_for<0, N::NL>([&](auto lc) __attribute__((always_inline)) {
         constexpr int l = decltype(lc)::value;
 #pragma unroll
         for (int c = 0; c < N::nchunk(l); ++c) {
             const int e = c * 32 + lane;
-            if (e < N::nent(l)) gp[N::toff(l) + e] = gacc[N::choff(l) + c];
+            if (e < N::nent(l)) sg[wid * N::NP + N::toff(l) + e] = gacc[N::choff(l) + c];
         }
     });
+    __syncthreads();
+    float* gp = a.gpartial + (int64_t)blockIdx.x * N::NP;
+    for (int p = threadIdx.x; p < N::NP; p += NT) {
+        float s = 0.0f;
+#pragma unroll
+        for (int w = 0; w < NT / 32; ++w) s += sg[w * N::NP + p];
+        gp[p] = s;
+    }
 }
 
 }  // namespace tiny

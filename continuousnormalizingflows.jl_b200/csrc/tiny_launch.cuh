@@ -13,7 +13,7 @@ template <class N>
 struct Launch {
     static constexpr size_t smem_rhs = 0;
     static constexpr size_t smem_solve = sizeof(float) * (6 * N::D * NT);
-    static constexpr size_t smem_bwd = sizeof(float) * (12 * N::D * NT);
+    static constexpr size_t smem_bwd = sizeof(float) * (12 * N::D * NT > (NT / 32) * N::NP ? 12 * N::D * NT : (NT / 32) * N::NP);
     static_assert(sizeof(WBlock<N>) + sizeof(SolveArgs) + 16 <= 32764, "weights must fit the kernel parameter space");
 
     // theta (host, native ComponentArray order) -> padded parameter block
@@ -24,6 +24,9 @@ struct Launch {
             for (int k = 0; k < nin; ++k)
                 for (int j = 0; j < nout; ++j) w.v[N::woff(l) + k * N::ld(l) + j] = theta[N::toff(l) + k * nout + j];
             for (int j = 0; j < nout; ++j) w.v[N::boff(l) + j] = theta[N::toff(l) + nin * nout + j];
+            // layout B: rows of W_l over the inputs that carry a z-derivative
+            for (int j = 0; j < nout; ++j)
+                for (int k = 0; k < N::kz(l); ++k) w.v[N::wtoff(l) + j * N::ldt(l) + k] = theta[N::toff(l) + k * nout + j];
         }
     }
 
@@ -100,7 +103,7 @@ struct Launch {
         f.adaptive_max_grid = &adaptive_max_grid;
         f.backward = &backward;
         f.backward_grid = &backward_grid;
-        f.backward_partials_per_block = NT / 32;
+        f.backward_partials_per_block = 1;
         return f;
     }
 };
