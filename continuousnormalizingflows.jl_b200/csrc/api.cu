@@ -123,6 +123,7 @@ struct DevBuf {
 struct icnf_handle {
     icnf_config cfg;
     const Family* fam = nullptr;
+    void* ws = nullptr;
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
@@ -279,7 +280,7 @@ int enqueue_solve(icnf_handle* h, const SolveRequest& r, cudaStream_t st) {
             a.steps = h->steps.as<StepRec>();
         }
         h->prof_begin(0, st);
-        cudaError_t e = h->fam->solve_fixed(h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st);
+        cudaError_t e = h->fam->solve_fixed(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st);
         h->prof_end(0, st);
         if (e != cudaSuccess) return h->cuda_fail(e, "solve_fixed launch");
         h->launches++;
@@ -308,7 +309,7 @@ int enqueue_solve(icnf_handle* h, const SolveRequest& r, cudaStream_t st) {
         a.steps = h->steps.as<StepRec>();
     }
     h->prof_begin(0, st);
-    cudaError_t e = h->fam->solve_adaptive(h->theta_host.data(), a, c.nvars, mf.exact, grid, st);
+    cudaError_t e = h->fam->solve_adaptive(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, grid, st);
     h->prof_end(0, st);
     if (e != cudaSuccess) return h->cuda_fail(e, "solve_adaptive launch");
     h->launches++;
@@ -414,6 +415,7 @@ int icnf_create(const icnf_config* cfg, icnf_handle** out) {
         delete h;
         return ICNF_ERR_UNSUPPORTED;
     }
+    if (h->fam->ws_create) h->ws = h->fam->ws_create(cfg);
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
         (e = cudaMallocHost((void**)&h->stats_host, sizeof(DevStats))) != cudaSuccess ||
         (e = cudaMallocHost((void**)&h->scalar_host, 4 * sizeof(float))) != cudaSuccess) {
@@ -429,6 +431,7 @@ void icnf_destroy(icnf_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->ws && h->fam && h->fam->ws_destroy) h->fam->ws_destroy(h->ws);
     DevBuf* bufs[] = {&h->theta_dev, &h->in, &h->eps, &h->ys, &h->out0, &h->out1, &h->out2, &h->wu0, &h->wu1, &h->wk0,
                       &h->wk1, &h->partials, &h->ckpt, &h->steps, &h->stats, &h->gpartial, &h->lossterm, &h->scalar,
                       &h->dtheta, &h->dxs};
@@ -509,6 +512,7 @@ int icnf_set_params(icnf_handle* h, const float* theta, int64_t n) {
     h->theta_host.assign(theta, theta + n);
     CK(h, h->theta_dev.reserve(sizeof(float) * n));
     CK(h, cudaMemcpyAsync(h->theta_dev.p, h->theta_host.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    if (h->fam->on_params) CK(h, h->fam->on_params(h->ws, h->theta_dev.as<float>(), h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     h->have_params = true;
     return ICNF_OK;
@@ -524,6 +528,7 @@ int icnf_set_params_dev(icnf_handle* h, const float* theta, int64_t n, void* str
     CK(h, cudaMemcpyAsync(h->theta_dev.p, theta, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
     // the tiny family passes the weights as a kernel parameter, so it needs them on the host
     CK(h, cudaMemcpyAsync(h->theta_host.data(), theta, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+    if (h->fam->on_params) CK(h, h->fam->on_params(h->ws, h->theta_dev.as<float>(), st));
     CK(h, cudaStreamSynchronize(st));
     h->have_params = true;
     return ICNF_OK;
@@ -544,7 +549,7 @@ int icnf_rhs_dev(icnf_handle* h, int mode, float t, const float* u, const float*
     a.theta = h->theta_dev.as<float>();
     a.u = u; a.eps = eps; a.ys = ys; a.du = du; a.B = B;
     a.mode = mode; a.reg_e = mf.reg_e; a.reg_n = mf.reg_n; a.squared = h->cfg.reg_squared; a.t = t;
-    cudaError_t e = h->fam->rhs(h->theta_host.data(), a, mf.exact, h->sm_count, pick_stream(h, stream));
+    cudaError_t e = h->fam->rhs(h->ws, h->theta_host.data(), a, mf.exact, h->sm_count, pick_stream(h, stream));
     if (e != cudaSuccess) return h->cuda_fail(e, "rhs launch");
     h->launches++;
     return ICNF_OK;
@@ -677,6 +682,8 @@ static int loss_grad_device(icnf_handle* h, int mode, const icnf_solver* sol, fl
     if (B <= 0) return h->fail(ICNF_ERR_INVALID, "loss needs at least one sample");
     const int64_t denom = global_batch > 0 ? global_batch : B;
     const bool want_grad = dtheta != nullptr || dxs != nullptr;
+    if (want_grad && !h->fam->supports_backward)
+        return h->fail(ICNF_ERR_UNSUPPORTED, "the %s kernel family has no backward kernel yet (network too wide for the tiny family)", h->fam->name);
     CK(h, h->lossterm.reserve(sizeof(float) * (size_t)B));
     SolveRequest r{mode, sol, t0, t1, xs, IN_XS, noise, eps, ys, nullptr, nullptr, nullptr, nullptr,
                    h->lossterm.as<float>(), want_grad, B};
@@ -713,7 +720,7 @@ static int loss_grad_device(icnf_handle* h, int mode, const icnf_solver* sol, fl
     b.inv_denominator = 1.0f / (float)denom;
     b.nvars = h->cfg.nvars;
     h->prof_begin(2, st);
-    cudaError_t e = h->fam->backward(h->theta_host.data(), b, mf.exact, grid, st);
+    cudaError_t e = h->fam->backward(h->ws, h->theta_host.data(), b, mf.exact, grid, st);
     h->prof_end(2, st);
     if (e != cudaSuccess) return h->cuda_fail(e, "backward launch");
     h->launches++;

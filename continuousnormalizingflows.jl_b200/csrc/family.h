@@ -28,14 +28,19 @@ struct Family {
     // `theta_host` is the HOST copy of the parameters (tiny kernels take the weights as a
     // kernel parameter; the generic family reads a.theta on the device and ignores it).
     // launchers return the CUDA error of the launch; `exact` selects the TestMode trace
-    cudaError_t (*rhs)(const float* theta_host, const RhsArgs& a, bool exact, int sm_count, cudaStream_t st);
-    cudaError_t (*solve_fixed)(const float* theta_host, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st);
-    cudaError_t (*solve_adaptive)(const float* theta_host, const SolveArgs& a, int nvars, bool exact, int grid, cudaStream_t st);
+    // `ws` is the family's per-handle workspace (null for families that need none)
+    void* (*ws_create)(const icnf_config* cfg);
+    void (*ws_destroy)(void* ws);
+    cudaError_t (*on_params)(void* ws, const float* theta_dev, cudaStream_t st);   // after every icnf_set_params
+    cudaError_t (*rhs)(void* ws, const float* theta_host, const RhsArgs& a, bool exact, int sm_count, cudaStream_t st);
+    cudaError_t (*solve_fixed)(void* ws, const float* theta_host, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st);
+    cudaError_t (*solve_adaptive)(void* ws, const float* theta_host, const SolveArgs& a, int nvars, bool exact, int grid, cudaStream_t st);
     // largest cooperative grid for the adaptive kernel on this device (0 = unsupported)
     int (*adaptive_max_grid)(bool exact, int sm_count);
-    cudaError_t (*backward)(const float* theta_host, const BackwardArgs& a, bool exact, int grid, cudaStream_t st);
+    cudaError_t (*backward)(void* ws, const float* theta_host, const BackwardArgs& a, bool exact, int grid, cudaStream_t st);
     int (*backward_grid)(bool exact, int sm_count, long long B);
     int backward_partials_per_block;  // gradient partial rows written per CTA
+    int supports_backward;
 };
 
 std::vector<const Family*>& tiny_registry();

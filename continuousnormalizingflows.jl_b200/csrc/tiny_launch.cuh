@@ -47,7 +47,7 @@ struct Launch {
         return (int)std::max(1LL, std::min(need, cap));
     }
 
-    static cudaError_t rhs(const float* theta, const RhsArgs& a, bool exact, int sm_count, cudaStream_t st) {
+    static cudaError_t rhs(void*, const float* theta, const RhsArgs& a, bool exact, int sm_count, cudaStream_t st) {
         auto k = exact ? rhs_kernel<N, true> : rhs_kernel<N, false>;
         int grid = grid_for(a.B, occupancy(k, smem_rhs), sm_count);
         WBlock<N> w;
@@ -55,7 +55,7 @@ struct Launch {
         k<<<grid, NT, smem_rhs, st>>>(w, a);
         return cudaGetLastError();
     }
-    static cudaError_t solve_fixed(const float* theta, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st) {
+    static cudaError_t solve_fixed(void*, const float* theta, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st) {
         auto k = exact ? solve_fixed_kernel<N, true> : solve_fixed_kernel<N, false>;
         int grid = grid_for(a.B, occupancy(k, smem_solve), sm_count);
         WBlock<N> w;
@@ -67,7 +67,7 @@ struct Launch {
         auto k = exact ? solve_adaptive_kernel<N, true> : solve_adaptive_kernel<N, false>;
         return occupancy(k, smem_solve) * sm_count;
     }
-    static cudaError_t solve_adaptive(const float* theta, const SolveArgs& a, int nvars, bool exact, int grid, cudaStream_t st) {
+    static cudaError_t solve_adaptive(void*, const float* theta, const SolveArgs& a, int nvars, bool exact, int grid, cudaStream_t st) {
         auto k = exact ? solve_adaptive_kernel<N, true> : solve_adaptive_kernel<N, false>;
         cudaError_t e = prep(k, smem_solve);
         if (e != cudaSuccess) return e;
@@ -82,7 +82,7 @@ struct Launch {
         auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
         return grid_for(B, occupancy(k, smem_bwd), sm_count);
     }
-    static cudaError_t backward(const float* theta, const BackwardArgs& a, bool exact, int grid, cudaStream_t st) {
+    static cudaError_t backward(void*, const float* theta, const BackwardArgs& a, bool exact, int grid, cudaStream_t st) {
         auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
         cudaError_t e = prep(k, smem_bwd);
         if (e != cudaSuccess) return e;
@@ -104,6 +104,7 @@ struct Launch {
         f.backward = &backward;
         f.backward_grid = &backward_grid;
         f.backward_partials_per_block = 1;
+        f.supports_backward = 1;
         return f;
     }
 };

@@ -18,8 +18,18 @@ SHAPES = {
 }
 
 
+# shapes served by the generic family (any width; fp32 tiled SGEMMs)
+GENERIC_SHAPES = {
+    "config3_gmm16": dict(nvariables=16, naugments=0),                                      # 17-68-68-16 softplus
+    "cond_generic": dict(nvariables=6, naugments=1, nconditions=3, n_hidden=40),           # 11-40-40-7 softplus
+    "deep4_tanh": dict(nvariables=5, naugments=0, nn=("tanh", (6, 33, 47, 21, 5))),         # exact trace by one-hot chains
+    "one_hidden_sigmoid": dict(nvariables=7, naugments=0, autonomous=True, nn=("sigmoid", (7, 50, 7))),
+    "linear9": dict(nvariables=9, naugments=0, autonomous=True, nn=("identity", (9, 9))),
+}
+
+
 def make_icnf(m, name, **extra):
-    kw = dict(SHAPES[name])
+    kw = dict(SHAPES[name] if name in SHAPES else GENERIC_SHAPES[name])
     nn = kw.pop("nn", None)
     if nn is not None:
         act, sizes = nn

@@ -1,0 +1,119 @@
+"""GPU parity tests of the generic kernel family (arbitrary MLP widths, fp32
+tiled SGEMMs with fused epilogues, device-resident Tsit5 controller) against the
+CPU oracle.  Same tolerance as the tiny family: RTOL = 1e-4 (north_star)."""
+import numpy as np
+import pytest
+
+from oracle import icnf_oracle as O
+from oracle import philox as P
+from tests.helpers import GENERIC_SHAPES, make_icnf, make_inputs, t64
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def m():
+    import cnf_b200
+    return cnf_b200
+
+
+def modes(m):
+    return [(m.TestMode(), O.TEST), (m.TrainMode(True), O.TRAIN_REG), (m.TrainMode(False), O.TRAIN_NOREG)]
+
+
+@pytest.mark.parametrize("shape", list(GENERIC_SHAPES))
+def test_rhs_matches_oracle(m, shape):
+    icnf = make_icnf(m, shape)
+    assert icnf.kernel_family == "generic"
+    B = 131
+    om, theta, xs, eps, ys = make_inputs(icnf, B)
+    u = np.random.default_rng(3).standard_normal((om.n_state, B)).astype(np.float32)
+    for mode, omode in modes(m):
+        du = m.augmented_f(icnf, mode, u, theta, 0.37, eps=eps, ys=ys)
+        ref = O.rhs_closed(om, omode, t64(u), t64(theta), 0.37, t64(eps), t64(ys)).numpy()
+        np.testing.assert_allclose(du, ref, rtol=RTOL, atol=2e-5)
+
+
+@pytest.mark.parametrize("shape", list(GENERIC_SHAPES))
+def test_fixed_step_solve_agrees_step_for_step(m, shape):
+    icnf = make_icnf(m, shape)
+    om, theta, xs, eps, ys = make_inputs(icnf, 70)
+    u0 = O.make_u0(om, t64(xs))
+    dt = 0.125
+    for mode, omode in modes(m):
+        for k in (1, 3, 8):
+            got = m.base_sol(icnf, mode, u0.numpy().astype(np.float32), theta, tspan=(0.0, k * dt), eps=eps, ys=ys,
+                             adaptive=False, dt=dt)
+            ref = O.solve(om, omode, u0, t64(theta), t64(eps), t64(ys), 0.0, k * dt,
+                          O.SolverOpts(adaptive=False, dt=dt)).numpy()
+            assert icnf.last_stats.naccept == k
+            np.testing.assert_allclose(got, ref, rtol=RTOL, atol=3e-5)
+
+
+@pytest.mark.parametrize("shape", list(GENERIC_SHAPES))
+@pytest.mark.parametrize("scale", [1.0, 2.0])
+def test_adaptive_inference_matches_oracle(m, shape, scale):
+    """See tests/test_gpu_parity.py: adaptive parity is tolerance-level; step counts are only
+    compared for the stiffer flow (scale 2), where rounding does not pick the steps."""
+    icnf = make_icnf(m, shape)
+    om, theta, xs, eps, ys = make_inputs(icnf, 300)
+    theta = (scale * theta).astype(np.float32)
+    for mode, omode in modes(m):
+        args = (xs,) if ys is None else (xs, ys)
+        logp, (E, n, A) = m.inference(icnf, mode, *args, theta, {}, eps=eps, tspan=icnf.tspan)
+        gs = icnf.last_stats
+        st = O.SolveStats()
+        rl, (rE, rn, rA) = O.inference(om, omode, t64(xs), t64(theta), t64(eps), t64(ys), stats=st)
+        assert gs.status == 0 and gs.t_final == pytest.approx(1.0)
+        assert gs.nf == 2 + 6 * (gs.naccept + gs.nreject)
+        if scale > 1.0:
+            assert abs(gs.naccept - st.naccept) <= 1 and abs(gs.nreject - st.nreject) <= 1, (gs, st.naccept, st.nreject)
+        tol = RTOL if scale == 1.0 else 5e-4
+        np.testing.assert_allclose(logp, rl.numpy(), rtol=tol, atol=2e-5)
+        np.testing.assert_allclose(E, rE.numpy(), rtol=tol, atol=2e-5)
+        np.testing.assert_allclose(A, rA.numpy(), rtol=tol, atol=2e-5)
+        np.testing.assert_allclose(n, rn.numpy(), rtol=tol, atol=2e-2 * float(rn.abs().mean()) + 1e-5)
+
+
+def test_generate_and_in_kernel_noise(m):
+    icnf = make_icnf(m, "cond_generic", epsdist="rademacher")
+    om, theta, xs, eps, ys = make_inputs(icnf, 90)
+    z0 = np.random.default_rng(9).standard_normal((om.d, 90)).astype(np.float32)
+    got = m.generate(icnf, m.TestMode(), ys, theta, {}, 90, z0=z0, tspan=icnf.tspan)
+    ref = O.generate(om, O.TEST, t64(z0), t64(theta), None, t64(ys)).numpy()
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=3e-5)
+    got = m.generate(icnf, m.TestMode(), ys, theta, {}, 90, seed=77, tspan=icnf.tspan)
+    zd = P.gaussian(77, om.d, 90, stream=P.STREAM_BASE)
+    ref = O.generate(om, O.TEST, t64(zd), t64(theta), None, t64(ys)).numpy()
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=5e-5)
+    logp, (E, n, A) = m.inference(icnf, m.TrainMode(True), xs, ys, theta, {}, seed=5, sample_offset=64,
+                                  tspan=icnf.tspan, adaptive=False, dt=0.25)
+    er = P.rademacher(5, om.d, 90, offset=64)
+    rl, (rE, rn, rA) = O.inference(om, O.TRAIN_REG, t64(xs), t64(theta), t64(er), t64(ys),
+                                   opts=O.SolverOpts(adaptive=False, dt=0.25))
+    np.testing.assert_allclose(logp, rl.numpy(), rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(n, rn.numpy(), rtol=RTOL, atol=2e-5)
+
+
+def test_config3_exact_trace_at_a_larger_batch(m):
+    # 16-D GMM data, TestMode: the bilinear closed-form trace against D' autograd pullbacks
+    icnf = make_icnf(m, "config3_gmm16")
+    om, theta, xs, eps, _ = make_inputs(icnf, 4099)
+    logp, _ = m.inference(icnf, m.TestMode(), xs, theta, {}, adaptive=False, dt=0.25, tspan=icnf.tspan)
+    sub = slice(0, 64)
+    ref, _ = O.inference(om, O.TEST, t64(xs[:, sub]), t64(theta), None, opts=O.SolverOpts(adaptive=False, dt=0.25),
+                         closed=False)
+    np.testing.assert_allclose(logp[sub], ref.detach().numpy(), rtol=RTOL, atol=2e-5)
+    assert np.isfinite(logp).all()
+
+
+def test_gradient_is_reported_unsupported_not_faked(m):
+    icnf = make_icnf(m, "config3_gmm16")
+    om, theta, xs, eps, _ = make_inputs(icnf, 8)
+    l = m.loss(icnf, m.TrainMode(True), xs, theta, {}, eps=eps, tspan=icnf.tspan, adaptive=False, dt=0.25)
+    rl = float(O.loss(om, O.TRAIN_REG, t64(xs), t64(theta), t64(eps), opts=O.SolverOpts(adaptive=False, dt=0.25)))
+    assert l == pytest.approx(rl, rel=RTOL)
+    with pytest.raises(m.ICNFError) as ei:
+        m.loss_and_gradient(icnf, m.TrainMode(True), xs, theta, {}, eps=eps)
+    assert ei.value.code == 7
