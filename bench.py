@@ -151,6 +151,41 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------ log p(x) side measurements
+def logp_extras(m, local, dev, flush_buf):
+    """The other half of BASELINE.json's metric: log-density evaluations per second
+    (TestMode = exact trace, Tsit5 adaptive rtol = atol = 1e-4), inputs resident in HBM,
+    CUDA-event timed, L2 flushed between iterations."""
+    out = {}
+    cases = [
+        ("config1_usage_B1024", dict(nvariables=1), 1024),                       # examples/usage.jl shape, tiny family
+        ("config2_moons_B65536", dict(nvariables=2, naugments=0), 65536),        # tiny family
+        ("config3_gmm16_B262144", dict(nvariables=16, naugments=0), 262144),     # 17-68-68-16, generic family
+    ]
+    for name, kw, B in cases:
+        icnf = m.ICNF(device=local, **kw)
+        rng = np.random.default_rng(7)
+        theta, _ = m.setup(rng, icnf)
+        xs = torch.from_numpy(rng.standard_normal((B, icnf.nvariables)).astype(np.float32)).to(dev)
+        mode = m.TestMode()
+        for _ in range(3):
+            m.inference(icnf, mode, xs.t(), theta, {})
+        torch.cuda.synchronize()
+        K, ms = 5, 0.0
+        for _ in range(K):
+            flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            m.inference(icnf, mode, xs.t(), theta, {})
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        st = icnf.last_stats
+        out[name] = {"logp_evals_per_sec": B * K / (ms * 1e-3), "ms_per_call": ms / K, "kernel_family": icnf.kernel_family,
+                     "solver_steps": st.naccept, "rhs_calls": st.nf}
+    return out
+
+
 # ------------------------------------------------------------------ our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -161,6 +196,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="samples per GPU per step")
     ap.add_argument("--cpu-batch", type=int, default=65536, help="batch of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the log p(x) evals/s side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -189,12 +225,9 @@ def main():
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def step_resident(i):
-        l, g = m.loss_and_gradient(icnf, mode, xs_dev.t(), theta, {}, seed=1000 + i, sample_offset=rank * B,
-                                   global_batch=B * world)
-        if world > 1:
-            dist.all_reduce(g)
-            dist.all_reduce(l)
-        return l, g
+        # local loss/gradient on this rank's columns, then ONE all-reduce of [gradient; loss] (NCCL) when N > 1
+        return m.dp_loss_and_gradient(icnf, mode, xs_dev.t(), theta, {}, rank=rank, world=world, global_batch=B * world,
+                                      seed=1000 + i)
 
     xs_np = xs_host.numpy().T       # 2 x B view of the pinned buffer, column-major
 
@@ -204,9 +237,8 @@ def main():
             l, g = m.loss_and_gradient(icnf, mode, xs_np, theta, {}, seed=1000 + i, global_batch=B)
             return float(l), g
         xd = xs_host.to(dev, non_blocking=True)
-        l, g = m.loss_and_gradient(icnf, mode, xd.t(), theta, {}, seed=1000 + i, sample_offset=rank * B, global_batch=B * world)
-        dist.all_reduce(g)
-        dist.all_reduce(l)
+        l, g = m.dp_loss_and_gradient(icnf, mode, xd.t(), theta, {}, rank=rank, world=world, global_batch=B * world,
+                                      seed=1000 + i)
         return float(l.cpu()), g.cpu().numpy()
 
     def timed(fn, K, W):
@@ -321,6 +353,8 @@ def main():
                                              "frac": fwd_flop / (fwd_ms * 1e-3) / 1e12 / fp32_peak}},
         "kernel_ms": {k: float(np.mean(v)) for k, v in kt.items()},
     }
+    if world == 1 and not args.no_extras:
+        line["extras"] = logp_extras(m, local, dev, flush_buf)
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         rate, ms, nfc = cpu_loss_grad_rate(args.cpu_batch, 5, 1, threads)

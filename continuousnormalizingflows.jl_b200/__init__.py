@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
     augmented_f, base_sol, generate, inference, loss, loss_and_gradient, measure_fp32_peak, setup,
 )
 from .dist import CondICNFDist, ICNFDist  # noqa: F401
+from .parallel import all_reduce_sum, dp_loss_and_gradient, shard_bounds  # noqa: F401
 from .mlj import Adam, CondICNFModel, ICNFModel, WeightDecay, make_opt_callback  # noqa: F401
 
 __all__ = [

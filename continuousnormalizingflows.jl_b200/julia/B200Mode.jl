@@ -1,0 +1,163 @@
+# B200Mode.jl -- Julia glue for libicnf_b200.so (NOT executed in the build container:
+# Julia is not installed there; the Python ctypes mirror in ../api.py exercises the
+# same C ABI).  A maintainer of ContinuousNormalizingFlows.jl adds this file to
+# src/ (or a package extension) and `include`s it after core/utils.jl.
+#
+# It adds one compute mode, `B200MatrixMode <: MatrixMode`, and specialises the three
+# seams of SURVEY.md 8(b) on it.  Everything else in the package -- `inference`,
+# `generate`, `ICNFDist`, `ICNFModel`, the MLJ fit loop -- keeps calling the same
+# generic functions and lands here through dispatch.
+
+const libicnf = "libicnf_b200.so"   # on LD_LIBRARY_PATH, or an absolute path
+
+struct B200MatrixMode{ADBack <: ADTypes.AbstractADType} <: MatrixMode{ADBack}
+    adback::ADBack          # unused: gradients come from icnf_loss_grad
+end
+B200MatrixMode() = B200MatrixMode(ADTypes.AutoZygote())
+
+# ---- C structs (include/icnf_b200.h) ---------------------------------------------
+struct IcnfConfig
+    abi_version::Int32
+    nvars::Int32
+    naug::Int32
+    ncond::Int32
+    autonomous::Int32
+    n_layers::Int32
+    sizes::NTuple{9, Int32}
+    activation::Int32
+    lambda1::Float32
+    lambda2::Float32
+    lambda3::Float32
+    reg_squared::Int32
+    precision::Int32
+    device::Int32
+end
+
+struct IcnfSolver
+    adaptive::Int32
+    dt::Float32
+    reltol::Float32
+    abstol::Float32
+    max_steps::Int32
+    beta1::Float32; beta2::Float32; gamma::Float32; qmin::Float32; qmax::Float32
+    qsteady_min::Float32; qsteady_max::Float32; qoldinit::Float32
+end
+
+struct IcnfNoise
+    kind::Int32
+    seed::UInt64
+    sample_offset::Int64
+end
+
+mutable struct IcnfStats
+    naccept::Int32; nreject::Int32; nf::Int32; status::Int32
+    t_final::Float32; dt_last::Float32
+    IcnfStats() = new(0, 0, 0, 0, 0.0f0, 0.0f0)
+end
+
+mode_code(::TestMode) = Int32(0)
+mode_code(::TrainMode{true}) = Int32(1)
+mode_code(::TrainMode{false}) = Int32(2)
+
+# ---- handle cache: never stored in ps / st / icnf, so machines stay serialisable
+#      (test/ci_tests/smoke_tests.jl:142) ------------------------------------------
+const HANDLES = IdDict{Any, Ptr{Cvoid}}()
+
+function dense_sizes(nn::Lux.Chain)
+    sizes = Int32[nn.layers[1].in_dims]
+    for l in nn.layers
+        push!(sizes, l.out_dims)
+    end
+    return sizes
+end
+
+function handle(icnf::ICNF{Float32, <:B200MatrixMode})
+    get!(HANDLES, icnf) do
+        sizes = dense_sizes(icnf.nn)
+        padded = ntuple(i -> i <= length(sizes) ? sizes[i] : Int32(0), 9)
+        act = icnf.nn.layers[1].activation === NNlib.softplus ? 0 :
+              icnf.nn.layers[1].activation === tanh ? 1 : 2
+        cfg = Ref(IcnfConfig(1, icnf.nvariables, icnf.naugments,
+            first(sizes) - icnf.nvariables - icnf.naugments - !(icnf isa ICNF{Float32, <:Any, <:Any, <:Any, true}),
+            icnf isa ICNF{Float32, <:Any, <:Any, <:Any, true}, length(sizes) - 1, padded, act,
+            icnf.λ₁, icnf.λ₂, icnf.λ₃, 0, 0, 0))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:icnf_create, libicnf), Cint, (Ref{IcnfConfig}, Ref{Ptr{Cvoid}}), cfg, out)
+        rc == 0 || error(unsafe_string(ccall((:icnf_last_error, libicnf), Cstring, (Ptr{Cvoid},), C_NULL)))
+        out[]
+    end
+end
+
+check(h, rc) = rc == 0 || error(unsafe_string(ccall((:icnf_last_error, libicnf), Cstring, (Ptr{Cvoid},), h)))
+
+function set_params!(h, ps)
+    θ = ComponentArrays.getdata(ps)::Vector{Float32}
+    GC.@preserve θ check(h, ccall((:icnf_set_params, libicnf), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int64), h, θ, length(θ)))
+end
+
+tsit5_opts(icnf) = Ref(IcnfSolver(1, 0.0f0, icnf.sol_kwargs.reltol, icnf.sol_kwargs.abstol, 0,
+    0, 0, 0, 0, 0, 0, 0, 0))
+
+# ---- S2: one ccall per solve (replaces base_sol, src/core/base_icnf.jl:134-140) ---
+function base_sol(
+    icnf::ICNF{Float32, <:B200MatrixMode, INPLACE},
+    prob::SciMLBase.AbstractODEProblem{<:AbstractMatrix{<:Real}, NTuple{2, Float32}, INPLACE},
+) where {INPLACE}
+    h = handle(icnf)
+    set_params!(h, prob.p)
+    f = prob.f.f                      # the closure built by make_ode_func: carries mode, ϵ, ys
+    u0 = Matrix{Float32}(prob.u0)
+    ufinal = similar(u0)
+    ϵ = f.ϵ
+    ys = f.nn isa CondLayer ? Matrix{Float32}(f.nn.ys) : nothing
+    noise = Ref(IcnfNoise(0, 0, 0))   # SUPPLIED: identical noise to the CPU path
+    stats = IcnfStats()
+    t0, t1 = prob.tspan
+    GC.@preserve u0 ufinal ϵ ys begin
+        check(h, ccall((:icnf_solve, libicnf), Cint,
+            (Ptr{Cvoid}, Cint, Ref{IcnfSolver}, Float32, Float32, Ptr{Float32}, Ref{IcnfNoise}, Ptr{Float32},
+             Ptr{Float32}, Ptr{Float32}, Ref{IcnfStats}, Int64),
+            h, mode_code(f.mode), tsit5_opts(icnf), t0, t1, u0, noise, ϵ,
+            isnothing(ys) ? C_NULL : pointer(ys), ufinal, stats, size(u0, 2)))
+    end
+    return ufinal
+end
+
+# ---- S3: loss and its gradient (replaces the Zygote + SciMLSensitivity path,
+#      src/core/icnf.jl:90-99, :628-649) ------------------------------------------
+function b200_loss_grad(icnf, mode, xs, ys, ps; want_dxs = false)
+    h = handle(icnf)
+    set_params!(h, ps)
+    B = size(xs, 2)
+    ϵ = similar(xs, icnf.nvariables + icnf.naugments, B)
+    Random.rand!(icnf.rng, icnf.epsdist, ϵ)                     # base_icnf.jl:258-259
+    t0, t1 = steer_tspan(icnf, mode)                            # base_icnf.jl:23-43
+    dθ = zeros(Float32, length(ComponentArrays.getdata(ps)))
+    dxs = want_dxs ? similar(xs) : nothing
+    loss = Ref{Float32}(0)
+    stats = IcnfStats()
+    noise = Ref(IcnfNoise(0, 0, 0))
+    GC.@preserve xs ys ϵ dθ dxs begin
+        check(h, ccall((:icnf_loss_grad, libicnf), Cint,
+            (Ptr{Cvoid}, Cint, Ref{IcnfSolver}, Float32, Float32, Ptr{Float32}, Ref{IcnfNoise}, Ptr{Float32},
+             Ptr{Float32}, Ref{Float32}, Ptr{Float32}, Ptr{Float32}, Ref{IcnfStats}, Int64, Int64),
+            h, mode_code(mode), tsit5_opts(icnf), t0, t1, xs, noise, ϵ,
+            isnothing(ys) ? C_NULL : pointer(ys), loss, dθ, want_dxs ? pointer(dxs) : C_NULL, stats, B, 0))
+    end
+    return loss[], dθ, dxs
+end
+
+function loss(icnf::ICNF{Float32, <:B200MatrixMode}, mode::Mode, xs::AbstractMatrix{<:Real}, ps::Any, st::NamedTuple)
+    return first(b200_loss_grad(icnf, mode, Matrix{Float32}(xs), nothing, ps))
+end
+
+function ChainRulesCore.rrule(
+    ::typeof(loss), icnf::ICNF{Float32, <:B200MatrixMode}, mode::Mode, xs::AbstractMatrix{<:Real}, ps::Any, st::NamedTuple,
+)
+    l, dθ, dxs = b200_loss_grad(icnf, mode, Matrix{Float32}(xs), nothing, ps; want_dxs = true)
+    function loss_pullback(l̄)
+        NT = ChainRulesCore.NoTangent()
+        return NT, NT, NT, l̄ .* dxs, ComponentArrays.ComponentArray(l̄ .* dθ, ComponentArrays.getaxes(ps)), NT
+    end
+    return l, loss_pullback
+end
