@@ -162,6 +162,8 @@ struct icnf_handle {
         return code;
     }
     int cuda_fail(cudaError_t e, const char* what) {
+        if (e == cudaErrorNotSupported)
+            return fail(ICNF_ERR_UNSUPPORTED, "%s: this kernel family does not implement the request", what);
         return fail(ICNF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     }
 };

@@ -60,7 +60,9 @@ enum Epilogue {
     EP_LIN = 1,     // out0 = acc + bias
     EP_MULD = 2,    // out1 = acc (optional), out0 = acc .* aux0
     EP_PLAIN = 3,   // out0 = acc
-    EP_TRACE = 4    // colsum[n] += sum_m acc .* aux0     (exact trace, two hidden layers)
+    EP_TRACE = 4,   // colsum[n] += sum_m acc .* aux0     (exact trace, two hidden layers)
+    EP_TANGENT = 5, // out0 = acc .* aux0 (d); out1 (+)= acc .* aux1 (v) .* sigma''(aux2 (h), aux0 (d))
+    EP_MULADD = 6   // out0 = acc .* aux0 + aux1
 };
 
 struct GemmArgs {
@@ -81,6 +83,9 @@ struct GemmArgs {
     float* out0;
     float* out1;
     const float* aux0;
+    const float* aux1;
+    const float* aux2;
+    int accumulate;    // EP_TANGENT: add into out1 instead of overwriting (several probes)
     float* colsum;
     const int* done;   // adaptive: skip when *done
 };
@@ -164,6 +169,13 @@ __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs g) {
                     break;
                 case EP_PLAIN: g.out0[o] = v; break;
                 case EP_TRACE: colpart[j] += v * g.aux0[o]; break;
+                case EP_TANGENT: {
+                    const float d = g.aux0[o];
+                    g.out0[o] = v * d;
+                    const float ex = v * g.aux1[o] * act_dd_rt(g.act, g.aux2[o], d);
+                    g.out1[o] = g.accumulate ? g.out1[o] + ex : ex;
+                } break;
+                case EP_MULADD: g.out0[o] = fmaf(v, g.aux0[o], g.aux1[o]); break;
             }
         }
     }
@@ -428,6 +440,11 @@ __global__ void g_ctrl_end_kernel(CtlArgs a) {
     float q = q11 / powf(c->qold, a.c.beta2);
     q = fmaxf(1.0f / a.c.qmax, fminf(1.0f / a.c.qmin, q / a.c.gamma));
     if (eest <= 1.0f) {
+        if (a.steps) {
+            if (c->naccept >= a.max_ckpt_steps) { c->status = ICNF_ERR_MAX_STEPS; c->done = 1; return; }
+            a.steps[c->naccept].t = c->t;
+            a.steps[c->naccept].dt = c->tdir * hmag;
+        }
         c->naccept++;
         c->dt_last = c->tdir * hmag;
         c->t = c->last ? c->t1 : c->t + c->tdir * hmag;
@@ -484,6 +501,192 @@ __global__ void g_output_kernel(OutArgs a) {
     if (a.out_logp) a.out_logp[b] = logp;
     if (a.out_regs) { a.out_regs[b * 3] = E; a.out_regs[b * 3 + 1] = n; a.out_regs[b * 3 + 2] = Aa; }
     if (a.out_lossterm) a.out_lossterm[b] = -logp + a.lam1 * E + a.lam2 * n + a.lam3 * Aa;
+}
+
+// z rows of a state buffer -> checkpoint slot (slot index read on the device when adaptive)
+__global__ void g_ckpt_kernel(const Ctrl* ctrl, const float* U0, const float* U1, float* ckpt, long long DB,
+                              int slot_fixed, int use_trial, int max_slot) {
+    if (ctrl && ctrl->done) return;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= DB) return;
+    const int cur = ctrl ? ctrl->cur : 0;
+    const int slot = ctrl ? ctrl->naccept + (use_trial ? 1 : 0) : slot_fixed;
+    if (slot > max_slot) return;   // capacity exhausted: g_ctrl_end_kernel reports ICNF_ERR_MAX_STEPS
+    const float* U = (ctrl ? ((cur ^ use_trial) ? U1 : U0) : U0);
+    ckpt[(long long)slot * DB + idx] = U[idx];
+}
+
+// ---- backward (discretise-then-optimise) element-wise pieces ----------------------------
+struct BwArgs {
+    long long B;
+    int D, nvars, i;
+    float h, cl, cE, cn;      // step size; cotangent scalars of this stage: h b_i (lbar, Ebar, nbar)
+    int squared, reg_a;
+    float lam3, wgt;
+    const float* zfinal;      // D x B
+    float* zbar;              // D x B
+    float* ZS;                // [6][D][B] stage inputs
+    float* KZ;                // [5][D][B] stage derivatives (z rows) of stages 1..5
+    float* KB;                // [6][D][B] stage cotangents
+    const float* zn;          // D x B checkpoint
+    const float* ZD; const float* Q; const float* E;
+    float* ZB; float* QB;     // outputs of the cotangent kernel (D x B each)
+    const float* sbar;        // D x B
+    float* dxs;
+};
+
+// zbar = d loss / d z(t1) = wgt * (z + lam3 * [0; z_aug / |z_aug|])
+__global__ void bw_init_kernel(BwArgs a) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    float za = 0.f;
+    for (int r = a.nvars; r < a.D; ++r) { const float z = a.zfinal[(long long)r * a.B + b]; za = fmaf(z, z, za); }
+    const float s = a.reg_a ? (a.squared ? 2.0f * a.lam3 : (za > 0.f ? a.lam3 * rsqrtf(za) : 0.f)) : 0.f;
+    for (int r = 0; r < a.D; ++r) {
+        const float z = a.zfinal[(long long)r * a.B + b];
+        a.zbar[(long long)r * a.B + b] = a.wgt * (r >= a.nvars ? fmaf(s, z, z) : z);
+    }
+}
+// ZS[i] = z_n + h sum_{j<i} a_ij KZ[j]
+__global__ void bw_stage_input_kernel(BwArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long DB = (long long)a.D * a.B;
+    if (idx >= DB) return;
+    float v = a.zn[idx];
+    for (int j = 0; j < a.i; ++j) v = fmaf(a.h * g_a[a.i][j], a.KZ[(long long)j * DB + idx], v);
+    a.ZS[(long long)a.i * DB + idx] = v;
+}
+// KB[i] = h b_i zbar, i = 0..5
+__global__ void bw_kbar_init_kernel(BwArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long DB = (long long)a.D * a.B;
+    if (idx >= DB) return;
+    const float zb = a.zbar[idx];
+    for (int i = 0; i < 6; ++i) a.KB[(long long)i * DB + idx] = a.h * g_a[6][i] * zb;
+}
+// per sample: zb = KB[i] + cE zdot/|zdot|,  qb = -cl eps + cn q/|q|
+__global__ void bw_cotangent_kernel(BwArgs a, int exact_probe) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    const long long DB = (long long)a.D * a.B;
+    float zz = 0.f, qq = 0.f;
+    for (int r = 0; r < a.D; ++r) {
+        const float zd = a.ZD[(long long)r * a.B + b];
+        zz = fmaf(zd, zd, zz);
+        if (exact_probe < 0) { const float q = a.Q[(long long)r * a.B + b]; qq = fmaf(q, q, qq); }
+    }
+    const float sz = (a.cE != 0.f) ? (a.squared ? 2.0f * a.cE : (zz > 0.f ? a.cE * rsqrtf(zz) : 0.f)) : 0.f;
+    const float sq = (a.cn != 0.f) ? (a.squared ? 2.0f * a.cn : (qq > 0.f ? a.cn * rsqrtf(qq) : 0.f)) : 0.f;
+    for (int r = 0; r < a.D; ++r) {
+        const long long o = (long long)r * a.B + b;
+        if (a.ZB) a.ZB[o] = fmaf(sz, a.ZD[o], a.KB[(long long)a.i * DB + o]);
+        if (exact_probe < 0) a.QB[o] = fmaf(sq, a.Q[o], -a.cl * a.E[o]);
+        else a.QB[o] = (r == exact_probe) ? -a.cl : 0.f;
+    }
+}
+// zbar += sbar; KB[j] += h a_ij sbar for j < i
+__global__ void bw_accumulate_kernel(BwArgs a) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long DB = (long long)a.D * a.B;
+    if (idx >= DB) return;
+    const float sb = a.sbar[idx];
+    a.zbar[idx] += sb;
+    for (int j = 0; j < a.i; ++j) a.KB[(long long)j * DB + idx] = fmaf(a.h * g_a[a.i][j], sb, a.KB[(long long)j * DB + idx]);
+}
+__global__ void bw_dxs_kernel(BwArgs a) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    for (int r = 0; r < a.nvars; ++r) a.dxs[b * a.nvars + r] = a.zbar[(long long)r * a.B + b];
+}
+// one-hot probe as a D x B matrix (exact-trace backward)
+__global__ void bw_onehot_kernel(float* E, int p, int D, long long B) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)D * B) return;
+    E[idx] = ((int)(idx / B) == p) ? 1.0f : 0.0f;
+}
+
+// Weight gradient: dW[j, k] += sum_b X1[j][b] Y1[k][b] + X2[j][b] Y2[k][b] (second product for
+// k < K2 only), db[j] += sum_b X1[j][b].  Reduction over samples is split across gridDim.z
+// and finished with float atomics into the (zero-initialised) gradient vector.
+struct WgradArgs {
+    const float* X1; const float* X2;     // nout x B
+    const float* Y1;                      // nin x B, or gathered [zi; t; ys] when gather != 0
+    const float* Y2;                      // K2 x B
+    int nout, nin, K2;
+    long long B;
+    int gather, D, tin, C;
+    const float* zi; const float* ys; float tval;
+    float* dW;                            // column-major nout x nin
+    float* db;                            // nout, or null
+    long long chunk;                      // samples per gridDim.z slice
+};
+
+__device__ __forceinline__ float wgrad_y1(const WgradArgs& g, int k, long long b) {
+    if (!g.gather) return g.Y1[(long long)k * g.B + b];
+    if (k < g.D) return g.zi[(long long)k * g.B + b];
+    if (g.tin && k == g.D) return g.tval;
+    return g.ys[(long long)(k - g.D - g.tin) * g.B + b];
+}
+
+__global__ void __launch_bounds__(GT) wgrad_kernel(WgradArgs g) {
+    __shared__ __align__(16) float Xs[BK][BM + 4];
+    __shared__ __align__(16) float Ys[BK][BN + 4];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int j0 = blockIdx.y * BM, k0 = blockIdx.x * BN;
+    const long long b_lo = (long long)blockIdx.z * g.chunk, b_hi = min(g.B, b_lo + g.chunk);
+    float acc[4][4];
+    float bacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    const int npass = (g.X2 && k0 < g.K2) ? 2 : 1;
+    for (int pass = 0; pass < npass; ++pass) {
+        const float* X = pass == 0 ? g.X1 : g.X2;
+        for (long long bb = b_lo; bb < b_hi; bb += BK) {
+            // tiles: 64 rows x 16 samples each; thread loads 4 elements (row r, samples s..)
+            {
+                const int r = threadIdx.x >> 2, s4 = (threadIdx.x & 3) * 4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const long long b = bb + s4 + i;
+                    const int j = j0 + r, k = k0 + r;
+                    Xs[s4 + i][r] = (b < b_hi && j < g.nout) ? X[(long long)j * g.B + b] : 0.f;
+                    float y = 0.f;
+                    if (b < b_hi) {
+                        if (pass == 0) { if (k < g.nin) y = wgrad_y1(g, k, b); }
+                        else if (k < g.K2) y = g.Y2[(long long)k * g.B + b];
+                    }
+                    Ys[s4 + i][r] = y;
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < BK; ++s) {
+                const float4 x = *reinterpret_cast<const float4*>(&Xs[s][ty * 4]);
+                const float4 y = *reinterpret_cast<const float4*>(&Ys[s][tx * 4]);
+                const float xv[4] = {x.x, x.y, x.z, x.w}, yv[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xv[i], yv[j], acc[i][j]);
+                    if (pass == 0 && tx == 0) bacc[i] += xv[i];
+                }
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int j = j0 + ty * 4 + i;
+        if (j >= g.nout) continue;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int k = k0 + tx * 4 + jj;
+            if (k < g.nin) atomicAdd(g.dW + (long long)k * g.nout + j, acc[i][jj]);
+        }
+        if (g.db && tx == 0 && blockIdx.x == 0) atomicAdd(g.db + j, bacc[i]);
+    }
 }
 
 // W' (transposed copy) for the VJP GEMMs: WT(k, j) at j * nin + k
@@ -566,7 +769,9 @@ struct Workspace {
     std::vector<size_t> wtoff;        // offsets in thetaT
     Buf thetaT, amat, gvec;
     Buf U0, U1, KF0, KF1, Kst, ZI, EPS, YS, ZD, Q, TR, F1, Hb, Db, Gb, ctrl;
+    Buf bZS, bKZ, bKB, bzbar, bV, bWv, bAEX, bAB, bSB;   // backward
     Ctrl* ctrl_host = nullptr;   // pinned, two slots
+    std::vector<StepRec> recs;   // fixed-step schedule staged for the backward pass
     cudaEvent_t ev[2] = {nullptr, nullptr};
     float trace_const = 0.f;
     long long launches = 0;
@@ -577,6 +782,11 @@ struct Workspace {
 #define GCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return e__; } while (0)
 
 static inline int blocks_for(long long n, int t = 256) { return (int)((n + t - 1) / t); }
+static inline float g_b_host(int i) {
+    static const float b[6] = {0.09646076681806523f, 0.01f, 0.4798896504144996f, 1.379008574103742f, -3.290069515436081f,
+                               2.324710524099774f};
+    return b[i];
+}
 static inline float g_c_host(int i) {
     static const float c[7] = {0.0f, 0.161f, 0.327f, 0.9f, 0.9800255409045097f, 1.0f, 1.0f};
     return c[i];
@@ -654,8 +864,8 @@ static cudaError_t launch_gemm(Workspace* w, GemmArgs& g, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-// network forward on ZI (+ t, ys) -> H_l, D_l, ZD; then trace / VJP chain -> TR or Q
-static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
+// network forward on zi (+ t, ys) -> H_l, D_l, zd_out
+static cudaError_t enqueue_forward(const RhsPlan& p, float c_i, const float* zi, float* zd_out) {
     Workspace* w = p.w;
     const long long B = p.B;
     const int NL = w->NL, D = w->D;
@@ -668,7 +878,7 @@ static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
         g.A = p.theta + w->woff[l]; g.lda = w->n[l + 1];
         g.M = w->n[l + 1]; g.K = w->n[l]; g.N = B;
         if (l == 0) {
-            g.gather = 1; g.D = D; g.tin = w->tin; g.C = w->C; g.zi = w->ZI.as<float>(); g.ys = w->YS.as<float>();
+            g.gather = 1; g.D = D; g.tin = w->tin; g.C = w->C; g.zi = zi; g.ys = w->YS.as<float>();
             g.ctrl = p.ctrl; g.t_fixed = p.t_fixed; g.c_i = c_i;
         } else {
             g.Bm = H + w->hoff[l - 1] * B; g.ldb = B;
@@ -676,10 +886,46 @@ static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
         g.bias = p.theta + w->boff[l];
         g.act = w->cfg.activation;
         if (l < NL - 1) { g.ep = EP_ACT; g.out0 = H + w->hoff[l] * B; g.out1 = Dv + w->hoff[l] * B; }
-        else { g.ep = EP_LIN; g.out0 = w->ZD.as<float>(); }
+        else { g.ep = EP_LIN; g.out0 = zd_out; }
         g.done = done;
         GCK(launch_gemm(w, g, p.st));
     }
+    return cudaSuccess;
+}
+
+// Hutchinson VJP chain g_L = probe (D x B): G_l, optionally V_l, and Q = probe' J
+static cudaError_t enqueue_chain(const RhsPlan& p, const float* probe, float* Vstore) {
+    Workspace* w = p.w;
+    const long long B = p.B;
+    const int NL = w->NL, D = w->D;
+    float* Dv = w->Db.as<float>();
+    float* G = w->Gb.as<float>();
+    const float* thetaT = w->thetaT.as<float>();
+    const int* done = p.ctrl ? &p.ctrl->done : nullptr;
+    for (int l = NL - 1; l >= 0; --l) {
+        GemmArgs g;
+        memset(&g, 0, sizeof g);
+        g.A = thetaT + w->wtoff[l]; g.lda = w->n[l];
+        g.M = (l == 0) ? D : w->n[l]; g.K = w->n[l + 1]; g.N = B;
+        g.Bm = (l == NL - 1) ? probe : G + w->hoff[l] * B; g.ldb = B;
+        if (l > 0) {
+            g.ep = EP_MULD; g.out0 = G + w->hoff[l - 1] * B; g.aux0 = Dv + w->hoff[l - 1] * B;
+            g.out1 = Vstore ? Vstore + w->hoff[l - 1] * B : nullptr;
+        } else { g.ep = EP_PLAIN; g.out0 = w->Q.as<float>(); }
+        g.done = done;
+        GCK(launch_gemm(w, g, p.st));
+    }
+    return cudaSuccess;
+}
+
+// forward, then trace / VJP chain -> TR or Q
+static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
+    Workspace* w = p.w;
+    const long long B = p.B;
+    const int NL = w->NL, D = w->D;
+    float* Dv = w->Db.as<float>();
+    const int* done = p.ctrl ? &p.ctrl->done : nullptr;
+    GCK(enqueue_forward(p, c_i, w->ZI.as<float>(), w->ZD.as<float>()));
     const float* thetaT = w->thetaT.as<float>();
     if (p.exact) {
         float* TR = w->TR.as<float>();
@@ -721,19 +967,7 @@ static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
             }
         }
     } else {
-        // Hutchinson VJP chain: g_L = eps
-        float* G = w->Gb.as<float>();
-        for (int l = NL - 1; l >= 0; --l) {
-            GemmArgs g;
-            memset(&g, 0, sizeof g);
-            g.A = thetaT + w->wtoff[l]; g.lda = w->n[l];
-            g.M = (l == 0) ? D : w->n[l]; g.K = w->n[l + 1]; g.N = B;
-            g.Bm = (l == NL - 1) ? w->EPS.as<float>() : G + w->hoff[l] * B; g.ldb = B;
-            if (l > 0) { g.ep = EP_MULD; g.out0 = G + w->hoff[l - 1] * B; g.aux0 = Dv + w->hoff[l - 1] * B; }
-            else { g.ep = EP_PLAIN; g.out0 = w->Q.as<float>(); }
-            g.done = done;
-            GCK(launch_gemm(w, g, p.st));
-        }
+        GCK(enqueue_chain(p, w->EPS.as<float>(), nullptr));
     }
     return cudaSuccess;
 }
@@ -823,13 +1057,16 @@ static cudaError_t enqueue_stage(Workspace* w, const SolveArgs& a, StageArgs s, 
 
 static cudaError_t solve_fixed(void* wsp, const float*, const SolveArgs& a, int nvars, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
-    if (a.ckpt) return cudaErrorNotSupported;   // training checkpoints: generic backward not built yet
     GCK(reserve_common(w, a.B));
     GCK(load_inputs(w, a, nvars, st));
     StageArgs s = make_stage_args(w, a.B, exact, a.reg_e, a.reg_n, a.squared);
     const float tdir = (a.t1 >= a.t0) ? 1.f : -1.f, span = fabsf(a.t1 - a.t0);
+    const long long DB = (long long)w->D * a.B;
     int cur = 0;
     float h = 0.f;
+    std::vector<StepRec>& recs = w->recs;
+    recs.clear();
+    if (a.ckpt) { g_ckpt_kernel<<<blocks_for(DB), 256, 0, st>>>(nullptr, w->U0.as<float>(), nullptr, a.ckpt, DB, 0, 0, a.max_ckpt_steps); w->launches++; }
     for (int step = 0; step < a.nsteps; ++step) {
         const float tb = fminf(span, step * a.dt);
         h = tdir * fminf(a.dt, span - tb);
@@ -839,13 +1076,19 @@ static cudaError_t solve_fixed(void* wsp, const float*, const SolveArgs& a, int 
         g_advance_kernel<<<blocks_for((long long)w->S * a.B), 256, 0, st>>>(s);
         w->launches++;
         cur ^= 1;
+        if (a.ckpt) {
+            g_ckpt_kernel<<<blocks_for(DB), 256, 0, st>>>(nullptr, s.U[cur], nullptr, a.ckpt, DB, step + 1, 0, a.max_ckpt_steps);
+            w->launches++;
+            recs.push_back(StepRec{t, h});
+        }
     }
+    if (a.steps && !recs.empty())
+        GCK(cudaMemcpyAsync(a.steps, recs.data(), sizeof(StepRec) * recs.size(), cudaMemcpyHostToDevice, st));
     return write_outputs(w, a, nvars, nullptr, cur, h, st);
 }
 
 static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, int nvars, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
-    if (a.ckpt) return cudaErrorNotSupported;
     GCK(reserve_common(w, a.B));
     GCK(load_inputs(w, a, nvars, st));
     Ctrl* ctrl = w->ctrl.as<Ctrl>();
@@ -853,7 +1096,10 @@ static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, i
     memset(&ca, 0, sizeof ca);
     ca.ctrl = ctrl; ca.c = a.ctl; ca.inv_count = 1.0 / ((double)a.B * (double)w->S);
     ca.t0 = a.t0; ca.t1 = a.t1; ca.span = fabsf(a.t1 - a.t0); ca.dt_user = a.dt;
+    ca.steps = a.ckpt ? a.steps : nullptr; ca.max_ckpt_steps = a.max_ckpt_steps;
+    const long long DB = (long long)w->D * a.B;
     g_ctrl_init_kernel<<<1, 1, 0, st>>>(ca);
+    if (a.ckpt) { g_ckpt_kernel<<<blocks_for(DB), 256, 0, st>>>(nullptr, w->U0.as<float>(), nullptr, a.ckpt, DB, 0, 0, a.max_ckpt_steps); w->launches++; }
     StageArgs s = make_stage_args(w, a.B, exact, a.reg_e, a.reg_n, a.squared);
     s.reltol = a.ctl.reltol; s.abstol = a.ctl.abstol;
     const int sb = blocks_for((long long)w->S * a.B);
@@ -886,6 +1132,7 @@ static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, i
         for (int stage = 1; stage < 6; ++stage) GCK(enqueue_stage(w, a, s, stage, exact, ctrl, 0.f, 0.f, 0, st));
         s.ctrl = ctrl;
         g_advance_kernel<<<sb, 256, 0, st>>>(s);
+        if (a.ckpt) { g_ckpt_kernel<<<blocks_for(DB), 256, 0, st>>>(ctrl, w->U0.as<float>(), w->U1.as<float>(), a.ckpt, DB, 0, 1, a.max_ckpt_steps); w->launches++; }
         GCK(enqueue_stage(w, a, s, 6, exact, ctrl, 0.f, 0.f, 0, st));
         s.ctrl = ctrl;
         g_error_kernel<<<sb, 256, 0, st>>>(s);
@@ -900,8 +1147,117 @@ static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, i
 }
 
 static int adaptive_max_grid(bool, int sm_count) { return sm_count; }   // not a cooperative kernel; any value > 0
-static cudaError_t backward(void*, const float*, const BackwardArgs&, bool, int, cudaStream_t) { return cudaErrorNotSupported; }
-static int backward_grid(bool, int sm_count, long long) { return sm_count; }
+// Reverse sweep over the recorded steps (discretise-then-optimise; derivation in tiny.cuh).
+static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool exact, int, cudaStream_t st) {
+    Workspace* w = (Workspace*)wsp;
+    if (exact) return cudaErrorNotSupported;   // TestMode gradient: tiny family only for now
+    const long long B = a.B;
+    const int NL = w->NL, D = w->D;
+    const long long DB = (long long)D * B;
+    GCK(cudaStreamSynchronize(st));
+    DevStats hs;
+    GCK(cudaMemcpy(&hs, a.stats, sizeof hs, cudaMemcpyDeviceToHost));
+    size_t np = 0;
+    for (int l = 0; l < NL; ++l) np += (size_t)w->n[l] * w->n[l + 1] + w->n[l + 1];
+    GCK(cudaMemsetAsync(a.gpartial, 0, sizeof(float) * np, st));
+    if (hs.status != ICNF_OK) return cudaSuccess;   // the caller reports the solver status
+    const int nsteps = hs.naccept;
+    std::vector<StepRec> steps(std::max(nsteps, 1));
+    if (nsteps) GCK(cudaMemcpy(steps.data(), a.steps, sizeof(StepRec) * nsteps, cudaMemcpyDeviceToHost));
+    const size_t f = sizeof(float);
+    GCK(w->bZS.reserve(f * 6 * DB)); GCK(w->bKZ.reserve(f * 5 * DB)); GCK(w->bKB.reserve(f * 6 * DB));
+    GCK(w->bzbar.reserve(f * DB)); GCK(w->bSB.reserve(f * DB));
+    GCK(w->bV.reserve(f * w->hrows * B)); GCK(w->bWv.reserve(f * (w->hrows + D) * B));
+    GCK(w->bAEX.reserve(f * w->hrows * B)); GCK(w->bAB.reserve(f * w->hrows * B));
+    float* H = w->Hb.as<float>(); float* Dv = w->Db.as<float>(); float* G = w->Gb.as<float>();
+    float* V = w->bV.as<float>(); float* AEX = w->bAEX.as<float>(); float* AB = w->bAB.as<float>();
+    float* Wv = w->bWv.as<float>();   // Wv_0 (D rows) at 0, Wv_l (n[l] rows) at (D + hoff[l-1]) * B
+    auto wv_ptr = [&](int l) { return l == 0 ? Wv : Wv + ((size_t)D + w->hoff[l - 1]) * B; };
+    const float* thetaT = w->thetaT.as<float>();
+
+    BwArgs b;
+    memset(&b, 0, sizeof b);
+    b.B = B; b.D = D; b.nvars = a.nvars; b.squared = a.squared; b.reg_a = a.reg_a; b.lam3 = a.lam3; b.wgt = a.inv_denominator;
+    b.zfinal = a.ckpt + (long long)nsteps * DB; b.zbar = w->bzbar.as<float>();
+    b.ZS = w->bZS.as<float>(); b.KZ = w->bKZ.as<float>(); b.KB = w->bKB.as<float>();
+    b.ZD = w->ZD.as<float>(); b.Q = w->Q.as<float>(); b.E = w->EPS.as<float>();
+    b.ZB = AB + w->hoff[NL - 1] * B; b.QB = wv_ptr(0); b.sbar = w->bSB.as<float>(); b.dxs = a.dxs;
+    const int db_blocks = blocks_for(DB), b_blocks = blocks_for(B);
+    bw_init_kernel<<<b_blocks, 256, 0, st>>>(b);
+    const float lbar = a.inv_denominator;
+    const float Ebar = a.reg_e ? a.lam1 * a.inv_denominator : 0.f, nbar = a.reg_n ? a.lam2 * a.inv_denominator : 0.f;
+    RhsPlan p{w, a.theta, B, false, a.reg_e, a.reg_n, a.squared, nullptr, 0.f, st};
+
+    for (int step = nsteps - 1; step >= 0; --step) {
+        const float t = steps[step].t, h = steps[step].dt;
+        b.h = h; b.zn = a.ckpt + (long long)step * DB;
+        for (int i = 0; i < 6; ++i) {
+            b.i = i;
+            bw_stage_input_kernel<<<db_blocks, 256, 0, st>>>(b);
+            if (i < 5) {
+                p.t_fixed = t + g_c_host(i) * h;
+                GCK(enqueue_forward(p, 0.f, b.ZS + (long long)i * DB, b.KZ + (long long)i * DB));
+            }
+        }
+        bw_kbar_init_kernel<<<db_blocks, 256, 0, st>>>(b);
+        w->launches += 7;
+        for (int i = 5; i >= 0; --i) {
+            const float* zi = b.ZS + (long long)i * DB;
+            const float ti = t + g_c_host(i) * h;
+            const float hb = h * g_b_host(i);
+            b.i = i; b.cl = hb * lbar; b.cE = hb * Ebar; b.cn = hb * nbar;
+            p.t_fixed = ti;
+            GCK(enqueue_forward(p, 0.f, zi, w->ZD.as<float>()));
+            GCK(enqueue_chain(p, w->EPS.as<float>(), V));
+            bw_cotangent_kernel<<<b_blocks, 256, 0, st>>>(b, -1);
+            // tangent pass
+            for (int l = 0; l < NL - 1; ++l) {
+                GemmArgs g;
+                memset(&g, 0, sizeof g);
+                g.A = a.theta + w->woff[l]; g.lda = w->n[l + 1];
+                g.M = w->n[l + 1]; g.K = (l == 0) ? D : w->n[l]; g.N = B;
+                g.Bm = wv_ptr(l); g.ldb = B;
+                g.ep = EP_TANGENT; g.act = w->cfg.activation;
+                g.out0 = wv_ptr(l + 1); g.out1 = AEX + w->hoff[l] * B;
+                g.aux0 = Dv + w->hoff[l] * B; g.aux1 = V + w->hoff[l] * B; g.aux2 = H + w->hoff[l] * B;
+                GCK(launch_gemm(w, g, st));
+            }
+            // backprop + weight gradients, top layer first
+            for (int l = NL - 1; l >= 0; --l) {
+                WgradArgs wg;
+                memset(&wg, 0, sizeof wg);
+                wg.X1 = AB + w->hoff[l] * B;
+                wg.X2 = (l == NL - 1) ? w->EPS.as<float>() : G + w->hoff[l] * B;
+                wg.Y2 = wv_ptr(l); wg.K2 = (l == 0) ? D : w->n[l];
+                wg.nout = w->n[l + 1]; wg.nin = w->n[l]; wg.B = B;
+                if (l == 0) { wg.gather = 1; wg.D = D; wg.tin = w->tin; wg.C = w->C; wg.zi = zi; wg.ys = w->YS.as<float>(); wg.tval = ti; }
+                else wg.Y1 = H + w->hoff[l - 1] * B;
+                wg.dW = a.gpartial + w->woff[l]; wg.db = a.gpartial + w->boff[l];
+                const int gx = (wg.nin + BN - 1) / BN, gy = (wg.nout + BM - 1) / BM;
+                int gz = (int)std::min<long long>((B + 255) / 256, std::max(1, 592 / (gx * gy)));
+                wg.chunk = ((B + gz - 1) / gz + BK - 1) / BK * BK;
+                gz = (int)((B + wg.chunk - 1) / wg.chunk);
+                wgrad_kernel<<<dim3(gx, gy, gz), GT, 0, st>>>(wg);
+                w->launches++;
+                GemmArgs g;
+                memset(&g, 0, sizeof g);
+                g.A = thetaT + w->wtoff[l]; g.lda = w->n[l];
+                g.M = (l == 0) ? D : w->n[l]; g.K = w->n[l + 1]; g.N = B;
+                g.Bm = AB + w->hoff[l] * B; g.ldb = B;
+                if (l > 0) {
+                    g.ep = EP_MULADD; g.out0 = AB + w->hoff[l - 1] * B;
+                    g.aux0 = Dv + w->hoff[l - 1] * B; g.aux1 = AEX + w->hoff[l - 1] * B;
+                } else { g.ep = EP_PLAIN; g.out0 = w->bSB.as<float>(); }
+                GCK(launch_gemm(w, g, st));
+            }
+            bw_accumulate_kernel<<<db_blocks, 256, 0, st>>>(b);
+            w->launches += 2;
+        }
+    }
+    if (a.dxs) { bw_dxs_kernel<<<b_blocks, 256, 0, st>>>(b); w->launches++; }
+    return cudaGetLastError();
+}
+static int backward_grid(bool, int, long long) { return 1; }
 
 }  // namespace generic
 
@@ -920,7 +1276,7 @@ const Family* generic_family() {
         g.backward = &generic::backward;
         g.backward_grid = &generic::backward_grid;
         g.backward_partials_per_block = 1;
-        g.supports_backward = 0;
+        g.supports_backward = 1;
         return g;
     }();
     return &f;
