@@ -456,7 +456,11 @@ int64_t icnf_n_params(const icnf_handle* h) {
     return n;
 }
 int32_t icnf_n_state(const icnf_handle* h) { return h ? h->S() : 0; }
-const char* icnf_kernel_family(const icnf_handle* h) { return (h && h->fam) ? h->fam->name : ""; }
+const char* icnf_kernel_family(const icnf_handle* h) {
+    if (!h || !h->fam) return "";
+    if (h->cfg.precision == ICNF_BF16_TC) return "tc";
+    return h->fam->name;
+}
 int64_t icnf_launch_count(const icnf_handle* h) { return h ? h->launches : 0; }
 
 int icnf_set_profiling(icnf_handle* h, int enabled) {

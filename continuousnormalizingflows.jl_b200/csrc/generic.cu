@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "family.h"
+#include "tc.h"
 
 namespace icnf {
 namespace generic {
@@ -770,6 +771,13 @@ struct Workspace {
     Buf thetaT, amat, gvec;
     Buf U0, U1, KF0, KF1, Kst, ZI, EPS, YS, ZD, Q, TR, F1, Hb, Db, Gb, ctrl;
     Buf bZS, bKZ, bKB, bzbar, bV, bWv, bAEX, bAB, bSB;   // backward
+    // precision = ICNF_BF16_TC: bf16 operands for the tcgen05 GEMM, [sample][unit] activations
+    bool tc = false;
+    Buf w16t, w16n, a16, X16, E16, H16, D16, G16;
+    std::vector<size_t> w16t_off, w16n_off;   // element offsets per layer
+    std::vector<size_t> h16_off;              // element offsets / B per layer
+    size_t h16_cols = 0;
+    static int pad8(int x) { return (x + 7) & ~7; }
     Ctrl* ctrl_host = nullptr;   // pinned, two slots
     std::vector<StepRec> recs;   // fixed-step schedule staged for the backward pass
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -806,6 +814,16 @@ static void* ws_create(const icnf_config* cfg) {
         w->hoff.push_back(h); h += w->n[l + 1];
     }
     w->hrows = h;
+    w->tc = (cfg->precision == ICNF_BF16_TC);
+    {
+        size_t o1 = 0, o2 = 0, oh = 0;
+        for (int l = 0; l < w->NL; ++l) {
+            w->w16t_off.push_back(o1); o1 += (size_t)w->n[l + 1] * Workspace::pad8(w->n[l]);
+            w->w16n_off.push_back(o2); o2 += (size_t)w->n[l] * Workspace::pad8(w->n[l + 1]);
+            w->h16_off.push_back(oh); oh += Workspace::pad8(w->n[l + 1]);
+        }
+        w->h16_cols = oh;
+    }
     cudaMallocHost((void**)&w->ctrl_host, 2 * sizeof(Ctrl));
     cudaEventCreateWithFlags(&w->ev[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&w->ev[1], cudaEventDisableTiming);
@@ -843,6 +861,29 @@ static cudaError_t on_params(void* p, const float* theta, cudaStream_t st) {
         g_trace_diag_kernel<<<blocks_for(D), 256, 0, st>>>(theta + w->woff[0], w->gvec.as<float>(), D);
     }
     w->launches += w->NL + 1;
+    if (w->tc) {
+        size_t t1 = 0, t2 = 0;
+        for (int l = 0; l < w->NL; ++l) {
+            t1 += (size_t)w->n[l + 1] * Workspace::pad8(w->n[l]);
+            t2 += (size_t)w->n[l] * Workspace::pad8(w->n[l + 1]);
+        }
+        GCK(w->w16t.reserve(t1 * 2)); GCK(w->w16n.reserve(t2 * 2));
+        for (int l = 0; l < w->NL; ++l) {
+            const int nin = w->n[l], nout = w->n[l + 1];
+            // forward operand: rows = output units j, K = inputs k  (W[j,k] at k * nout + j)
+            GCK(tc::pack_matrix(theta + w->woff[l], 1, nout, w->w16t.as<__nv_bfloat16>() + w->w16t_off[l], nout, nin,
+                                Workspace::pad8(nin), st));
+            // VJP operand: rows = inputs k, K = output units j
+            GCK(tc::pack_matrix(theta + w->woff[l], nout, 1, w->w16n.as<__nv_bfloat16>() + w->w16n_off[l], nin, nout,
+                                Workspace::pad8(nout), st));
+        }
+        if (w->NL == 3) {
+            const int n1 = w->n[1], n2 = w->n[2];
+            GCK(w->a16.reserve((size_t)n2 * Workspace::pad8(n1) * 2));
+            GCK(tc::pack_matrix(w->amat.as<float>(), 1, n2, w->a16.as<__nv_bfloat16>(), n2, n1, Workspace::pad8(n1), st));
+        }
+        w->launches += 2 * w->NL + 1;
+    }
     return cudaGetLastError();
 }
 
@@ -918,9 +959,84 @@ static cudaError_t enqueue_chain(const RhsPlan& p, const float* probe, float* Vs
     return cudaSuccess;
 }
 
+// ---- precision = ICNF_BF16_TC: the same RHS on the tcgen05 GEMM (tc_gemm.cuh) -------------------
+static cudaError_t tc_reserve(Workspace* w, long long B) {
+    GCK(w->X16.reserve((size_t)B * Workspace::pad8(w->n[0]) * 2));
+    GCK(w->E16.reserve((size_t)B * Workspace::pad8(w->D) * 2));
+    GCK(w->H16.reserve((size_t)B * w->h16_cols * 2));
+    GCK(w->D16.reserve((size_t)B * w->h16_cols * 2));
+    GCK(w->G16.reserve((size_t)B * w->h16_cols * 2));
+    return cudaSuccess;
+}
+
+static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
+    Workspace* w = p.w;
+    const long long B = p.B;
+    const int NL = w->NL, D = w->D;
+    const int* done = p.ctrl ? &p.ctrl->done : nullptr;
+    GCK(tc_reserve(w, B));
+    __nv_bfloat16* X = w->X16.as<__nv_bfloat16>();
+    __nv_bfloat16* H = w->H16.as<__nv_bfloat16>();
+    __nv_bfloat16* Dv = w->D16.as<__nv_bfloat16>();
+    __nv_bfloat16* G = w->G16.as<__nv_bfloat16>();
+    auto act_ptr = [&](__nv_bfloat16* base, int l) { return base + w->h16_off[l] * (size_t)B; };
+    auto pitch = [&](int l) { return Workspace::pad8(w->n[l + 1]); };
+    GCK(tc::pack_input(w->ZI.as<float>(), w->YS.as<float>(), X, B, D, w->tin, w->C, Workspace::pad8(w->n[0]), p.t_fixed,
+                       (const float*)p.ctrl, c_i, done, p.st));
+    w->launches++;
+    for (int l = 0; l < NL; ++l) {
+        tc::TcArgs g;
+        memset(&g, 0, sizeof g);
+        g.M = (int)B; g.N = w->n[l + 1]; g.K = w->n[l];
+        g.bias = p.theta + w->boff[l]; g.act = w->cfg.activation; g.done = done;
+        if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = act_ptr(H, l); g.out1 = act_ptr(Dv, l); g.ldo = pitch(l); }
+        else { g.ep = tc::TEP_LIN_SOA; g.out_f32 = w->ZD.as<float>(); g.n_limit = D; }
+        const __nv_bfloat16* A = (l == 0) ? X : act_ptr(H, l - 1);
+        const int lda = (l == 0) ? Workspace::pad8(w->n[0]) : pitch(l - 1);
+        GCK(tc::gemm(A, lda, w->w16t.as<__nv_bfloat16>() + w->w16t_off[l], Workspace::pad8(w->n[l]), g, p.st));
+        w->launches++;
+    }
+    if (p.exact) {
+        float* TR = w->TR.as<float>();
+        if (NL == 1) {
+            g_trace_dot_kernel<<<blocks_for(B), 256, 0, p.st>>>(w->gvec.as<float>(), nullptr, TR, D, B, 0.f, done);
+        } else if (NL == 2) {
+            GCK(tc::trace_dot(w->gvec.as<float>(), act_ptr(Dv, 0), TR, w->n[1], pitch(0), B, done, p.st));
+        } else if (NL == 3) {
+            tc::TcArgs g;
+            memset(&g, 0, sizeof g);
+            g.M = (int)B; g.N = w->n[2]; g.K = w->n[1]; g.ep = tc::TEP_TRACE; g.done = done;
+            g.aux = act_ptr(Dv, 1); g.ldo = pitch(1); g.out_f32 = TR;
+            g.atomic_rowsum = (g.N > tc::TBN);
+            if (g.atomic_rowsum) GCK(cudaMemsetAsync(TR, 0, sizeof(float) * B, p.st));
+            GCK(tc::gemm(act_ptr(Dv, 0), pitch(0), w->a16.as<__nv_bfloat16>(), Workspace::pad8(w->n[1]), g, p.st));
+        } else {
+            return cudaErrorNotSupported;   // exact trace of deeper networks: fp32 families only
+        }
+        w->launches++;
+        return cudaGetLastError();
+    }
+    __nv_bfloat16* E = w->E16.as<__nv_bfloat16>();
+    GCK(tc::pack_soa(w->EPS.as<float>(), E, B, D, Workspace::pad8(D), done, p.st));
+    w->launches++;
+    for (int l = NL - 1; l >= 0; --l) {
+        tc::TcArgs g;
+        memset(&g, 0, sizeof g);
+        g.M = (int)B; g.N = (l == 0) ? D : w->n[l]; g.K = w->n[l + 1]; g.done = done;
+        if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = act_ptr(G, l - 1); g.aux = act_ptr(Dv, l - 1); g.ldo = pitch(l - 1); }
+        else { g.ep = tc::TEP_PLAIN_SOA; g.out_f32 = w->Q.as<float>(); g.n_limit = D; }
+        const __nv_bfloat16* A = (l == NL - 1) ? E : act_ptr(G, l);
+        const int lda = (l == NL - 1) ? Workspace::pad8(D) : pitch(l);
+        GCK(tc::gemm(A, lda, w->w16n.as<__nv_bfloat16>() + w->w16n_off[l], Workspace::pad8(w->n[l + 1]), g, p.st));
+        w->launches++;
+    }
+    return cudaSuccess;
+}
+
 // forward, then trace / VJP chain -> TR or Q
 static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
     Workspace* w = p.w;
+    if (w->tc) return tc_rhs_core(p, c_i);
     const long long B = p.B;
     const int NL = w->NL, D = w->D;
     float* Dv = w->Db.as<float>();
@@ -1151,6 +1267,7 @@ static int adaptive_max_grid(bool, int sm_count) { return sm_count; }   // not a
 static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
     if (exact) return cudaErrorNotSupported;   // TestMode gradient: tiny family only for now
+    if (w->tc) return cudaErrorNotSupported;   // bf16 tensor-core mode covers the forward solve; gradients: fp32
     const long long B = a.B;
     const int NL = w->NL, D = w->D;
     const long long DB = (long long)D * B;
@@ -1264,7 +1381,7 @@ static int backward_grid(bool, int, long long) { return 1; }
 const Family* generic_family() {
     static Family f = [] {
         Family g{};
-        g.name = "generic";
+        g.name = "generic";   // api.cu reports "tc" when precision = ICNF_BF16_TC
         g.n_params = 0;
         g.ws_create = &generic::ws_create;
         g.ws_destroy = &generic::ws_destroy;

@@ -1,0 +1,45 @@
+// tc.h -- host interface of the tensor-core GEMM (tc.cu) used by the generic family when
+// precision = ICNF_BF16_TC.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace icnf {
+namespace tc {
+
+constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 4, TTHREADS = 192;
+constexpr int A_TILE_BYTES = TBM * TBK * 2, B_TILE_BYTES = TBN * TBK * 2;
+constexpr int SMEM_BYTES = TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+enum TcEpilogue {
+    TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)
+    TEP_LIN_SOA = 1,    // out_f32[n * M + m] = acc + bias[n]              (fp32, [unit][sample])
+    TEP_MULD = 2,       // G[m][n] = acc * aux[m][n]                        (bf16)
+    TEP_PLAIN_SOA = 3,  // out_f32[n * M + m] = acc
+    TEP_TRACE = 4       // rowsum[m] (+)= sum_n acc * aux[m][n]
+};
+
+struct TcArgs {
+    int M, N, K;               // samples, units, reduction
+    int ep, act;
+    const float* bias;         // N
+    __nv_bfloat16* out0;       // H or G
+    __nv_bfloat16* out1;       // Dv
+    const __nv_bfloat16* aux;  // D (same pitch as out0)
+    int ldo;                   // row pitch (elements) of out0/out1/aux
+    float* out_f32;            // SoA output / row sums
+    int n_limit;               // SoA: only units < n_limit are written
+    int atomic_rowsum;         // TEP_TRACE with several unit tiles
+    const int* done;
+};
+
+cudaError_t gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, TcArgs g, cudaStream_t st);
+cudaError_t pack_matrix(const float* src, long long rs, long long cs, __nv_bfloat16* dst, int rows, int cols, int pitch,
+                        cudaStream_t st);
+cudaError_t pack_input(const float* zi, const float* ys, __nv_bfloat16* X, long long B, int D, int tin, int C, int pitch,
+                       float t_fixed, const float* ctrl_f, float c_i, const int* done, cudaStream_t st);
+cudaError_t trace_dot(const float* gvec, const __nv_bfloat16* D1, float* TR, int n1, int pitch, long long B, const int* done,
+                      cudaStream_t st);
+cudaError_t pack_soa(const float* src, __nv_bfloat16* dst, long long B, int rows, int pitch, const int* done, cudaStream_t st);
+}  // namespace tc
+}  // namespace icnf

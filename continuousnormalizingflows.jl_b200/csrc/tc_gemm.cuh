@@ -1,0 +1,253 @@
+// tc_gemm.cuh -- tcgen05 / TMEM / TMA GEMM with fused epilogues for wide MLPs (sm_100a).
+//
+//   D[m][n] = sum_k A[m][k] * B[n][k]        A: samples x K  (bf16, K contiguous)
+//                                            B: units   x K  (bf16, K contiguous)
+//
+// One CTA computes a 128 (samples) x 128 (units) tile: warp 0 streams 64-wide K blocks of
+// both operands into a 4-stage shared-memory ring with TMA (cp.async.bulk.tensor, 128-byte
+// swizzle), one elected thread of warp 1 issues tcgen05.mma (M = 128, N = 128, K = 16,
+// bf16 x bf16 -> fp32) into a 128-column TMEM accumulator and releases ring slots with
+// tcgen05.commit, and warps 2..5 run the epilogue straight out of TMEM (tcgen05.ld, one
+// sample row per thread) -- bias + activation + sigma', the VJP's ".* d", or the
+// exact-trace contraction -- so activations go to HBM once, in bf16.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "tc.h"
+
+namespace icnf {
+namespace tc {
+
+// ---- PTX wrappers -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.b32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4 in [0,14), LBO (unused for swizzled K-major) = 1 in [16,30),
+// SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46), version 1 in [46,48), SWIZZLE_128B = 2 in [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(TTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                              const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+    if (g.done && *g.done) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + TSTAGES * A_TILE_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TSTAGES * (A_TILE_BYTES + B_TILE_BYTES));
+    uint64_t* empty = full + TSTAGES;
+    uint64_t* tmem_full = empty + TSTAGES;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
+    const int nkb = (g.K + TBK - 1) / TBK;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+        for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TBN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TSTAGES;
+                const uint32_t ph = (kb / TSTAGES) & 1;
+                mbar_wait(&empty[s], ph ^ 1);
+                mbar_expect_tx(&full[s], A_TILE_BYTES + B_TILE_BYTES);
+                tma_load_2d(sA + s * A_TILE_BYTES, &mapA, &full[s], kb * TBK, m0);
+                tma_load_2d(sB + s * B_TILE_BYTES, &mapB, &full[s], kb * TBK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TBM, TBN);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const int s = kb % TSTAGES;
+                const uint32_t ph = (kb / TSTAGES) & 1;
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = make_desc(smem_u32(sA + s * A_TILE_BYTES));
+                const uint64_t bdesc = make_desc(smem_u32(sB + s * B_TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < TBK / 16; ++k) {
+                    // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+                    tc_mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                }
+                tc_commit(&empty[s]);
+            }
+            tc_commit(tmem_full);
+        }
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        const bool row_ok = m < g.M;
+        float rowsum = 0.f;
+        for (int c0 = 0; c0 < TBN; c0 += 32) {
+            if (n0 + c0 >= g.N) break;   // warp-uniform
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+            if (!row_ok) continue;
+            const int nb = n0 + c0;
+            if (g.ep == TEP_ACT) {
+                uint32_t hp[16], dp[16];
+#pragma unroll
+                for (int j = 0; j < 32; j += 2) {
+                    float h0 = 0.f, d0 = 0.f, h1 = 0.f, d1 = 0.f;
+                    if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + g.bias[nb + j], h0, d0);
+                    if (nb + j + 1 < g.N) act_eval_rt(g.act, __uint_as_float(r[j + 1]) + g.bias[nb + j + 1], h1, d1);
+                    hp[j / 2] = pack_bf16(h0, h1);
+                    dp[j / 2] = pack_bf16(d0, d1);
+                }
+                uint4* ho = reinterpret_cast<uint4*>(g.out0 + (size_t)m * g.ldo + nb);
+                uint4* dO = reinterpret_cast<uint4*>(g.out1 + (size_t)m * g.ldo + nb);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (nb + v * 8 < g.ldo) {
+                        ho[v] = make_uint4(hp[4 * v], hp[4 * v + 1], hp[4 * v + 2], hp[4 * v + 3]);
+                        dO[v] = make_uint4(dp[4 * v], dp[4 * v + 1], dp[4 * v + 2], dp[4 * v + 3]);
+                    }
+                }
+            } else if (g.ep == TEP_MULD) {
+                const uint4* ax = reinterpret_cast<const uint4*>(g.aux + (size_t)m * g.ldo + nb);
+                uint4* go = reinterpret_cast<uint4*>(g.out0 + (size_t)m * g.ldo + nb);
+#pragma unroll
+                for (int v = 0; v < 4; ++v) {
+                    if (nb + v * 8 >= g.ldo) continue;
+                    const uint4 a4 = ax[v];
+                    const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+                    uint32_t ow[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[e]);
+                        const int j = v * 8 + e * 2;
+                        const float g0 = (nb + j < g.N) ? __uint_as_float(r[j]) * __low2float(d2) : 0.f;
+                        const float g1 = (nb + j + 1 < g.N) ? __uint_as_float(r[j + 1]) * __high2float(d2) : 0.f;
+                        ow[e] = pack_bf16(g0, g1);
+                    }
+                    go[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                }
+            } else if (g.ep == TEP_TRACE) {
+                const __nv_bfloat16* ax = g.aux + (size_t)m * g.ldo + nb;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (nb + j < g.N) rowsum = fmaf(__uint_as_float(r[j]), __bfloat162float(ax[j]), rowsum);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = nb + j;
+                    if (n < g.N && n < g.n_limit) {
+                        float v = __uint_as_float(r[j]);
+                        if (g.ep == TEP_LIN_SOA) v += g.bias[n];
+                        g.out_f32[(size_t)n * g.M + m] = v;
+                    }
+                }
+            }
+        }
+        if (g.ep == TEP_TRACE && row_ok) {
+            if (g.atomic_rowsum) atomicAdd(g.out_f32 + m, rowsum);
+            else g.out_f32[m] = rowsum;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TBN));
+    }
+}
+
+}  // namespace tc
+}  // namespace icnf

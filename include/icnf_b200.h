@@ -236,6 +236,10 @@ ICNF_API int icnf_kernel_times(icnf_handle* h, float* ms4);
 /* FP32 FMA-pipe throughput of `device` from an FFMA-chain microbenchmark, in
  * TFLOP/s: the roofline denominator of the narrow-MLP kernels. */
 ICNF_API int icnf_measure_fp32_peak(int device, float* tflops);
+/* Self-test of the tcgen05 GEMM behind precision = ICNF_BF16_TC: D (N x M, stored
+ * D[n * M + m]) = A (M x K, row-major) * B (N x K, row-major)' with inputs rounded to
+ * bf16 and fp32 accumulation; host buffers; runs on the current device. */
+ICNF_API int icnf_tc_gemm_selftest(int M, int N, int K, const float* A, const float* B, float* D);
 
 #ifdef __cplusplus
 }

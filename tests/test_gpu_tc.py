@@ -1,0 +1,101 @@
+"""GPU tests of precision = ICNF_BF16_TC: the tcgen05 / TMEM / TMA GEMM (selftest against
+bf16-rounded fp32 products) and the wide-MLP RHS / solve built on it.
+
+Tolerance: bf16 has 8 mantissa bits, so this mode cannot meet the fp32 families' 1e-4;
+the tests hold it to BF16_TOL = 2e-2 (normalised error against the float64 oracle) and
+check that the fp32 generic family on the same inputs stays at 1e-4 ('bf16 RHS
+vs 1e-4' hard part)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import icnf_oracle as O
+from tests.helpers import make_inputs, norm_rel_err, t64
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def m():
+    import cnf_b200
+    return cnf_b200
+
+
+def _bf16(x):
+    return torch.tensor(x).to(torch.bfloat16).to(torch.float64).numpy()
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64), (300, 200, 150), (1000, 512, 785), (77, 16, 17), (4096, 388, 97)])
+def test_tcgen05_gemm_selftest(m, shape):
+    torch.zeros(1, device="cuda")
+    M, N, K = shape
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((M, K)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    D = np.zeros((N, M), np.float32)
+    assert m.lib.icnf_tc_gemm_selftest(M, N, K, A.ctypes.data, B.ctypes.data, D.ctypes.data) == 0
+    ref = _bf16(B) @ _bf16(A).T
+    assert np.abs(D - ref).max() / np.abs(ref).max() < 1e-5
+
+
+WIDE = {
+    "cond64": dict(nvariables=64, naugments=0, nconditions=32, n_hidden=256),          # config 5 (97-256-256-64)
+    "ffjord_small": dict(nvariables=96, naugments=0, nn=("softplus", (97, 128, 160, 128, 96))),   # config-4-like, 4 layers
+}
+
+
+def _make(m, name, **extra):
+    kw = dict(WIDE[name])
+    nn = kw.pop("nn", None)
+    if nn is not None:
+        act, sizes = nn
+        kw["nn"] = m.Chain(*[m.Dense(sizes[i], sizes[i + 1], act if i < len(sizes) - 2 else "identity")
+                             for i in range(len(sizes) - 1)])
+    kw.update(extra)
+    return m.ICNF(**kw)
+
+
+@pytest.mark.parametrize("name", list(WIDE))
+def test_rhs_bf16_tc_close_to_oracle(m, name):
+    icnf = _make(m, name, precision="bf16_tc")
+    assert icnf.kernel_family == "tc"
+    B = 515
+    om, theta, xs, eps, ys = make_inputs(icnf, B)
+    u = np.random.default_rng(3).standard_normal((om.n_state, B)).astype(np.float32)
+    modes = [(m.TrainMode(True), O.TRAIN_REG), (m.TrainMode(False), O.TRAIN_NOREG)]
+    if len(icnf.sizes) == 4:
+        modes.append((m.TestMode(), O.TEST))
+    for mode, omode in modes:
+        du = m.augmented_f(icnf, mode, u, theta, 0.37, eps=eps, ys=ys)
+        ref = O.rhs_closed(om, omode, t64(u), t64(theta), 0.37, t64(eps), t64(ys)).numpy()
+        for r0, r1 in ((0, om.d), (om.d, om.d + 1), (om.d + 1, om.n_state)):
+            assert norm_rel_err(du[r0:r1], ref[r0:r1]) < BF16_TOL, (mode, r0, norm_rel_err(du[r0:r1], ref[r0:r1]))
+
+
+def test_solve_bf16_tc_vs_fp32_generic(m):
+    icnf16 = _make(m, "cond64", precision="bf16_tc")
+    icnf32 = _make(m, "cond64")
+    assert icnf32.kernel_family == "generic"
+    B = 700
+    om, theta, xs, eps, ys = make_inputs(icnf16, B)
+    theta = (0.5 * theta).astype(np.float32)
+    kw = dict(eps=eps, tspan=icnf16.tspan)
+    l32, r32 = m.inference(icnf32, m.TrainMode(True), xs, ys, theta, {}, **kw)
+    l16, r16 = m.inference(icnf16, m.TrainMode(True), xs, ys, theta, {}, **kw)
+    ref, rr = O.inference(om, O.TRAIN_REG, t64(xs), t64(theta), t64(eps), t64(ys))
+    assert norm_rel_err(l32, ref.numpy()) < 1e-4
+    assert norm_rel_err(l16, ref.numpy()) < BF16_TOL
+    assert norm_rel_err(r16[0], rr[0].numpy()) < BF16_TOL
+    z0 = np.random.default_rng(5).standard_normal((om.d, B)).astype(np.float32)
+    g16 = m.generate(icnf16, m.TestMode(), ys, theta, {}, B, z0=z0, tspan=icnf16.tspan)
+    gref = O.generate(om, O.TEST, t64(z0), t64(theta), None, t64(ys)).numpy()
+    assert norm_rel_err(g16, gref) < BF16_TOL
+
+
+def test_bf16_tc_gradient_is_reported_unsupported(m):
+    icnf = _make(m, "cond64", precision="bf16_tc")
+    om, theta, xs, eps, ys = make_inputs(icnf, 16)
+    with pytest.raises(m.ICNFError) as ei:
+        m.loss_and_gradient(icnf, m.TrainMode(True), xs, ys, theta, {}, eps=eps)
+    assert ei.value.code == 7
