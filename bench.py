@@ -157,32 +157,45 @@ def logp_extras(m, local, dev, flush_buf):
     (TestMode = exact trace, Tsit5 adaptive rtol = atol = 1e-4), inputs resident in HBM,
     CUDA-event timed, L2 flushed between iterations."""
     out = {}
+    ffjord = m.Chain(m.Dense(785, 512, "softplus"), m.Dense(512, 512, "softplus"), m.Dense(512, 512, "softplus"), m.Dense(512, 784))
     cases = [
-        ("config1_usage_B1024", dict(nvariables=1), 1024),                       # examples/usage.jl shape, tiny family
-        ("config2_moons_B65536", dict(nvariables=2, naugments=0), 65536),        # tiny family
-        ("config3_gmm16_B262144", dict(nvariables=16, naugments=0), 262144),     # 17-68-68-16, generic family
+        # name, ICNF kwargs, batch, mode
+        ("config1_usage_B1024", dict(nvariables=1), 1024, m.TestMode()),                     # examples/usage.jl shape, tiny
+        ("config2_moons_B65536", dict(nvariables=2, naugments=0), 65536, m.TestMode()),      # tiny
+        ("config3_gmm16_B262144", dict(nvariables=16, naugments=0), 262144, m.TestMode()),   # 17-68-68-16, generic fp32
+        ("config3_gmm16_B262144_bf16tc", dict(nvariables=16, naugments=0, precision="bf16_tc"), 262144, m.TestMode()),
+        ("config5_cond64_B65536_fp32", dict(nvariables=64, naugments=0, nconditions=32), 65536, m.TestMode()),   # 97-388-388-64
+        ("config5_cond64_B65536_bf16tc", dict(nvariables=64, naugments=0, nconditions=32, precision="bf16_tc"), 65536, m.TestMode()),
+        ("config4_ffjord784_B8192_fp32", dict(nvariables=784, naugments=0, nn=ffjord), 8192, m.TrainMode(False)),
+        ("config4_ffjord784_B8192_bf16tc", dict(nvariables=784, naugments=0, nn=ffjord, precision="bf16_tc"), 8192, m.TrainMode(False)),
     ]
-    for name, kw, B in cases:
-        icnf = m.ICNF(device=local, **kw)
+    for name, kw, B, mode in cases:
+        icnf = m.ICNF(device=local, epsdist="rademacher", **kw)
         rng = np.random.default_rng(7)
         theta, _ = m.setup(rng, icnf)
         xs = torch.from_numpy(rng.standard_normal((B, icnf.nvariables)).astype(np.float32)).to(dev)
-        mode = m.TestMode()
-        for _ in range(3):
-            m.inference(icnf, mode, xs.t(), theta, {})
+        args = (xs.t(),)
+        if icnf.nconditions:
+            args += (torch.from_numpy(rng.standard_normal((B, icnf.nconditions)).astype(np.float32)).to(dev).t(),)
+        for _ in range(2):
+            m.inference(icnf, mode, *args, theta, {}, seed=3)
         torch.cuda.synchronize()
-        K, ms = 5, 0.0
+        K, ms = 3, 0.0
         for _ in range(K):
             flush_buf.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            m.inference(icnf, mode, xs.t(), theta, {})
+            m.inference(icnf, mode, *args, theta, {}, seed=3)
             b.record()
             torch.cuda.synchronize()
             ms += a.elapsed_time(b)
         st = icnf.last_stats
+        P = sum(icnf.sizes[i] * icnf.sizes[i + 1] for i in range(len(icnf.sizes) - 1))
+        flop_rhs = 4 * P if not isinstance(mode, m.TestMode) else 2 * P + 2 * icnf.sizes[1] * icnf.sizes[2]
         out[name] = {"logp_evals_per_sec": B * K / (ms * 1e-3), "ms_per_call": ms / K, "kernel_family": icnf.kernel_family,
-                     "solver_steps": st.naccept, "rhs_calls": st.nf}
+                     "mode": repr(mode), "solver_steps": st.naccept, "rhs_calls": st.nf,
+                     "algorithmic_tflops": flop_rhs * st.nf * B / (ms / K * 1e-3) / 1e12}
+        del icnf
     return out
 
 

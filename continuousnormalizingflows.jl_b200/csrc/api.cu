@@ -291,15 +291,13 @@ int enqueue_solve(icnf_handle* h, const SolveRequest& r, cudaStream_t st) {
     // adaptive: cooperative persistent kernel
     const int grid_cap = h->fam->adaptive_max_grid(mf.exact, h->sm_count);
     if (grid_cap <= 0) return h->fail(ICNF_ERR_UNSUPPORTED, "adaptive kernel cannot be made resident on this device");
-    const long long need = (r.B + 127) / 128;
-    const int grid = (int)std::max(1LL, std::min<long long>(need, grid_cap));
     a.dt = (r.sol && r.sol->dt > 0) ? r.sol->dt : 0.0f;
     const size_t sb = sizeof(float) * (size_t)S * r.B;
     CK(h, h->wu0.reserve(sb));
     CK(h, h->wu1.reserve(sb));
     CK(h, h->wk0.reserve(sb));
     CK(h, h->wk1.reserve(sb));
-    CK(h, h->partials.reserve(sizeof(double) * 2 * (size_t)grid_cap));
+    CK(h, h->partials.reserve(sizeof(double) * 4 * 32 * (size_t)h->sm_count));
     a.wu[0] = h->wu0.as<float>(); a.wu[1] = h->wu1.as<float>();
     a.wk[0] = h->wk0.as<float>(); a.wk[1] = h->wk1.as<float>();
     a.partials = h->partials.as<double>();
@@ -311,7 +309,7 @@ int enqueue_solve(icnf_handle* h, const SolveRequest& r, cudaStream_t st) {
         a.steps = h->steps.as<StepRec>();
     }
     h->prof_begin(0, st);
-    cudaError_t e = h->fam->solve_adaptive(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, grid, st);
+    cudaError_t e = h->fam->solve_adaptive(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st);
     h->prof_end(0, st);
     if (e != cudaSuccess) return h->cuda_fail(e, "solve_adaptive launch");
     h->launches++;

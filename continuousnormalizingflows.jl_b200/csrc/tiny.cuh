@@ -30,11 +30,18 @@ namespace tiny {
 
 namespace cg = cooperative_groups;
 
-constexpr int NT = 128;  // threads per CTA
+constexpr int NT = 128;  // threads per CTA (rhs, fixed-step solve, backward)
+// The adaptive kernel is grid-synchronised: every sample should be resident at once (or the
+// whole grid waits for the threads that own two) and the barrier should have few arrivals.
+// It is compiled for up to 512 threads at <= 128 registers (512 resident threads per SM,
+// 75 776 on 148 SMs >= the 65 536-sample batch); the launcher picks the CTA size so that
+// the batch spreads over all SMs with one CTA each when it is large enough.
+constexpr int NTA = 512;
+constexpr int NTA_MINB = 1;
 // minimum resident CTAs per SM the compiler must allow for (caps registers per thread);
 // values chosen from the sweep recorded in profiles/ (scripts/sweep_tiny_bounds.sh)
 #ifndef ICNF_TINY_MINB_FWD
-#define ICNF_TINY_MINB_FWD 1
+#define ICNF_TINY_MINB_FWD 4
 #endif
 #ifndef ICNF_TINY_MINB_BWD
 #define ICNF_TINY_MINB_BWD 1
@@ -85,7 +92,11 @@ struct Net {
         for (int i = 0; i < l; ++i) o += ldt(i) * n(i + 1);
         return o;
     }
-    static constexpr int WPAD = wtoff(NL_);
+    // exact-trace block (TestMode): two hidden layers: Amat(j, k) = W2[j,k] sum_i W1[k,i] W3[i,j] at
+    // troff + k * ld(1) + j; one hidden layer: gvec[k] = sum_i W1[k,i] W2[i,k]; none: the constant trace
+    static constexpr int troff = wtoff(NL_);
+    static constexpr int trsize = NL_ == 3 ? ld(1) * n(1) : NL_ == 2 ? ((n(1) + 3) & ~3) : NL_ == 1 ? 4 : 0;
+    static constexpr int WPAD = troff + trsize;
     static constexpr int NP2 = (nmax() + 1) / 2;   // packed pairs per activation vector
     // native (ComponentArray) offsets
     __host__ __device__ static constexpr int toff(int l) {
@@ -234,18 +245,43 @@ __device__ __forceinline__ void rhs_eval(const WBlock<N>& sw, const float (&x)[N
 #pragma unroll
     for (int j = 0; j < N::D; ++j) kz[j] = EL(A.h[N::NL - 1], j);
     if constexpr (EXACT) {
-        // exact trace by D' one-hot pullbacks (utils.jl:35-54); the one-hot probe is a
-        // compile-time constant so the first chain link folds to a weight row
+        // Exact trace (what the reference gets from D' one-hot pullbacks, utils.jl:35-54) in
+        // closed form: tr J = tr(W_L D_{L-1} ... D_1 W_1[:, 1:D']).  Two hidden layers:
+        // d2' (W2 .* (W1z W3)') d1 with the sample-independent matrix prepared by the host.
         float tr = 0.0f;
-        static_for<0, N::D>([&](auto pc) __attribute__((always_inline)) {
-            constexpr int p = decltype(pc)::value;
-            float probe[N::D], q[N::D];
+        if constexpr (N::NL == 3) {
+            constexpr int n1 = N::n(1), n2 = N::n(2), np = (n2 + 1) / 2;
+            float2 acc[np];
 #pragma unroll
-            for (int j = 0; j < N::D; ++j) probe[j] = (j == p) ? 1.0f : 0.0f;
-            Chain<N> Cn;
-            vjp_chain<N>(sw, A, probe, Cn, q);
-            tr += q[p];
-        });
+            for (int k = 0; k < n1; ++k) {
+                const float dk = EL(A.d[0], k);
+#pragma unroll
+                for (int jp = 0; jp < np; ++jp) {
+                    const float2 ap = make_float2(sw.v[N::troff + k * N::ld(1) + 2 * jp], sw.v[N::troff + k * N::ld(1) + 2 * jp + 1]);
+                    if (k == 0) acc[jp] = __fmul2_rn(ap, bc2(dk));
+                    else acc[jp] = __ffma2_rn(ap, bc2(dk), acc[jp]);
+                }
+            }
+            float2 t2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int jp = 0; jp < np; ++jp) t2 = __ffma2_rn(acc[jp], A.d[1][jp], t2);
+            tr = t2.x + t2.y;
+        } else if constexpr (N::NL == 2) {
+#pragma unroll
+            for (int k = 0; k < N::n(1); ++k) tr = fmaf(sw.v[N::troff + k], EL(A.d[0], k), tr);
+        } else if constexpr (N::NL == 1) {
+            tr = sw.v[N::troff];
+        } else {
+            static_for<0, N::D>([&](auto pc) __attribute__((always_inline)) {
+                constexpr int p = decltype(pc)::value;
+                float probe[N::D], q[N::D];
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) probe[j] = (j == p) ? 1.0f : 0.0f;
+                Chain<N> Cn;
+                vjp_chain<N>(sw, A, probe, Cn, q);
+                tr += q[p];
+            });
+        }
         kl = -tr;
         kE = 0.0f;
         kn = 0.0f;
@@ -364,7 +400,7 @@ __device__ __forceinline__ void write_outputs(const SolveArgs& a, int64_t b, int
 // stage-derivative storage in shared memory: K(i)[r] for stage i, row r, this thread
 struct StageMem {
     float* base;
-    __device__ __forceinline__ float& at(int idx) { return base[idx * NT + threadIdx.x]; }
+    __device__ __forceinline__ float& at(int idx) { return base[idx * blockDim.x + threadIdx.x]; }
 };
 
 // ------------------------------------------------------------------ S1: one RHS
@@ -473,252 +509,258 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_FWD) solve_fixed_kernel(con
 // result is bit-reproducible), then every thread runs the same PI controller.
 struct GridReducer {
     cg::grid_group grid;
-    double* partials;  // [2][gridDim.x]
-    double* sred;      // shared, >= NT/32 + 1
+    double* partials;  // [2 parities][2 values][gridDim.x]
+    double* sred;      // shared, 2 * (warps per CTA)
     int parity;
-    __device__ double sum(double local) {
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        double v = warp_sum(local);
-        if (lane == 0) sred[w] = v;
+    // grid-wide sums of two per-thread values with ONE grid synchronisation
+    __device__ void sum2(double a, double b, double& ta, double& tb) {
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+        a = warp_sum(a);
+        b = warp_sum(b);
+        if (lane == 0) { sred[w] = a; sred[nw + w] = b; }
         __syncthreads();
+        double* P = partials + (size_t)parity * 2 * gridDim.x;
         if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (int i = 0; i < NT / 32; ++i) s += sred[i];
-            partials[(size_t)parity * gridDim.x + blockIdx.x] = s;
+            double sa = 0.0, sb = 0.0;
+            for (int i = 0; i < nw; ++i) { sa += sred[i]; sb += sred[nw + i]; }
+            P[blockIdx.x] = sa;
+            P[gridDim.x + blockIdx.x] = sb;
         }
         __threadfence();
         grid.sync();
-        double acc = 0.0;
-        for (int i = threadIdx.x; i < (int)gridDim.x; i += NT) acc += __ldcg(partials + (size_t)parity * gridDim.x + i);
-        acc = warp_sum(acc);
+        double xa = 0.0, xb = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+            xa += __ldcg(P + i);
+            xb += __ldcg(P + gridDim.x + i);
+        }
+        xa = warp_sum(xa);
+        xb = warp_sum(xb);
         __syncthreads();
-        if (lane == 0) sred[w] = acc;
+        if (lane == 0) { sred[w] = xa; sred[nw + w] = xb; }
         __syncthreads();
-        double tot = 0.0;
-        for (int i = 0; i < NT / 32; ++i) tot += sred[i];
+        ta = 0.0; tb = 0.0;
+        for (int i = 0; i < nw; ++i) { ta += sred[i]; tb += sred[nw + i]; }
         __syncthreads();
         parity ^= 1;
-        return tot;
     }
 };
 
+// One kernel, one RHS call site: the loop below runs "phases" (k1 at t0, the probe of the
+// automatic initial step, then step attempts); each phase evaluates 1 or 6 stages per
+// sample and ends in one grid-wide reduction.
 template <class N, bool EXACT>
-__global__ void __launch_bounds__(NT, ICNF_TINY_MINB_FWD) solve_adaptive_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
+__global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
     extern __shared__ __align__(16) float smem[];
     StageMem K{smem};
-    __shared__ double sred[NT / 32 + 1];
+    __shared__ double sred[2 * (NTA / 32) + 2];
     GridReducer red{cg::this_grid(), a.partials, sred, 0};
 
     const float tdir = (a.t1 >= a.t0) ? 1.0f : -1.0f;
     const float span = fabsf(a.t1 - a.t0);
-    const int64_t stride = (int64_t)gridDim.x * NT;
-    const int64_t b0 = (int64_t)blockIdx.x * NT + threadIdx.x;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t b0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const Controller ctl = a.ctl;
     const double inv_count = 1.0 / ((double)a.B * (double)N::S);
+    enum { P_INIT = 0, P_PROBE = 1, P_STEP = 2 };
+    int phase = P_INIT;
     int cur = 0;
-    int nacc = 0, nrej = 0, nf = 0, status = ICNF_OK;
-    float t = a.t0;
+    int nacc = 0, nrej = 0, nf = 0, status = ICNF_OK, attempts = 0;
+    float t = a.t0, dt = (a.dt > 0.0f) ? fminf(a.dt, span) : 0.0f, dt0 = 0.0f, d1 = 0.0f;
+    float qold = ctl.qoldinit, dt_last = 0.0f;
+    bool last = false;
+    float hmag = 0.0f;
 
-    // ---- init: u0, k1 = f(u0, t0), and the norms of the automatic initial step
-    double d0s = 0.0, d1s = 0.0;
-    for (int64_t b = b0; b < a.B; b += stride) {
-        Sample<N> sm;
-        load_sample_consts<N>(a, b, sm);
-        float z[N::D], l, E, n;
-        load_state<N>(a, b, nvars, z, l, E, n);
-#pragma unroll
-        for (int j = 0; j < N::D; ++j) sm.x[j] = z[j];
-        if constexpr (N::TIN) sm.x[N::D] = t;
-        float kz[N::D], kl, kE, kn;
-        rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kl, kE, kn);
-        float* u = a.wu[0] + b * N::S;
-        float* k = a.wk[0] + b * N::S;
-#pragma unroll
-        for (int j = 0; j < N::D; ++j) {
-            u[j] = z[j];
-            k[j] = kz[j];
-            float sk = ctl.abstol + fabsf(z[j]) * ctl.reltol;
-            d0s += (double)((z[j] / sk) * (z[j] / sk));
-            d1s += (double)((kz[j] / sk) * (kz[j] / sk));
+    while (span > 0.0f) {
+        float h = 0.0f;
+        if (phase == P_STEP) {
+            const float remaining = fabsf(a.t1 - t);
+            if (remaining <= 1e-7f * fmaxf(1.0f, fabsf(a.t1))) break;
+            last = dt >= remaining * (1.0f - 1e-6f);
+            hmag = last ? remaining : dt;
+            h = tdir * hmag;
+            if (!(hmag > 0.0f) || t + h == t) { status = ICNF_ERR_DT_UNDERFLOW; break; }
+            if (++attempts > ctl.max_steps || (a.ckpt && nacc >= a.max_ckpt_steps)) { status = ICNF_ERR_MAX_STEPS; break; }
+        } else if (phase == P_PROBE) {
+            h = tdir * dt0;
         }
-        u[N::D] = l; u[N::D + 1] = E; u[N::D + 2] = n;
-        k[N::D] = kl; k[N::D + 1] = kE; k[N::D + 2] = kn;
-        const float ex[3] = {l, E, n}, kx[3] = {kl, kE, kn};
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            float sk = ctl.abstol + fabsf(ex[r]) * ctl.reltol;
-            d0s += (double)((ex[r] / sk) * (ex[r] / sk));
-            d1s += (double)((kx[r] / sk) * (kx[r] / sk));
-        }
-        if (a.ckpt) {
-#pragma unroll
-            for (int j = 0; j < N::D; ++j) a.ckpt[b * N::D + j] = z[j];
-        }
-    }
-    nf = 1;
-    float dt;
-    if (a.dt > 0.0f) {
-        dt = fminf(a.dt, span);
-    } else {
-        // Hairer-Wanner starting step as OrdinaryDiffEq applies it
-        const float d0 = (float)sqrt(red.sum(d0s) * inv_count);
-        const float d1 = (float)sqrt(red.sum(d1s) * inv_count);
-        float dt0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
-        dt0 = fminf(dt0, span);
-        double d2s = 0.0;
+        const int nstage = (phase == P_STEP) ? 6 : 1;
+        double acc_a = 0.0, acc_b = 0.0;
         for (int64_t b = b0; b < a.B; b += stride) {
             Sample<N> sm;
             load_sample_consts<N>(a, b, sm);
-            const float* u = a.wu[0] + b * N::S;
-            const float* k = a.wk[0] + b * N::S;
+            float z[N::D], ux[3];
+            float k1z[N::D], k1x[3];
+            if (phase == P_INIT) {
+                load_state<N>(a, b, nvars, z, ux[0], ux[1], ux[2]);
+            } else {
+                const float* u = a.wu[cur] + b * N::S;
+                const float* k1 = a.wk[cur] + b * N::S;
 #pragma unroll
-            for (int j = 0; j < N::D; ++j) sm.x[j] = fmaf(tdir * dt0, k[j], u[j]);
-            if constexpr (N::TIN) sm.x[N::D] = t + tdir * dt0;
-            float kz[N::D], kl, kE, kn;
-            rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kl, kE, kn);
+                for (int j = 0; j < N::D; ++j) { z[j] = u[j]; k1z[j] = k1[j]; K.at(j) = k1[j]; }
 #pragma unroll
-            for (int j = 0; j < N::D; ++j) {
-                float sk = ctl.abstol + fabsf(u[j]) * ctl.reltol;
-                float df = (kz[j] - k[j]) / sk;
-                d2s += (double)(df * df);
+                for (int r = 0; r < 3; ++r) { ux[r] = u[N::D + r]; k1x[r] = k1[N::D + r]; }
             }
-            const float kx[3] = {kl, kE, kn};
+            float zs[N::D], ze[N::D], sx[3], exs[3];
+            if (phase == P_STEP) {
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float sk = ctl.abstol + fabsf(u[N::D + r]) * ctl.reltol;
-                float df = (kx[r] - k[N::D + r]) / sk;
-                d2s += (double)(df * df);
-            }
-        }
-        nf += 1;
-        const float d2 = (float)sqrt(red.sum(d2s) * inv_count) / dt0;
-        const float dm = fmaxf(d1, d2);
-        float dt1 = (dm <= 1e-15f) ? fmaxf(1e-6f, dt0 * 1e-3f) : exp10f(-(2.0f + log10f(dm)) / 6.0f);
-        dt = fminf(fminf(100.0f * dt0, dt1), span);
-    }
-
-    // ---- step loop
-    float qold = ctl.qoldinit;
-    float dt_last = 0.0f;
-    int attempts = 0;
-    while (true) {
-        const float remaining = fabsf(a.t1 - t);
-        if (remaining <= 1e-7f * fmaxf(1.0f, fabsf(a.t1))) break;
-        const bool last = dt >= remaining * (1.0f - 1e-6f);
-        const float hmag = last ? remaining : dt;
-        const float h = tdir * hmag;
-        if (!(hmag > 0.0f) || t + h == t) { status = ICNF_ERR_DT_UNDERFLOW; break; }
-        if (++attempts > ctl.max_steps || (a.ckpt && nacc >= a.max_ckpt_steps)) { status = ICNF_ERR_MAX_STEPS; break; }
-
-        double es = 0.0;
-        for (int64_t b = b0; b < a.B; b += stride) {
-            Sample<N> sm;
-            load_sample_consts<N>(a, b, sm);
-            const float* u = a.wu[cur] + b * N::S;
-            const float* k1 = a.wk[cur] + b * N::S;
-            float z[N::D], zs[N::D], ze[N::D];
-            float ux[3], sx[3], exs[3];
+                for (int j = 0; j < N::D; ++j) { zs[j] = c_a[6][0] * k1z[j]; ze[j] = c_bt[0] * k1z[j]; }
 #pragma unroll
-            for (int j = 0; j < N::D; ++j) {
-                z[j] = u[j];
-                float kk = k1[j];
-                K.at(j) = kk;
-                zs[j] = c_a[6][0] * kk;
-                ze[j] = c_bt[0] * kk;
+                for (int r = 0; r < 3; ++r) { sx[r] = c_a[6][0] * k1x[r]; exs[r] = c_bt[0] * k1x[r]; }
             }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                ux[r] = u[N::D + r];
-                float kk = k1[N::D + r];
-                sx[r] = c_a[6][0] * kk;
-                exs[r] = c_bt[0] * kk;
-            }
-            for (int i = 1; i < 6; ++i) {
+            float kz[N::D], kx[3];
+            for (int s = 0; s < nstage; ++s) {
+                const int i = s + 1;   // Tsit5 stage index (1..6) when stepping
+                // ---- stage input
 #pragma unroll
                 for (int j = 0; j < N::D; ++j) sm.x[j] = z[j];
-                for (int jj = 0; jj < i; ++jj) {
-                    const float c = h * c_a[i][jj];
+                float tt = t;
+                if (phase == P_PROBE) {
 #pragma unroll
-                    for (int j = 0; j < N::D; ++j) sm.x[j] = fmaf(c, K.at(jj * N::D + j), sm.x[j]);
+                    for (int j = 0; j < N::D; ++j) sm.x[j] = fmaf(h, k1z[j], z[j]);
+                    tt = t + h;
+                } else if (phase == P_STEP) {
+                    for (int jj = 0; jj < i; ++jj) {
+                        const float c = h * c_a[i][jj];
+#pragma unroll
+                        for (int j = 0; j < N::D; ++j) sm.x[j] = fmaf(c, K.at(jj * N::D + j), sm.x[j]);
+                    }
+                    tt = (i == 6 && last) ? a.t1 : fmaf(c_c[i], h, t);
                 }
-                if constexpr (N::TIN) sm.x[N::D] = fmaf(c_c[i], h, t);
-                float kz[N::D], kx[3];
+                if constexpr (N::TIN) sm.x[N::D] = tt;
+                // ---- the one RHS call site
                 rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kx[0], kx[1], kx[2]);
-                const float bi = c_a[6][i], bti = c_bt[i];
+                // ---- stage bookkeeping
+                if (phase == P_STEP && i < 6) {
+                    const float bi = c_a[6][i], bti = c_bt[i];
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) {
+                        K.at(i * N::D + j) = kz[j];
+                        zs[j] = fmaf(bi, kz[j], zs[j]);
+                        ze[j] = fmaf(bti, kz[j], ze[j]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) { sx[r] = fmaf(bi, kx[r], sx[r]); exs[r] = fmaf(bti, kx[r], exs[r]); }
+                }
+            }
+            // ---- per-sample epilogue of the phase
+            if (phase == P_INIT) {
+                float* u = a.wu[0] + b * N::S;
+                float* k = a.wk[0] + b * N::S;
 #pragma unroll
                 for (int j = 0; j < N::D; ++j) {
-                    K.at(i * N::D + j) = kz[j];
-                    zs[j] = fmaf(bi, kz[j], zs[j]);
-                    ze[j] = fmaf(bti, kz[j], ze[j]);
+                    u[j] = z[j]; k[j] = kz[j];
+                    const float sk = ctl.abstol + fabsf(z[j]) * ctl.reltol;
+                    acc_a += (double)((z[j] / sk) * (z[j] / sk));
+                    acc_b += (double)((kz[j] / sk) * (kz[j] / sk));
                 }
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    sx[r] = fmaf(bi, kx[r], sx[r]);
-                    exs[r] = fmaf(bti, kx[r], exs[r]);
+                    u[N::D + r] = ux[r]; k[N::D + r] = kx[r];
+                    const float sk = ctl.abstol + fabsf(ux[r]) * ctl.reltol;
+                    acc_a += (double)((ux[r] / sk) * (ux[r] / sk));
+                    acc_b += (double)((kx[r] / sk) * (kx[r] / sk));
+                }
+                if (a.ckpt) {
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) a.ckpt[b * N::D + j] = z[j];
+                }
+            } else if (phase == P_PROBE) {
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) {
+                    const float sk = ctl.abstol + fabsf(z[j]) * ctl.reltol;
+                    const float df = (kz[j] - k1z[j]) / sk;
+                    acc_a += (double)(df * df);
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float sk = ctl.abstol + fabsf(ux[r]) * ctl.reltol;
+                    const float df = (kx[r] - k1x[r]) / sk;
+                    acc_a += (double)(df * df);
+                }
+            } else {
+                // kz/kx hold the FSAL stage k7 = f(u_new); sm.x[0..D') holds u_new's z rows
+                float* uo = a.wu[cur ^ 1] + b * N::S;
+                float* ko = a.wk[cur ^ 1] + b * N::S;
+#pragma unroll
+                for (int j = 0; j < N::D; ++j) {
+                    const float zn = fmaf(h, zs[j], z[j]);
+                    const float e = h * fmaf(c_bt[6], kz[j], ze[j]);
+                    const float sk = ctl.abstol + fmaxf(fabsf(z[j]), fabsf(zn)) * ctl.reltol;
+                    const float r = e / sk;
+                    acc_a += (double)(r * r);
+                    uo[j] = zn;
+                    ko[j] = kz[j];
+                    if (a.ckpt) a.ckpt[((int64_t)(nacc + 1) * a.B + b) * N::D + j] = zn;
+                }
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float un = fmaf(h, sx[r], ux[r]);
+                    const float e = h * fmaf(c_bt[6], kx[r], exs[r]);
+                    const float sk = ctl.abstol + fmaxf(fabsf(ux[r]), fabsf(un)) * ctl.reltol;
+                    const float q = e / sk;
+                    acc_a += (double)(q * q);
+                    uo[N::D + r] = un;
+                    ko[N::D + r] = kx[r];
                 }
             }
-            // u_new and the FSAL stage k7 = f(u_new, t + h)
-            float zn[N::D], un[3];
-#pragma unroll
-            for (int j = 0; j < N::D; ++j) { zn[j] = fmaf(h, zs[j], z[j]); sm.x[j] = zn[j]; }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) un[r] = fmaf(h, sx[r], ux[r]);
-            if constexpr (N::TIN) sm.x[N::D] = last ? a.t1 : t + h;
-            float k7[N::D], k7x[3];
-            rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, k7, k7x[0], k7x[1], k7x[2]);
-            float* uo = a.wu[cur ^ 1] + b * N::S;
-            float* ko = a.wk[cur ^ 1] + b * N::S;
-#pragma unroll
-            for (int j = 0; j < N::D; ++j) {
-                float e = h * fmaf(c_bt[6], k7[j], ze[j]);
-                float sk = ctl.abstol + fmaxf(fabsf(z[j]), fabsf(zn[j])) * ctl.reltol;
-                float r = e / sk;
-                es += (double)(r * r);
-                uo[j] = zn[j];
-                ko[j] = k7[j];
-            }
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float e = h * fmaf(c_bt[6], k7x[r], exs[r]);
-                float sk = ctl.abstol + fmaxf(fabsf(ux[r]), fabsf(un[r])) * ctl.reltol;
-                float q = e / sk;
-                es += (double)(q * q);
-                uo[N::D + r] = un[r];
-                ko[N::D + r] = k7x[r];
-            }
-            if (a.ckpt) {
-#pragma unroll
-                for (int j = 0; j < N::D; ++j) a.ckpt[((int64_t)(nacc + 1) * a.B + b) * N::D + j] = zn[j];
-            }
         }
-        nf += 6;
-        const float eest = (float)sqrt(red.sum(es) * inv_count);
-        if (!isfinite(eest)) { status = ICNF_ERR_NONFINITE; break; }
-        const float q11 = eest > 0.0f ? powf(eest, ctl.beta1) : 0.0f;
-        float q = q11 / powf(qold, ctl.beta2);
-        q = fmaxf(1.0f / ctl.qmax, fminf(1.0f / ctl.qmin, q / ctl.gamma));
-        if (eest <= 1.0f) {
-            if (a.steps && blockIdx.x == 0 && threadIdx.x == 0) { a.steps[nacc].t = t; a.steps[nacc].dt = h; }
-            nacc++;
-            dt_last = h;
-            t = last ? a.t1 : t + h;
-            cur ^= 1;
-            if (q >= ctl.qsteady_min && q <= ctl.qsteady_max) q = 1.0f;
-            qold = fmaxf(eest, ctl.qoldinit);
-            dt = hmag / q;
+        double ta, tb;
+        red.sum2(acc_a, acc_b, ta, tb);
+        // ---- control (identical arithmetic in every thread)
+        if (phase == P_INIT) {
+            nf = 1;
+            if (a.dt > 0.0f) {
+                phase = P_STEP;
+            } else {
+                // Hairer-Wanner starting step as OrdinaryDiffEq applies it
+                const float d0 = (float)sqrt(ta * inv_count);
+                d1 = (float)sqrt(tb * inv_count);
+                dt0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+                dt0 = fminf(dt0, span);
+                phase = P_PROBE;
+            }
+        } else if (phase == P_PROBE) {
+            nf += 1;
+            const float d2 = (float)sqrt(ta * inv_count) / dt0;
+            const float dm = fmaxf(d1, d2);
+            const float dt1 = (dm <= 1e-15f) ? fmaxf(1e-6f, dt0 * 1e-3f) : exp10f(-(2.0f + log10f(dm)) / 6.0f);
+            dt = fminf(fminf(100.0f * dt0, dt1), span);
+            phase = P_STEP;
         } else {
-            nrej++;
-            dt = hmag / fminf(1.0f / ctl.qmin, q11 / ctl.gamma);
+            nf += 6;
+            const float eest = (float)sqrt(ta * inv_count);
+            if (!isfinite(eest)) { status = ICNF_ERR_NONFINITE; break; }
+            const float q11 = eest > 0.0f ? powf(eest, ctl.beta1) : 0.0f;
+            float q = q11 / powf(qold, ctl.beta2);
+            q = fmaxf(1.0f / ctl.qmax, fminf(1.0f / ctl.qmin, q / ctl.gamma));
+            if (eest <= 1.0f) {
+                if (a.steps && blockIdx.x == 0 && threadIdx.x == 0) { a.steps[nacc].t = t; a.steps[nacc].dt = h; }
+                nacc++;
+                dt_last = h;
+                t = last ? a.t1 : t + h;
+                cur ^= 1;
+                if (q >= ctl.qsteady_min && q <= ctl.qsteady_max) q = 1.0f;
+                qold = fmaxf(eest, ctl.qoldinit);
+                dt = hmag / q;
+            } else {
+                nrej++;
+                dt = hmag / fminf(1.0f / ctl.qmin, q11 / ctl.gamma);
+            }
         }
     }
 
     // ---- readout
     for (int64_t b = b0; b < a.B; b += stride) {
-        const float* u = a.wu[cur] + b * N::S;
-        float z[N::D];
+        float z[N::D], l, E, n;
+        if (span > 0.0f) {
+            const float* u = a.wu[cur] + b * N::S;
 #pragma unroll
-        for (int j = 0; j < N::D; ++j) z[j] = u[j];
-        write_outputs<N>(a, b, nvars, z, u[N::D], u[N::D + 1], u[N::D + 2]);
+            for (int j = 0; j < N::D; ++j) z[j] = u[j];
+            l = u[N::D]; E = u[N::D + 1]; n = u[N::D + 2];
+        } else {
+            load_state<N>(a, b, nvars, z, l, E, n);
+        }
+        write_outputs<N>(a, b, nvars, z, l, E, n);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
         a.stats->naccept = nacc;

@@ -5,6 +5,7 @@
 
 #include "family.h"
 #include "tiny.cuh"
+#include "tiny_ub.cuh"
 
 namespace icnf {
 namespace tiny {
@@ -28,6 +29,26 @@ struct Launch {
             for (int j = 0; j < nout; ++j)
                 for (int k = 0; k < N::kz(l); ++k) w.v[N::wtoff(l) + j * N::ldt(l) + k] = theta[N::toff(l) + k * nout + j];
         }
+        // exact-trace block
+        auto W = [&](int l, int j, int k) { return theta[N::toff(l) + k * N::n(l + 1) + j]; };
+        if (N::NL == 3) {
+            for (int k = 0; k < N::n(1); ++k)
+                for (int j = 0; j < N::n(2); ++j) {
+                    float s = 0.f;
+                    for (int i = 0; i < N::D; ++i) s += W(0, k, i) * W(2, i, j);
+                    w.v[N::troff + k * N::ld(1) + j] = W(1, j, k) * s;
+                }
+        } else if (N::NL == 2) {
+            for (int k = 0; k < N::n(1); ++k) {
+                float s = 0.f;
+                for (int i = 0; i < N::D; ++i) s += W(0, k, i) * W(1, i, k);
+                w.v[N::troff + k] = s;
+            }
+        } else if (N::NL == 1) {
+            float s = 0.f;
+            for (int i = 0; i < N::D; ++i) s += W(0, i, i);
+            w.v[N::troff] = s;
+        }
     }
 
     template <class K>
@@ -35,10 +56,10 @@ struct Launch {
         return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     }
     template <class K>
-    static int occupancy(K kernel, size_t smem) {
+    static int occupancy(K kernel, size_t smem, int threads = NT) {
         int nb = 0;
         if (prep(kernel, smem) != cudaSuccess) return 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, NT, smem) != cudaSuccess) return 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess) return 0;
         return nb;
     }
     static int grid_for(long long B, int per_sm, int sm_count) {
@@ -65,31 +86,69 @@ struct Launch {
     }
     static int adaptive_max_grid(bool exact, int sm_count) {
         auto k = exact ? solve_adaptive_kernel<N, true> : solve_adaptive_kernel<N, false>;
-        return occupancy(k, smem_solve) * sm_count;
+        return occupancy(k, sizeof(float) * 6 * N::D * 64, 64) * sm_count;
     }
-    static cudaError_t solve_adaptive(void*, const float* theta, const SolveArgs& a, int nvars, bool exact, int grid, cudaStream_t st) {
+    // CTA size: spread the batch over all SMs, one CTA each once it is large enough
+    static int adaptive_block(long long B, int sm_count) {
+        long long per_sm = (B + sm_count - 1) / sm_count;
+        long long bs = ((per_sm + 31) / 32) * 32;
+        return (int)std::max(64LL, std::min<long long>(NTA, bs));
+    }
+    static cudaError_t solve_adaptive(void*, const float* theta, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st) {
         auto k = exact ? solve_adaptive_kernel<N, true> : solve_adaptive_kernel<N, false>;
-        cudaError_t e = prep(k, smem_solve);
-        if (e != cudaSuccess) return e;
+        const int bs = adaptive_block(a.B, sm_count);
+        const size_t smem = sizeof(float) * 6 * N::D * bs;
+        const int per_sm = occupancy(k, smem, bs);
+        if (per_sm <= 0) return cudaErrorLaunchOutOfResources;
+        const long long need = (a.B + bs - 1) / bs;
+        const int grid = (int)std::max(1LL, std::min<long long>(need, (long long)per_sm * sm_count));
         SolveArgs aa = a;
         int nv = nvars;
         WBlock<N> w;
         pack(theta, w);
         void* args[] = {(void*)&w, (void*)&aa, (void*)&nv};
-        return cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(NT), args, smem_solve, st);
+        return cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(bs), args, smem, st);
     }
+    // networks with at least one hidden layer use the unit-parallel backward (tiny_ub.cuh)
+    static constexpr bool USE_UB = (N::NL >= 2);
+    static constexpr size_t ub_floats() {
+        if constexpr (USE_UB) {
+            using C = UBCfg<N>;
+            size_t a = (size_t)C::WSM + 12 * N::D * C::SPB, b = (size_t)(NT / 32) * N::NP;
+            return a > b ? a : b;
+        } else {
+            return 0;
+        }
+    }
+    static constexpr size_t smem_ub = sizeof(float) * ub_floats();
     static int backward_grid(bool exact, int sm_count, long long B) {
-        auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
-        return grid_for(B, occupancy(k, smem_bwd), sm_count);
+        if constexpr (USE_UB) {
+            auto k = exact ? backward_ub_kernel<N, true> : backward_ub_kernel<N, false>;
+            const long long spb = UBCfg<N>::SPB;
+            long long need = (B + spb - 1) / spb;
+            long long cap = (long long)std::max(occupancy(k, smem_ub), 1) * sm_count;
+            return (int)std::max(1LL, std::min(need, cap));
+        } else {
+            auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
+            return grid_for(B, occupancy(k, smem_bwd), sm_count);
+        }
     }
     static cudaError_t backward(void*, const float* theta, const BackwardArgs& a, bool exact, int grid, cudaStream_t st) {
-        auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
-        cudaError_t e = prep(k, smem_bwd);
-        if (e != cudaSuccess) return e;
-        WBlock<N> w;
-        pack(theta, w);
-        k<<<grid, NT, smem_bwd, st>>>(w, a);
-        return cudaGetLastError();
+        if constexpr (USE_UB) {
+            auto k = exact ? backward_ub_kernel<N, true> : backward_ub_kernel<N, false>;
+            cudaError_t e = prep(k, smem_ub);
+            if (e != cudaSuccess) return e;
+            k<<<grid, NT, smem_ub, st>>>(a);
+            return cudaGetLastError();
+        } else {
+            auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
+            cudaError_t e = prep(k, smem_bwd);
+            if (e != cudaSuccess) return e;
+            WBlock<N> w;
+            pack(theta, w);
+            k<<<grid, NT, smem_bwd, st>>>(w, a);
+            return cudaGetLastError();
+        }
     }
     static Family make() {
         Family f{};
@@ -105,6 +164,7 @@ struct Launch {
         f.backward_grid = &backward_grid;
         f.backward_partials_per_block = 1;
         f.supports_backward = 1;
+        f.adaptive_threads = 64;
         return f;
     }
 };
