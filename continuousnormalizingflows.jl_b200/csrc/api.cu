@@ -234,11 +234,14 @@ struct SolveRequest {
     float *out_u, *out_logp, *out_regs, *out_x, *out_lossterm;
     bool want_ckpt;
     int64_t B;
+    float* out_loss = nullptr;   // scalar loss (fused by the family when it can)
+    float loss_scale = 0.f;
+    bool loss_fused = false;     // set by enqueue_solve
 };
 
 // Enqueue one solve on `st`.  All pointers are device pointers.  Statistics land in
 // h->stats (device).
-int enqueue_solve(icnf_handle* h, const SolveRequest& r, cudaStream_t st) {
+int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
     const icnf_config& c = h->cfg;
     const ModeFlags mf = mode_flags(c, r.mode);
     const int D = h->D(), S = h->S();
@@ -298,6 +301,10 @@ int enqueue_solve(icnf_handle* h, const SolveRequest& r, cudaStream_t st) {
     CK(h, h->wk0.reserve(sb));
     CK(h, h->wk1.reserve(sb));
     CK(h, h->partials.reserve(sizeof(double) * 4 * 32 * (size_t)h->sm_count));
+    if (r.out_loss && h->fam->fuses_loss_sum_adaptive) {
+        a.out_loss = r.out_loss; a.loss_scale = r.loss_scale; a.out_lossterm = nullptr;
+        r.loss_fused = true;
+    }
     a.wu[0] = h->wu0.as<float>(); a.wu[1] = h->wu1.as<float>();
     a.wk[0] = h->wk0.as<float>(); a.wk[1] = h->wk1.as<float>();
     a.partials = h->partials.as<double>();
@@ -691,9 +698,11 @@ static int loss_grad_device(icnf_handle* h, int mode, const icnf_solver* sol, fl
     CK(h, h->lossterm.reserve(sizeof(float) * (size_t)B));
     SolveRequest r{mode, sol, t0, t1, xs, IN_XS, noise, eps, ys, nullptr, nullptr, nullptr, nullptr,
                    h->lossterm.as<float>(), want_grad, B};
+    r.out_loss = loss;
+    r.loss_scale = 1.0f / (float)denom;
     int rc = enqueue_solve(h, r, st);
     if (rc) return rc;
-    if (loss) {
+    if (loss && !r.loss_fused) {
         h->prof_begin(1, st);
         sum_kernel<<<1, 1024, 0, st>>>(h->lossterm.as<float>(), (long long)B, 1.0f / (float)denom, loss);
         h->prof_end(1, st);

@@ -184,7 +184,9 @@ struct SolveArgs {
     float* out_logp;         // B or null
     float* out_regs;         // 3 x B or null
     float* out_x;            // nvars x B or null (generate)
-    float* out_lossterm;     // per-block partial sums of the per-sample loss, or null
+    float* out_lossterm;     // per-sample loss terms, or null
+    float* out_loss;         // scalar loss = loss_scale * sum of the per-sample terms (families that fuse the sum), or null
+    float loss_scale;
     float* ckpt;             // [step][B][D'] z at the start of every accepted step (training), or null
     StepRec* steps;          // accepted (t, dt), or null
     DevStats* stats;         // device

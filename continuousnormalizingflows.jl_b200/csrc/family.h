@@ -41,6 +41,7 @@ struct Family {
     int (*backward_grid)(bool exact, int sm_count, long long B);
     int backward_partials_per_block;  // gradient partial rows written per CTA
     int supports_backward;
+    int fuses_loss_sum_adaptive;     // the adaptive solve writes the scalar loss itself (SolveArgs::out_loss)
     int adaptive_threads;            // CTA size of the cooperative adaptive kernel (0: not cooperative)
 };
 

@@ -293,27 +293,38 @@ __global__ void g_stage_input_kernel(StageArgs a) {
     a.ZI[idx] = v;
 }
 
-// assemble k_stage = [zdot; -trace; |zdot|; |eps'J|] for every sample (one thread per sample)
-__global__ void g_rhs_finish_kernel(StageArgs a, float* Kout_fixed) {
+// assemble k_stage = [zdot; -trace; |zdot|; |eps'J|].  CTA = 32 samples x 8 row groups: the D' rows
+// are split over the 8 warps (coalesced along samples), partial dot products meet in shared memory.
+__global__ void __launch_bounds__(256) g_rhs_finish_kernel(StageArgs a, float* Kout_fixed) {
     if (a.ctrl && a.ctrl->done) return;
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+    __shared__ float red[3][8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long b = (long long)blockIdx.x * 32 + lane;
     const int cur = a.ctrl ? a.ctrl->cur : a.cur_fixed;
     float* K = Kout_fixed ? Kout_fixed : stage_k(a, a.stage, cur);
     float zz = 0.f, qq = 0.f, s = 0.f;
-    for (int r = 0; r < a.D; ++r) {
-        const float zd = a.ZD[(long long)r * a.B + b];
-        K[(long long)r * a.B + b] = zd;
-        zz = fmaf(zd, zd, zz);
-        if (!a.exact) {
-            const float q = a.Q[(long long)r * a.B + b], e = a.E[(long long)r * a.B + b];
-            s = fmaf(q, e, s);
-            qq = fmaf(q, q, qq);
+    if (b < a.B) {
+        for (int r = w; r < a.D; r += 8) {
+            const float zd = a.ZD[(long long)r * a.B + b];
+            K[(long long)r * a.B + b] = zd;
+            zz = fmaf(zd, zd, zz);
+            if (!a.exact) {
+                const float q = a.Q[(long long)r * a.B + b], e = a.E[(long long)r * a.B + b];
+                s = fmaf(q, e, s);
+                qq = fmaf(q, q, qq);
+            }
         }
     }
-    K[(long long)a.D * a.B + b] = a.exact ? -a.TR[b] : -s;
-    K[(long long)(a.D + 1) * a.B + b] = (!a.exact && a.reg_e) ? (a.squared ? zz : sqrtf(zz)) : 0.f;
-    K[(long long)(a.D + 2) * a.B + b] = (!a.exact && a.reg_n) ? (a.squared ? qq : sqrtf(qq)) : 0.f;
+    red[0][w][lane] = zz; red[1][w][lane] = qq; red[2][w][lane] = s;
+    __syncthreads();
+    if (w == 0 && b < a.B) {
+        zz = qq = s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { zz += red[0][i][lane]; qq += red[1][i][lane]; s += red[2][i][lane]; }
+        K[(long long)a.D * a.B + b] = a.exact ? -a.TR[b] : -s;
+        K[(long long)(a.D + 1) * a.B + b] = (!a.exact && a.reg_e) ? (a.squared ? zz : sqrtf(zz)) : 0.f;
+        K[(long long)(a.D + 2) * a.B + b] = (!a.exact && a.reg_n) ? (a.squared ? qq : sqrtf(qq)) : 0.f;
+    }
 }
 
 // trial state u_new = u + dt sum_i b_i k_i  (all S rows), written to the other state buffer
@@ -565,20 +576,29 @@ __global__ void bw_kbar_init_kernel(BwArgs a) {
     const float zb = a.zbar[idx];
     for (int i = 0; i < 6; ++i) a.KB[(long long)i * DB + idx] = a.h * g_a[6][i] * zb;
 }
-// per sample: zb = KB[i] + cE zdot/|zdot|,  qb = -cl eps + cn q/|q|
-__global__ void bw_cotangent_kernel(BwArgs a, int exact_probe) {
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= a.B) return;
+// per sample: zb = KB[i] + cE zdot/|zdot|,  qb = -cl eps + cn q/|q|   (CTA = 32 samples x 8 row groups)
+__global__ void __launch_bounds__(256) bw_cotangent_kernel(BwArgs a, int exact_probe) {
+    __shared__ float red[2][8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long b = (long long)blockIdx.x * 32 + lane;
     const long long DB = (long long)a.D * a.B;
     float zz = 0.f, qq = 0.f;
-    for (int r = 0; r < a.D; ++r) {
-        const float zd = a.ZD[(long long)r * a.B + b];
-        zz = fmaf(zd, zd, zz);
-        if (exact_probe < 0) { const float q = a.Q[(long long)r * a.B + b]; qq = fmaf(q, q, qq); }
+    if (b < a.B) {
+        for (int r = w; r < a.D; r += 8) {
+            const float zd = a.ZD[(long long)r * a.B + b];
+            zz = fmaf(zd, zd, zz);
+            if (exact_probe < 0) { const float q = a.Q[(long long)r * a.B + b]; qq = fmaf(q, q, qq); }
+        }
     }
+    red[0][w][lane] = zz; red[1][w][lane] = qq;
+    __syncthreads();
+    zz = qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { zz += red[0][i][lane]; qq += red[1][i][lane]; }
+    if (b >= a.B) return;
     const float sz = (a.cE != 0.f) ? (a.squared ? 2.0f * a.cE : (zz > 0.f ? a.cE * rsqrtf(zz) : 0.f)) : 0.f;
     const float sq = (a.cn != 0.f) ? (a.squared ? 2.0f * a.cn : (qq > 0.f ? a.cn * rsqrtf(qq) : 0.f)) : 0.f;
-    for (int r = 0; r < a.D; ++r) {
+    for (int r = w; r < a.D; r += 8) {
         const long long o = (long long)r * a.B + b;
         if (a.ZB) a.ZB[o] = fmaf(sz, a.ZD[o], a.KB[(long long)a.i * DB + o]);
         if (exact_probe < 0) a.QB[o] = fmaf(sq, a.Q[o], -a.cl * a.E[o]);
@@ -1007,8 +1027,8 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
             memset(&g, 0, sizeof g);
             g.M = (int)B; g.N = w->n[2]; g.K = w->n[1]; g.ep = tc::TEP_TRACE; g.done = done;
             g.aux = act_ptr(Dv, 1); g.ldo = pitch(1); g.out_f32 = TR;
-            g.atomic_rowsum = (g.N > tc::TBN);
-            if (g.atomic_rowsum) GCK(cudaMemsetAsync(TR, 0, sizeof(float) * B, p.st));
+            g.atomic_rowsum = 1;
+            GCK(cudaMemsetAsync(TR, 0, sizeof(float) * B, p.st));
             GCK(tc::gemm(act_ptr(Dv, 0), pitch(0), w->a16.as<__nv_bfloat16>(), Workspace::pad8(w->n[1]), g, p.st));
         } else {
             return cudaErrorNotSupported;   // exact trace of deeper networks: fp32 families only
@@ -1125,7 +1145,7 @@ static cudaError_t rhs(void* wsp, const float*, const RhsArgs& a, bool exact, in
     RhsPlan p{w, a.theta, B, exact, a.reg_e, a.reg_n, a.squared, nullptr, a.t, st};
     GCK(enqueue_rhs_core(p, 0.f));
     StageArgs s = make_stage_args(w, B, exact, a.reg_e, a.reg_n, a.squared);
-    g_rhs_finish_kernel<<<blocks_for(B), 256, 0, st>>>(s, w->F1.as<float>());
+    g_rhs_finish_kernel<<<blocks_for(B, 32), 256, 0, st>>>(s, w->F1.as<float>());
     g_from_soa_kernel<<<blocks_for(B), 256, 0, st>>>(w->F1.as<float>(), a.du, B, w->S);
     w->launches += 5;
     return cudaGetLastError();
@@ -1166,7 +1186,7 @@ static cudaError_t enqueue_stage(Workspace* w, const SolveArgs& a, StageArgs s, 
     w->launches++;
     RhsPlan p{w, a.theta, a.B, exact, a.reg_e, a.reg_n, a.squared, ctrl, t_step + g_c_host(stage) * h_fixed, st};
     GCK(enqueue_rhs_core(p, g_c_host(stage)));
-    g_rhs_finish_kernel<<<blocks_for(a.B), 256, 0, st>>>(s, nullptr);
+    g_rhs_finish_kernel<<<blocks_for(a.B, 32), 256, 0, st>>>(s, nullptr);
     w->launches++;
     return cudaGetLastError();
 }
@@ -1232,7 +1252,7 @@ static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, i
         g_stage_input_kernel<<<blocks_for((long long)w->D * a.B), 256, 0, st>>>(s1);
         RhsPlan p{w, a.theta, a.B, exact, a.reg_e, a.reg_n, a.squared, ctrl, 0.f, st};
         GCK(enqueue_rhs_core(p, 1.0f));
-        g_rhs_finish_kernel<<<blocks_for(a.B), 256, 0, st>>>(s1, w->F1.as<float>());
+        g_rhs_finish_kernel<<<blocks_for(a.B, 32), 256, 0, st>>>(s1, w->F1.as<float>());
         g_initnorm_kernel<<<sb, 256, 0, st>>>(s, 1, w->F1.as<float>());
         g_ctrl_initdt_kernel<<<1, 1, 0, st>>>(ca, 1);
         w->launches += 7;
@@ -1326,7 +1346,7 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
             p.t_fixed = ti;
             GCK(enqueue_forward(p, 0.f, zi, w->ZD.as<float>()));
             GCK(enqueue_chain(p, w->EPS.as<float>(), V));
-            bw_cotangent_kernel<<<b_blocks, 256, 0, st>>>(b, -1);
+            bw_cotangent_kernel<<<blocks_for(B, 32), 256, 0, st>>>(b, -1);
             // tangent pass
             for (int l = 0; l < NL - 1; ++l) {
                 GemmArgs g;

@@ -7,9 +7,11 @@
 namespace icnf {
 namespace tc {
 
-constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 4, TTHREADS = 192;
+// 3 stages = 96 KB of operand ring per CTA, so two CTAs share an SM and one CTA's epilogue
+// overlaps the other's main loop
+constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3, TTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int A_TILE_BYTES = TBM * TBK * 2, B_TILE_BYTES = TBN * TBK * 2;
-constexpr int SMEM_BYTES = TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int SMEM_BYTES = TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + TBN * 4 /*bias*/;
 
 enum TcEpilogue {
     TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)

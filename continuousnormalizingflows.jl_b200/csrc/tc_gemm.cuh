@@ -7,8 +7,8 @@
 // both operands into a 4-stage shared-memory ring with TMA (cp.async.bulk.tensor, 128-byte
 // swizzle), one elected thread of warp 1 issues tcgen05.mma (M = 128, N = 128, K = 16,
 // bf16 x bf16 -> fp32) into a 128-column TMEM accumulator and releases ring slots with
-// tcgen05.commit, and warps 2..5 run the epilogue straight out of TMEM (tcgen05.ld, one
-// sample row per thread) -- bias + activation + sigma', the VJP's ".* d", or the
+// tcgen05.commit, and warps 2..9 run the epilogue straight out of TMEM (tcgen05.ld, one
+// sample row and half of the columns per thread) -- bias + activation + sigma', the VJP's ".* d", or the
 // exact-trace contraction -- so activations go to HBM once, in bf16.
 #pragma once
 #include <cuda.h>
@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(TTHREADS, 1) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(TTHREADS, 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                               const __grid_constant__ CUtensorMap mapB, TcArgs g) {
     if (g.done && *g.done) return;
     extern __shared__ uint8_t smem_raw[];
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_gemm_kernel(const __grid_const
     uint64_t* empty = full + TSTAGES;
     uint64_t* tmem_full = empty + TSTAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    float* sbias = reinterpret_cast<float*>(smem + TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
@@ -169,13 +170,21 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_gemm_kernel(const __grid_const
         }
     } else {
         // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // stage this tile's bias slice while the main loop runs
+        {
+            const int e = threadIdx.x - 64;   // 0..255
+            if (e < TBN) sbias[e] = (g.bias && n0 + e < g.N) ? __ldg(g.bias + n0 + e) : 0.f;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
         mbar_wait(tmem_full, 0);
         tc_fence_after();
+        // two warps per TMEM lane quarter, each taking half of the columns
         const int q = warp & 3;
+        const int chalf = (warp - 2) >> 2;
         const int m = m0 + q * 32 + lane;
         const bool row_ok = m < g.M;
         float rowsum = 0.f;
-        for (int c0 = 0; c0 < TBN; c0 += 32) {
+        for (int c0 = chalf * (TBN / 2); c0 < (chalf + 1) * (TBN / 2); c0 += 32) {
             if (n0 + c0 >= g.N) break;   // warp-uniform
             uint32_t r[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -186,8 +195,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
                     float h0 = 0.f, d0 = 0.f, h1 = 0.f, d1 = 0.f;
-                    if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + g.bias[nb + j], h0, d0);
-                    if (nb + j + 1 < g.N) act_eval_rt(g.act, __uint_as_float(r[j + 1]) + g.bias[nb + j + 1], h1, d1);
+                    if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + sbias[c0 + j], h0, d0);
+                    if (nb + j + 1 < g.N) act_eval_rt(g.act, __uint_as_float(r[j + 1]) + sbias[c0 + j + 1], h1, d1);
                     hp[j / 2] = pack_bf16(h0, h1);
                     dp[j / 2] = pack_bf16(d0, d1);
                 }
@@ -230,16 +239,13 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_gemm_kernel(const __grid_const
                     const int n = nb + j;
                     if (n < g.N && n < g.n_limit) {
                         float v = __uint_as_float(r[j]);
-                        if (g.ep == TEP_LIN_SOA) v += g.bias[n];
+                        if (g.ep == TEP_LIN_SOA) v += sbias[c0 + j];
                         g.out_f32[(size_t)n * g.M + m] = v;
                     }
                 }
             }
         }
-        if (g.ep == TEP_TRACE && row_ok) {
-            if (g.atomic_rowsum) atomicAdd(g.out_f32 + m, rowsum);
-            else g.out_f32[m] = rowsum;
-        }
+        if (g.ep == TEP_TRACE && row_ok) atomicAdd(g.out_f32 + m, rowsum);   // two column halves (and unit tiles) per row
     }
     tc_fence_before();
     __syncthreads();

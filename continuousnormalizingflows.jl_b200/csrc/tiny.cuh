@@ -364,8 +364,9 @@ __device__ __forceinline__ void load_state(const SolveArgs& a, int64_t b, int nv
 
 // readout of the final state: inference_sol + reg_z_aug + generate_sol + per-sample loss
 template <class N>
-__device__ __forceinline__ void write_outputs(const SolveArgs& a, int64_t b, int nvars, const float (&z)[N::D],
-                                              float l, float E, float n) {
+__device__ __forceinline__ float write_outputs(const SolveArgs& a, int64_t b, int nvars, const float (&z)[N::D],
+                                               float l, float E, float n) {
+    float lossterm = 0.0f;
     if (a.out_u) {
 #pragma unroll
         for (int j = 0; j < N::D; ++j) a.out_u[b * N::S + j] = z[j];
@@ -378,7 +379,7 @@ __device__ __forceinline__ void write_outputs(const SolveArgs& a, int64_t b, int
         for (int j = 0; j < N::D; ++j)
             if (j < nvars) a.out_x[b * nvars + j] = z[j];
     }
-    if (a.out_logp || a.out_regs || a.out_lossterm) {
+    if (a.out_logp || a.out_regs || a.out_lossterm || a.out_loss) {
         float zz = 0.0f, za = 0.0f;
 #pragma unroll
         for (int j = 0; j < N::D; ++j) {
@@ -393,8 +394,10 @@ __device__ __forceinline__ void write_outputs(const SolveArgs& a, int64_t b, int
             a.out_regs[b * 3 + 1] = n;
             a.out_regs[b * 3 + 2] = Aa;
         }
-        if (a.out_lossterm) a.out_lossterm[b] = -logp + a.lam1 * E + a.lam2 * n + a.lam3 * Aa;
+        lossterm = -logp + a.lam1 * E + a.lam2 * n + a.lam3 * Aa;
+        if (a.out_lossterm) a.out_lossterm[b] = lossterm;
     }
+    return lossterm;
 }
 
 // stage-derivative storage in shared memory: K(i)[r] for stage i, row r, this thread
@@ -749,7 +752,8 @@ __global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __g
         }
     }
 
-    // ---- readout
+    // ---- readout (the mean of the loss rides on one more grid reduction)
+    double loss_local = 0.0;
     for (int64_t b = b0; b < a.B; b += stride) {
         float z[N::D], l, E, n;
         if (span > 0.0f) {
@@ -760,7 +764,12 @@ __global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __g
         } else {
             load_state<N>(a, b, nvars, z, l, E, n);
         }
-        write_outputs<N>(a, b, nvars, z, l, E, n);
+        loss_local += (double)write_outputs<N>(a, b, nvars, z, l, E, n);
+    }
+    if (a.out_loss) {
+        double tot, unused;
+        red.sum2(loss_local, 0.0, tot, unused);
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.out_loss[0] = (float)(tot * (double)a.loss_scale);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
         a.stats->naccept = nacc;

@@ -164,6 +164,7 @@ struct Launch {
         f.backward_grid = &backward_grid;
         f.backward_partials_per_block = 1;
         f.supports_backward = 1;
+        f.fuses_loss_sum_adaptive = 1;
         f.adaptive_threads = 64;
         return f;
     }
