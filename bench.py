@@ -343,6 +343,12 @@ def main():
     bwd_flop = B * nacc * (5 * 2 * PW + 6 * (8 * PW + 4 * PW))       # 82 P flop per step per sample
     fwd_flop = B * nf * 4 * PW                                        # Hutchinson RHS = 4 P flop
     achieved_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tiny::backward_ub_kernel"]
+        traffic = tr["dram_bytes_per_launch"] * (B / tr["batch"])
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -356,10 +362,10 @@ def main():
                 else "pinned H2D copy + icnf_loss_grad_dev + NCCL all-reduce + D2H of loss and gradient"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "tiny::backward_kernel", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "tiny::backward_ub_kernel", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "note": "narrow-MLP path is FP32-issue bound, not HBM bound (SURVEY 8(d)); see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32_fma", "kernel": "tiny::backward_kernel", "achieved": bwd_flop / (bwd_ms * 1e-3) / 1e12,
+        "roofline_fp32": {"bound": "fp32_fma", "kernel": "tiny::backward_ub_kernel", "achieved": bwd_flop / (bwd_ms * 1e-3) / 1e12,
                           "peak": fp32_peak, "unit": "TFLOP/s", "frac": bwd_flop / (bwd_ms * 1e-3) / 1e12 / fp32_peak,
                           "peak_source": "FFMA-chain microbenchmark in this run (icnf_measure_fp32_peak)",
                           "forward_kernel": {"kernel": "tiny::solve_adaptive_kernel", "achieved": fwd_flop / (fwd_ms * 1e-3) / 1e12,

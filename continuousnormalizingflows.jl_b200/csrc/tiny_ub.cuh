@@ -161,8 +161,11 @@ __device__ __forceinline__ void ub_wt_hidden(const float* sw, const float (&vec_
     }
 }
 
+#ifndef ICNF_UB_MINB
+#define ICNF_UB_MINB 3
+#endif
 template <class N, bool EXACT>
-__global__ void __launch_bounds__(NT, 3) backward_ub_kernel(BackwardArgs a) {
+__global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardArgs a) {
     using C = UBCfg<N>;
     constexpr int G = C::G, NH = C::NH, lh = NH - 1, D = N::D;
     extern __shared__ __align__(16) float smem[];

@@ -1,0 +1,19 @@
+#!/bin/bash
+# Run on the GPU box (under gpurun): the bench, the reference arm, the ncu launch list of the
+# bench command and one full ncu capture per dominant kernel.  Outputs land in gpurun_out/.
+set -x
+python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err
+python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench_full.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_bench.csv \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:backward_ub -s 3 -c 1 -o gpurun_out/prof_bwd \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:solve_adaptive -s 3 -c 1 -o gpurun_out/prof_fwd \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 40 -c 1 -o gpurun_out/prof_tc \
+    python scripts/time_wide.py bf16_tc > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 40 -c 1 -o gpurun_out/prof_generic \
+    python scripts/time_wide.py fp32 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 150 --csv --log-file gpurun_out/launches_tc.csv \
+    python scripts/time_wide.py bf16_tc > /dev/null 2>&1
+ls -la gpurun_out
