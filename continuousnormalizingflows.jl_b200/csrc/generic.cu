@@ -111,21 +111,35 @@ __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs g) {
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
 
     for (int k0 = 0; k0 < g.K; k0 += BK) {
-        // A chunk: BK x BM, each thread 4 elements along m
+        // A and B chunks: BK x 64 each; every thread moves 4 consecutive elements of one k row and
+        // stores them with one 128-bit shared-memory store (no bank conflicts)
         {
-            const int kk = threadIdx.x >> 4, mm = (threadIdx.x & 15) * 4;
+            const int kk = threadIdx.x >> 4, c4 = (threadIdx.x & 15) * 4;
             const int k = k0 + kk;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int m = m0 + mm + i;
-                As[kk][mm + i] = (k < g.K && m < g.M) ? __ldg(g.A + (long long)k * g.lda + m) : 0.0f;
+            float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < g.K) {
+                const float* ap = g.A + (long long)k * g.lda + m0 + c4;
+                if (m0 + c4 + 3 < g.M && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0)) {
+                    av = __ldg(reinterpret_cast<const float4*>(ap));
+                } else {
+                    if (m0 + c4 + 0 < g.M) av.x = __ldg(ap + 0);
+                    if (m0 + c4 + 1 < g.M) av.y = __ldg(ap + 1);
+                    if (m0 + c4 + 2 < g.M) av.z = __ldg(ap + 2);
+                    if (m0 + c4 + 3 < g.M) av.w = __ldg(ap + 3);
+                }
+                const long long n = n0 + c4;
+                const float* bp = g.gather ? nullptr : g.Bm + (long long)k * g.ldb + n;
+                if (bp && n + 3 < g.N && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+                    bv = *reinterpret_cast<const float4*>(bp);
+                } else {
+                    if (n + 0 < g.N) bv.x = gemm_b_elem(g, k, n + 0, tnow);
+                    if (n + 1 < g.N) bv.y = gemm_b_elem(g, k, n + 1, tnow);
+                    if (n + 2 < g.N) bv.z = gemm_b_elem(g, k, n + 2, tnow);
+                    if (n + 3 < g.N) bv.w = gemm_b_elem(g, k, n + 3, tnow);
+                }
             }
-            const int nn = (threadIdx.x & 15) * 4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const long long n = n0 + nn + i;
-                Bs[kk][nn + i] = (k < g.K && n < g.N) ? gemm_b_elem(g, k, n, tnow) : 0.0f;
-            }
+            *reinterpret_cast<float4*>(&As[kk][c4]) = av;
+            *reinterpret_cast<float4*>(&Bs[kk][c4]) = bv;
         }
         __syncthreads();
 #pragma unroll

@@ -58,27 +58,45 @@ struct UBCfg {
     static constexpr int loff = coff(NH);
     static constexpr int lboff = loff + N::n(N::NL - 1) * lpitch;
     static constexpr int WSM = lboff + pad4(N::D);
-    // gradient accumulators per lane: owned rows of every hidden layer (+ bias), owned columns of the last layer (+ bias)
-    static constexpr int nacc() {
+    // gradient accumulators per lane.  Hidden layer l, owned unit u: KP(l) float2 pairs over the inputs
+    // (accW) and one bias scalar (accB); output layer: owned columns (accL) and its bias.
+    __host__ __device__ static constexpr int KP(int l) { return (N::n(l) + 1) / 2; }
+    __host__ __device__ static constexpr int woff2(int l) {   // offset into accW (float2 units)
         int o = 0;
-        for (int l = 0; l < NH; ++l) o += U(l) * (N::n(l) + 1);
-        return o + U(NH - 1) * N::D + N::D;
-    }
-    __host__ __device__ static constexpr int aoff(int l) {
-        int o = 0;
-        for (int i = 0; i < l; ++i) o += U(i) * (N::n(i) + 1);
+        for (int i = 0; i < l; ++i) o += U(i) * KP(i);
         return o;
     }
-    static constexpr int aloff = aoff(NH);
-    static constexpr int NACC = nacc();
+    static constexpr int NACCW = woff2(NH);
+    __host__ __device__ static constexpr int boffa(int l) {
+        int o = 0;
+        for (int i = 0; i < l; ++i) o += U(i);
+        return o;
+    }
+    static constexpr int NACCB = boffa(NH);
+    static constexpr int NACCL = U(NH - 1) * N::D + N::D;
+    static constexpr int NP2 = (N::NMAX + 1) / 2;
     static constexpr int SPB = NT / G;   // samples per CTA
 };
 
 // all-gather of a vector distributed over the lane group: full[k] = own[k / G] of lane (k % G)
 template <int G, int n, int UM, int NM>
-__device__ __forceinline__ void group_gather(const float (&own)[UM], float (&full)[NM], int gbase) {
+__device__ __forceinline__ void group_gather(const float (&own)[UM], float2 (&full)[NM], int gbase) {
 #pragma unroll
-    for (int k = 0; k < n; ++k) full[k] = __shfl_sync(0xffffffffu, own[k / G], gbase + (k % G));
+    for (int k = 0; k < n; ++k) {
+        const float v = __shfl_sync(0xffffffffu, own[k / G], gbase + (k % G));
+        if (k & 1) full[k >> 1].y = v;
+        else full[k >> 1].x = v;
+    }
+    if (n & 1) full[n >> 1].y = 0.f;
+}
+// dot product of a shared-memory weight slice with a vector held as float2 pairs (FFMA2)
+template <int n, int NM>
+__device__ __forceinline__ float dot_pairs(const float* wrow, const float2 (&vec)[NM]) {
+    const float2* w2 = reinterpret_cast<const float2*>(wrow);
+    float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int kp = 0; kp < (n + 1) / 2; ++kp) acc = __ffma2_rn(w2[kp], vec[kp], acc);
+    return acc.x + acc.y;
 }
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
@@ -91,7 +109,7 @@ template <class N>
 struct UState {
     using C = UBCfg<N>;
     float h[C::NH][C::UMAX], d[C::NH][C::UMAX];        // owned activations
-    float fin[C::NH][N::NMAX];                          // gathered input vector of hidden layer l (l >= 1): h_{l-1}
+    float2 fin[C::NH][C::NP2];                          // gathered input vector of hidden layer l as pairs (l = 0: [z; t; ys])
 };
 
 // forward on owned units; zdot replicated in every lane of the group
@@ -102,21 +120,19 @@ __device__ __forceinline__ void ub_forward(const float* sw, const float (&x)[N::
     static_for<0, C::NH>([&](auto lc) __attribute__((always_inline)) {
         constexpr int l = decltype(lc)::value;
         constexpr int nin = N::n(l), nout = N::n(l + 1);
-        if constexpr (l > 0) group_gather<C::G, nin>(S.h[l - 1], S.fin[l], gbase);
+        if constexpr (l > 0) {
+            group_gather<C::G, nin>(S.h[l - 1], S.fin[l], gbase);
+        } else {
+#pragma unroll
+            for (int kp = 0; kp < (nin + 1) / 2; ++kp)
+                S.fin[0][kp] = make_float2(x[2 * kp], (2 * kp + 1 < nin) ? x[2 * kp + 1] : 0.f);
+        }
 #pragma unroll
         for (int u = 0; u < C::U(l); ++u) {
             const int j = g + C::G * u;
             float hval = 0.f, dval = 0.f;
             if (j < nout) {
-                const float* row = sw + C::roff(l) + j * C::rpitch(l);
-                float a = sw[C::boff(l) + j];
-#pragma unroll
-                for (int k = 0; k < nin; ++k) {
-                    float in;
-                    if constexpr (l == 0) in = x[k];
-                    else in = S.fin[l][k];
-                    a = fmaf(row[k], in, a);
-                }
+                const float a = sw[C::boff(l) + j] + dot_pairs<nin>(sw + C::roff(l) + j * C::rpitch(l), S.fin[l]);
                 act_eval<N::ACT>(a, hval, dval);
             }
             S.h[l][u] = hval;
@@ -146,23 +162,17 @@ __device__ __forceinline__ void ub_wt_hidden(const float* sw, const float (&vec_
                                              float (&out)[UBCfg<N>::UMAX]) {
     using C = UBCfg<N>;
     constexpr int nout = N::n(l + 1), nin = N::n(l);
-    float full[N::NMAX];
+    float2 full[C::NP2];
     group_gather<C::G, nout>(vec_own, full, gbase);
 #pragma unroll
     for (int u = 0; u < C::U(l - 1); ++u) {
         const int k = g + C::G * u;
-        float s = 0.f;
-        if (k < nin) {
-            const float* col = sw + C::coff(l) + k * C::cpitch(l);
-#pragma unroll
-            for (int j = 0; j < nout; ++j) s = fmaf(col[j], full[j], s);
-        }
-        out[u] = s;
+        out[u] = (k < nin) ? dot_pairs<nout>(sw + C::coff(l) + k * C::cpitch(l), full) : 0.f;
     }
 }
 
 #ifndef ICNF_UB_MINB
-#define ICNF_UB_MINB 3
+#define ICNF_UB_MINB 2   // 2 CTAs per SM: no spills at ~235 registers beats 3 CTAs with spills (sweep in profiles/README.md)
 #endif
 template <class N, bool EXACT>
 __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardArgs a) {
@@ -197,9 +207,14 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
     const int g = lane % G, gbase = lane - g;
     const int slot = threadIdx.x / G;                   // sample slot inside the CTA
     const int nsteps = a.stats->naccept;
-    float acc[C::NACC];
+    float2 accW[C::NACCW];
+    float accB[C::NACCB], accL[C::NACCL];
 #pragma unroll
-    for (int i = 0; i < C::NACC; ++i) acc[i] = 0.f;
+    for (int i = 0; i < C::NACCW; ++i) accW[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < C::NACCB; ++i) accB[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < C::NACCL; ++i) accL[i] = 0.f;
 
     const int64_t stride = (int64_t)gridDim.x * C::SPB;
     const int64_t nloop = (a.B + stride - 1) / stride;
@@ -387,27 +402,31 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
                     static_for<0, NH>([&](auto lc) __attribute__((always_inline)) {
                         constexpr int l = decltype(lc)::value;
                         constexpr int nin = N::n(l), nout = N::n(l + 1);
-                        float wfull[N::NMAX];
-                        if constexpr (l > 0) group_gather<G, nin>(wv[l - 1], wfull, gbase);
+                        // tangent input of this layer as pairs: qb (first D' inputs, zero elsewhere) or gathered w_{l-1}
+                        float2 wfull[C::NP2];
+                        if constexpr (l > 0) {
+                            group_gather<G, nin>(wv[l - 1], wfull, gbase);
+                        } else {
+#pragma unroll
+                            for (int kp = 0; kp < (nin + 1) / 2; ++kp)
+                                wfull[kp] = make_float2(2 * kp < D ? qb[2 * kp < D ? 2 * kp : 0] : 0.f,
+                                                        2 * kp + 1 < D ? qb[2 * kp + 1 < D ? 2 * kp + 1 : 0] : 0.f);
+                        }
+                        constexpr int kpn = (l == 0) ? (D + 1) / 2 : (nin + 1) / 2;   // pairs that can be non-zero
 #pragma unroll
                         for (int u = 0; u < C::U(l); ++u) {
                             const int j = g + G * u;
                             float r = 0.f;
                             if (j < nout) {
-                                const float* row = sw + C::roff(l) + j * C::rpitch(l);
-                                if constexpr (l == 0) {
+                                const float2* w2 = reinterpret_cast<const float2*>(sw + C::roff(l) + j * C::rpitch(l));
+                                float2 racc = make_float2(0.f, 0.f);
 #pragma unroll
-                                    for (int k = 0; k < D; ++k) {
-                                        r = fmaf(row[k], qb[k], r);
-                                        acc[C::aoff(l) + u * (nin + 1) + k] = fmaf(gch[l][u], qb[k], acc[C::aoff(l) + u * (nin + 1) + k]);
-                                    }
-                                } else {
-#pragma unroll
-                                    for (int k = 0; k < nin; ++k) {
-                                        r = fmaf(row[k], wfull[k], r);
-                                        acc[C::aoff(l) + u * (nin + 1) + k] = fmaf(gch[l][u], wfull[k], acc[C::aoff(l) + u * (nin + 1) + k]);
-                                    }
+                                for (int kp = 0; kp < kpn; ++kp) {
+                                    racc = __ffma2_rn(w2[kp], wfull[kp], racc);
+                                    accW[C::woff2(l) + u * C::KP(l) + kp] =
+                                        __ffma2_rn(bc2(gch[l][u]), wfull[kp], accW[C::woff2(l) + u * C::KP(l) + kp]);
                                 }
+                                r = racc.x + racc.y;
                             }
                             wv[l][u] = r * S.d[l][u];
                             aex[l][u] = fmaf(r * v[l][u], act_dd<N::ACT>(S.h[l][u], S.d[l][u]), aex[l][u]);
@@ -417,7 +436,7 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
 #pragma unroll
                     for (int u = 0; u < C::U(lh); ++u)
 #pragma unroll
-                        for (int j = 0; j < D; ++j) acc[C::aloff + u * D + j] = fmaf(probe[j], wv[lh][u], acc[C::aloff + u * D + j]);
+                        for (int j = 0; j < D; ++j) accL[u * D + j] = fmaf(probe[j], wv[lh][u], accL[u * D + j]);
                 }
 
                 // ---- backprop with output cotangent zb
@@ -431,30 +450,26 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
 #pragma unroll
                         for (int j = 0; j < D; ++j) {
                             s = fmaf(col[j], zb[j], s);
-                            acc[C::aloff + u * D + j] = fmaf(zb[j], S.h[lh][u], acc[C::aloff + u * D + j]);
+                            accL[u * D + j] = fmaf(zb[j], S.h[lh][u], accL[u * D + j]);
                         }
                     }
                     ab[lh][u] = fmaf(s, S.d[lh][u], aex[lh][u]);
                 }
                 if (g == 0) {
 #pragma unroll
-                    for (int j = 0; j < D; ++j) acc[C::aloff + C::U(lh) * D + j] += zb[j];
+                    for (int j = 0; j < D; ++j) accL[C::U(lh) * D + j] += zb[j];
                 }
                 static_rfor<NH>([&](auto lc) __attribute__((always_inline)) {
                     constexpr int l = decltype(lc)::value;
-                    constexpr int nin = N::n(l);
                     // owned rows of dW_l and db_l
 #pragma unroll
                     for (int u = 0; u < C::U(l); ++u) {
                         if (g + G * u < N::n(l + 1)) {
 #pragma unroll
-                            for (int k = 0; k < nin; ++k) {
-                                float in;
-                                if constexpr (l == 0) in = x[k];
-                                else in = S.fin[l][k];
-                                acc[C::aoff(l) + u * (nin + 1) + k] = fmaf(ab[l][u], in, acc[C::aoff(l) + u * (nin + 1) + k]);
-                            }
-                            acc[C::aoff(l) + u * (nin + 1) + nin] += ab[l][u];
+                            for (int kp = 0; kp < C::KP(l); ++kp)
+                                accW[C::woff2(l) + u * C::KP(l) + kp] =
+                                    __ffma2_rn(bc2(ab[l][u]), S.fin[l][kp], accW[C::woff2(l) + u * C::KP(l) + kp]);
+                            accB[C::boffa(l) + u] += ab[l][u];
                         }
                     }
                     if constexpr (l >= 1) {
@@ -501,9 +516,16 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
 
     // ---- sum the accumulators over the samples of the warp (lanes with the same g), then over warps
 #pragma unroll
-    for (int i = 0; i < C::NACC; ++i) {
+    for (int o = G; o < 32; o <<= 1) {
 #pragma unroll
-        for (int o = G; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+        for (int i = 0; i < C::NACCW; ++i) {
+            accW[i].x += __shfl_xor_sync(0xffffffffu, accW[i].x, o);
+            accW[i].y += __shfl_xor_sync(0xffffffffu, accW[i].y, o);
+        }
+#pragma unroll
+        for (int i = 0; i < C::NACCB; ++i) accB[i] += __shfl_xor_sync(0xffffffffu, accB[i], o);
+#pragma unroll
+        for (int i = 0; i < C::NACCL; ++i) accL[i] += __shfl_xor_sync(0xffffffffu, accL[i], o);
     }
     __syncthreads();
     float* sg = smem;   // [NT / 32][NP], reuses the weight / stage area
@@ -517,8 +539,11 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
                 const int j = g + G * u;
                 if (j < nout) {
 #pragma unroll
-                    for (int k = 0; k < nin; ++k) sg[wid * N::NP + N::toff(l) + k * nout + j] = acc[C::aoff(l) + u * (nin + 1) + k];
-                    sg[wid * N::NP + N::toff(l) + nin * nout + j] = acc[C::aoff(l) + u * (nin + 1) + nin];
+                    for (int k = 0; k < nin; ++k) {
+                        const float2 pr = accW[C::woff2(l) + u * C::KP(l) + (k >> 1)];
+                        sg[wid * N::NP + N::toff(l) + k * nout + j] = (k & 1) ? pr.y : pr.x;
+                    }
+                    sg[wid * N::NP + N::toff(l) + nin * nout + j] = accB[C::boffa(l) + u];
                 }
             }
         });
@@ -528,12 +553,12 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
             const int k = g + G * u;
             if (k < nk) {
 #pragma unroll
-                for (int j = 0; j < D; ++j) sg[wid * N::NP + N::toff(nl) + k * D + j] = acc[C::aloff + u * D + j];
+                for (int j = 0; j < D; ++j) sg[wid * N::NP + N::toff(nl) + k * D + j] = accL[u * D + j];
             }
         }
         if (g == 0) {
 #pragma unroll
-            for (int j = 0; j < D; ++j) sg[wid * N::NP + N::toff(nl) + nk * D + j] = acc[C::aloff + C::U(lh) * D + j];
+            for (int j = 0; j < D; ++j) sg[wid * N::NP + N::toff(nl) + nk * D + j] = accL[C::U(lh) * D + j];
         }
     }
     __syncthreads();
