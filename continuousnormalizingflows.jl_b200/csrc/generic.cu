@@ -654,6 +654,7 @@ struct WgradArgs {
     float* dW;                            // column-major nout x nin
     float* db;                            // nout, or null
     long long chunk;                      // samples per gridDim.z slice
+    int first_pass;                       // 0: both products; 1: only the X2 Y2' product (extra exact-trace probes)
 };
 
 __device__ __forceinline__ float wgrad_y1(const WgradArgs& g, int k, long long b) {
@@ -676,7 +677,7 @@ __global__ void __launch_bounds__(GT) wgrad_kernel(WgradArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     const int npass = (g.X2 && k0 < g.K2) ? 2 : 1;
-    for (int pass = 0; pass < npass; ++pass) {
+    for (int pass = g.first_pass; pass < npass; ++pass) {
         const float* X = pass == 0 ? g.X1 : g.X2;
         for (long long bb = b_lo; bb < b_hi; bb += BK) {
             // tiles: 64 rows x 16 samples each; thread loads 4 elements (row r, samples s..)
@@ -1300,7 +1301,6 @@ static int adaptive_max_grid(bool, int sm_count) { return sm_count; }   // not a
 // Reverse sweep over the recorded steps (discretise-then-optimise; derivation in tiny.cuh).
 static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
-    if (exact) return cudaErrorNotSupported;   // TestMode gradient: tiny family only for now
     if (w->tc) return cudaErrorNotSupported;   // bf16 tensor-core mode covers the forward solve; gradients: fp32
     const long long B = a.B;
     const int NL = w->NL, D = w->D;
@@ -1359,26 +1359,58 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
             b.i = i; b.cl = hb * lbar; b.cE = hb * Ebar; b.cn = hb * nbar;
             p.t_fixed = ti;
             GCK(enqueue_forward(p, 0.f, zi, w->ZD.as<float>()));
-            GCK(enqueue_chain(p, w->EPS.as<float>(), V));
-            bw_cotangent_kernel<<<blocks_for(B, 32), 256, 0, st>>>(b, -1);
-            // tangent pass
-            for (int l = 0; l < NL - 1; ++l) {
-                GemmArgs g;
-                memset(&g, 0, sizeof g);
-                g.A = a.theta + w->woff[l]; g.lda = w->n[l + 1];
-                g.M = w->n[l + 1]; g.K = (l == 0) ? D : w->n[l]; g.N = B;
-                g.Bm = wv_ptr(l); g.ldb = B;
-                g.ep = EP_TANGENT; g.act = w->cfg.activation;
-                g.out0 = wv_ptr(l + 1); g.out1 = AEX + w->hoff[l] * B;
-                g.aux0 = Dv + w->hoff[l] * B; g.aux1 = V + w->hoff[l] * B; g.aux2 = H + w->hoff[l] * B;
-                GCK(launch_gemm(w, g, st));
+            // TrainMode: one probe (eps).  TestMode: D' one-hot probes e_p, each with cotangent -cl on
+            // (e_p' J)_p; their second-order terms accumulate in AEX, their g w' products go straight
+            // into the gradient (utils.jl:35-54 differentiated).
+            const int nprobe = exact ? D : 1;
+            for (int pr = 0; pr < nprobe; ++pr) {
+                const float* probe = w->EPS.as<float>();
+                if (exact) {
+                    bw_onehot_kernel<<<db_blocks, 256, 0, st>>>(w->F1.as<float>(), pr, D, B);
+                    probe = w->F1.as<float>();
+                    w->launches++;
+                }
+                GCK(enqueue_chain(p, probe, V));
+                BwArgs bc = b;
+                if (pr > 0) bc.ZB = nullptr;
+                bw_cotangent_kernel<<<blocks_for(B, 32), 256, 0, st>>>(bc, exact ? pr : -1);
+                for (int l = 0; l < NL - 1; ++l) {
+                    GemmArgs g;
+                    memset(&g, 0, sizeof g);
+                    g.A = a.theta + w->woff[l]; g.lda = w->n[l + 1];
+                    g.M = w->n[l + 1]; g.K = (l == 0) ? D : w->n[l]; g.N = B;
+                    g.Bm = wv_ptr(l); g.ldb = B;
+                    g.ep = EP_TANGENT; g.act = w->cfg.activation; g.accumulate = (pr > 0);
+                    g.out0 = wv_ptr(l + 1); g.out1 = AEX + w->hoff[l] * B;
+                    g.aux0 = Dv + w->hoff[l] * B; g.aux1 = V + w->hoff[l] * B; g.aux2 = H + w->hoff[l] * B;
+                    GCK(launch_gemm(w, g, st));
+                }
+                if (exact) {
+                    // this probe's chain gradient g_l w_l' for every layer
+                    for (int l = NL - 1; l >= 0; --l) {
+                        WgradArgs wg;
+                        memset(&wg, 0, sizeof wg);
+                        wg.first_pass = 1;
+                        wg.X1 = nullptr;
+                        wg.X2 = (l == NL - 1) ? probe : G + w->hoff[l] * B;
+                        wg.Y2 = wv_ptr(l); wg.K2 = (l == 0) ? D : w->n[l];
+                        wg.nout = w->n[l + 1]; wg.nin = w->n[l]; wg.B = B;
+                        wg.dW = a.gpartial + w->woff[l]; wg.db = nullptr;
+                        const int gx = (wg.K2 + BN - 1) / BN, gy = (wg.nout + BM - 1) / BM;
+                        int gz = (int)std::min<long long>((B + 255) / 256, std::max(1, 592 / (gx * gy)));
+                        wg.chunk = ((B + gz - 1) / gz + BK - 1) / BK * BK;
+                        gz = (int)((B + wg.chunk - 1) / wg.chunk);
+                        wgrad_kernel<<<dim3(gx, gy, gz), GT, 0, st>>>(wg);
+                        w->launches++;
+                    }
+                }
             }
             // backprop + weight gradients, top layer first
             for (int l = NL - 1; l >= 0; --l) {
                 WgradArgs wg;
                 memset(&wg, 0, sizeof wg);
                 wg.X1 = AB + w->hoff[l] * B;
-                wg.X2 = (l == NL - 1) ? w->EPS.as<float>() : G + w->hoff[l] * B;
+                wg.X2 = exact ? nullptr : ((l == NL - 1) ? w->EPS.as<float>() : G + w->hoff[l] * B);
                 wg.Y2 = wv_ptr(l); wg.K2 = (l == 0) ? D : w->n[l];
                 wg.nout = w->n[l + 1]; wg.nin = w->n[l]; wg.B = B;
                 if (l == 0) { wg.gather = 1; wg.D = D; wg.tin = w->tin; wg.C = w->C; wg.zi = zi; wg.ys = w->YS.as<float>(); wg.tval = ti; }

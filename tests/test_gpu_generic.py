@@ -116,7 +116,7 @@ def test_loss_and_gradient_match_oracle(m, shape, adaptive):
     om, theta, xs, eps, ys = make_inputs(icnf, 77)
     sol = dict(adaptive=False, dt=0.25) if not adaptive else dict(adaptive=True)
     opts = O.SolverOpts(adaptive=False, dt=0.25) if not adaptive else O.SolverOpts()
-    for mode, omode in [(m.TrainMode(True), O.TRAIN_REG), (m.TrainMode(False), O.TRAIN_NOREG)]:
+    for mode, omode in [(m.TrainMode(True), O.TRAIN_REG), (m.TrainMode(False), O.TRAIN_NOREG), (m.TestMode(), O.TEST)]:
         args = (xs,) if ys is None else (xs, ys)
         l, g, gx = m.loss_and_gradient(icnf, mode, *args, theta, {}, want_dxs=True, eps=eps, tspan=icnf.tspan, **sol)
         rl, rg, rgx = O.loss_grad(om, omode, t64(xs), t64(theta), t64(eps), t64(ys), opts=opts, want_dxs=True)
@@ -126,12 +126,3 @@ def test_loss_and_gradient_match_oracle(m, shape, adaptive):
         np.testing.assert_allclose(g, rg.numpy(), rtol=5e-3, atol=2e-4 * float(rg.abs().max()))
 
 
-def test_testmode_gradient_is_reported_unsupported_not_faked(m):
-    icnf = make_icnf(m, "config3_gmm16")
-    om, theta, xs, eps, _ = make_inputs(icnf, 8)
-    l = m.loss(icnf, m.TestMode(), xs, theta, {}, tspan=icnf.tspan, adaptive=False, dt=0.25)
-    rl = float(O.loss(om, O.TEST, t64(xs), t64(theta), None, opts=O.SolverOpts(adaptive=False, dt=0.25)))
-    assert l == pytest.approx(rl, rel=RTOL)
-    with pytest.raises(m.ICNFError) as ei:
-        m.loss_and_gradient(icnf, m.TestMode(), xs, theta, {})
-    assert ei.value.code == 7
