@@ -96,6 +96,8 @@ SYMBOLS = [
     ("icnf_set_profiling", C.c_int, [_P, C.c_int]),
     ("icnf_kernel_times", C.c_int, [_P, C.POINTER(C.c_float)]),
     ("icnf_measure_fp32_peak", C.c_int, [C.c_int, C.POINTER(C.c_float)]),
+    ("icnf_adam_step_dev", C.c_int, [_F, _F, _F, _F, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
+                                     C.c_float, _P]),
     ("icnf_tc_gemm_selftest", C.c_int, [C.c_int, C.c_int, C.c_int, _F, _F, _F]),
 ]
 

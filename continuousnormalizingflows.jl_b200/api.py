@@ -260,11 +260,11 @@ class ICNF:
             if not p.is_cuda:
                 p = p.cpu().numpy()
             else:
-                key = ("t", p.data_ptr(), p._version, p.numel())
-                if key != self._params_key:
-                    self._check(lib.icnf_set_params_dev(self._h, p.data_ptr(), p.numel(),
-                                                        torch.cuda.current_stream(p.device).cuda_stream))
-                    self._params_key = key
+                # device-resident parameters can be changed behind torch's back (icnf_adam_step_dev
+                # updates them in place), so they are handed to the library on every call
+                self._check(lib.icnf_set_params_dev(self._h, p.data_ptr(), p.numel(),
+                                                    torch.cuda.current_stream(p.device).cuda_stream))
+                self._params_key = None
                 return
         p = np.ascontiguousarray(np.asarray(ps, dtype=np.float32).reshape(-1))
         key = ("n", p.tobytes())

@@ -68,6 +68,21 @@ __global__ void sum_kernel(const float* __restrict__ x, long long n, float scale
     }
 }
 
+// OptimiserChain(WeightDecay(lambda), Adam(eta, (beta1, beta2), epsilon)) of the MLJ adapter
+// (src/exts/mlj_ext/core_icnf.jl:17-24), Optimisers.jl semantics: g += lambda * theta, then Adam.
+__global__ void adam_step_kernel(float* __restrict__ theta, const float* __restrict__ grad, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, float eta, float beta1, float beta2, float epsilon,
+                                 float lambda, float bp1, float bp2) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float g = fmaf(lambda, theta[i], grad[i]);
+    const float mi = beta1 * m[i] + (1.0f - beta1) * g;
+    const float vi = beta2 * v[i] + (1.0f - beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    theta[i] -= eta * (mi / (1.0f - bp1)) / (sqrtf(vi / (1.0f - bp2)) + epsilon);
+}
+
 // FP32 FMA-pipe microbenchmark (the roofline denominator of the narrow-MLP kernels, which
 // MEASURED_PEAKS.json does not carry): 16 independent FFMA chains per thread.
 __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, float a, float b) {
@@ -485,6 +500,16 @@ int icnf_kernel_times(icnf_handle* h, float* ms4) {
         CK(h, cudaEventElapsedTime(&ms4[s], h->prof_ev[s][0], h->prof_ev[s][1]));
     }
     return ICNF_OK;
+}
+
+int icnf_adam_step_dev(float* theta, const float* grad, float* m, float* v, int64_t n, int64_t step, float eta, float beta1,
+                       float beta2, float epsilon, float lambda, void* stream) {
+    if (!theta || !grad || !m || !v || n < 0 || step < 1) return ICNF_ERR_INVALID;
+    if (n == 0) return ICNF_OK;
+    const float bp1 = powf(beta1, (float)step), bp2 = powf(beta2, (float)step);
+    adam_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(theta, grad, m, v, n, eta, beta1, beta2,
+                                                                                  epsilon, lambda, bp1, bp2);
+    return cudaGetLastError() == cudaSuccess ? ICNF_OK : ICNF_ERR_CUDA;
 }
 
 int icnf_measure_fp32_peak(int device, float* tflops) {

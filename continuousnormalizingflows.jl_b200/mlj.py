@@ -27,6 +27,30 @@ class WeightDecay:
     lam: float = 1e-4
 
 
+class _DeviceOptimiserChain:
+    """The same optimiser with theta, m and v resident on the GPU (icnf_adam_step_dev): the
+    gradient never leaves the device between icnf_loss_grad_dev and the update."""
+
+    def __init__(self, wd: WeightDecay, adam: Adam, theta0: np.ndarray, device: int):
+        import torch
+        self.torch = torch
+        self.wd, self.adam = wd, adam
+        self.theta = torch.tensor(theta0, dtype=torch.float32, device=f"cuda:{device}")
+        self.m = torch.zeros_like(self.theta)
+        self.v = torch.zeros_like(self.theta)
+        self.t = 0
+
+    def step(self, grad) -> None:
+        from ._lib import lib
+        self.t += 1
+        b1, b2 = self.adam.beta
+        rc = lib.icnf_adam_step_dev(self.theta.data_ptr(), grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                    self.theta.numel(), self.t, self.adam.eta, b1, b2, self.adam.epsilon, self.wd.lam,
+                                    self.torch.cuda.current_stream(self.theta.device).cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"icnf_adam_step_dev failed with status {rc}")
+
+
 class _OptimiserChain:
     """Optimisers.jl semantics: WeightDecay adds lambda*theta to the gradient, Adam
     then rescales it; theta <- theta - update."""
@@ -58,11 +82,12 @@ def make_opt_callback(n: int) -> Callable:
 class ICNFModel:
     def __init__(self, icnf: Optional[ICNF] = None, batchsize: int = 1024, epochs: int = 300,
                  adam: Adam = Adam(), weight_decay: WeightDecay = WeightDecay(), callback: Optional[Callable] = None,
-                 rng=None):
+                 rng=None, device_optimiser: bool = False):
         self.icnf = icnf if icnf is not None else ICNF()
         self.batchsize, self.epochs = int(batchsize), int(epochs)
         self.adam, self.weight_decay = adam, weight_decay
         self.callback = callback
+        self.device_optimiser = bool(device_optimiser)   # keep data, parameters and optimiser state on the GPU
         self.rng = np.random.default_rng(rng)
         self.fitresult = None
         self.report = {}
@@ -78,16 +103,36 @@ class ICNFModel:
         x = np.ascontiguousarray(np.asarray(X, dtype=np.float32).T)       # permutedims(matrix(X)), core_icnf.jl:33
         y = None if Y is None else np.ascontiguousarray(np.asarray(Y, dtype=np.float32).T)
         ps, st = setup(self.icnf.rng, self.icnf)
-        opt = _OptimiserChain(self.weight_decay, self.adam, ps.size)
         it, last = 0, float("nan")
-        for _ in range(self.epochs):
-            for idx in self._batches(x.shape[1]):
-                it += 1
-                args = (x[:, idx],) if y is None else (x[:, idx], y[:, idx])
-                last, g = loss_and_gradient(self.icnf, TrainMode(True), *args, ps, st)
-                ps = opt.step(ps, g)
-                if self.callback and self.callback(it, last):
-                    break
+        if self.device_optimiser:
+            import torch
+            dev = f"cuda:{self.icnf.device}"
+            opt = _DeviceOptimiserChain(self.weight_decay, self.adam, ps, self.icnf.device)
+            xd = torch.tensor(x.T.copy(), device=dev)                      # (n, nvars) records
+            yd = None if y is None else torch.tensor(y.T.copy(), device=dev)
+            for _ in range(self.epochs):
+                for idx in self._batches(x.shape[1]):
+                    it += 1
+                    sel = torch.as_tensor(idx, device=dev)
+                    args = (xd[sel].t(),) if yd is None else (xd[sel].t(), yd[sel].t())
+                    l, g = loss_and_gradient(self.icnf, TrainMode(True), *args, opt.theta, st)
+                    opt.step(g)
+                    if self.callback:
+                        last = float(l)
+                        if self.callback(it, last):
+                            break
+            last = float(l)
+            ps = opt.theta.cpu().numpy()
+        else:
+            opt = _OptimiserChain(self.weight_decay, self.adam, ps.size)
+            for _ in range(self.epochs):
+                for idx in self._batches(x.shape[1]):
+                    it += 1
+                    args = (x[:, idx],) if y is None else (x[:, idx], y[:, idx])
+                    last, g = loss_and_gradient(self.icnf, TrainMode(True), *args, ps, st)
+                    ps = opt.step(ps, g)
+                    if self.callback and self.callback(it, last):
+                        break
         self.fitresult = (ps, st)
         self.report = {"iterations": it, "final_loss": last}
         return self

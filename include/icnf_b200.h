@@ -226,6 +226,14 @@ ICNF_API int icnf_loss_grad_dev(icnf_handle* h, int mode, const icnf_solver* sol
 ICNF_API int64_t icnf_launch_count(const icnf_handle* h);
 
 
+/* -- optimiser step ------------------------------------------ */
+/* One step of `OptimiserChain(WeightDecay(lambda), Adam(eta, (beta1, beta2), epsilon))`, the
+ * MLJ adapter's default (src/exts/mlj_ext/core_icnf.jl:17-24), on device-resident vectors:
+ * g = grad + lambda * theta; m, v updated in place; theta -= eta * mhat / (sqrt(vhat) + epsilon).
+ * `step` counts from 1.  All pointers are device pointers of length n; enqueued on `stream`. */
+ICNF_API int icnf_adam_step_dev(float* theta, const float* grad, float* m, float* v, int64_t n, int64_t step, float eta,
+                                float beta1, float beta2, float epsilon, float lambda, void* stream);
+
 /* -- measurement support (bench.py) ------------------------------------------ */
 /* When enabled, CUDA events are recorded on the launching stream around every
  * kernel of the next calls; icnf_kernel_times returns the device time in ms of the
