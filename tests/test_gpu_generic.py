@@ -126,3 +126,34 @@ def test_loss_and_gradient_match_oracle(m, shape, adaptive):
         np.testing.assert_allclose(g, rg.numpy(), rtol=5e-3, atol=2e-4 * float(rg.abs().max()))
 
 
+
+
+def test_full_size_properties_config3(m):
+    """BASELINE config 3 at its full batch (262 144, 16-D): size-independent properties instead of an
+    oracle run -- (i) a linear field has a closed-form log-density, (ii) flowing forward then
+    backward returns the input, (iii) sharding the batch does not change any sample's result."""
+    import math
+    import torch
+    B, D = 262144, 16
+    rng = np.random.default_rng(0)
+    # (i) dz/dt = A z through the generic family (one Dense layer, identity)
+    Amat = (0.15 * rng.standard_normal((D, D))).astype(np.float32)
+    lin = m.ICNF(nvariables=D, naugments=0, autonomous=True, nn=m.Chain(m.Dense(D, D)))
+    assert lin.kernel_family == "generic"
+    theta = np.concatenate([Amat.flatten(order="F"), np.zeros(D, np.float32)])
+    xs = rng.standard_normal((D, B)).astype(np.float32)
+    logp, _ = m.inference(lin, m.TestMode(), xs, theta, {}, reltol=1e-6, abstol=1e-6)
+    z1 = torch.matrix_exp(torch.tensor(Amat, dtype=torch.float64)).numpy() @ xs.astype(np.float64)
+    want = -0.5 * D * math.log(2 * math.pi) - 0.5 * (z1 ** 2).sum(0) + float(np.trace(Amat.astype(np.float64)))
+    np.testing.assert_allclose(logp, want, rtol=RTOL, atol=1e-4)
+    # (ii) + (iii) on the config-3 network
+    icnf = make_icnf(m, "config3_gmm16")
+    om, th, _, _, _ = make_inputs(icnf, 1)
+    u0 = np.zeros((D + 3, B), np.float32, order="F")
+    u0[:D] = xs
+    kw = dict(adaptive=False, dt=0.125)
+    fwd = m.base_sol(icnf, m.TestMode(), u0, th, tspan=(0.0, 1.0), **kw)
+    back = m.base_sol(icnf, m.TestMode(), np.asfortranarray(fwd), th, tspan=(1.0, 0.0), **kw)
+    assert np.abs(back[:D] - u0[:D]).max() < 2e-4
+    part = m.base_sol(icnf, m.TestMode(), np.asfortranarray(u0[:, 1000:3000]), th, tspan=(0.0, 1.0), **kw)
+    np.testing.assert_allclose(part, fwd[:, 1000:3000], rtol=1e-6, atol=1e-6)
