@@ -524,8 +524,12 @@ def _loss_impl(icnf: ICNF, mode: Mode, xs, ys, ps, want_grad: bool, want_dxs: bo
     npar = icnf.n_params
     if dev:
         device = xa.keep.device
-        lossv = torch.empty(1, dtype=torch.float32, device=device)
-        dth = torch.empty(npar, dtype=torch.float32, device=device) if want_grad else None
+        # gradient and loss share one buffer [dtheta; loss] so that a data-parallel caller can
+        # all-reduce both with a single collective and no concatenation
+        buf = torch.empty(npar + 1, dtype=torch.float32, device=device)
+        lossv = buf[npar:]
+        dth = buf[:npar] if want_grad else None
+        icnf._grad_loss_buf = buf if want_grad else None
         dxs = torch.empty((xa.B, icnf.nvariables), dtype=torch.float32, device=device) if want_dxs else None
         ds = _dev_stats(icnf)
         icnf._check(lib.icnf_loss_grad_dev(icnf._h, mode.code, C.byref(solver), t0, t1, xa.ptr, C.byref(noise), ea.ptr,

@@ -59,7 +59,9 @@ def dp_loss_and_gradient(icnf, mode, xs_local, *args, rank: int, world: int, glo
     fn = local_fn or api.loss_and_gradient
     l, g = fn(icnf, mode, xs_local, *args, sample_offset=lo, global_batch=global_batch, **kw)
     if torch is not None and isinstance(g, torch.Tensor):
-        packed = torch.cat([g.reshape(-1), l.reshape(1)])
+        packed = getattr(icnf, "_grad_loss_buf", None)
+        if packed is None or packed.data_ptr() != g.data_ptr():     # not the shared [dtheta; loss] buffer
+            packed = torch.cat([g.reshape(-1), l.reshape(1)])
         all_reduce_sum(packed, group)
         return packed[-1], packed[:-1]
     packed = np.concatenate([np.asarray(g, dtype=np.float32).reshape(-1), np.asarray([l], dtype=np.float32)])
