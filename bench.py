@@ -168,8 +168,12 @@ def logp_extras(m, local, dev, flush_buf):
         ("config5_cond64_B65536_bf16tc", dict(nvariables=64, naugments=0, nconditions=32, precision="bf16_tc"), 65536, m.TestMode()),
         ("config4_ffjord784_B8192_fp32", dict(nvariables=784, naugments=0, nn=ffjord), 8192, m.TrainMode(False)),
         ("config4_ffjord784_B8192_bf16tc", dict(nvariables=784, naugments=0, nn=ffjord, precision="bf16_tc"), 8192, m.TrainMode(False)),
+        # the same two with a fixed step (8 steps, 48 RHS calls): bf16 rounding cannot inflate the step count
+        ("config4_ffjord784_B8192_fp32_fixed8", dict(nvariables=784, naugments=0, nn=ffjord), 8192, m.TrainMode(False)),
+        ("config4_ffjord784_B8192_bf16tc_fixed8", dict(nvariables=784, naugments=0, nn=ffjord, precision="bf16_tc"), 8192, m.TrainMode(False)),
     ]
     for name, kw, B, mode in cases:
+        sol = dict(adaptive=False, dt=0.125) if name.endswith("_fixed8") else {}
         icnf = m.ICNF(device=local, epsdist="rademacher", **kw)
         rng = np.random.default_rng(7)
         theta, _ = m.setup(rng, icnf)
@@ -178,14 +182,14 @@ def logp_extras(m, local, dev, flush_buf):
         if icnf.nconditions:
             args += (torch.from_numpy(rng.standard_normal((B, icnf.nconditions)).astype(np.float32)).to(dev).t(),)
         for _ in range(2):
-            m.inference(icnf, mode, *args, theta, {}, seed=3)
+            m.inference(icnf, mode, *args, theta, {}, seed=3, **sol)
         torch.cuda.synchronize()
         K, ms = 3, 0.0
         for _ in range(K):
             flush_buf.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            m.inference(icnf, mode, *args, theta, {}, seed=3)
+            m.inference(icnf, mode, *args, theta, {}, seed=3, **sol)
             b.record()
             torch.cuda.synchronize()
             ms += a.elapsed_time(b)

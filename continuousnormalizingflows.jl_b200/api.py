@@ -209,8 +209,11 @@ class ICNF:
 
     def __del__(self):
         h = getattr(self, "_h", None)
-        if h is not None and h.value:
-            lib.icnf_destroy(h)
+        if h is not None and h.value and lib is not None:     # `lib` is None during interpreter shutdown
+            try:
+                lib.icnf_destroy(h)
+            except Exception:
+                pass
             self._h = C.c_void_p()
 
     @property

@@ -98,6 +98,144 @@ __device__ __forceinline__ float gemm_b_elem(const GemmArgs& g, int k, long long
     return g.ys[(long long)(k - g.D - g.tin) * g.N + n];
 }
 
+// epilogue of one output element (m, n) with accumulator v; EP_TRACE returns its contribution
+__device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, int m, long long n, float v) {
+    const long long o = (long long)m * g.N + n;
+    switch (g.ep) {
+        case EP_ACT: {
+            float h, d;
+            act_eval_rt(g.act, v + g.bias[m], h, d);
+            g.out0[o] = h;
+            g.out1[o] = d;
+        } break;
+        case EP_LIN: g.out0[o] = v + g.bias[m]; break;
+        case EP_MULD:
+            if (g.out1) g.out1[o] = v;
+            g.out0[o] = v * g.aux0[o];
+            break;
+        case EP_PLAIN: g.out0[o] = v; break;
+        case EP_TRACE: return v * g.aux0[o];
+        case EP_TANGENT: {
+            const float d = g.aux0[o];
+            g.out0[o] = v * d;
+            const float ex = v * g.aux1[o] * act_dd_rt(g.act, g.aux2[o], d);
+            g.out1[o] = g.accumulate ? g.out1[o] + ex : ex;
+        } break;
+        case EP_MULADD: g.out0[o] = fmaf(v, g.aux0[o], g.aux1[o]); break;
+    }
+    return 0.f;
+}
+
+// 128 x 128 x 16 tiles, 8 x 8 outputs per thread (as 4 + 4 rows / columns 64 apart, so that every
+// 128-bit shared-memory read of a half-warp is contiguous), register-prefetched double buffering.
+constexpr int LM = 128, LN = 128, LK = 16;
+__global__ void __launch_bounds__(GT, 2) gemm128_kernel(GemmArgs g) {
+    if (g.done && *g.done) return;
+    __shared__ __align__(16) float As[2][LK][LM];
+    __shared__ __align__(16) float Bs[2][LK][LN];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long n0 = (long long)blockIdx.x * LN;
+    const int m0 = blockIdx.y * LM;
+    const float tnow = g.ctrl ? fmaf(g.c_i, g.ctrl->tdir * g.ctrl->dt, g.ctrl->t) : g.t_fixed;
+    float2 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+
+    // each thread moves two float4 of A and two of B per chunk: rows kk and kk + 8, columns c4..c4+3
+    const int kk0 = threadIdx.x >> 5, c4 = (threadIdx.x & 31) * 4;
+    float4 ra[2], rb[2];
+    auto load_chunk = [&](int k0) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int k = k0 + kk0 + 8 * h;
+            float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < g.K) {
+                const float* ap = g.A + (long long)k * g.lda + m0 + c4;
+                if (m0 + c4 + 3 < g.M && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0)) {
+                    av = __ldg(reinterpret_cast<const float4*>(ap));
+                } else {
+                    if (m0 + c4 + 0 < g.M) av.x = __ldg(ap + 0);
+                    if (m0 + c4 + 1 < g.M) av.y = __ldg(ap + 1);
+                    if (m0 + c4 + 2 < g.M) av.z = __ldg(ap + 2);
+                    if (m0 + c4 + 3 < g.M) av.w = __ldg(ap + 3);
+                }
+                const long long n = n0 + c4;
+                const float* bp = g.gather ? nullptr : g.Bm + (long long)k * g.ldb + n;
+                if (bp && n + 3 < g.N && ((reinterpret_cast<uintptr_t>(bp) & 15) == 0)) {
+                    bv = *reinterpret_cast<const float4*>(bp);
+                } else {
+                    if (n + 0 < g.N) bv.x = gemm_b_elem(g, k, n + 0, tnow);
+                    if (n + 1 < g.N) bv.y = gemm_b_elem(g, k, n + 1, tnow);
+                    if (n + 2 < g.N) bv.z = gemm_b_elem(g, k, n + 2, tnow);
+                    if (n + 3 < g.N) bv.w = gemm_b_elem(g, k, n + 3, tnow);
+                }
+            }
+            ra[h] = av;
+            rb[h] = bv;
+        }
+    };
+    auto store_chunk = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            *reinterpret_cast<float4*>(&As[buf][kk0 + 8 * h][c4]) = ra[h];
+            *reinterpret_cast<float4*>(&Bs[buf][kk0 + 8 * h][c4]) = rb[h];
+        }
+    };
+    load_chunk(0);
+    store_chunk(0);
+    __syncthreads();
+    const int nchunk = (g.K + LK - 1) / LK;
+    for (int c = 0; c < nchunk; ++c) {
+        const int buf = c & 1;
+        if (c + 1 < nchunk) load_chunk((c + 1) * LK);
+#pragma unroll
+        for (int kk = 0; kk < LK; ++kk) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                  make_float2(b1.z, b1.w)};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(av[i], av[i]), bp[j], acc[i][j]);
+        }
+        if (c + 1 < nchunk) store_chunk(buf ^ 1);
+        __syncthreads();
+    }
+    float colpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= g.M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n >= g.N) continue;
+            const float2 a2 = acc[i][j >> 1];
+            colpart[j] += gemm_epilogue(g, m, n, (j & 1) ? a2.y : a2.x);
+        }
+    }
+    if (g.ep == EP_TRACE) {
+        __syncthreads();
+        float* red = &As[0][0][0];   // 16 x 128 floats
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[ty * 128 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4))] = colpart[j];
+        __syncthreads();
+        if (threadIdx.x < LN) {
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) s += red[r * 128 + threadIdx.x];
+            const long long n = n0 + threadIdx.x;
+            if (n < g.N) atomicAdd(g.colsum + n, s);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs g) {
     if (g.done && *g.done) return;
     __shared__ __align__(16) float As[BK][BM];
@@ -934,6 +1072,12 @@ struct RhsPlan {
 };
 
 static cudaError_t launch_gemm(Workspace* w, GemmArgs& g, cudaStream_t st) {
+    if (g.M >= 96) {   // wide layers: 128 x 128 tiles
+        dim3 grid((unsigned)((g.N + LN - 1) / LN), (unsigned)((g.M + LM - 1) / LM));
+        gemm128_kernel<<<grid, GT, 0, st>>>(g);
+        w->launches++;
+        return cudaGetLastError();
+    }
     dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM));
     gemm_kernel<<<grid, GT, 0, st>>>(g);
     w->launches++;

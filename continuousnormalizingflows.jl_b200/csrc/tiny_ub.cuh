@@ -92,11 +92,16 @@ __device__ __forceinline__ void group_gather(const float (&own)[UM], float2 (&fu
 // dot product of a shared-memory weight slice with a vector held as float2 pairs (FFMA2)
 template <int n, int NM>
 __device__ __forceinline__ float dot_pairs(const float* wrow, const float2 (&vec)[NM]) {
+    // two independent accumulator chains: a lane owns only 2-3 units per layer, so the
+    // dot products themselves must supply the instruction-level parallelism
     const float2* w2 = reinterpret_cast<const float2*>(wrow);
-    float2 acc = make_float2(0.f, 0.f);
+    float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int kp = 0; kp < (n + 1) / 2; ++kp) acc = __ffma2_rn(w2[kp], vec[kp], acc);
-    return acc.x + acc.y;
+    for (int kp = 0; kp < (n + 1) / 2; ++kp) {
+        if (kp & 1) acc1 = __ffma2_rn(w2[kp], vec[kp], acc1);
+        else acc0 = __ffma2_rn(w2[kp], vec[kp], acc0);
+    }
+    return (acc0.x + acc1.x) + (acc0.y + acc1.y);
 }
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
@@ -419,14 +424,15 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
                             float r = 0.f;
                             if (j < nout) {
                                 const float2* w2 = reinterpret_cast<const float2*>(sw + C::roff(l) + j * C::rpitch(l));
-                                float2 racc = make_float2(0.f, 0.f);
+                                float2 racc = make_float2(0.f, 0.f), racc1 = make_float2(0.f, 0.f);
 #pragma unroll
                                 for (int kp = 0; kp < kpn; ++kp) {
-                                    racc = __ffma2_rn(w2[kp], wfull[kp], racc);
+                                    if (kp & 1) racc1 = __ffma2_rn(w2[kp], wfull[kp], racc1);
+                                    else racc = __ffma2_rn(w2[kp], wfull[kp], racc);
                                     accW[C::woff2(l) + u * C::KP(l) + kp] =
                                         __ffma2_rn(bc2(gch[l][u]), wfull[kp], accW[C::woff2(l) + u * C::KP(l) + kp]);
                                 }
-                                r = racc.x + racc.y;
+                                r = (racc.x + racc1.x) + (racc.y + racc1.y);
                             }
                             wv[l][u] = r * S.d[l][u];
                             aex[l][u] = fmaf(r * v[l][u], act_dd<N::ACT>(S.h[l][u], S.d[l][u]), aex[l][u]);
