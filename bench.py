@@ -166,8 +166,11 @@ def logp_extras(m, local, dev, flush_buf):
         ("config3_gmm16_B262144_bf16tc", dict(nvariables=16, naugments=0, precision="bf16_tc"), 262144, m.TestMode()),
         ("config5_cond64_B65536_fp32", dict(nvariables=64, naugments=0, nconditions=32), 65536, m.TestMode()),   # 97-388-388-64
         ("config5_cond64_B65536_bf16tc", dict(nvariables=64, naugments=0, nconditions=32, precision="bf16_tc"), 65536, m.TestMode()),
+        ("config5_cond64_B65536_bf16x3tc", dict(nvariables=64, naugments=0, nconditions=32, precision="bf16x3_tc"), 65536, m.TestMode()),
         ("config4_ffjord784_B8192_fp32", dict(nvariables=784, naugments=0, nn=ffjord), 8192, m.TrainMode(False)),
         ("config4_ffjord784_B8192_bf16tc", dict(nvariables=784, naugments=0, nn=ffjord, precision="bf16_tc"), 8192, m.TrainMode(False)),
+        # split bf16 (hi + lo, 3 MMAs per K step): tensor cores at fp32-level accuracy, same step count as fp32
+        ("config4_ffjord784_B8192_bf16x3tc", dict(nvariables=784, naugments=0, nn=ffjord, precision="bf16x3_tc"), 8192, m.TrainMode(False)),
         # the same two with a fixed step (8 steps, 48 RHS calls): bf16 rounding cannot inflate the step count
         ("config4_ffjord784_B8192_fp32_fixed8", dict(nvariables=784, naugments=0, nn=ffjord), 8192, m.TrainMode(False)),
         ("config4_ffjord784_B8192_bf16tc_fixed8", dict(nvariables=784, naugments=0, nn=ffjord, precision="bf16_tc"), 8192, m.TrainMode(False)),

@@ -24,7 +24,7 @@ ACT = {"softplus": 0, "tanh": 1, "sigmoid": 2, "identity": 3}
 EPS_SUPPLIED, EPS_GAUSSIAN, EPS_RADEMACHER = 0, 1, 2
 EPS = {"supplied": 0, "gaussian": 1, "rademacher": 2}
 # icnf_precision
-PRECISION = {"fp32": 0, "bf16_tc": 1}
+PRECISION = {"fp32": 0, "bf16_tc": 1, "bf16x3_tc": 2}
 
 
 class Config(C.Structure):
@@ -98,7 +98,7 @@ SYMBOLS = [
     ("icnf_measure_fp32_peak", C.c_int, [C.c_int, C.POINTER(C.c_float)]),
     ("icnf_adam_step_dev", C.c_int, [_F, _F, _F, _F, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, _P]),
-    ("icnf_tc_gemm_selftest", C.c_int, [C.c_int, C.c_int, C.c_int, _F, _F, _F]),
+    ("icnf_tc_gemm_selftest", C.c_int, [C.c_int, C.c_int, C.c_int, _F, _F, _F, C.c_int]),
 ]
 
 

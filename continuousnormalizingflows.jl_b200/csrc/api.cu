@@ -478,7 +478,7 @@ int64_t icnf_n_params(const icnf_handle* h) {
 int32_t icnf_n_state(const icnf_handle* h) { return h ? h->S() : 0; }
 const char* icnf_kernel_family(const icnf_handle* h) {
     if (!h || !h->fam) return "";
-    if (h->cfg.precision == ICNF_BF16_TC) return "tc";
+    if (h->cfg.precision == ICNF_BF16_TC || h->cfg.precision == ICNF_BF16X3_TC) return "tc";
     return h->fam->name;
 }
 int64_t icnf_launch_count(const icnf_handle* h) { return h ? h->launches : 0; }

@@ -946,6 +946,8 @@ struct Workspace {
     Buf bZS, bKZ, bKB, bzbar, bV, bWv, bAEX, bAB, bSB;   // backward
     // precision = ICNF_BF16_TC: bf16 operands for the tcgen05 GEMM, [sample][unit] activations
     bool tc = false;
+    int split = 0;   // ICNF_BF16X3_TC: every bf16 row is [hi | lo], three MMAs per K step
+    int rs(int cols) const { return (split ? 2 : 1) * pad8(cols); }   // row stride of a bf16 matrix with `cols` columns
     Buf w16t, w16n, a16, X16, E16, H16, D16, G16;
     std::vector<size_t> w16t_off, w16n_off;   // element offsets per layer
     std::vector<size_t> h16_off;              // element offsets / B per layer
@@ -987,13 +989,14 @@ static void* ws_create(const icnf_config* cfg) {
         w->hoff.push_back(h); h += w->n[l + 1];
     }
     w->hrows = h;
-    w->tc = (cfg->precision == ICNF_BF16_TC);
+    w->tc = (cfg->precision == ICNF_BF16_TC || cfg->precision == ICNF_BF16X3_TC);
+    w->split = (cfg->precision == ICNF_BF16X3_TC) ? 1 : 0;
     {
         size_t o1 = 0, o2 = 0, oh = 0;
         for (int l = 0; l < w->NL; ++l) {
-            w->w16t_off.push_back(o1); o1 += (size_t)w->n[l + 1] * Workspace::pad8(w->n[l]);
-            w->w16n_off.push_back(o2); o2 += (size_t)w->n[l] * Workspace::pad8(w->n[l + 1]);
-            w->h16_off.push_back(oh); oh += Workspace::pad8(w->n[l + 1]);
+            w->w16t_off.push_back(o1); o1 += (size_t)w->n[l + 1] * w->rs(w->n[l]);
+            w->w16n_off.push_back(o2); o2 += (size_t)w->n[l] * w->rs(w->n[l + 1]);
+            w->h16_off.push_back(oh); oh += w->rs(w->n[l + 1]);
         }
         w->h16_cols = oh;
     }
@@ -1037,23 +1040,23 @@ static cudaError_t on_params(void* p, const float* theta, cudaStream_t st) {
     if (w->tc) {
         size_t t1 = 0, t2 = 0;
         for (int l = 0; l < w->NL; ++l) {
-            t1 += (size_t)w->n[l + 1] * Workspace::pad8(w->n[l]);
-            t2 += (size_t)w->n[l] * Workspace::pad8(w->n[l + 1]);
+            t1 += (size_t)w->n[l + 1] * w->rs(w->n[l]);
+            t2 += (size_t)w->n[l] * w->rs(w->n[l + 1]);
         }
         GCK(w->w16t.reserve(t1 * 2)); GCK(w->w16n.reserve(t2 * 2));
         for (int l = 0; l < w->NL; ++l) {
             const int nin = w->n[l], nout = w->n[l + 1];
             // forward operand: rows = output units j, K = inputs k  (W[j,k] at k * nout + j)
             GCK(tc::pack_matrix(theta + w->woff[l], 1, nout, w->w16t.as<__nv_bfloat16>() + w->w16t_off[l], nout, nin,
-                                Workspace::pad8(nin), st));
+                                Workspace::pad8(nin), w->split, st));
             // VJP operand: rows = inputs k, K = output units j
             GCK(tc::pack_matrix(theta + w->woff[l], nout, 1, w->w16n.as<__nv_bfloat16>() + w->w16n_off[l], nin, nout,
-                                Workspace::pad8(nout), st));
+                                Workspace::pad8(nout), w->split, st));
         }
         if (w->NL == 3) {
             const int n1 = w->n[1], n2 = w->n[2];
-            GCK(w->a16.reserve((size_t)n2 * Workspace::pad8(n1) * 2));
-            GCK(tc::pack_matrix(w->amat.as<float>(), 1, n2, w->a16.as<__nv_bfloat16>(), n2, n1, Workspace::pad8(n1), st));
+            GCK(w->a16.reserve((size_t)n2 * w->rs(n1) * 2));
+            GCK(tc::pack_matrix(w->amat.as<float>(), 1, n2, w->a16.as<__nv_bfloat16>(), n2, n1, Workspace::pad8(n1), w->split, st));
         }
         w->launches += 2 * w->NL + 1;
     }
@@ -1140,8 +1143,8 @@ static cudaError_t enqueue_chain(const RhsPlan& p, const float* probe, float* Vs
 
 // ---- precision = ICNF_BF16_TC: the same RHS on the tcgen05 GEMM (tc_gemm.cuh) -------------------
 static cudaError_t tc_reserve(Workspace* w, long long B) {
-    GCK(w->X16.reserve((size_t)B * Workspace::pad8(w->n[0]) * 2));
-    GCK(w->E16.reserve((size_t)B * Workspace::pad8(w->D) * 2));
+    GCK(w->X16.reserve((size_t)B * w->rs(w->n[0]) * 2));
+    GCK(w->E16.reserve((size_t)B * w->rs(w->D) * 2));
     GCK(w->H16.reserve((size_t)B * w->h16_cols * 2));
     GCK(w->D16.reserve((size_t)B * w->h16_cols * 2));
     GCK(w->G16.reserve((size_t)B * w->h16_cols * 2));
@@ -1158,21 +1161,25 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
     __nv_bfloat16* H = w->H16.as<__nv_bfloat16>();
     __nv_bfloat16* Dv = w->D16.as<__nv_bfloat16>();
     __nv_bfloat16* G = w->G16.as<__nv_bfloat16>();
+    auto P8 = [](int x) { return Workspace::pad8(x); };
     auto act_ptr = [&](__nv_bfloat16* base, int l) { return base + w->h16_off[l] * (size_t)B; };
-    auto pitch = [&](int l) { return Workspace::pad8(w->n[l + 1]); };
-    GCK(tc::pack_input(w->ZI.as<float>(), w->YS.as<float>(), X, B, D, w->tin, w->C, Workspace::pad8(w->n[0]), p.t_fixed,
-                       (const float*)p.ctrl, c_i, done, p.st));
+    // activations of layer l have n[l+1] columns: half pitch P8(n[l+1]), row stride rs(n[l+1])
+    auto set_split = [&](tc::TcArgs& g, int a_cols, int b_cols, int o_cols) {
+        g.split = w->split; g.lo_a = P8(a_cols); g.lo_b = P8(b_cols); g.lo_o = P8(o_cols);
+    };
+    GCK(tc::pack_input(w->ZI.as<float>(), w->YS.as<float>(), X, B, D, w->tin, w->C, P8(w->n[0]), p.t_fixed,
+                       (const float*)p.ctrl, c_i, done, w->split, p.st));
     w->launches++;
     for (int l = 0; l < NL; ++l) {
         tc::TcArgs g;
         memset(&g, 0, sizeof g);
         g.M = (int)B; g.N = w->n[l + 1]; g.K = w->n[l];
         g.bias = p.theta + w->boff[l]; g.act = w->cfg.activation; g.done = done;
-        if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = act_ptr(H, l); g.out1 = act_ptr(Dv, l); g.ldo = pitch(l); }
+        set_split(g, w->n[l], w->n[l], w->n[l + 1]);
+        if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = act_ptr(H, l); g.out1 = act_ptr(Dv, l); g.ldo = w->rs(w->n[l + 1]); }
         else { g.ep = tc::TEP_LIN_SOA; g.out_f32 = w->ZD.as<float>(); g.n_limit = D; }
         const __nv_bfloat16* A = (l == 0) ? X : act_ptr(H, l - 1);
-        const int lda = (l == 0) ? Workspace::pad8(w->n[0]) : pitch(l - 1);
-        GCK(tc::gemm(A, lda, w->w16t.as<__nv_bfloat16>() + w->w16t_off[l], Workspace::pad8(w->n[l]), g, p.st));
+        GCK(tc::gemm(A, w->rs(w->n[l]), w->w16t.as<__nv_bfloat16>() + w->w16t_off[l], w->rs(w->n[l]), g, p.st));
         w->launches++;
     }
     if (p.exact) {
@@ -1180,15 +1187,16 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
         if (NL == 1) {
             g_trace_dot_kernel<<<blocks_for(B), 256, 0, p.st>>>(w->gvec.as<float>(), nullptr, TR, D, B, 0.f, done);
         } else if (NL == 2) {
-            GCK(tc::trace_dot(w->gvec.as<float>(), act_ptr(Dv, 0), TR, w->n[1], pitch(0), B, done, p.st));
+            GCK(tc::trace_dot(w->gvec.as<float>(), act_ptr(Dv, 0), TR, w->n[1], P8(w->n[1]), B, done, w->split, p.st));
         } else if (NL == 3) {
             tc::TcArgs g;
             memset(&g, 0, sizeof g);
             g.M = (int)B; g.N = w->n[2]; g.K = w->n[1]; g.ep = tc::TEP_TRACE; g.done = done;
-            g.aux = act_ptr(Dv, 1); g.ldo = pitch(1); g.out_f32 = TR;
+            set_split(g, w->n[1], w->n[1], w->n[2]);
+            g.aux = act_ptr(Dv, 1); g.ldo = w->rs(w->n[2]); g.out_f32 = TR;
             g.atomic_rowsum = 1;
             GCK(cudaMemsetAsync(TR, 0, sizeof(float) * B, p.st));
-            GCK(tc::gemm(act_ptr(Dv, 0), pitch(0), w->a16.as<__nv_bfloat16>(), Workspace::pad8(w->n[1]), g, p.st));
+            GCK(tc::gemm(act_ptr(Dv, 0), w->rs(w->n[1]), w->a16.as<__nv_bfloat16>(), w->rs(w->n[1]), g, p.st));
         } else {
             return cudaErrorNotSupported;   // exact trace of deeper networks: fp32 families only
         }
@@ -1196,17 +1204,17 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
         return cudaGetLastError();
     }
     __nv_bfloat16* E = w->E16.as<__nv_bfloat16>();
-    GCK(tc::pack_soa(w->EPS.as<float>(), E, B, D, Workspace::pad8(D), done, p.st));
+    GCK(tc::pack_soa(w->EPS.as<float>(), E, B, D, P8(D), done, w->split, p.st));
     w->launches++;
     for (int l = NL - 1; l >= 0; --l) {
         tc::TcArgs g;
         memset(&g, 0, sizeof g);
         g.M = (int)B; g.N = (l == 0) ? D : w->n[l]; g.K = w->n[l + 1]; g.done = done;
-        if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = act_ptr(G, l - 1); g.aux = act_ptr(Dv, l - 1); g.ldo = pitch(l - 1); }
+        set_split(g, w->n[l + 1], w->n[l + 1], w->n[l]);
+        if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = act_ptr(G, l - 1); g.aux = act_ptr(Dv, l - 1); g.ldo = w->rs(w->n[l]); }
         else { g.ep = tc::TEP_PLAIN_SOA; g.out_f32 = w->Q.as<float>(); g.n_limit = D; }
         const __nv_bfloat16* A = (l == NL - 1) ? E : act_ptr(G, l);
-        const int lda = (l == NL - 1) ? Workspace::pad8(D) : pitch(l);
-        GCK(tc::gemm(A, lda, w->w16n.as<__nv_bfloat16>() + w->w16n_off[l], Workspace::pad8(w->n[l + 1]), g, p.st));
+        GCK(tc::gemm(A, w->rs(w->n[l + 1]), w->w16n.as<__nv_bfloat16>() + w->w16n_off[l], w->rs(w->n[l + 1]), g, p.st));
         w->launches++;
     }
     return cudaSuccess;

@@ -34,35 +34,46 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// lda / ldb are the full row pitches; with g.split every row is [hi | lo] and the tensor map's inner
+// extent covers both halves (the zero padding between K and the pitch keeps the hi tiles clean)
 cudaError_t gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, TcArgs g, cudaStream_t st) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SPLIT);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     CUtensorMap mapA, mapB;
-    if (!make_map(&mapA, A, (uint64_t)g.M, (uint64_t)g.K, (uint64_t)lda, TBM) ||
-        !make_map(&mapB, B, (uint64_t)g.N, (uint64_t)g.K, (uint64_t)ldb, TBN))
+    const uint64_t ka = g.split ? (uint64_t)g.lo_a + g.K : (uint64_t)g.K;
+    const uint64_t kb = g.split ? (uint64_t)g.lo_b + g.K : (uint64_t)g.K;
+    if (!make_map(&mapA, A, (uint64_t)g.M, ka, (uint64_t)lda, TBM) || !make_map(&mapB, B, (uint64_t)g.N, kb, (uint64_t)ldb, TBN))
         return cudaErrorInvalidValue;
     dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN);
-    tc_gemm_kernel<<<grid, TTHREADS, SMEM_BYTES, st>>>(mapA, mapB, g);
+    if (g.split) tc_gemm_kernel<true><<<grid, TTHREADS, SMEM_BYTES_SPLIT, st>>>(mapA, mapB, g);
+    else tc_gemm_kernel<false><<<grid, TTHREADS, SMEM_BYTES, st>>>(mapA, mapB, g);
     return cudaGetLastError();
 }
 
 // ---- packing kernels ------------------------------------------------------------------------
 // fp32 matrix element (r, c) at src[r * rs + c * cs] -> bf16 dst[r * pitch + c], zero padding up to pitch
+// `pitch` = columns of one half; with split the row is [hi (pitch) | lo (pitch)]
 __global__ void pack_matrix_kernel(const float* src, long long rs, long long cs, __nv_bfloat16* dst, int rows, int cols,
-                                   int pitch) {
+                                   int pitch, int split) {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)rows * pitch) return;
     const int r = (int)(idx / pitch), c = (int)(idx - (long long)r * pitch);
-    dst[idx] = __float2bfloat16_rn(c < cols ? src[r * rs + c * cs] : 0.f);
+    const float x = c < cols ? src[r * rs + c * cs] : 0.f;
+    const long long rowp = (long long)r * (split ? 2 * pitch : pitch);
+    const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+    dst[rowp + c] = hi;
+    if (split) dst[rowp + pitch + c] = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 cudaError_t pack_matrix(const float* src, long long rs, long long cs, __nv_bfloat16* dst, int rows, int cols, int pitch,
-                        cudaStream_t st) {
+                        int split, cudaStream_t st) {
     const long long n = (long long)rows * pitch;
-    pack_matrix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, rs, cs, dst, rows, cols, pitch);
+    pack_matrix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, rs, cs, dst, rows, cols, pitch, split);
     return cudaGetLastError();
 }
 
@@ -71,7 +82,7 @@ cudaError_t pack_matrix(const float* src, long long rs, long long cs, __nv_bfloa
 // then `ys`; pack_soa is the special case tin = 0, C = 0.
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* zi, const float* ys, __nv_bfloat16* X, long long B, int D,
                                                         int tin, int C, int pitch, float t_fixed, const float* ctrl_f, float c_i,
-                                                        const int* done) {
+                                                        const int* done, int split) {
     if (done && *done) return;
     __shared__ float tile[32][33];
     const long long b0 = (long long)blockIdx.x * 32;
@@ -93,34 +104,46 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* zi, const f
     for (int bb = ty; bb < 32; bb += 8) {
         const long long b = b0 + bb;
         const int k = k0 + tx;
-        if (b < B && k < pitch) X[b * pitch + k] = __float2bfloat16_rn(tile[tx][bb]);
+        if (b < B && k < pitch) {
+            const float x = tile[tx][bb];
+            const long long rowp = b * (split ? 2 * pitch : pitch);
+            const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+            X[rowp + k] = hi;
+            if (split) X[rowp + pitch + k] = __float2bfloat16_rn(x - __bfloat162float(hi));
+        }
     }
 }
 cudaError_t pack_input(const float* zi, const float* ys, __nv_bfloat16* X, long long B, int D, int tin, int C, int pitch,
-                       float t_fixed, const float* ctrl_f, float c_i, const int* done, cudaStream_t st) {
+                       float t_fixed, const float* ctrl_f, float c_i, const int* done, int split, cudaStream_t st) {
     dim3 grid((unsigned)((B + 31) / 32), (unsigned)((pitch + 31) / 32));
-    pack_rows_kernel<<<grid, 256, 0, st>>>(zi, ys, X, B, D, tin, C, pitch, t_fixed, ctrl_f, c_i, done);
+    pack_rows_kernel<<<grid, 256, 0, st>>>(zi, ys, X, B, D, tin, C, pitch, t_fixed, ctrl_f, c_i, done, split);
     return cudaGetLastError();
 }
-cudaError_t pack_soa(const float* src, __nv_bfloat16* dst, long long B, int rows, int pitch, const int* done, cudaStream_t st) {
+cudaError_t pack_soa(const float* src, __nv_bfloat16* dst, long long B, int rows, int pitch, const int* done, int split,
+                     cudaStream_t st) {
     dim3 grid((unsigned)((B + 31) / 32), (unsigned)((pitch + 31) / 32));
-    pack_rows_kernel<<<grid, 256, 0, st>>>(src, nullptr, dst, B, rows, 0, 0, pitch, 0.f, nullptr, 0.f, done);
+    pack_rows_kernel<<<grid, 256, 0, st>>>(src, nullptr, dst, B, rows, 0, 0, pitch, 0.f, nullptr, 0.f, done, split);
     return cudaGetLastError();
 }
 
 // one hidden layer exact trace: TR[b] = sum_k gvec[k] * D1[b][k]
 __global__ void trace_dot_kernel(const float* gvec, const __nv_bfloat16* D1, float* TR, int n1, int pitch, long long B,
-                                 const int* done) {
+                                 const int* done, int split) {
     if (done && *done) return;
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const long long rowp = b * (split ? 2 * pitch : pitch);
     float s = 0.f;
-    for (int k = 0; k < n1; ++k) s = fmaf(gvec[k], __bfloat162float(D1[b * pitch + k]), s);
+    for (int k = 0; k < n1; ++k) {
+        float d = __bfloat162float(D1[rowp + k]);
+        if (split) d += __bfloat162float(D1[rowp + pitch + k]);
+        s = fmaf(gvec[k], d, s);
+    }
     TR[b] = s;
 }
 cudaError_t trace_dot(const float* gvec, const __nv_bfloat16* D1, float* TR, int n1, int pitch, long long B, const int* done,
-                      cudaStream_t st) {
-    trace_dot_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(gvec, D1, TR, n1, pitch, B, done);
+                      int split, cudaStream_t st) {
+    trace_dot_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(gvec, D1, TR, n1, pitch, B, done, split);
     return cudaGetLastError();
 }
 
@@ -130,25 +153,27 @@ cudaError_t trace_dot(const float* gvec, const __nv_bfloat16* D1, float* TR, int
 // Self-test of the tensor-core GEMM: D (N x M, SoA: D[n * M + m]) = A (M x K) * B (N x K)' with
 // bf16-rounded inputs; host fp32 buffers in and out.
 extern "C" __attribute__((visibility("default"))) int icnf_tc_gemm_selftest(int M, int N, int K, const float* A,
-                                                                           const float* B, float* D) {
+                                                                           const float* B, float* D, int split) {
     using namespace icnf::tc;
     const int kp = (K + 7) & ~7;
+    const int rp = split ? 2 * kp : kp;
     float *dA = nullptr, *dB = nullptr, *dD = nullptr;
     __nv_bfloat16 *a16 = nullptr, *b16 = nullptr;
     int rc = 0;
     auto ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == 0) rc = 2; return e == cudaSuccess; };
     if (ok(cudaMalloc(&dA, sizeof(float) * M * K)) && ok(cudaMalloc(&dB, sizeof(float) * N * K)) &&
-        ok(cudaMalloc(&dD, sizeof(float) * M * N)) && ok(cudaMalloc(&a16, 2 * (size_t)M * kp)) &&
-        ok(cudaMalloc(&b16, 2 * (size_t)N * kp))) {
+        ok(cudaMalloc(&dD, sizeof(float) * M * N)) && ok(cudaMalloc(&a16, 2 * (size_t)M * rp)) &&
+        ok(cudaMalloc(&b16, 2 * (size_t)N * rp))) {
         ok(cudaMemcpy(dA, A, sizeof(float) * M * K, cudaMemcpyHostToDevice));
         ok(cudaMemcpy(dB, B, sizeof(float) * N * K, cudaMemcpyHostToDevice));
         ok(cudaMemset(dD, 0, sizeof(float) * M * N));
-        ok(pack_matrix(dA, K, 1, a16, M, K, kp, 0));
-        ok(pack_matrix(dB, K, 1, b16, N, K, kp, 0));
+        ok(pack_matrix(dA, K, 1, a16, M, K, kp, split, 0));
+        ok(pack_matrix(dB, K, 1, b16, N, K, kp, split, 0));
         TcArgs g;
         memset(&g, 0, sizeof g);
         g.M = M; g.N = N; g.K = K; g.ep = TEP_PLAIN_SOA; g.out_f32 = dD; g.n_limit = N;
-        ok(gemm(a16, kp, b16, kp, g, 0));
+        g.split = split; g.lo_a = kp; g.lo_b = kp;
+        ok(gemm(a16, rp, b16, rp, g, 0));
         ok(cudaDeviceSynchronize());
         ok(cudaMemcpy(D, dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost));
     }

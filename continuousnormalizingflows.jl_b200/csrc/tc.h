@@ -12,6 +12,8 @@ namespace tc {
 constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3, TTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int A_TILE_BYTES = TBM * TBK * 2, B_TILE_BYTES = TBN * TBK * 2;
 constexpr int SMEM_BYTES = TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + TBN * 4 /*bias*/;
+// split precision (bf16 x 3: every operand is hi + lo, three MMAs per K step): four tiles per stage
+constexpr int SMEM_BYTES_SPLIT = TSTAGES * 2 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256 + TBN * 4;
 
 enum TcEpilogue {
     TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)
@@ -33,15 +35,19 @@ struct TcArgs {
     int n_limit;               // SoA: only units < n_limit are written
     int atomic_rowsum;         // TEP_TRACE with several unit tiles
     const int* done;
+    // split precision: every bf16 matrix row is [hi (pitch) | lo (pitch)]; lo_* = column offset of the
+    // lo half in A, B and in out0/out1/aux (ldo is then the full row pitch, 2 x lo_o)
+    int split, lo_a, lo_b, lo_o;
 };
 
 cudaError_t gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, TcArgs g, cudaStream_t st);
 cudaError_t pack_matrix(const float* src, long long rs, long long cs, __nv_bfloat16* dst, int rows, int cols, int pitch,
-                        cudaStream_t st);
+                        int split, cudaStream_t st);
 cudaError_t pack_input(const float* zi, const float* ys, __nv_bfloat16* X, long long B, int D, int tin, int C, int pitch,
-                       float t_fixed, const float* ctrl_f, float c_i, const int* done, cudaStream_t st);
+                       float t_fixed, const float* ctrl_f, float c_i, const int* done, int split, cudaStream_t st);
 cudaError_t trace_dot(const float* gvec, const __nv_bfloat16* D1, float* TR, int n1, int pitch, long long B, const int* done,
-                      cudaStream_t st);
-cudaError_t pack_soa(const float* src, __nv_bfloat16* dst, long long B, int rows, int pitch, const int* done, cudaStream_t st);
+                      int split, cudaStream_t st);
+cudaError_t pack_soa(const float* src, __nv_bfloat16* dst, long long B, int rows, int pitch, const int* done, int split,
+                     cudaStream_t st);
 }  // namespace tc
 }  // namespace icnf

@@ -103,18 +103,88 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-__global__ void __launch_bounds__(TTHREADS, 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                              const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+// value -> (hi, lo) bf16 pair: hi = bf16(x), lo = bf16(x - hi); hi + lo carries 16 mantissa bits
+__device__ __forceinline__ void split_bf16(float x, float& hi, float& lo) {
+    hi = __bfloat162float(__float2bfloat16_rn(x));
+    lo = x - hi;
+}
+
+// store 32 consecutive columns of one row as bf16 (and their lo halves when SPLIT)
+template <bool SPLIT>
+__device__ __forceinline__ void store_row32(__nv_bfloat16* base, size_t row_off, int nb, int pitch, int lo_o,
+                                            const float (&v)[32]) {
+    uint32_t hp[16], lp[16];
+#pragma unroll
+    for (int j = 0; j < 32; j += 2) {
+        if constexpr (SPLIT) {
+            float h0, l0, h1, l1;
+            split_bf16(v[j], h0, l0);
+            split_bf16(v[j + 1], h1, l1);
+            hp[j / 2] = pack_bf16(h0, h1);
+            lp[j / 2] = pack_bf16(l0, l1);
+        } else {
+            hp[j / 2] = pack_bf16(v[j], v[j + 1]);
+        }
+    }
+    uint4* ho = reinterpret_cast<uint4*>(base + row_off + nb);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (nb + q * 8 < pitch) {
+            ho[q] = make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]);
+            if constexpr (SPLIT) {
+                uint4* lo = reinterpret_cast<uint4*>(base + row_off + lo_o + nb);
+                lo[q] = make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]);
+            }
+        }
+    }
+}
+// load 32 consecutive columns of one row (hi + lo when SPLIT) as fp32
+template <bool SPLIT>
+__device__ __forceinline__ void load_row32(const __nv_bfloat16* base, size_t row_off, int nb, int pitch, int lo_o,
+                                           float (&v)[32]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (nb + q * 8 < pitch) {
+            const uint4 a4 = *reinterpret_cast<const uint4*>(base + row_off + nb + q * 8);
+            const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
+            uint32_t lw[4] = {0u, 0u, 0u, 0u};
+            if constexpr (SPLIT) {
+                const uint4 l4 = *reinterpret_cast<const uint4*>(base + row_off + lo_o + nb + q * 8);
+                lw[0] = l4.x; lw[1] = l4.y; lw[2] = l4.z; lw[3] = l4.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const __nv_bfloat162 h2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[e]);
+                float x0 = __low2float(h2), x1 = __high2float(h2);
+                if constexpr (SPLIT) {
+                    const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&lw[e]);
+                    x0 += __low2float(l2);
+                    x1 += __high2float(l2);
+                }
+                v[q * 8 + e * 2] = x0;
+                v[q * 8 + e * 2 + 1] = x1;
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[q * 8 + e] = 0.f;
+        }
+    }
+}
+
+template <bool SPLIT>
+__global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                          const __grid_constant__ CUtensorMap mapB, TcArgs g) {
     if (g.done && *g.done) return;
+    constexpr int NT_A = SPLIT ? 2 : 1;   // tiles per operand and stage
+    constexpr int STAGE_BYTES = NT_A * (A_TILE_BYTES + B_TILE_BYTES);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + TSTAGES * A_TILE_BYTES;
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TSTAGES * (A_TILE_BYTES + B_TILE_BYTES));
+    // stage s: [A_hi | A_lo? | B_hi | B_lo?]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TSTAGES * STAGE_BYTES);
     uint64_t* empty = full + TSTAGES;
     uint64_t* tmem_full = empty + TSTAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* sbias = reinterpret_cast<float*>(smem + TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 256);
+    float* sbias = reinterpret_cast<float*>(smem + TSTAGES * STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
@@ -142,10 +212,13 @@ __global__ void __launch_bounds__(TTHREADS, 2) tc_gemm_kernel(const __grid_const
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % TSTAGES;
                 const uint32_t ph = (kb / TSTAGES) & 1;
+                uint8_t* st = smem + s * STAGE_BYTES;
                 mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], A_TILE_BYTES + B_TILE_BYTES);
-                tma_load_2d(sA + s * A_TILE_BYTES, &mapA, &full[s], kb * TBK, m0);
-                tma_load_2d(sB + s * B_TILE_BYTES, &mapB, &full[s], kb * TBK, n0);
+                mbar_expect_tx(&full[s], STAGE_BYTES);
+                tma_load_2d(st, &mapA, &full[s], kb * TBK, m0);
+                if constexpr (SPLIT) tma_load_2d(st + A_TILE_BYTES, &mapA, &full[s], g.lo_a + kb * TBK, m0);
+                tma_load_2d(st + NT_A * A_TILE_BYTES, &mapB, &full[s], kb * TBK, n0);
+                if constexpr (SPLIT) tma_load_2d(st + NT_A * A_TILE_BYTES + B_TILE_BYTES, &mapB, &full[s], g.lo_b + kb * TBK, n0);
             }
         }
     } else if (warp == 1) {
@@ -155,21 +228,31 @@ __global__ void __launch_bounds__(TTHREADS, 2) tc_gemm_kernel(const __grid_const
             for (int kb = 0; kb < nkb; ++kb) {
                 const int s = kb % TSTAGES;
                 const uint32_t ph = (kb / TSTAGES) & 1;
+                uint8_t* st = smem + s * STAGE_BYTES;
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
-                const uint64_t adesc = make_desc(smem_u32(sA + s * A_TILE_BYTES));
-                const uint64_t bdesc = make_desc(smem_u32(sB + s * B_TILE_BYTES));
+                const uint64_t a_hi = make_desc(smem_u32(st));
+                const uint64_t b_hi = make_desc(smem_u32(st + NT_A * A_TILE_BYTES));
 #pragma unroll
                 for (int k = 0; k < TBK / 16; ++k) {
                     // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-                    tc_mma_bf16(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                    tc_mma_bf16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                }
+                if constexpr (SPLIT) {
+                    // a b ~ a_hi b_hi + a_lo b_hi + a_hi b_lo  (lo x lo is below fp32 rounding)
+                    const uint64_t a_lo = make_desc(smem_u32(st + A_TILE_BYTES));
+                    const uint64_t b_lo = make_desc(smem_u32(st + NT_A * A_TILE_BYTES + B_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                 }
                 tc_commit(&empty[s]);
             }
             tc_commit(tmem_full);
         }
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4 =====
         // stage this tile's bias slice while the main loop runs
         {
             const int e = threadIdx.x - 64;   // 0..255
@@ -183,6 +266,7 @@ __global__ void __launch_bounds__(TTHREADS, 2) tc_gemm_kernel(const __grid_const
         const int chalf = (warp - 2) >> 2;
         const int m = m0 + q * 32 + lane;
         const bool row_ok = m < g.M;
+        const int pitch = SPLIT ? g.lo_o : g.ldo;   // columns of one half
         float rowsum = 0.f;
         for (int c0 = chalf * (TBN / 2); c0 < (chalf + 1) * (TBN / 2); c0 += 32) {
             if (n0 + c0 >= g.N) break;   // warp-uniform
@@ -190,49 +274,28 @@ __global__ void __launch_bounds__(TTHREADS, 2) tc_gemm_kernel(const __grid_const
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
             if (!row_ok) continue;
             const int nb = n0 + c0;
+            const size_t row_off = (size_t)m * g.ldo;
             if (g.ep == TEP_ACT) {
-                uint32_t hp[16], dp[16];
+                float hv[32], dv[32];
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float h0 = 0.f, d0 = 0.f, h1 = 0.f, d1 = 0.f;
-                    if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + sbias[c0 + j], h0, d0);
-                    if (nb + j + 1 < g.N) act_eval_rt(g.act, __uint_as_float(r[j + 1]) + sbias[c0 + j + 1], h1, d1);
-                    hp[j / 2] = pack_bf16(h0, h1);
-                    dp[j / 2] = pack_bf16(d0, d1);
+                for (int j = 0; j < 32; ++j) {
+                    hv[j] = 0.f; dv[j] = 0.f;
+                    if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + sbias[c0 + j], hv[j], dv[j]);
                 }
-                uint4* ho = reinterpret_cast<uint4*>(g.out0 + (size_t)m * g.ldo + nb);
-                uint4* dO = reinterpret_cast<uint4*>(g.out1 + (size_t)m * g.ldo + nb);
-#pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    if (nb + v * 8 < g.ldo) {
-                        ho[v] = make_uint4(hp[4 * v], hp[4 * v + 1], hp[4 * v + 2], hp[4 * v + 3]);
-                        dO[v] = make_uint4(dp[4 * v], dp[4 * v + 1], dp[4 * v + 2], dp[4 * v + 3]);
-                    }
-                }
+                store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, hv);
+                store_row32<SPLIT>(g.out1, row_off, nb, pitch, g.lo_o, dv);
             } else if (g.ep == TEP_MULD) {
-                const uint4* ax = reinterpret_cast<const uint4*>(g.aux + (size_t)m * g.ldo + nb);
-                uint4* go = reinterpret_cast<uint4*>(g.out0 + (size_t)m * g.ldo + nb);
+                float dv[32], gv[32];
+                load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    if (nb + v * 8 >= g.ldo) continue;
-                    const uint4 a4 = ax[v];
-                    const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
-                    uint32_t ow[4];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const __nv_bfloat162 d2 = *reinterpret_cast<const __nv_bfloat162*>(&aw[e]);
-                        const int j = v * 8 + e * 2;
-                        const float g0 = (nb + j < g.N) ? __uint_as_float(r[j]) * __low2float(d2) : 0.f;
-                        const float g1 = (nb + j + 1 < g.N) ? __uint_as_float(r[j + 1]) * __high2float(d2) : 0.f;
-                        ow[e] = pack_bf16(g0, g1);
-                    }
-                    go[v] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                }
+                for (int j = 0; j < 32; ++j) gv[j] = (nb + j < g.N) ? __uint_as_float(r[j]) * dv[j] : 0.f;
+                store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, gv);
             } else if (g.ep == TEP_TRACE) {
-                const __nv_bfloat16* ax = g.aux + (size_t)m * g.ldo + nb;
+                float dv[32];
+                load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
 #pragma unroll
                 for (int j = 0; j < 32; ++j)
-                    if (nb + j < g.N) rowsum = fmaf(__uint_as_float(r[j]), __bfloat162float(ax[j]), rowsum);
+                    if (nb + j < g.N) rowsum = fmaf(__uint_as_float(r[j]), dv[j], rowsum);
             } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {

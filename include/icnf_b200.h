@@ -87,7 +87,9 @@ typedef enum icnf_eps_kind {
 
 typedef enum icnf_precision {
     ICNF_FP32 = 0,              /* fp32 FMA path (parity path, every width)              */
-    ICNF_BF16_TC = 1            /* bf16 tcgen05 tensor-core RHS for wide MLPs            */
+    ICNF_BF16_TC = 1,           /* bf16 tcgen05 tensor-core RHS for wide MLPs (about 1e-2 accurate) */
+    ICNF_BF16X3_TC = 2          /* split bf16 (hi + lo operands, 3 tcgen05 MMAs per K step): tensor
+                                 * cores at about 1e-5 relative accuracy, for the 1e-4 parity bar */
 } icnf_precision;
 
 /* Mirror of the `ICNF` struct and keyword constructor (src/core/icnf.jl:16-141).
@@ -246,8 +248,9 @@ ICNF_API int icnf_kernel_times(icnf_handle* h, float* ms4);
 ICNF_API int icnf_measure_fp32_peak(int device, float* tflops);
 /* Self-test of the tcgen05 GEMM behind precision = ICNF_BF16_TC: D (N x M, stored
  * D[n * M + m]) = A (M x K, row-major) * B (N x K, row-major)' with inputs rounded to
- * bf16 and fp32 accumulation; host buffers; runs on the current device. */
-ICNF_API int icnf_tc_gemm_selftest(int M, int N, int K, const float* A, const float* B, float* D);
+ * bf16 (split = 0) or to bf16 hi + lo pairs (split = 1, ICNF_BF16X3_TC) and fp32
+ * accumulation; host buffers; runs on the current device. */
+ICNF_API int icnf_tc_gemm_selftest(int M, int N, int K, const float* A, const float* B, float* D, int split);
 
 #ifdef __cplusplus
 }

@@ -34,9 +34,15 @@ def test_tcgen05_gemm_selftest(m, shape):
     A = rng.standard_normal((M, K)).astype(np.float32)
     B = rng.standard_normal((N, K)).astype(np.float32)
     D = np.zeros((N, M), np.float32)
-    assert m.lib.icnf_tc_gemm_selftest(M, N, K, A.ctypes.data, B.ctypes.data, D.ctypes.data) == 0
+    assert m.lib.icnf_tc_gemm_selftest(M, N, K, A.ctypes.data, B.ctypes.data, D.ctypes.data, 0) == 0
     ref = _bf16(B) @ _bf16(A).T
     assert np.abs(D - ref).max() / np.abs(ref).max() < 1e-5
+    # split precision (hi + lo operands, three MMAs): close to the exact fp32 product
+    D3 = np.zeros((N, M), np.float32)
+    assert m.lib.icnf_tc_gemm_selftest(M, N, K, A.ctypes.data, B.ctypes.data, D3.ctypes.data, 1) == 0
+    exact = B.astype(np.float64) @ A.astype(np.float64).T
+    assert np.abs(D3 - exact).max() / np.abs(exact).max() < 3e-5
+    assert np.abs(D3 - exact).max() < 0.02 * np.abs(D - exact).max()
 
 
 WIDE = {
@@ -91,6 +97,48 @@ def test_solve_bf16_tc_vs_fp32_generic(m):
     g16 = m.generate(icnf16, m.TestMode(), ys, theta, {}, B, z0=z0, tspan=icnf16.tspan)
     gref = O.generate(om, O.TEST, t64(z0), t64(theta), None, t64(ys)).numpy()
     assert norm_rel_err(g16, gref) < BF16_TOL
+
+
+X3_TOL = 1e-4   # the north-star tolerance: split precision must meet it like the fp32 families
+
+
+@pytest.mark.parametrize("name", list(WIDE))
+def test_rhs_bf16x3_tc_meets_fp32_tolerance(m, name):
+    icnf = _make(m, name, precision="bf16x3_tc")
+    assert icnf.kernel_family == "tc"
+    B = 515
+    om, theta, xs, eps, ys = make_inputs(icnf, B)
+    u = np.random.default_rng(3).standard_normal((om.n_state, B)).astype(np.float32)
+    modes = [(m.TrainMode(True), O.TRAIN_REG), (m.TrainMode(False), O.TRAIN_NOREG)]
+    if len(icnf.sizes) == 4:
+        modes.append((m.TestMode(), O.TEST))
+    for mode, omode in modes:
+        du = m.augmented_f(icnf, mode, u, theta, 0.37, eps=eps, ys=ys)
+        ref = O.rhs_closed(om, omode, t64(u), t64(theta), 0.37, t64(eps), t64(ys)).numpy()
+        for r0, r1 in ((0, om.d), (om.d, om.d + 1), (om.d + 1, om.n_state)):
+            assert norm_rel_err(du[r0:r1], ref[r0:r1]) < X3_TOL, (mode, r0, norm_rel_err(du[r0:r1], ref[r0:r1]))
+
+
+def test_solve_bf16x3_tc_matches_oracle_and_step_count(m):
+    icnf3 = _make(m, "cond64", precision="bf16x3_tc")
+    icnf32 = _make(m, "cond64")
+    B = 700
+    om, theta, xs, eps, ys = make_inputs(icnf3, B)
+    theta = (0.5 * theta).astype(np.float32)
+    kw = dict(eps=eps, tspan=icnf3.tspan)
+    l3, r3 = m.inference(icnf3, m.TrainMode(True), xs, ys, theta, {}, **kw)
+    s3 = icnf3.last_stats
+    l32, r32 = m.inference(icnf32, m.TrainMode(True), xs, ys, theta, {}, **kw)
+    s32 = icnf32.last_stats
+    ref, rr = O.inference(om, O.TRAIN_REG, t64(xs), t64(theta), t64(eps), t64(ys))
+    assert norm_rel_err(l3, ref.numpy()) < X3_TOL
+    assert norm_rel_err(r3[0], rr[0].numpy()) < 1e-3
+    # no bf16 noise floor: the adaptive controller takes (almost) the same steps as fp32
+    assert abs(s3.naccept - s32.naccept) <= 1, (s3.naccept, s32.naccept)
+    z0 = np.random.default_rng(5).standard_normal((om.d, B)).astype(np.float32)
+    g3 = m.generate(icnf3, m.TestMode(), ys, theta, {}, B, z0=z0, tspan=icnf3.tspan)
+    gref = O.generate(om, O.TEST, t64(z0), t64(theta), None, t64(ys)).numpy()
+    assert norm_rel_err(g3, gref) < X3_TOL
 
 
 def test_bf16_tc_gradient_is_reported_unsupported(m):
