@@ -294,7 +294,7 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
         a.dt = r.sol->dt;
         if (r.want_ckpt) {
             a.max_ckpt_steps = a.nsteps;
-            CK(h, h->ckpt.reserve(sizeof(float) * (size_t)(a.nsteps + 1) * r.B * D));
+            CK(h, h->ckpt.reserve(sizeof(float) * (size_t)(a.nsteps + 1) * r.B * D * std::max(1, h->fam->ckpt_stages)));
             CK(h, h->steps.reserve(sizeof(StepRec) * (size_t)(a.nsteps + 1)));
             a.ckpt = h->ckpt.as<float>();
             a.steps = h->steps.as<StepRec>();
@@ -325,7 +325,7 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
     a.partials = h->partials.as<double>();
     if (r.want_ckpt) {
         a.max_ckpt_steps = std::min(a.ctl.max_steps, 256);
-        CK(h, h->ckpt.reserve(sizeof(float) * (size_t)(a.max_ckpt_steps + 1) * r.B * D));
+        CK(h, h->ckpt.reserve(sizeof(float) * (size_t)(a.max_ckpt_steps + 1) * r.B * D * std::max(1, h->fam->ckpt_stages)));
         CK(h, h->steps.reserve(sizeof(StepRec) * (size_t)(a.max_ckpt_steps + 1)));
         a.ckpt = h->ckpt.as<float>();
         a.steps = h->steps.as<StepRec>();

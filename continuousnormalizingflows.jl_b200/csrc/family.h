@@ -43,6 +43,7 @@ struct Family {
     int supports_backward;
     int fuses_loss_sum_adaptive;     // the adaptive solve writes the scalar loss itself (SolveArgs::out_loss)
     int adaptive_threads;            // CTA size of the cooperative adaptive kernel (0: not cooperative)
+    int ckpt_stages;                 // training checkpoints per step and sample, in units of D' floats (tiny: 6 stage inputs)
 };
 
 std::vector<const Family*>& tiny_registry();

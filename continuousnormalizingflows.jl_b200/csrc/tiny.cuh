@@ -400,6 +400,14 @@ __device__ __forceinline__ float write_outputs(const SolveArgs& a, int64_t b, in
     return lossterm;
 }
 
+// Training checkpoints: the forward solve records the INPUT of every Tsit5 stage of every accepted
+// step, ckpt[step][sample][stage 0..5][D'] (stage 0 = the state at the start of the step; slot
+// `nsteps`, stage 0 = the final state), so the backward sweep never re-integrates a step.
+template <class N>
+__host__ __device__ __forceinline__ int64_t ckpt_index(int64_t step, int64_t B, int64_t b, int stage) {
+    return ((step * B + b) * 6 + stage) * N::D;
+}
+
 // stage-derivative storage in shared memory: K(i)[r] for stage i, row r, this thread
 struct StageMem {
     float* base;
@@ -442,10 +450,6 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_FWD) solve_fixed_kernel(con
         load_sample_consts<N>(a, b, sm);
         float z[N::D], l, E, n;
         load_state<N>(a, b, nvars, z, l, E, n);
-        if (a.ckpt) {
-#pragma unroll
-            for (int j = 0; j < N::D; ++j) a.ckpt[b * N::D + j] = z[j];
-        }
         for (int step = 0; step < a.nsteps; ++step) {
             const float tb = fminf(span, step * a.dt);
             const float hmag = fminf(a.dt, span - tb);
@@ -463,6 +467,10 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_FWD) solve_fixed_kernel(con
                     for (int j = 0; j < N::D; ++j) sm.x[j] = fmaf(c, K.at(jj * N::D + j), sm.x[j]);
                 }
                 if constexpr (N::TIN) sm.x[N::D] = fmaf(c_c[i], h, t);
+                if (a.ckpt) {
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) a.ckpt[ckpt_index<N>(step, a.B, b, i) + j] = sm.x[j];
+                }
                 float kz[N::D], kl, kE, kn;
                 rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kl, kE, kn);
                 const float bi = c_a[6][i];
@@ -480,10 +488,10 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_FWD) solve_fixed_kernel(con
             l = fmaf(h, sl, l);
             E = fmaf(h, sE, E);
             n = fmaf(h, sn, n);
-            if (a.ckpt) {
+        }
+        if (a.ckpt) {
 #pragma unroll
-                for (int j = 0; j < N::D; ++j) a.ckpt[((int64_t)(step + 1) * a.B + b) * N::D + j] = z[j];
-            }
+            for (int j = 0; j < N::D; ++j) a.ckpt[ckpt_index<N>(a.nsteps, a.B, b, 0) + j] = z[j];
         }
         write_outputs<N>(a, b, nvars, z, l, E, n);
     }
@@ -630,6 +638,10 @@ __global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __g
                     tt = (i == 6 && last) ? a.t1 : fmaf(c_c[i], h, t);
                 }
                 if constexpr (N::TIN) sm.x[N::D] = tt;
+                if (a.ckpt && phase == P_STEP && i < 6) {
+#pragma unroll
+                    for (int j = 0; j < N::D; ++j) a.ckpt[ckpt_index<N>(nacc, a.B, b, i) + j] = sm.x[j];
+                }
                 // ---- the one RHS call site
                 rhs_eval<N, EXACT>(sw, sm.x, sm.eps, a.reg_e, a.reg_n, a.squared, kz, kx[0], kx[1], kx[2]);
                 // ---- stage bookkeeping
@@ -665,7 +677,7 @@ __global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __g
                 }
                 if (a.ckpt) {
 #pragma unroll
-                    for (int j = 0; j < N::D; ++j) a.ckpt[b * N::D + j] = z[j];
+                    for (int j = 0; j < N::D; ++j) a.ckpt[ckpt_index<N>(0, a.B, b, 0) + j] = z[j];
                 }
             } else if (phase == P_PROBE) {
 #pragma unroll
@@ -693,7 +705,7 @@ __global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __g
                     acc_a += (double)(r * r);
                     uo[j] = zn;
                     ko[j] = kz[j];
-                    if (a.ckpt) a.ckpt[((int64_t)(nacc + 1) * a.B + b) * N::D + j] = zn;
+                    if (a.ckpt) a.ckpt[ckpt_index<N>(nacc + 1, a.B, b, 0) + j] = zn;
                 }
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
@@ -950,8 +962,7 @@ __device__ __forceinline__ void zdot_eval(const WBlock<N>& sw, const float (&x)[
 template <class N, bool EXACT>
 __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_BWD) backward_kernel(const __grid_constant__ WBlock<N> sw, BackwardArgs a) {
     extern __shared__ __align__(16) float smem[];
-    StageMem Z{smem};                  // stage inputs Z_i, 6 x D'
-    StageMem KB{smem + 6 * N::D * NT};  // stage cotangents Kbar_i, 6 x D'
+    StageMem KB{smem};                 // stage cotangents Kbar_i, 6 x D'
     const int nsteps = a.stats->naccept;
     float gacc[N::NCHUNK];
 #pragma unroll
@@ -991,7 +1002,7 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_BWD) backward_kernel(const 
         //   L_b = (1/B) [ D'/2 log 2pi + |z|^2/2 + dlogp + l1 E + l2 n + l3 |z_aug| ]
         float zbar[N::D];
         {
-            const float* zf = a.ckpt + ((int64_t)nsteps * a.B + b) * N::D;
+            const float* zf = a.ckpt + ckpt_index<N>(nsteps, a.B, b, 0);
             float za = 0.0f;
 #pragma unroll
             for (int j = 0; j < N::D; ++j) {
@@ -1013,32 +1024,6 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_BWD) backward_kernel(const 
 
         for (int step = nsteps - 1; step >= 0; --step) {
             const float t = a.steps[step].t, h = a.steps[step].dt;
-            float z[N::D];
-            {
-                const float* zc = a.ckpt + ((int64_t)step * a.B + b) * N::D;
-#pragma unroll
-                for (int j = 0; j < N::D; ++j) z[j] = zc[j];
-            }
-            // rebuild the stage inputs Z_1..Z_6 (needs zdot of stages 1..5 only); KB
-            // temporarily holds those stage derivatives
-            for (int i = 0; i < 6; ++i) {
-#pragma unroll
-                for (int j = 0; j < N::D; ++j) x[j] = z[j];
-                for (int jj = 0; jj < i; ++jj) {
-                    const float c = h * c_a[i][jj];
-#pragma unroll
-                    for (int j = 0; j < N::D; ++j) x[j] = fmaf(c, KB.at(jj * N::D + j), x[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < N::D; ++j) Z.at(i * N::D + j) = x[j];
-                if (i < 5) {
-                    if constexpr (N::TIN) x[N::D] = fmaf(c_c[i], h, t);
-                    float kz[N::D];
-                    zdot_eval<N>(sw, x, kz);
-#pragma unroll
-                    for (int j = 0; j < N::D; ++j) KB.at(i * N::D + j) = kz[j];
-                }
-            }
             // Kbar_i = h b_i zbar_{n+1}
             for (int i = 0; i < 6; ++i) {
                 const float c = h * c_a[6][i];
@@ -1049,7 +1034,7 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_BWD) backward_kernel(const 
                 float kb[N::D], sbar[N::D];
 #pragma unroll
                 for (int j = 0; j < N::D; ++j) {
-                    x[j] = Z.at(i * N::D + j);
+                    x[j] = a.ckpt[ckpt_index<N>(step, a.B, b, i) + j];
                     kb[j] = KB.at(i * N::D + j);
                 }
                 if constexpr (N::TIN) x[N::D] = fmaf(c_c[i], h, t);

@@ -14,7 +14,7 @@ template <class N>
 struct Launch {
     static constexpr size_t smem_rhs = 0;
     static constexpr size_t smem_solve = sizeof(float) * (6 * N::D * NT);
-    static constexpr size_t smem_bwd = sizeof(float) * (12 * N::D * NT > (NT / 32) * N::NP ? 12 * N::D * NT : (NT / 32) * N::NP);
+    static constexpr size_t smem_bwd = sizeof(float) * (6 * N::D * NT > (NT / 32) * N::NP ? 6 * N::D * NT : (NT / 32) * N::NP);
     static_assert(sizeof(WBlock<N>) + sizeof(SolveArgs) + 16 <= 32764, "weights must fit the kernel parameter space");
 
     // theta (host, native ComponentArray order) -> padded parameter block
@@ -114,7 +114,7 @@ struct Launch {
     static constexpr size_t ub_floats() {
         if constexpr (USE_UB) {
             using C = UBCfg<N>;
-            size_t a = (size_t)C::WSM + 12 * N::D * C::SPB, b = (size_t)(NT / 32) * N::NP;
+            size_t a = (size_t)C::WSM + 6 * N::D * C::SPB, b = (size_t)(NT / 32) * N::NP;
             return a > b ? a : b;
         } else {
             return 0;
@@ -166,6 +166,7 @@ struct Launch {
         f.supports_backward = 1;
         f.fuses_loss_sum_adaptive = 1;
         f.adaptive_threads = 64;
+        f.ckpt_stages = 6;
         return f;
     }
 };

@@ -185,8 +185,7 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
     constexpr int G = C::G, NH = C::NH, lh = NH - 1, D = N::D;
     extern __shared__ __align__(16) float smem[];
     float* sw = smem;                                   // weights, C::WSM floats
-    float* sZ = smem + C::WSM;                          // stage inputs  [6 * D][SPB]
-    float* sKB = sZ + 6 * D * C::SPB;                   // stage cotangents [6 * D][SPB]
+    float* sKB = smem + C::WSM;                         // stage cotangents [6 * D][SPB]
     // ---- stage the weights (rows, columns, output layer) from the native ComponentArray layout
     for (int idx = threadIdx.x; idx < C::WSM; idx += NT) sw[idx] = 0.f;
     __syncthreads();
@@ -253,7 +252,7 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
 
         float zbar[D];
         {
-            const float* zf = a.ckpt + ((int64_t)nsteps * a.B + b) * D;
+            const float* zf = a.ckpt + ckpt_index<N>(nsteps, a.B, b, 0);
             float za = 0.f;
 #pragma unroll
             for (int j = 0; j < D; ++j) {
@@ -276,38 +275,7 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
         UState<N> S;
         for (int step = nsteps - 1; step >= 0; --step) {
             const float t = a.steps[step].t, h = a.steps[step].dt;
-            float z[D];
-            {
-                const float* zc = a.ckpt + ((int64_t)step * a.B + b) * D;
-#pragma unroll
-                for (int j = 0; j < D; ++j) z[j] = zc[j];
-            }
-            // rebuild the stage inputs (every lane of the group computes the same replicated values;
-            // lane 0 of the group publishes them); sKB temporarily holds the stage derivatives
-            for (int i = 0; i < 6; ++i) {
-#pragma unroll
-                for (int j = 0; j < D; ++j) x[j] = z[j];
-                for (int jj = 0; jj < i; ++jj) {
-                    const float c = h * c_a[i][jj];
-#pragma unroll
-                    for (int j = 0; j < D; ++j) x[j] = fmaf(c, sKB[(jj * D + j) * C::SPB + slot], x[j]);
-                }
-                __syncwarp();
-                if (g == 0) {
-#pragma unroll
-                    for (int j = 0; j < D; ++j) sZ[(i * D + j) * C::SPB + slot] = x[j];
-                }
-                if (i < 5) {
-                    if constexpr (N::TIN) x[D] = fmaf(c_c[i], h, t);
-                    float kz[D];
-                    ub_forward<N>(sw, x, g, gbase, S, kz);
-                    if (g == 0) {
-#pragma unroll
-                        for (int j = 0; j < D; ++j) sKB[(i * D + j) * C::SPB + slot] = kz[j];
-                    }
-                }
-                __syncwarp();
-            }
+            __syncwarp();
             if (g == 0) {
                 for (int i = 0; i < 6; ++i) {
                     const float c = h * c_a[6][i];
@@ -321,7 +289,7 @@ __global__ void __launch_bounds__(NT, ICNF_UB_MINB) backward_ub_kernel(BackwardA
                 float kb[D], zdot[D];
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    x[j] = sZ[(i * D + j) * C::SPB + slot];
+                    x[j] = a.ckpt[ckpt_index<N>(step, a.B, b, i) + j];
                     kb[j] = sKB[(i * D + j) * C::SPB + slot];
                 }
                 if constexpr (N::TIN) x[D] = fmaf(c_c[i], h, t);
