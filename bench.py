@@ -347,7 +347,7 @@ def main():
     # dominant kernel = backward.  Algorithmic bytes per sample per launch: eps regenerated in-kernel,
     # weights in the parameter bank; it reads the z checkpoints (naccept+1 records of D' floats).
     bwd_bytes = B * (nacc + 1) * 2 * 4.0
-    bwd_flop = B * nacc * (5 * 2 * PW + 6 * (8 * PW + 4 * PW))       # 82 P flop per step per sample
+    bwd_flop = B * nacc * 6 * (8 * PW + 4 * PW)                     # 6 stages x 12 P flop per step per sample (stage inputs are checkpointed)
     fwd_flop = B * nf * 4 * PW                                        # Hutchinson RHS = 4 P flop
     achieved_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
     traffic = None

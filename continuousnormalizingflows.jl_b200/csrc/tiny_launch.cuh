@@ -6,6 +6,7 @@
 #include "family.h"
 #include "tiny.cuh"
 #include "tiny_ub.cuh"
+#include "tiny_sp.cuh"
 
 namespace icnf {
 namespace tiny {
@@ -15,7 +16,7 @@ struct Launch {
     static constexpr size_t smem_rhs = 0;
     static constexpr size_t smem_solve = sizeof(float) * (6 * N::D * NT);
     static constexpr size_t smem_bwd = sizeof(float) * (6 * N::D * NT > (NT / 32) * N::NP ? 6 * N::D * NT : (NT / 32) * N::NP);
-    static_assert(sizeof(WBlock<N>) + sizeof(SolveArgs) + 16 <= 32764, "weights must fit the kernel parameter space");
+    static_assert(2 * sizeof(WBlock<N>) + sizeof(SolveArgs) + 16 <= 32764, "weights must fit the kernel parameter space");
 
     // theta (host, native ComponentArray order) -> padded parameter block
     static void pack(const float* theta, WBlock<N>& w) {
@@ -121,8 +122,42 @@ struct Launch {
         }
     }
     static constexpr size_t smem_ub = sizeof(float) * ub_floats();
+    // sample-parallel backward (tiny_sp.cuh): CTA size (= samples per tile) and grid for a batch.
+    // The CTA size is the smallest multiple of 32 that lets the batch finish in the fewest
+    // rounds of ICNF_SP_MINB CTAs per SM, capped by ICNF_SP_MAXT and by shared memory.
+#ifndef ICNF_TINY_BWD
+#define ICNF_TINY_BWD 2   // 1: unit-parallel (tiny_ub.cuh), 2: sample-parallel (tiny_sp.cuh)
+#endif
+    static constexpr bool USE_SP = USE_UB && (ICNF_TINY_BWD == 2);
+    template <bool EXACT>
+    static void sp_plan(long long B, int sm_count, int& ns, int& grid) {
+        using C = SPCfg<N, EXACT>;
+        const size_t budget = (size_t)(227 * 1024) / ICNF_SP_MINB - 1024;
+        int cap = ICNF_SP_MAXT;
+        while (cap > 32 && C::smem_bytes(cap) > budget) cap -= 32;
+        const int lo = ((C::NBLK + 31) / 32) * 32;
+        const long long slots = (long long)ICNF_SP_MINB * sm_count;
+        const long long rounds = std::max(1LL, (B + slots * cap - 1) / (slots * cap));
+        long long per = (B + slots * rounds - 1) / (slots * rounds);
+        ns = (int)std::min<long long>(cap, std::max<long long>(lo, ((per + 31) / 32) * 32));
+        grid = (int)std::max(1LL, std::min(slots, (B + ns - 1) / ns));
+    }
+    static int cached_sm_count() {
+        static int n = 0;
+        if (!n) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        }
+        return n;
+    }
     static int backward_grid(bool exact, int sm_count, long long B) {
-        if constexpr (USE_UB) {
+        if constexpr (USE_SP) {
+            int ns, grid;
+            if (exact) sp_plan<true>(B, sm_count, ns, grid);
+            else sp_plan<false>(B, sm_count, ns, grid);
+            return grid;
+        } else if constexpr (USE_UB) {
             auto k = exact ? backward_ub_kernel<N, true> : backward_ub_kernel<N, false>;
             const long long spb = UBCfg<N>::SPB;
             long long need = (B + spb - 1) / spb;
@@ -133,8 +168,24 @@ struct Launch {
             return grid_for(B, occupancy(k, smem_bwd), sm_count);
         }
     }
+    template <bool EXACT>
+    static cudaError_t backward_sp(const float* theta, const BackwardArgs& a, int grid, cudaStream_t st) {
+        using C = SPCfg<N, EXACT>;
+        int ns, g2;
+        sp_plan<EXACT>(a.B, cached_sm_count(), ns, g2);
+        auto k = backward_sp_kernel<N, EXACT>;
+        const size_t smem = C::smem_bytes(ns);
+        cudaError_t e = prep(k, smem);
+        if (e != cudaSuccess) return e;
+        WBlock<N> w;
+        pack(theta, w);
+        k<<<grid, ns, smem, st>>>(w, w, a);   // two copies: see the note on common-subexpression elimination in tiny_sp.cuh
+        return cudaGetLastError();
+    }
     static cudaError_t backward(void*, const float* theta, const BackwardArgs& a, bool exact, int grid, cudaStream_t st) {
-        if constexpr (USE_UB) {
+        if constexpr (USE_SP) {
+            return exact ? backward_sp<true>(theta, a, grid, st) : backward_sp<false>(theta, a, grid, st);
+        } else if constexpr (USE_UB) {
             auto k = exact ? backward_ub_kernel<N, true> : backward_ub_kernel<N, false>;
             cudaError_t e = prep(k, smem_ub);
             if (e != cudaSuccess) return e;
