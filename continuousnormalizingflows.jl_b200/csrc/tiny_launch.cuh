@@ -132,9 +132,7 @@ struct Launch {
     template <bool EXACT>
     static void sp_plan(long long B, int sm_count, int& ns, int& grid) {
         using C = SPCfg<N, EXACT>;
-        const size_t budget = (size_t)(227 * 1024) / ICNF_SP_MINB - 1024;
-        int cap = ICNF_SP_MAXT;
-        while (cap > 32 && C::smem_bytes(cap) > budget) cap -= 32;
+        const int cap = C::PITCH;
         const int lo = ((C::NBLK + 31) / 32) * 32;
         const long long slots = (long long)ICNF_SP_MINB * sm_count;
         const long long rounds = std::max(1LL, (B + slots * cap - 1) / (slots * cap));

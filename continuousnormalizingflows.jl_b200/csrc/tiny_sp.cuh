@@ -72,16 +72,24 @@ struct SPCfg {
     __host__ __device__ static constexpr int nblk(int l) { return transposed(l) ? nblk_t(l) : nblk_n(l); }
     __host__ __device__ static constexpr int blkoff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += nblk(i); return o; }
     static constexpr int NBLK = blkoff(NL);
+    // samples per pair-row = largest CTA size: compile time, so every record access has an immediate offset;
+    // the largest multiple of 32 (<= ICNF_SP_MAXT) that leaves room for ICNF_SP_MINB CTAs per SM
+    __host__ __device__ static constexpr int pitch() {
+        int p = ICNF_SP_MAXT;
+        while (p > 32 && (size_t)NPR * p * 8 > (size_t)(227 * 1024) / ICNF_SP_MINB - 1024) p -= 32;
+        return p;
+    }
+    static constexpr int PITCH = pitch();
     __host__ __device__ static constexpr size_t smem_bytes(int ns) {
-        size_t rec = (size_t)NPR * ns * 8;
+        size_t rec = (size_t)NPR * PITCH * 8;
         size_t red = (size_t)(ns / NBLK > 0 ? ns / NBLK : 1) * N::NP * 4;
         return rec > red ? rec : red;
     }
 };
 
 // store a vector held as float2 pairs (n valid entries, optional constant 1 at index n) as pair-rows
-template <int n, bool ONE, int NM>
-__device__ __forceinline__ void sp_store(float2* rec, int row0, int NS, const float2 (&v)[NM]) {
+template <int NS, int n, bool ONE, int NM>
+__device__ __forceinline__ void sp_store(float2* rec, int row0, const float2 (&v)[NM]) {
     constexpr int np = ONE ? (n + 2) / 2 : (n + 1) / 2;
 #pragma unroll
     for (int p = 0; p < np; ++p) {
@@ -98,14 +106,15 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
     using C = SPCfg<N, EXACT>;
     constexpr int NL = N::NL, NH = NL - 1, D = N::D;
     extern __shared__ __align__(16) float smem[];
-    const int NS = blockDim.x, tid = threadIdx.x;
+    constexpr int NS = C::PITCH;               // row pitch; the CTA has blockDim.x <= NS threads (= samples per tile)
+    const int NT_ = blockDim.x, tid = threadIdx.x;
     float2* rec = reinterpret_cast<float2*>(smem) + tid;      // this thread's column; row r at rec[r * NS]
     float* kbm = smem + (size_t)C::KB0 * NS * 2 + tid;        // stage cotangents, float rows [6 D'][NS]
     const float4* rec4 = reinterpret_cast<const float4*>(smem);
     const int nsteps = a.stats->naccept;
 
     // ---- dW-phase role of this thread: block `blk`, sample group `grp`
-    const int NG = max(NS / C::NBLK, 1);
+    const int NG = max(NT_ / C::NBLK, 1);
     const int blk = tid / NG, grp = tid - blk * NG;
     const bool dw_active = blk < C::NBLK;
     int Lb[2] = {0, 0}, Rb[2] = {0, 0}, nL[2] = {0, 0}, nR[2] = {0, 0};   // pair-row bases and valid counts, terms A / B
@@ -133,11 +142,25 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
     });
     if (nL[1] == 0) nR[1] = 0;
     if (nR[1] == 0) nL[1] = 0;
-    const int half = NS >> 1;   // float4 units per pair-row
+    constexpr int half = NS >> 1;   // float4 units per pair-row
     float2 acc[2 * C::LCH][2];
 #pragma unroll
     for (int i = 0; i < 2 * C::LCH; ++i) { acc[i][0] = make_float2(0.f, 0.f); acc[i][1] = make_float2(0.f, 0.f); }
 
+    // one L pair-row against the block's R pair-rows, two samples per 128-bit load
+    auto dw_row = [&](const float4 l4, const float4 r0, const float4 r1, bool two, float2 (&a0)[2], float2 (&a1)[2])
+                      __attribute__((always_inline)) {
+        a0[0] = __ffma2_rn(bc2(l4.x), make_float2(r0.x, r0.y), a0[0]);
+        a1[0] = __ffma2_rn(bc2(l4.y), make_float2(r0.x, r0.y), a1[0]);
+        a0[0] = __ffma2_rn(bc2(l4.z), make_float2(r0.z, r0.w), a0[0]);
+        a1[0] = __ffma2_rn(bc2(l4.w), make_float2(r0.z, r0.w), a1[0]);
+        if (two) {
+            a0[1] = __ffma2_rn(bc2(l4.x), make_float2(r1.x, r1.y), a0[1]);
+            a1[1] = __ffma2_rn(bc2(l4.y), make_float2(r1.x, r1.y), a1[1]);
+            a0[1] = __ffma2_rn(bc2(l4.z), make_float2(r1.z, r1.w), a0[1]);
+            a1[1] = __ffma2_rn(bc2(l4.w), make_float2(r1.z, r1.w), a1[1]);
+        }
+    };
     auto dw_phase = [&](bool termA, int nduo) __attribute__((always_inline)) {
         if (!dw_active) return;
         for (int d = grp; d < nduo; d += NG) {
@@ -151,33 +174,30 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
                 const bool two = nR[term] > 1;
                 float4 r1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (two) r1 = rp[half];
+                if (nL[term] == C::LCH) {
+                    if (two) {
 #pragma unroll
-                for (int i = 0; i < C::LCH; ++i) {
-                    if (i < nL[term]) {
-                        const float4 l4 = lp[i * half];
-                        acc[2 * i][0] = __ffma2_rn(bc2(l4.x), make_float2(r0.x, r0.y), acc[2 * i][0]);
-                        acc[2 * i + 1][0] = __ffma2_rn(bc2(l4.y), make_float2(r0.x, r0.y), acc[2 * i + 1][0]);
-                        acc[2 * i][0] = __ffma2_rn(bc2(l4.z), make_float2(r0.z, r0.w), acc[2 * i][0]);
-                        acc[2 * i + 1][0] = __ffma2_rn(bc2(l4.w), make_float2(r0.z, r0.w), acc[2 * i + 1][0]);
-                        if (two) {
-                            acc[2 * i][1] = __ffma2_rn(bc2(l4.x), make_float2(r1.x, r1.y), acc[2 * i][1]);
-                            acc[2 * i + 1][1] = __ffma2_rn(bc2(l4.y), make_float2(r1.x, r1.y), acc[2 * i + 1][1]);
-                            acc[2 * i][1] = __ffma2_rn(bc2(l4.z), make_float2(r1.z, r1.w), acc[2 * i][1]);
-                            acc[2 * i + 1][1] = __ffma2_rn(bc2(l4.w), make_float2(r1.z, r1.w), acc[2 * i + 1][1]);
-                        }
+                        for (int i = 0; i < C::LCH; ++i) dw_row(lp[i * half], r0, r1, true, acc[2 * i], acc[2 * i + 1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < C::LCH; ++i) dw_row(lp[i * half], r0, r1, false, acc[2 * i], acc[2 * i + 1]);
                     }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < C::LCH; ++i)
+                        if (i < nL[term]) dw_row(lp[i * half], r0, r1, two, acc[2 * i], acc[2 * i + 1]);
                 }
             }
         }
     };
 
-    const int64_t ntiles = (a.B + NS - 1) / NS;
+    const int64_t ntiles = (a.B + NT_ - 1) / NT_;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t braw = tile * NS + tid;
+        const int64_t braw = tile * NT_ + tid;
         const bool valid = braw < a.B;
         const int64_t b = valid ? braw : a.B - 1;
         const float wgt = valid ? a.inv_denominator : 0.f;
-        const int nvalid = (int)min((int64_t)NS, a.B - tile * NS);
+        const int nvalid = (int)min((int64_t)NT_, a.B - tile * NT_);
         const int nduo = (nvalid + 1) >> 1;
 
         float eps[D], x[N::n(0)];
@@ -224,6 +244,12 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
         const float Ebar = a.reg_e ? a.lam1 * wgt : 0.f;
         const float nbar = a.reg_n ? a.lam2 * wgt : 0.f;
 
+        float xnext[D];
+        if (nsteps > 0) {
+            const float* zc = a.ckpt + ckpt_index<N>(nsteps - 1, a.B, b, 5);
+#pragma unroll
+            for (int j = 0; j < D; ++j) xnext[j] = zc[j];
+        }
         for (int step = nsteps - 1; step >= 0; --step) {
             const float t = a.steps[step].t, h = a.steps[step].dt;
             for (int i = 0; i < 6; ++i) {
@@ -233,12 +259,18 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
             }
             for (int i = 5; i >= 0; --i) {
                 float zb[D];
-                {
-                    const float* zc = a.ckpt + ckpt_index<N>(step, a.B, b, i);
 #pragma unroll
-                    for (int j = 0; j < D; ++j) {
-                        x[j] = zc[j];
-                        zb[j] = kbm[(i * D + j) * NS];
+                for (int j = 0; j < D; ++j) {
+                    x[j] = xnext[j];
+                    zb[j] = kbm[(i * D + j) * NS];
+                }
+                {   // prefetch the next stage input (previous stage, or stage 5 of the previous step): its
+                    // latency hides behind this stage's work instead of stalling the whole CTA after the barrier
+                    const int ni = i > 0 ? i - 1 : 5, nstep = i > 0 ? step : step - 1;
+                    if (nstep >= 0) {
+                        const float* zc = a.ckpt + ckpt_index<N>(nstep, a.B, b, ni);
+#pragma unroll
+                        for (int j = 0; j < D; ++j) xnext[j] = zc[j];
                     }
                 }
                 if constexpr (N::TIN) x[D] = fmaf(c_c[i], h, t);
@@ -253,11 +285,11 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
 #pragma unroll
                     for (int p = 0; p < (N::n(0) + 1) / 2; ++p)
                         xin[p] = make_float2(x[2 * p], (2 * p + 1 < N::n(0)) ? x[(2 * p + 1 < N::n(0)) ? 2 * p + 1 : 0] : 0.f);
-                    sp_store<N::n(0), true>(rec, C::FIN(0), NS, xin);
+                    sp_store<NS, N::n(0), true>(rec, C::FIN(0), xin);
                 }
                 static_for<0, NH>([&](auto lc) __attribute__((always_inline)) {
                     constexpr int l = decltype(lc)::value;
-                    sp_store<N::n(l + 1), true>(rec, C::FIN(l + 1), NS, A.h[l]);
+                    sp_store<NS, N::n(l + 1), true>(rec, C::FIN(l + 1), A.h[l]);
                 });
                 if (!EXACT && cE != 0.f) {
                     float zz = 0.f;
@@ -270,7 +302,7 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
                 float2 ab[N::NP2];
 #pragma unroll
                 for (int c = 0; c < (D + 1) / 2; ++c) ab[c] = make_float2(zb[2 * c], (2 * c + 1 < D) ? zb[(2 * c + 1 < D) ? 2 * c + 1 : 0] : 0.f);
-                sp_store<D, false>(rec, C::AB(NL - 1), NS, ab);
+                sp_store<NS, D, false>(rec, C::AB(NL - 1), ab);
 
                 // ---------------- probes: VJP chain, cotangent on q, tangent pass
                 constexpr int NPROBE = EXACT ? D : 1;
@@ -282,7 +314,7 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
                     float2 g[N::NP2];
 #pragma unroll
                     for (int c = 0; c < (D + 1) / 2; ++c) g[c] = make_float2(probe[2 * c], (2 * c + 1 < D) ? probe[(2 * c + 1 < D) ? 2 * c + 1 : 0] : 0.f);
-                    sp_store<D, false>(rec, C::GG(NL - 1), NS, g);
+                    sp_store<NS, D, false>(rec, C::GG(NL - 1), g);
                     float q[D];
                     static_rfor<NL>([&](auto lc) __attribute__((always_inline)) {
                         constexpr int l = decltype(lc)::value;
@@ -316,7 +348,7 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
                     float2 wv[N::NP2];
 #pragma unroll
                     for (int c = 0; c < (D + 1) / 2; ++c) wv[c] = make_float2(qb[2 * c], (2 * c + 1 < D) ? qb[(2 * c + 1 < D) ? 2 * c + 1 : 0] : 0.f);
-                    sp_store<D, false>(rec, C::WT(0), NS, wv);
+                    sp_store<NS, D, false>(rec, C::WT(0), wv);
                     static_for<0, NH>([&](auto lc) __attribute__((always_inline)) {
                         constexpr int l = decltype(lc)::value;
                         constexpr int kk = N::kz(l), np = C::out_p(l);
@@ -387,7 +419,7 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
     // ---- reduce the register tiles over the sample groups, write this CTA's partial gradient
     __syncthreads();
     float* red = smem;   // [NG][NP]
-    for (int i = tid; i < NG * N::NP; i += NS) red[i] = 0.f;
+    for (int i = tid; i < NG * N::NP; i += NT_) red[i] = 0.f;
     __syncthreads();
     if (dw_active) {
         static_for<0, NL>([&](auto lc) __attribute__((always_inline)) {
@@ -418,7 +450,7 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
     }
     __syncthreads();
     float* gp = a.gpartial + (int64_t)blockIdx.x * N::NP;
-    for (int p = tid; p < N::NP; p += NS) {
+    for (int p = tid; p < N::NP; p += NT_) {
         float s = 0.f;
         for (int w = 0; w < NG; ++w) s += red[w * N::NP + p];
         gp[p] = s;
