@@ -16,7 +16,7 @@ struct Launch {
     static constexpr size_t smem_rhs = 0;
     static constexpr size_t smem_solve = sizeof(float) * (6 * N::D * NT);
     static constexpr size_t smem_bwd = sizeof(float) * (6 * N::D * NT > (NT / 32) * N::NP ? 6 * N::D * NT : (NT / 32) * N::NP);
-    static_assert(2 * sizeof(WBlock<N>) + sizeof(SolveArgs) + 16 <= 32764, "weights must fit the kernel parameter space");
+    static_assert(2 * sizeof(WBlock<N>) + sizeof(SolveArgs) + sizeof(SPPlan) + 16 <= 32764, "weights must fit the kernel parameter space");
 
     // theta (host, native ComponentArray order) -> padded parameter block
     static void pack(const float* theta, WBlock<N>& w) {
@@ -166,18 +166,50 @@ struct Launch {
             return grid_for(B, occupancy(k, smem_bwd), sm_count);
         }
     }
+    // hand the CTA's threads to the dW blocks.  A warp must not mix blocks (their control flow and
+    // shared-memory rows differ: measured 1.6x slower when it does), so with at least one warp per
+    // block the unit is a warp and spare warps go to the block whose threads have the most work
+    // (sample pairs per thread x cost per pair); smaller CTAs split their threads evenly.
+    template <bool EXACT>
+    static SPPlan sp_threads(int ns) {
+        using C = SPCfg<N, EXACT>;
+        int ng[C::NBLK];
+        const int nduo = ns / 2, nwarp = ns / 32;
+        // shared-memory bound of the final reduction: groups * NP floats must fit the record area
+        const int gmax = std::max(1, (int)((size_t)C::NPR * C::PITCH * 8 / ((size_t)N::NP * 4)));
+        if (nwarp >= C::NBLK) {
+            for (int b = 0; b < C::NBLK; ++b) ng[b] = 32;
+            auto load = [&](int b) { return (long long)((nduo + ng[b] - 1) / ng[b]) * C::cost(b); };
+            for (int left = nwarp - C::NBLK; left > 0; --left) {
+                int best = -1;
+                for (int b = 0; b < C::NBLK; ++b)
+                    if (ng[b] + 32 <= std::min(nduo, gmax) && (best < 0 || load(b) > load(best))) best = b;
+                if (best < 0) break;
+                ng[best] += 32;
+            }
+        } else {
+            for (int b = 0; b < C::NBLK; ++b) ng[b] = std::max(1, std::min(ns / C::NBLK, gmax));
+        }
+        SPPlan p{};
+        int o = 0, mg = 1;
+        for (int b = 0; b < C::NBLK; ++b) { p.first[b] = (unsigned short)o; o += ng[b]; mg = std::max(mg, ng[b]); }
+        for (int b = C::NBLK; b < 34; ++b) p.first[b] = (unsigned short)o;
+        p.max_groups = (unsigned short)mg;
+        return p;
+    }
     template <bool EXACT>
     static cudaError_t backward_sp(const float* theta, const BackwardArgs& a, int grid, cudaStream_t st) {
         using C = SPCfg<N, EXACT>;
         int ns, g2;
         sp_plan<EXACT>(a.B, cached_sm_count(), ns, g2);
         auto k = backward_sp_kernel<N, EXACT>;
-        const size_t smem = C::smem_bytes(ns);
+        const SPPlan plan = sp_threads<EXACT>(ns);
+        const size_t smem = C::smem_bytes(plan.max_groups);
         cudaError_t e = prep(k, smem);
         if (e != cudaSuccess) return e;
         WBlock<N> w;
         pack(theta, w);
-        k<<<grid, ns, smem, st>>>(w, w, a);   // two copies: see the note on common-subexpression elimination in tiny_sp.cuh
+        k<<<grid, ns, smem, st>>>(w, w, plan, a);   // two copies: see the note on common-subexpression elimination in tiny_sp.cuh
         return cudaGetLastError();
     }
     static cudaError_t backward(void*, const float* theta, const BackwardArgs& a, bool exact, int grid, cudaStream_t st) {

@@ -72,6 +72,45 @@ struct SPCfg {
     __host__ __device__ static constexpr int nblk(int l) { return transposed(l) ? nblk_t(l) : nblk_n(l); }
     __host__ __device__ static constexpr int blkoff(int l) { int o = 0; for (int i = 0; i < l; ++i) o += nblk(i); return o; }
     static constexpr int NBLK = blkoff(NL);
+    struct Blk { int Lb[2], Rb[2], nL[2], nR[2]; };
+    __host__ __device__ static constexpr Blk desc(int blk) {
+        Blk b{{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+        for (int l = 0; l < NL; ++l) {
+            const int off = blkoff(l), nb = nblk(l);
+            if (blk < off || blk >= off + nb) continue;
+            const int i = blk - off;
+            const int lo = out_p(l), fi = fin_p(l), wt = wt_p(l);
+            if (!transposed(l)) {
+                const int nrc = cdiv(fi, 2), lc = i / nrc, rc = i - lc * nrc;
+                b.Lb[0] = AB(l) + lc * LCH; b.Lb[1] = GG(l) + lc * LCH;
+                b.nL[0] = b.nL[1] = (lo - lc * LCH < LCH) ? lo - lc * LCH : LCH;
+                b.Rb[0] = FIN(l) + 2 * rc; b.nR[0] = (fi - 2 * rc < 2) ? fi - 2 * rc : 2;
+                b.Rb[1] = WT(l) + 2 * rc;
+                const int w = (wt - 2 * rc < 2) ? wt - 2 * rc : 2;
+                b.nR[1] = w > 0 ? w : 0;
+            } else {
+                const int nrc = cdiv(lo, 2), lc = i / nrc, rc = i - lc * nrc;
+                b.Lb[0] = FIN(l) + lc * LCH; b.nL[0] = (fi - lc * LCH < LCH) ? fi - lc * LCH : LCH;
+                b.Lb[1] = WT(l) + lc * LCH;
+                const int w = (wt - lc * LCH < LCH) ? wt - lc * LCH : LCH;
+                b.nL[1] = w > 0 ? w : 0;
+                b.Rb[0] = AB(l) + 2 * rc; b.Rb[1] = GG(l) + 2 * rc;
+                b.nR[0] = b.nR[1] = (lo - 2 * rc < 2) ? lo - 2 * rc : 2;
+            }
+        }
+        if (b.nL[1] == 0) b.nR[1] = 0;
+        if (b.nR[1] == 0) b.nL[1] = 0;
+        return b;
+    }
+    // issue slots one sample pair costs a thread of this block (128-bit loads + FFMA2): the launcher hands
+    // out the CTA's threads to the blocks in proportion, so that every warp leaves the dW phase together
+    __host__ __device__ static constexpr int cost(int blk) {
+        const Blk b = desc(blk);
+        int c = 4;
+        for (int t = 0; t < 2; ++t)
+            if (b.nR[t] > 0) c += b.nL[t] + b.nR[t] + 4 * b.nL[t] * b.nR[t];
+        return c;
+    }
     // samples per pair-row = largest CTA size: compile time, so every record access has an immediate offset;
     // the largest multiple of 32 (<= ICNF_SP_MAXT) that leaves room for ICNF_SP_MINB CTAs per SM
     __host__ __device__ static constexpr int pitch() {
@@ -80,9 +119,9 @@ struct SPCfg {
         return p;
     }
     static constexpr int PITCH = pitch();
-    __host__ __device__ static constexpr size_t smem_bytes(int ns) {
+    __host__ __device__ static constexpr size_t smem_bytes(int max_groups) {
         size_t rec = (size_t)NPR * PITCH * 8;
-        size_t red = (size_t)(ns / NBLK > 0 ? ns / NBLK : 1) * N::NP * 4;
+        size_t red = (size_t)max_groups * N::NP * 4;
         return rec > red ? rec : red;
     }
 };
@@ -100,9 +139,16 @@ __device__ __forceinline__ void sp_store(float2* rec, int row0, const float2 (&v
     }
 }
 
+// thread ranges of the dW blocks inside a CTA: block b owns threads [first[b], first[b + 1])
+struct SPPlan {
+    unsigned short first[34];
+    unsigned short max_groups;
+};
+
 template <class N, bool EXACT>
 __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
-    backward_sp_kernel(const __grid_constant__ WBlock<N> sw, const __grid_constant__ WBlock<N> sw2, BackwardArgs a) {
+    backward_sp_kernel(const __grid_constant__ WBlock<N> sw, const __grid_constant__ WBlock<N> sw2,
+                       const __grid_constant__ SPPlan plan, BackwardArgs a) {
     using C = SPCfg<N, EXACT>;
     constexpr int NL = N::NL, NH = NL - 1, D = N::D;
     extern __shared__ __align__(16) float smem[];
@@ -113,35 +159,16 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
     const float4* rec4 = reinterpret_cast<const float4*>(smem);
     const int nsteps = a.stats->naccept;
 
-    // ---- dW-phase role of this thread: block `blk`, sample group `grp`
-    const int NG = max(NT_ / C::NBLK, 1);
-    const int blk = tid / NG, grp = tid - blk * NG;
+    // ---- dW-phase role of this thread: block `blk`, sample group `grp` of NG
+    static_assert(C::NBLK <= 33, "dW blocks per CTA");
+    int blk = 0;
+    while (blk < C::NBLK && tid >= (int)plan.first[blk + 1]) ++blk;
     const bool dw_active = blk < C::NBLK;
-    int Lb[2] = {0, 0}, Rb[2] = {0, 0}, nL[2] = {0, 0}, nR[2] = {0, 0};   // pair-row bases and valid counts, terms A / B
-    static_for<0, NL>([&](auto lc) __attribute__((always_inline)) {
-        constexpr int l = decltype(lc)::value;
-        constexpr int nb = C::nblk(l), off = C::blkoff(l);
-        if (blk >= off && blk < off + nb) {
-            const int i = blk - off;
-            if constexpr (!C::transposed(l)) {
-                constexpr int nrc = C::cdiv(C::fin_p(l), 2);          // R chunks
-                const int lc_ = i / nrc, rc = i - lc_ * nrc;
-                Lb[0] = C::AB(l) + lc_ * C::LCH; Lb[1] = C::GG(l) + lc_ * C::LCH;
-                nL[0] = nL[1] = min(C::LCH, C::out_p(l) - lc_ * C::LCH);
-                Rb[0] = C::FIN(l) + 2 * rc; nR[0] = min(2, C::fin_p(l) - 2 * rc);
-                Rb[1] = C::WT(l) + 2 * rc; nR[1] = max(0, min(2, C::wt_p(l) - 2 * rc));
-            } else {
-                constexpr int nrc = C::cdiv(C::out_p(l), 2);
-                const int lc_ = i / nrc, rc = i - lc_ * nrc;
-                Lb[0] = C::FIN(l) + lc_ * C::LCH; nL[0] = min(C::LCH, C::fin_p(l) - lc_ * C::LCH);
-                Lb[1] = C::WT(l) + lc_ * C::LCH; nL[1] = max(0, min(C::LCH, C::wt_p(l) - lc_ * C::LCH));
-                Rb[0] = C::AB(l) + 2 * rc; Rb[1] = C::GG(l) + 2 * rc;
-                nR[0] = nR[1] = min(2, C::out_p(l) - 2 * rc);
-            }
-        }
-    });
-    if (nL[1] == 0) nR[1] = 0;
-    if (nR[1] == 0) nL[1] = 0;
+    const int NG = dw_active ? (int)plan.first[blk + 1] - (int)plan.first[blk] : 1;
+    const int grp = dw_active ? tid - (int)plan.first[blk] : 0;
+    const typename C::Blk bd = C::desc(dw_active ? blk : 0);
+    int Lb[2] = {bd.Lb[0], bd.Lb[1]}, Rb[2] = {bd.Rb[0], bd.Rb[1]};   // pair-row bases and valid counts, terms A / B
+    int nL[2] = {bd.nL[0], bd.nL[1]}, nR[2] = {bd.nR[0], bd.nR[1]};
     constexpr int half = NS >> 1;   // float4 units per pair-row
     float2 acc[2 * C::LCH][2];
 #pragma unroll
@@ -418,8 +445,9 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
 
     // ---- reduce the register tiles over the sample groups, write this CTA's partial gradient
     __syncthreads();
-    float* red = smem;   // [NG][NP]
-    for (int i = tid; i < NG * N::NP; i += NT_) red[i] = 0.f;
+    float* red = smem;   // [max_groups][NP]
+    const int NGM = plan.max_groups;
+    for (int i = tid; i < NGM * N::NP; i += NT_) red[i] = 0.f;
     __syncthreads();
     if (dw_active) {
         static_for<0, NL>([&](auto lc) __attribute__((always_inline)) {
@@ -452,7 +480,7 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
     float* gp = a.gpartial + (int64_t)blockIdx.x * N::NP;
     for (int p = tid; p < N::NP; p += NT_) {
         float s = 0.f;
-        for (int w = 0; w < NG; ++w) s += red[w * N::NP + p];
+        for (int w = 0; w < NGM; ++w) s += red[w * N::NP + p];
         gp[p] = s;
     }
 }
