@@ -1453,7 +1453,8 @@ static int adaptive_max_grid(bool, int sm_count) { return sm_count; }   // not a
 // Reverse sweep over the recorded steps (discretise-then-optimise; derivation in tiny.cuh).
 static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
-    if (w->tc) return cudaErrorNotSupported;   // bf16 tensor-core mode covers the forward solve; gradients: fp32
+    // tensor-core precisions: the forward solve (and its checkpoints) ran on tcgen05; the reverse sweep below
+    // is the fp32 one (FFMA2 SGEMMs), evaluated at those checkpoints
     const long long B = a.B;
     const int NL = w->NL, D = w->D;
     const long long DB = (long long)D * B;

@@ -141,9 +141,18 @@ def test_solve_bf16x3_tc_matches_oracle_and_step_count(m):
     assert norm_rel_err(g3, gref) < X3_TOL
 
 
-def test_bf16_tc_gradient_is_reported_unsupported(m):
-    icnf = _make(m, "cond64", precision="bf16_tc")
-    om, theta, xs, eps, ys = make_inputs(icnf, 16)
-    with pytest.raises(m.ICNFError) as ei:
-        m.loss_and_gradient(icnf, m.TrainMode(True), xs, ys, theta, {}, eps=eps)
-    assert ei.value.code == 7
+@pytest.mark.parametrize("prec,tol", [("bf16x3_tc", 2e-4), ("bf16_tc", BF16_TOL)])
+def test_tc_training_gradient(m, prec, tol):
+    """Training through the tensor-core precisions: the forward solve runs on tcgen05, the reverse
+    sweep is the fp32 one over the forward's checkpoints."""
+    icnf = _make(m, "cond64", precision=prec)
+    B = 96
+    om, theta, xs, eps, ys = make_inputs(icnf, B)
+    theta = (0.5 * theta).astype(np.float32)
+    sol = dict(adaptive=False, dt=0.25)
+    l, g, gx = m.loss_and_gradient(icnf, m.TrainMode(True), xs, ys, theta, {}, want_dxs=True, eps=eps, tspan=icnf.tspan, **sol)
+    rl, rg, rgx = O.loss_grad(om, O.TRAIN_REG, t64(xs), t64(theta), t64(eps), t64(ys),
+                              opts=O.SolverOpts(adaptive=False, dt=0.25), want_dxs=True)
+    assert abs(l - float(rl)) <= tol * abs(float(rl)) + 1e-5
+    assert norm_rel_err(g, rg.numpy()) < tol, norm_rel_err(g, rg.numpy())
+    assert norm_rel_err(gx, rgx.numpy()) < tol, norm_rel_err(gx, rgx.numpy())
