@@ -345,14 +345,15 @@ def main():
     nacc = float(np.mean(nacc_list))
     nf = float(np.mean(nf_list))
     # dominant kernel = backward.  Algorithmic bytes per sample per launch: eps regenerated in-kernel,
-    # weights in the parameter bank; it reads the z checkpoints (naccept+1 records of D' floats).
-    bwd_bytes = B * (nacc + 1) * 2 * 4.0
+    # weights in the parameter bank; it reads the stage-input checkpoints (6 records of D' floats per
+    # accepted step, plus the final state).
+    bwd_bytes = B * (6 * nacc + 1) * 2 * 4.0
     bwd_flop = B * nacc * 6 * (8 * PW + 4 * PW)                     # 6 stages x 12 P flop per step per sample (stage inputs are checkpointed)
     fwd_flop = B * nf * 4 * PW                                        # Hutchinson RHS = 4 P flop
     achieved_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tiny::backward_ub_kernel"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["tiny::backward_sp_kernel"]
         traffic = tr["dram_bytes_per_launch"] * (B / tr["batch"])
     except Exception:
         pass
@@ -369,10 +370,10 @@ def main():
                 else "pinned H2D copy + icnf_loss_grad_dev + NCCL all-reduce + D2H of loss and gradient"},
         "gpu_launches": launches,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "tiny::backward_ub_kernel", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "tiny::backward_sp_kernel", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "note": "narrow-MLP path is FP32-issue bound, not HBM bound (SURVEY 8(d)); see roofline_fp32"},
-        "roofline_fp32": {"bound": "fp32_fma", "kernel": "tiny::backward_ub_kernel", "achieved": bwd_flop / (bwd_ms * 1e-3) / 1e12,
+        "roofline_fp32": {"bound": "fp32_fma", "kernel": "tiny::backward_sp_kernel", "achieved": bwd_flop / (bwd_ms * 1e-3) / 1e12,
                           "peak": fp32_peak, "unit": "TFLOP/s", "frac": bwd_flop / (bwd_ms * 1e-3) / 1e12 / fp32_peak,
                           "peak_source": "FFMA-chain microbenchmark in this run (icnf_measure_fp32_peak)",
                           "forward_kernel": {"kernel": "tiny::solve_adaptive_kernel", "achieved": fwd_flop / (fwd_ms * 1e-3) / 1e12,

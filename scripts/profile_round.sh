@@ -6,7 +6,7 @@ python bench.py > gpurun_out/bench_full.json 2> gpurun_out/bench_full.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>> gpurun_out/bench_full.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_bench.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:backward_ub -s 3 -c 1 -o gpurun_out/prof_bwd \
+ncu --set full --clock-control none --import-source on -k regex:backward_sp -s 3 -c 1 -o gpurun_out/prof_bwd \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:solve_adaptive -s 3 -c 1 -o gpurun_out/prof_fwd \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
@@ -14,6 +14,13 @@ ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 40 -c
     python scripts/time_wide.py bf16_tc > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 40 -c 1 -o gpurun_out/prof_generic \
     python scripts/time_wide.py fp32 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 40 -c 1 -o gpurun_out/prof_tc_x3 \
+    python scripts/time_wide.py bf16x3_tc > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 150 --csv --log-file gpurun_out/launches_tc.csv \
     python scripts/time_wide.py bf16_tc > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 200 --csv --log-file gpurun_out/launches_tc_x3.csv \
+    python scripts/time_wide.py bf16x3_tc > /dev/null 2>&1
+python scripts/time_wide.py fp32 > gpurun_out/time_wide.txt 2>&1
+python scripts/time_wide.py bf16_tc >> gpurun_out/time_wide.txt 2>&1
+python scripts/time_wide.py bf16x3_tc >> gpurun_out/time_wide.txt 2>&1
 ls -la gpurun_out
