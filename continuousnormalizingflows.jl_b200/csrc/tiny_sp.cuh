@@ -38,6 +38,9 @@ namespace tiny {
 #ifndef ICNF_SP_MINB
 #define ICNF_SP_MINB 2
 #endif
+#ifndef ICNF_SP_MAXREG
+#define ICNF_SP_MAXREG 128   // 2 CTAs x 224 threads x 144 registers = 63 K of the SM's 64 K registers
+#endif
 
 template <class N, bool EXACT>
 struct SPCfg {
@@ -61,7 +64,8 @@ struct SPCfg {
     static constexpr int CC0 = WT0 + sum_wt(NL);
     __host__ __device__ static constexpr int CC(int l) { return EXACT ? CC0 + sum_out(l) : AB(l); }   // one probe: c lives where abar will
     static constexpr int KB0 = CC0 + (EXACT ? sum_out(NH) : 0);
-    static constexpr int NPR = KB0 + 3 * D;                  // stage cotangents: 6 D' float rows = 3 D' pair-rows
+    static constexpr int XN0 = KB0 + 3 * D;                  // stage cotangents: 6 D' float rows = 3 D' pair-rows
+    static constexpr int NPR = XN0 + (D + 1) / 2;            // prefetched next stage input: D' floats per sample
     // ---- dW blocks: LCH L pair-rows x 2 R pair-rows.  "normal" orientation: L = layer outputs (abar / g),
     //      R = layer inputs (fin / w); "transposed": L = inputs, R = outputs (cheaper when n_out is tiny)
     static constexpr int LCH = 6;
@@ -146,7 +150,7 @@ struct SPPlan {
 };
 
 template <class N, bool EXACT>
-__global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
+__global__ void __maxnreg__(ICNF_SP_MAXREG)
     backward_sp_kernel(const __grid_constant__ WBlock<N> sw, const __grid_constant__ WBlock<N> sw2,
                        const __grid_constant__ SPPlan plan, BackwardArgs a) {
     using C = SPCfg<N, EXACT>;
@@ -156,6 +160,16 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
     const int NT_ = blockDim.x, tid = threadIdx.x;
     float2* rec = reinterpret_cast<float2*>(smem) + tid;      // this thread's column; row r at rec[r * NS]
     float* kbm = smem + (size_t)C::KB0 * NS * 2 + tid;        // stage cotangents, float rows [6 D'][NS]
+    float* xnm = smem + (size_t)C::XN0 * NS * 2 + tid * D;    // next stage input of this thread (cp.async target)
+    const unsigned xn_sa = (unsigned)__cvta_generic_to_shared(xnm);
+    // asynchronous global -> shared copy of one stage input: no register holds the value while it is in
+    // flight (a register prefetch was spilled at once and stalled on its own load)
+    auto prefetch_x = [&](const float* src) __attribute__((always_inline)) {
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(xn_sa + 4u * j), "l"(src + j) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     const float4* rec4 = reinterpret_cast<const float4*>(smem);
     const int nsteps = a.stats->naccept;
 
@@ -271,12 +285,7 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
         const float Ebar = a.reg_e ? a.lam1 * wgt : 0.f;
         const float nbar = a.reg_n ? a.lam2 * wgt : 0.f;
 
-        float xnext[D];
-        if (nsteps > 0) {
-            const float* zc = a.ckpt + ckpt_index<N>(nsteps - 1, a.B, b, 5);
-#pragma unroll
-            for (int j = 0; j < D; ++j) xnext[j] = zc[j];
-        }
+        if (nsteps > 0) prefetch_x(a.ckpt + ckpt_index<N>(nsteps - 1, a.B, b, 5));
         for (int step = nsteps - 1; step >= 0; --step) {
             const float t = a.steps[step].t, h = a.steps[step].dt;
             for (int i = 0; i < 6; ++i) {
@@ -286,19 +295,16 @@ __global__ void __launch_bounds__(ICNF_SP_MAXT, ICNF_SP_MINB)
             }
             for (int i = 5; i >= 0; --i) {
                 float zb[D];
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < D; ++j) {
-                    x[j] = xnext[j];
+                    x[j] = xnm[j];
                     zb[j] = kbm[(i * D + j) * NS];
                 }
                 {   // prefetch the next stage input (previous stage, or stage 5 of the previous step): its
                     // latency hides behind this stage's work instead of stalling the whole CTA after the barrier
                     const int ni = i > 0 ? i - 1 : 5, nstep = i > 0 ? step : step - 1;
-                    if (nstep >= 0) {
-                        const float* zc = a.ckpt + ckpt_index<N>(nstep, a.B, b, ni);
-#pragma unroll
-                        for (int j = 0; j < D; ++j) xnext[j] = zc[j];
-                    }
+                    if (nstep >= 0) prefetch_x(a.ckpt + ckpt_index<N>(nstep, a.B, b, ni));
                 }
                 if constexpr (N::TIN) x[D] = fmaf(c_c[i], h, t);
                 const float hb = h * c_a[6][i];
