@@ -180,9 +180,16 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
     const bool dw_active = blk < C::NBLK;
     const int NG = dw_active ? (int)plan.first[blk + 1] - (int)plan.first[blk] : 1;
     const int grp = dw_active ? tid - (int)plan.first[blk] : 0;
-    const typename C::Blk bd = C::desc(dw_active ? blk : 0);
-    int Lb[2] = {bd.Lb[0], bd.Lb[1]}, Rb[2] = {bd.Rb[0], bd.Rb[1]};   // pair-row bases and valid counts, terms A / B
-    int nL[2] = {bd.nL[0], bd.nL[1]}, nR[2] = {bd.nR[0], bd.nR[1]};
+    // the block descriptor stays packed in two registers between stages (pair-row bases; valid counts, group)
+    static_assert(C::NPR < 256 && ICNF_SP_MAXT <= 256, "descriptor packing");
+    unsigned desc0, desc1;
+    {
+        const typename C::Blk bd = C::desc(dw_active ? blk : 0);
+        desc0 = (unsigned)bd.Lb[0] | ((unsigned)bd.Lb[1] << 8) | ((unsigned)bd.Rb[0] << 16) | ((unsigned)bd.Rb[1] << 24);
+        desc1 = (unsigned)bd.nL[0] | ((unsigned)bd.nL[1] << 4) | ((unsigned)bd.nR[0] << 8) | ((unsigned)bd.nR[1] << 12) |
+                ((unsigned)grp << 16) | ((unsigned)(NG - 1) << 24);
+        if (!dw_active) desc1 = 0u;   // no terms: nR = 0
+    }
     constexpr int half = NS >> 1;   // float4 units per pair-row
     float2 acc[2 * C::LCH][2];
 #pragma unroll
@@ -203,8 +210,13 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
         }
     };
     auto dw_phase = [&](bool termA, int nduo) __attribute__((always_inline)) {
-        if (!dw_active) return;
-        for (int d = grp; d < nduo; d += NG) {
+        const int Lb[2] = {(int)(desc0 & 255u), (int)((desc0 >> 8) & 255u)};
+        const int Rb[2] = {(int)((desc0 >> 16) & 255u), (int)(desc0 >> 24)};
+        const int nL[2] = {(int)(desc1 & 15u), (int)((desc1 >> 4) & 15u)};
+        const int nR[2] = {(int)((desc1 >> 8) & 15u), (int)((desc1 >> 12) & 15u)};
+        const int grp_ = (int)((desc1 >> 16) & 255u), NG_ = (int)(desc1 >> 24) + 1;
+        if ((nR[0] | nR[1]) == 0) return;
+        for (int d = grp_; d < nduo; d += NG_) {
 #pragma unroll
             for (int term = 0; term < 2; ++term) {
                 if (term == 0 && !termA) continue;
@@ -455,12 +467,15 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
     const int NGM = plan.max_groups;
     for (int i = tid; i < NGM * N::NP; i += NT_) red[i] = 0.f;
     __syncthreads();
-    if (dw_active) {
+    int blk2 = 0;   // recomputed: the role variables are not kept live across the main loop
+    while (blk2 < C::NBLK && tid >= (int)plan.first[blk2 + 1]) ++blk2;
+    const int grp2 = (int)((desc1 >> 16) & 255u);
+    if (blk2 < C::NBLK) {
         static_for<0, NL>([&](auto lc) __attribute__((always_inline)) {
             constexpr int l = decltype(lc)::value;
             constexpr int nb = C::nblk(l), off = C::blkoff(l), nin = N::n(l), nout = N::n(l + 1);
-            if (blk >= off && blk < off + nb) {
-                const int i = blk - off;
+            if (blk2 >= off && blk2 < off + nb) {
+                const int i = blk2 - off;
                 constexpr int nrc = C::transposed(l) ? C::cdiv(C::out_p(l), 2) : C::cdiv(C::fin_p(l), 2);
                 const int lc_ = i / nrc, rc = i - lc_ * nrc;
 #pragma unroll
@@ -475,7 +490,7 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
                             const int k = C::transposed(l) ? lidx : ridx;    // input (k == nin: bias)
                             const float v = e ? acc[li][c].y : acc[li][c].x;
                             if (j < nout && k <= nin)
-                                red[grp * N::NP + N::toff(l) + (k < nin ? k * nout + j : nin * nout + j)] = v;
+                                red[grp2 * N::NP + N::toff(l) + (k < nin ? k * nout + j : nin * nout + j)] = v;
                         }
                     }
                 }
