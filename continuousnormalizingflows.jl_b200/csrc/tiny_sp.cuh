@@ -293,10 +293,6 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
 #pragma unroll
             for (int j = 0; j < D; ++j) zbar[j] *= wgt;
         }
-        const float lbar = wgt;
-        const float Ebar = a.reg_e ? a.lam1 * wgt : 0.f;
-        const float nbar = a.reg_n ? a.lam2 * wgt : 0.f;
-
         if (nsteps > 0) prefetch_x(a.ckpt + ckpt_index<N>(nsteps - 1, a.B, b, 5));
         for (int step = nsteps - 1; step >= 0; --step) {
             const float t = a.steps[step].t, h = a.steps[step].dt;
@@ -320,7 +316,7 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
                 }
                 if constexpr (N::TIN) x[D] = fmaf(c_c[i], h, t);
                 const float hb = h * c_a[6][i];
-                const float cl = hb * lbar, cE = hb * Ebar, cn = hb * nbar;
+                const float cl = hb * wgt, cE = a.reg_e ? cl * a.lam1 : 0.f, cn = a.reg_n ? cl * a.lam2 : 0.f;
 
                 // ---------------- main pass: forward
                 Acts<N> A;
