@@ -213,6 +213,33 @@ def test_gradient_shards_sum_to_the_whole(m):
     assert norm_rel_err(ga + gb, g) < 1e-5
 
 
+def test_gradient_large_batch_several_tiles_per_cta(m):
+    """Batch beyond one round of the backward grid (several tiles per CTA, last tile ragged): the
+    whole-batch gradient equals the sum of its shards' gradients and is reproducible bit for bit."""
+    icnf = make_icnf(m, "config2_moons")
+    B = 200_003
+    om, theta, xs, _, _ = make_inputs(icnf, B)
+    kw = dict(seed=5, tspan=icnf.tspan, adaptive=False, dt=0.5)
+    l, g = m.loss_and_gradient(icnf, m.TrainMode(True), xs, theta, {}, **kw)
+    l2, g2 = m.loss_and_gradient(icnf, m.TrainMode(True), xs, theta, {}, **kw)
+    assert l == l2 and np.array_equal(g, g2)
+    cut = 70_001
+    la, ga = m.loss_and_gradient(icnf, m.TrainMode(True), xs[:, :cut], theta, {}, sample_offset=0, global_batch=B, **kw)
+    lb, gb = m.loss_and_gradient(icnf, m.TrainMode(True), xs[:, cut:], theta, {}, sample_offset=cut, global_batch=B, **kw)
+    assert la + lb == pytest.approx(l, rel=1e-5)
+    assert norm_rel_err(ga + gb, g) < 2e-5
+
+
+@pytest.mark.parametrize("B", [1, 2, 31, 33])
+def test_gradient_tiny_batches(m, B):
+    icnf = make_icnf(m, "config2_moons")
+    om, theta, xs, eps, _ = make_inputs(icnf, B)
+    l, g = m.loss_and_gradient(icnf, m.TrainMode(True), xs, theta, {}, eps=eps, tspan=icnf.tspan, adaptive=False, dt=0.25)
+    rl, rg = O.loss_grad(om, O.TRAIN_REG, t64(xs), t64(theta), t64(eps), None, opts=O.SolverOpts(adaptive=False, dt=0.25))[:2]
+    assert abs(l - float(rl)) <= 1e-4 * abs(float(rl)) + 1e-6
+    assert norm_rel_err(g, rg.numpy()) < 1e-4
+
+
 def test_zero_norm_has_zero_subgradient(m):
     # |zdot| = 0 and |eps'J| = 0 when the network is identically zero: the gradient must be finite
     icnf = make_icnf(m, "config2_moons")
