@@ -440,9 +440,82 @@ __global__ void g_stage_input_kernel(StageArgs a) {
     if (a.kind == 1) {
         v = fmaf(a.ctrl->tdir * a.ctrl->dt0, a.KF[cur][idx], v);
     } else {
-        for (int j = 0; j < a.stage; ++j) v = fmaf(h * g_a[a.stage][j], stage_k(a, j, cur)[idx], v);
+        float kv[6];   // all loads in flight before the dependent FMA chain
+#pragma unroll
+        for (int j = 0; j < 6; ++j) kv[j] = (j < a.stage) ? stage_k(a, j, cur)[idx] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 6; ++j)
+            if (j < a.stage) v = fmaf(h * g_a[a.stage][j], kv[j], v);
     }
     a.ZI[idx] = v;
+}
+
+// Tensor-core precisions: the stage input goes straight into the GEMM operand layout -- bf16 (or hi | lo
+// split) rows [sample][k] with the time and condition columns appended -- through a shared-memory
+// transpose, instead of a ZI round trip plus a separate pack kernel.  Tile: 32 samples x 64 inputs.
+struct PackArgs {
+    __nv_bfloat16* X;
+    const float* ys;    // C x B (SoA) or null
+    int tin, C, pitch, split;
+    float t_fixed, c_i;
+};
+__global__ void __launch_bounds__(256) g_stage_input_pack_kernel(StageArgs a, PackArgs p) {
+    if (a.ctrl && a.ctrl->done) return;
+    __shared__ float tile[32][65];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long b0 = (long long)blockIdx.x * 32;
+    const int k0 = blockIdx.y * 64;
+    const int cur = a.ctrl ? a.ctrl->cur : a.cur_fixed;
+    const float h = a.ctrl ? a.ctrl->tdir * a.ctrl->dt : a.dt_fixed;
+    const float tnow = a.ctrl ? fmaf(p.c_i, a.ctrl->tdir * a.ctrl->dt, a.ctrl->t) : p.t_fixed;
+    const long long b = b0 + lane;
+    float coef[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) coef[j] = (a.kind == 0 && j < a.stage) ? h * g_a[a.stage][j] : 0.f;
+    const float* kp[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) kp[j] = stage_k(a, j < a.stage ? j : 0, cur);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int kk = w + 8 * i, k = k0 + kk;
+        float v = 0.f;
+        if (b < a.B) {
+            if (k < a.D) {
+                const long long idx = (long long)k * a.B + b;
+                v = a.U[cur][idx];
+                if (a.kind == 1) {
+                    v = fmaf(a.ctrl->tdir * a.ctrl->dt0, a.KF[cur][idx], v);
+                } else {
+                    float kv[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) kv[j] = (j < a.stage) ? kp[j][idx] : 0.f;
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) v = fmaf(coef[j], kv[j], v);
+                }
+            } else if (p.tin && k == a.D) {
+                v = tnow;
+            } else if (k < a.D + p.tin + p.C) {
+                v = p.ys[(long long)(k - a.D - p.tin) * a.B + b];
+            }
+        }
+        tile[lane][kk] = v;
+    }
+    __syncthreads();
+    const int rs = p.split ? 2 * p.pitch : p.pitch;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int bb = w + 8 * i;
+        const long long bo = b0 + bb;
+        const int k = k0 + 2 * lane;
+        if (bo < a.B && k < p.pitch) {   // pitch is a multiple of 8: the pair never straddles it
+            const float x0 = tile[bb][2 * lane], x1 = tile[bb][2 * lane + 1];
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(x0, x1);
+            *reinterpret_cast<__nv_bfloat162*>(p.X + bo * rs + k) = hi;
+            if (p.split)
+                *reinterpret_cast<__nv_bfloat162*>(p.X + bo * rs + p.pitch + k) =
+                    __floats2bfloat162_rn(x0 - __low2float(hi), x1 - __high2float(hi));
+        }
+    }
 }
 
 // assemble k_stage = [zdot; -trace; |zdot|; |eps'J|].  CTA = 32 samples x 8 row groups: the D' rows
@@ -456,14 +529,24 @@ __global__ void __launch_bounds__(256) g_rhs_finish_kernel(StageArgs a, float* K
     float* K = Kout_fixed ? Kout_fixed : stage_k(a, a.stage, cur);
     float zz = 0.f, qq = 0.f, s = 0.f;
     if (b < a.B) {
-        for (int r = w; r < a.D; r += 8) {
-            const float zd = a.ZD[(long long)r * a.B + b];
-            K[(long long)r * a.B + b] = zd;
-            zz = fmaf(zd, zd, zz);
-            if (!a.exact) {
-                const float q = a.Q[(long long)r * a.B + b], e = a.E[(long long)r * a.B + b];
-                s = fmaf(q, e, s);
-                qq = fmaf(q, q, qq);
+        // four rows (x three arrays) in flight per thread: this kernel is pure HBM streaming
+        for (int r0 = w; r0 < a.D; r0 += 32) {
+            float zd[4], q[4], e[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + 8 * u;
+                const long long o = (long long)r * a.B + b;
+                zd[u] = (r < a.D) ? a.ZD[o] : 0.f;
+                q[u] = (r < a.D && !a.exact) ? a.Q[o] : 0.f;
+                e[u] = (r < a.D && !a.exact) ? a.E[o] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + 8 * u;
+                if (r < a.D) K[(long long)r * a.B + b] = zd[u];
+                zz = fmaf(zd[u], zd[u], zz);
+                s = fmaf(q[u], e[u], s);
+                qq = fmaf(q[u], q[u], qq);
             }
         }
     }
@@ -947,6 +1030,7 @@ struct Workspace {
     // precision = ICNF_BF16_TC: bf16 operands for the tcgen05 GEMM, [sample][unit] activations
     bool tc = false;
     int split = 0;   // ICNF_BF16X3_TC: every bf16 row is [hi | lo], three MMAs per K step
+    bool e16_valid = false;   // E16 holds the packed probe of the current solve (eps is constant over a solve)
     int rs(int cols) const { return (split ? 2 : 1) * pad8(cols); }   // row stride of a bf16 matrix with `cols` columns
     Buf w16t, w16n, a16, X16, E16, H16, D16, G16;
     std::vector<size_t> w16t_off, w16n_off;   // element offsets per layer
@@ -1072,6 +1156,7 @@ struct RhsPlan {
     const Ctrl* ctrl;     // adaptive time source / done flag
     float t_fixed;
     cudaStream_t st;
+    bool x_packed = false;   // tensor-core precisions: X16 already holds this evaluation's packed input
 };
 
 static cudaError_t launch_gemm(Workspace* w, GemmArgs& g, cudaStream_t st) {
@@ -1167,9 +1252,11 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
     auto set_split = [&](tc::TcArgs& g, int a_cols, int b_cols, int o_cols) {
         g.split = w->split; g.lo_a = P8(a_cols); g.lo_b = P8(b_cols); g.lo_o = P8(o_cols);
     };
-    GCK(tc::pack_input(w->ZI.as<float>(), w->YS.as<float>(), X, B, D, w->tin, w->C, P8(w->n[0]), p.t_fixed,
-                       (const float*)p.ctrl, c_i, done, w->split, p.st));
-    w->launches++;
+    if (!p.x_packed) {
+        GCK(tc::pack_input(w->ZI.as<float>(), w->YS.as<float>(), X, B, D, w->tin, w->C, P8(w->n[0]), p.t_fixed,
+                           (const float*)p.ctrl, c_i, done, w->split, p.st));
+        w->launches++;
+    }
     for (int l = 0; l < NL; ++l) {
         tc::TcArgs g;
         memset(&g, 0, sizeof g);
@@ -1204,8 +1291,11 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
         return cudaGetLastError();
     }
     __nv_bfloat16* E = w->E16.as<__nv_bfloat16>();
-    GCK(tc::pack_soa(w->EPS.as<float>(), E, B, D, P8(D), done, w->split, p.st));
-    w->launches++;
+    if (!w->e16_valid) {   // once per solve
+        GCK(tc::pack_soa(w->EPS.as<float>(), E, B, D, P8(D), nullptr, w->split, p.st));
+        w->launches++;
+        w->e16_valid = true;
+    }
     for (int l = NL - 1; l >= 0; --l) {
         tc::TcArgs g;
         memset(&g, 0, sizeof g);
@@ -1307,6 +1397,7 @@ static cudaError_t rhs(void* wsp, const float*, const RhsArgs& a, bool exact, in
     GCK(reserve_common(w, B));
     g_to_soa_kernel<<<blocks_for(B), 256, 0, st>>>(a.u, w->U0.as<float>(), B, w->S);
     if (!exact) g_to_soa_kernel<<<blocks_for(B), 256, 0, st>>>(a.eps, w->EPS.as<float>(), B, w->D);
+    w->e16_valid = false;
     if (w->C) g_to_soa_kernel<<<blocks_for(B), 256, 0, st>>>(a.ys, w->YS.as<float>(), B, w->C);
     GCK(cudaMemcpyAsync(w->ZI.p, w->U0.p, sizeof(float) * w->D * B, cudaMemcpyDeviceToDevice, st));
     RhsPlan p{w, a.theta, B, exact, a.reg_e, a.reg_n, a.squared, nullptr, a.t, st};
@@ -1328,6 +1419,7 @@ static cudaError_t load_inputs(Workspace* w, const SolveArgs& a, int nvars, cuda
     io.D = w->D; io.S = w->S; io.C = w->C; io.nvars = nvars;
     g_load_kernel<<<blocks_for(a.B), 256, 0, st>>>(io);
     w->launches++;
+    w->e16_valid = false;
     return cudaGetLastError();
 }
 
@@ -1349,9 +1441,18 @@ static cudaError_t write_outputs(Workspace* w, const SolveArgs& a, int nvars, co
 static cudaError_t enqueue_stage(Workspace* w, const SolveArgs& a, StageArgs s, int stage, bool exact, Ctrl* ctrl,
                                  float t_step, float h_fixed, int cur_fixed, cudaStream_t st) {
     s.ctrl = ctrl; s.stage = stage; s.dt_fixed = h_fixed; s.cur_fixed = cur_fixed; s.kind = 0;
-    g_stage_input_kernel<<<blocks_for((long long)w->D * a.B), 256, 0, st>>>(s);
-    w->launches++;
     RhsPlan p{w, a.theta, a.B, exact, a.reg_e, a.reg_n, a.squared, ctrl, t_step + g_c_host(stage) * h_fixed, st};
+    if (w->tc) {
+        GCK(tc_reserve(w, a.B));
+        PackArgs pk{w->X16.as<__nv_bfloat16>(), w->YS.as<float>(), w->tin, w->C, Workspace::pad8(w->n[0]), w->split,
+                    p.t_fixed, g_c_host(stage)};
+        dim3 grid((unsigned)((a.B + 31) / 32), (unsigned)((pk.pitch + 63) / 64));
+        g_stage_input_pack_kernel<<<grid, 256, 0, st>>>(s, pk);
+        p.x_packed = true;
+    } else {
+        g_stage_input_kernel<<<blocks_for((long long)w->D * a.B), 256, 0, st>>>(s);
+    }
+    w->launches++;
     GCK(enqueue_rhs_core(p, g_c_host(stage)));
     g_rhs_finish_kernel<<<blocks_for(a.B, 32), 256, 0, st>>>(s, nullptr);
     w->launches++;

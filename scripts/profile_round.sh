@@ -12,7 +12,7 @@ ncu --set full --clock-control none --import-source on -k regex:solve_adaptive -
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 40 -c 1 -o gpurun_out/prof_tc \
     python scripts/time_wide.py bf16_tc > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -s 40 -c 1 -o gpurun_out/prof_generic \
+ncu --set full --clock-control none --import-source on -k regex:gemm128_kernel -s 40 -c 1 -o gpurun_out/prof_generic \
     python scripts/time_wide.py fp32 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 40 -c 1 -o gpurun_out/prof_tc_x3 \
     python scripts/time_wide.py bf16x3_tc > /dev/null 2>&1
