@@ -164,6 +164,7 @@ def logp_extras(m, local, dev, flush_buf):
         ("config2_moons_B65536", dict(nvariables=2, naugments=0), 65536, m.TestMode()),      # tiny
         ("config3_gmm16_B262144", dict(nvariables=16, naugments=0), 262144, m.TestMode()),   # 17-68-68-16, generic fp32
         ("config3_gmm16_B262144_bf16tc", dict(nvariables=16, naugments=0, precision="bf16_tc"), 262144, m.TestMode()),
+        ("config3_gmm16_B262144_bf16x3tc", dict(nvariables=16, naugments=0, precision="bf16x3_tc"), 262144, m.TestMode()),
         ("config5_cond64_B65536_fp32", dict(nvariables=64, naugments=0, nconditions=32), 65536, m.TestMode()),   # 97-388-388-64
         ("config5_cond64_B65536_bf16tc", dict(nvariables=64, naugments=0, nconditions=32, precision="bf16_tc"), 65536, m.TestMode()),
         ("config5_cond64_B65536_bf16x3tc", dict(nvariables=64, naugments=0, nconditions=32, precision="bf16x3_tc"), 65536, m.TestMode()),

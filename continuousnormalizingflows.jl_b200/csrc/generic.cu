@@ -348,6 +348,155 @@ __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs g) {
     }
 }
 
+// Weights-stationary GEMM for narrow layers (M, K <= 128; config 3's 17-68-68-16): the tiled kernels above
+// are latency-bound there (a 64 x 64 tile has 2-5 K iterations, each a global round trip, and reloads the
+// weights for every tile).  Here a persistent CTA keeps the whole A (M x K) in shared memory, streams
+// sample tiles of the B operand with cp.async into a double buffer, and every thread owns a 4 x 4 block
+// of the M x TS output tile (rows 4 ty .. 4 ty + 3, samples 4 tx .. 4 tx + 3): 2 LDS.128 per 8 FFMA2.
+struct WsShape {
+    int nty, ntx, threads, Mp, TS;
+    size_t smem;
+};
+static WsShape ws_shape(int M, int K) {
+    WsShape w;
+    w.nty = (M + 3) / 4;
+    w.ntx = std::min(16, 256 / w.nty);
+    w.threads = ((w.nty * w.ntx + 31) / 32) * 32;
+    w.Mp = 4 * w.nty;
+    w.TS = 4 * w.ntx;
+    w.smem = sizeof(float) * ((size_t)K * w.Mp + 2 * (size_t)K * w.TS + 1024);
+    return w;
+}
+__global__ void __launch_bounds__(256) gemm_ws_kernel(GemmArgs g, int nty, int ntx, long long ntiles) {
+    if (g.done && *g.done) return;
+    extern __shared__ __align__(16) float ws_sm[];
+    const int Mp = 4 * nty, TS = 4 * ntx, K = g.K;
+    float* Ws = ws_sm;                       // [K][Mp]
+    float* Xs = ws_sm + (size_t)K * Mp;      // [2][K][TS]
+    float* red = Xs + 2 * (size_t)K * TS;    // [nty][TS] (EP_TRACE)
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int ty = tid / ntx, tx = tid - ty * ntx;
+    const bool active = ty < nty;
+    const float tnow = g.ctrl ? fmaf(g.c_i, g.ctrl->tdir * g.ctrl->dt, g.ctrl->t) : g.t_fixed;
+    for (int e = tid; e < K * Mp; e += nthr) {
+        const int k = e / Mp, m = e - k * Mp;
+        Ws[e] = (m < g.M) ? __ldg(g.A + (long long)k * g.lda + m) : 0.f;
+    }
+    auto issue_tile = [&](long long tile, float* dst) {
+        const long long n0 = tile * TS;
+        for (int e = tid; e < K * TS; e += nthr) {
+            const int k = e / TS, sidx = e - k * TS;
+            const long long n = n0 + sidx;
+            const float* src = nullptr;
+            float cv = 0.f;
+            if (n < g.N) {
+                if (!g.gather) src = g.Bm + (long long)k * g.ldb + n;
+                else if (k < g.D) src = g.zi + (long long)k * g.N + n;
+                else if (g.tin && k == g.D) cv = tnow;
+                else src = g.ys + (long long)(k - g.D - g.tin) * g.N + n;
+            }
+            if (src) {
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(src) : "memory");
+            } else {
+                dst[e] = cv;
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    long long tile = blockIdx.x;
+    if (tile < ntiles) issue_tile(tile, Xs);
+    int buf = 0;
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) {
+            issue_tile(next, Xs + (size_t)(buf ^ 1) * K * TS);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const float* Xb = Xs + (size_t)buf * K * TS;
+        float2 acc[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
+        if (active) {
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const float4 a = *reinterpret_cast<const float4*>(Ws + k * Mp + 4 * ty);
+                const float4 b = *reinterpret_cast<const float4*>(Xb + k * TS + 4 * tx);
+                const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
+                acc[0][0] = __ffma2_rn(make_float2(a.x, a.x), b01, acc[0][0]);
+                acc[0][1] = __ffma2_rn(make_float2(a.x, a.x), b23, acc[0][1]);
+                acc[1][0] = __ffma2_rn(make_float2(a.y, a.y), b01, acc[1][0]);
+                acc[1][1] = __ffma2_rn(make_float2(a.y, a.y), b23, acc[1][1]);
+                acc[2][0] = __ffma2_rn(make_float2(a.z, a.z), b01, acc[2][0]);
+                acc[2][1] = __ffma2_rn(make_float2(a.z, a.z), b23, acc[2][1]);
+                acc[3][0] = __ffma2_rn(make_float2(a.w, a.w), b01, acc[3][0]);
+                acc[3][1] = __ffma2_rn(make_float2(a.w, a.w), b23, acc[3][1]);
+            }
+        }
+        // ---- epilogue: one float4 of four samples per row when the row pitch allows it
+        const long long n0 = tile * TS + 4 * tx;
+        const bool vec = ((g.N & 3) == 0) && (n0 + 3 < g.N);
+        float colpart[4] = {0.f, 0.f, 0.f, 0.f};
+        if (active) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = 4 * ty + i;
+                if (m >= g.M) continue;
+                const float v4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
+                const long long o = (long long)m * g.N + n0;
+                if (vec && (g.ep == EP_ACT || g.ep == EP_LIN || g.ep == EP_PLAIN || g.ep == EP_MULD || g.ep == EP_TRACE)) {
+                    if (g.ep == EP_ACT) {
+                        const float bm = g.bias[m];
+                        float4 h, d;
+                        act_eval_rt(g.act, v4[0] + bm, h.x, d.x);
+                        act_eval_rt(g.act, v4[1] + bm, h.y, d.y);
+                        act_eval_rt(g.act, v4[2] + bm, h.z, d.z);
+                        act_eval_rt(g.act, v4[3] + bm, h.w, d.w);
+                        *reinterpret_cast<float4*>(g.out0 + o) = h;
+                        *reinterpret_cast<float4*>(g.out1 + o) = d;
+                    } else if (g.ep == EP_LIN) {
+                        const float bm = g.bias[m];
+                        *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0] + bm, v4[1] + bm, v4[2] + bm, v4[3] + bm);
+                    } else if (g.ep == EP_PLAIN) {
+                        *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                    } else if (g.ep == EP_MULD) {
+                        const float4 x = *reinterpret_cast<const float4*>(g.aux0 + o);
+                        if (g.out1) *reinterpret_cast<float4*>(g.out1 + o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+                        *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0] * x.x, v4[1] * x.y, v4[2] * x.z, v4[3] * x.w);
+                    } else {
+                        const float4 x = *reinterpret_cast<const float4*>(g.aux0 + o);
+                        colpart[0] = fmaf(v4[0], x.x, colpart[0]);
+                        colpart[1] = fmaf(v4[1], x.y, colpart[1]);
+                        colpart[2] = fmaf(v4[2], x.z, colpart[2]);
+                        colpart[3] = fmaf(v4[3], x.w, colpart[3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n0 + j < g.N) colpart[j] += gemm_epilogue(g, m, n0 + j, v4[j]);
+                }
+            }
+        }
+        if (g.ep == EP_TRACE) {
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) red[ty * TS + 4 * tx + j] = colpart[j];
+            }
+            __syncthreads();
+            for (int c = tid; c < TS; c += nthr) {
+                float sum = 0.f;
+                for (int r = 0; r < nty; ++r) sum += red[r * TS + c];
+                const long long n = tile * TS + c;
+                if (n < g.N) atomicAdd(g.colsum + n, sum);
+            }
+        }
+        __syncthreads();   // the buffer just read is the next cp.async target
+    }
+}
+
 // ------------------------------------------------------------------ element-wise kernels
 struct IoArgs {
     const float* in; const float* eps; const float* ys;
@@ -1160,6 +1309,26 @@ struct RhsPlan {
 };
 
 static cudaError_t launch_gemm(Workspace* w, GemmArgs& g, cudaStream_t st) {
+    if (g.M <= 128 && g.K <= 128 && g.N >= 2048) {   // narrow layers, large batch: weights-stationary persistent kernel
+        static int sms = 0;
+        static bool attr_set = false;
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        if (!attr_set) {
+            GCK(cudaFuncSetAttribute(gemm_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_set = true;
+        }
+        const WsShape ws = ws_shape(g.M, g.K);
+        const long long ntiles = (g.N + ws.TS - 1) / ws.TS;
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)(200 * 1024) / (ws.smem + 1024)));
+        const int grid = (int)std::min<long long>(ntiles, (long long)sms * per_sm);
+        gemm_ws_kernel<<<grid, ws.threads, ws.smem, st>>>(g, ws.nty, ws.ntx, ntiles);
+        w->launches++;
+        return cudaGetLastError();
+    }
     if (g.M >= 96) {   // wide layers: 128 x 128 tiles
         dim3 grid((unsigned)((g.N + LN - 1) / LN), (unsigned)((g.M + LM - 1) / LM));
         gemm128_kernel<<<grid, GT, 0, st>>>(g);
