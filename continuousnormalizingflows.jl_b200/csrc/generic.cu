@@ -382,24 +382,42 @@ __global__ void __launch_bounds__(256) gemm_ws_kernel(GemmArgs g, int nty, int n
         const int k = e / Mp, m = e - k * Mp;
         Ws[e] = (m < g.M) ? __ldg(g.A + (long long)k * g.lda + m) : 0.f;
     }
+    // 16-byte copies when every row start is 16-byte aligned (tile starts are multiples of 4 samples)
+    const bool al16 = ((g.N & 3) == 0) && (g.gather ? true : ((g.ldb & 3) == 0)) &&
+                      ((reinterpret_cast<uintptr_t>(g.gather ? g.zi : g.Bm) & 15) == 0) &&
+                      (!g.gather || !g.C || (reinterpret_cast<uintptr_t>(g.ys) & 15) == 0);
+    const int lane = tid & 31, wid = tid >> 5, nwarp = nthr >> 5;
     auto issue_tile = [&](long long tile, float* dst) {
         const long long n0 = tile * TS;
-        for (int e = tid; e < K * TS; e += nthr) {
-            const int k = e / TS, sidx = e - k * TS;
-            const long long n = n0 + sidx;
-            const float* src = nullptr;
-            float cv = 0.f;
-            if (n < g.N) {
-                if (!g.gather) src = g.Bm + (long long)k * g.ldb + n;
-                else if (k < g.D) src = g.zi + (long long)k * g.N + n;
-                else if (g.tin && k == g.D) cv = tnow;
-                else src = g.ys + (long long)(k - g.D - g.tin) * g.N + n;
-            }
-            if (src) {
-                const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + e);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(src) : "memory");
+        for (int k = wid; k < K; k += nwarp) {   // one warp per row: no index division, coalesced along samples
+            const float* row = nullptr;
+            bool is_t = false;
+            if (!g.gather) row = g.Bm + (long long)k * g.ldb;
+            else if (k < g.D) row = g.zi + (long long)k * g.N;
+            else if (g.tin && k == g.D) is_t = true;
+            else row = g.ys + (long long)(k - g.D - g.tin) * g.N;
+            float* drow = dst + k * TS;
+            if (row && al16) {
+                for (int q = lane; q < ntx; q += 32) {
+                    const long long n = n0 + 4 * q;
+                    if (n + 3 < g.N) {
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(drow + 4 * q);
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(row + n) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) drow[4 * q + j] = (n + j < g.N) ? row[n + j] : 0.f;
+                    }
+                }
             } else {
-                dst[e] = cv;
+                for (int sidx = lane; sidx < TS; sidx += 32) {
+                    const long long n = n0 + sidx;
+                    if (row && n < g.N) {
+                        const unsigned sa = (unsigned)__cvta_generic_to_shared(drow + sidx);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(row + n) : "memory");
+                    } else {
+                        drow[sidx] = (is_t && n < g.N) ? tnow : 0.f;
+                    }
+                }
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
