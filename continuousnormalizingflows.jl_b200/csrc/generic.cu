@@ -360,14 +360,14 @@ struct WsShape {
 static WsShape ws_shape(int M, int K) {
     WsShape w;
     w.nty = (M + 3) / 4;
-    w.ntx = std::min(16, 256 / w.nty);
-    w.threads = ((w.nty * w.ntx + 31) / 32) * 32;
+    w.ntx = 16;   // 64 samples per tile: a quarter-warp's 128-bit loads cover 8 consecutive 16-byte chunks (no bank conflicts)
+    w.threads = ((w.nty * w.ntx + 31) / 32) * 32;   // <= 512
     w.Mp = 4 * w.nty;
     w.TS = 4 * w.ntx;
-    w.smem = sizeof(float) * ((size_t)K * w.Mp + 2 * (size_t)K * w.TS + 1024);
+    w.smem = sizeof(float) * ((size_t)K * w.Mp + 2 * (size_t)K * w.TS + (size_t)w.nty * w.TS);
     return w;
 }
-__global__ void __launch_bounds__(256) gemm_ws_kernel(GemmArgs g, int nty, int ntx, long long ntiles) {
+__global__ void __launch_bounds__(512) gemm_ws_kernel(GemmArgs g, int nty, int ntx, long long ntiles) {
     if (g.done && *g.done) return;
     extern __shared__ __align__(16) float ws_sm[];
     const int Mp = 4 * nty, TS = 4 * ntx, K = g.K;
@@ -439,10 +439,12 @@ __global__ void __launch_bounds__(256) gemm_ws_kernel(GemmArgs g, int nty, int n
 #pragma unroll
         for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
         if (active) {
+            const float* wp = Ws + 4 * ty;
+            const float* xp = Xb + 4 * tx;
 #pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                const float4 a = *reinterpret_cast<const float4*>(Ws + k * Mp + 4 * ty);
-                const float4 b = *reinterpret_cast<const float4*>(Xb + k * TS + 4 * tx);
+            for (int k = 0; k < K; ++k, wp += Mp, xp += TS) {
+                const float4 a = *reinterpret_cast<const float4*>(wp);
+                const float4 b = *reinterpret_cast<const float4*>(xp);
                 const float2 b01 = make_float2(b.x, b.y), b23 = make_float2(b.z, b.w);
                 acc[0][0] = __ffma2_rn(make_float2(a.x, a.x), b01, acc[0][0]);
                 acc[0][1] = __ffma2_rn(make_float2(a.x, a.x), b23, acc[0][1]);
@@ -469,10 +471,17 @@ __global__ void __launch_bounds__(256) gemm_ws_kernel(GemmArgs g, int nty, int n
                     if (g.ep == EP_ACT) {
                         const float bm = g.bias[m];
                         float4 h, d;
-                        act_eval_rt(g.act, v4[0] + bm, h.x, d.x);
-                        act_eval_rt(g.act, v4[1] + bm, h.y, d.y);
-                        act_eval_rt(g.act, v4[2] + bm, h.z, d.z);
-                        act_eval_rt(g.act, v4[3] + bm, h.w, d.w);
+                        if (g.act == ICNF_ACT_SOFTPLUS) {   // the common case without a per-element switch
+                            act_eval<ICNF_ACT_SOFTPLUS>(v4[0] + bm, h.x, d.x);
+                            act_eval<ICNF_ACT_SOFTPLUS>(v4[1] + bm, h.y, d.y);
+                            act_eval<ICNF_ACT_SOFTPLUS>(v4[2] + bm, h.z, d.z);
+                            act_eval<ICNF_ACT_SOFTPLUS>(v4[3] + bm, h.w, d.w);
+                        } else {
+                            act_eval_rt(g.act, v4[0] + bm, h.x, d.x);
+                            act_eval_rt(g.act, v4[1] + bm, h.y, d.y);
+                            act_eval_rt(g.act, v4[2] + bm, h.z, d.z);
+                            act_eval_rt(g.act, v4[3] + bm, h.w, d.w);
+                        }
                         *reinterpret_cast<float4*>(g.out0 + o) = h;
                         *reinterpret_cast<float4*>(g.out1 + o) = d;
                     } else if (g.ep == EP_LIN) {
