@@ -1,5 +1,6 @@
 // tc.cu -- host side of the tensor-core GEMM (tc_gemm.cuh): TMA tensor maps, launch helper,
 // bf16 packing kernels, and a self-test entry point.
+#include <algorithm>
 #include "tc_gemm.cuh"
 
 #include <cstring>
@@ -50,7 +51,15 @@ cudaError_t gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ld
     const uint64_t kb = g.split ? (uint64_t)g.lo_b + g.K : (uint64_t)g.K;
     if (!make_map(&mapA, A, (uint64_t)g.M, ka, (uint64_t)lda, TBM) || !make_map(&mapB, B, (uint64_t)g.N, kb, (uint64_t)ldb, TBN))
         return cudaErrorInvalidValue;
-    dim3 grid((g.M + TBM - 1) / TBM, (g.N + TBN - 1) / TBN);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // persistent grid: one (split) or two CTAs per SM, each walking tiles blockIdx.x, + gridDim.x, ...
+    const long long ntiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + TBN - 1) / TBN);
+    const dim3 grid((unsigned)std::min<long long>(ntiles, (long long)sms * (g.split ? 1 : 2)));
     if (g.split) tc_gemm_kernel<true><<<grid, TTHREADS, SMEM_BYTES_SPLIT, st>>>(mapA, mapB, g);
     else tc_gemm_kernel<false><<<grid, TTHREADS, SMEM_BYTES, st>>>(mapA, mapB, g);
     return cudaGetLastError();

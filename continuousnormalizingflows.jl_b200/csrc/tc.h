@@ -11,9 +11,9 @@ namespace tc {
 // overlaps the other's main loop
 constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3, TTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int A_TILE_BYTES = TBM * TBK * 2, B_TILE_BYTES = TBN * TBK * 2;
-constexpr int SMEM_BYTES = TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + TBN * 4 /*bias*/;
+constexpr int SMEM_BYTES = TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + 2 * TBN * 4 /*bias, double-buffered*/;
 // split precision (bf16 x 3: every operand is hi + lo, three MMAs per K step): four tiles per stage
-constexpr int SMEM_BYTES_SPLIT = TSTAGES * 2 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256 + TBN * 4;
+constexpr int SMEM_BYTES_SPLIT = TSTAGES * 2 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256 + 2 * TBN * 4;
 
 enum TcEpilogue {
     TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)

@@ -171,6 +171,14 @@ __device__ __forceinline__ void load_row32(const __nv_bfloat16* base, size_t row
     }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent: the grid is one or two CTAs per SM and every CTA walks tiles blockIdx.x, + gridDim.x, ...
+// (unit tiles fastest, so concurrently running CTAs share the same sample rows of A in L2).  The
+// accumulator is double-buffered in TMEM (2 x 128 columns): while the epilogue warps drain tile i
+// the MMA warp already accumulates tile i + 1, and the TMA warp runs ahead across tile boundaries.
 template <bool SPLIT>
 __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                           const __grid_constant__ CUtensorMap mapB, TcArgs g) {
@@ -182,23 +190,25 @@ __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
     // stage s: [A_hi | A_lo? | B_hi | B_lo?]
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + TSTAGES * STAGE_BYTES);
     uint64_t* empty = full + TSTAGES;
-    uint64_t* tmem_full = empty + TSTAGES;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full + 1);
-    float* sbias = reinterpret_cast<float*>(smem + TSTAGES * STAGE_BYTES + 256);
+    uint64_t* tmem_full = empty + TSTAGES;     // [2]
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* sbias = reinterpret_cast<float*>(smem + TSTAGES * STAGE_BYTES + 256);   // [2][TBN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TBM, n0 = blockIdx.y * TBN;
     const int nkb = (g.K + TBK - 1) / TBK;
+    const int ntn = (g.N + TBN - 1) / TBN;
+    const int ntiles = ((g.M + TBM - 1) / TBM) * ntn;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
         for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TBN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(2 * TBN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -209,112 +219,131 @@ __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TSTAGES;
-                const uint32_t ph = (kb / TSTAGES) & 1;
-                uint8_t* st = smem + s * STAGE_BYTES;
-                mbar_wait(&empty[s], ph ^ 1);
-                mbar_expect_tx(&full[s], STAGE_BYTES);
-                tma_load_2d(st, &mapA, &full[s], kb * TBK, m0);
-                if constexpr (SPLIT) tma_load_2d(st + A_TILE_BYTES, &mapA, &full[s], g.lo_a + kb * TBK, m0);
-                tma_load_2d(st + NT_A * A_TILE_BYTES, &mapB, &full[s], kb * TBK, n0);
-                if constexpr (SPLIT) tma_load_2d(st + NT_A * A_TILE_BYTES + B_TILE_BYTES, &mapB, &full[s], g.lo_b + kb * TBK, n0);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const int m0 = (tile / ntn) * TBM, n0 = (tile % ntn) * TBN;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % TSTAGES;
+                    const uint32_t ph = (it / TSTAGES) & 1;
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_wait(&empty[s], ph ^ 1);
+                    mbar_expect_tx(&full[s], STAGE_BYTES);
+                    tma_load_2d(st, &mapA, &full[s], kb * TBK, m0);
+                    if constexpr (SPLIT) tma_load_2d(st + A_TILE_BYTES, &mapA, &full[s], g.lo_a + kb * TBK, m0);
+                    tma_load_2d(st + NT_A * A_TILE_BYTES, &mapB, &full[s], kb * TBK, n0);
+                    if constexpr (SPLIT) tma_load_2d(st + NT_A * A_TILE_BYTES + B_TILE_BYTES, &mapB, &full[s], g.lo_b + kb * TBK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(TBM, TBN);
-            for (int kb = 0; kb < nkb; ++kb) {
-                const int s = kb % TSTAGES;
-                const uint32_t ph = (kb / TSTAGES) & 1;
-                uint8_t* st = smem + s * STAGE_BYTES;
-                mbar_wait(&full[s], ph);
+            int it = 0, i = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+                const int as = i & 1;
+                mbar_wait(&tmem_empty[as], ((i >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint64_t a_hi = make_desc(smem_u32(st));
-                const uint64_t b_hi = make_desc(smem_u32(st + NT_A * A_TILE_BYTES));
+                const uint32_t tacc = tmem_base + (uint32_t)(as * TBN);
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % TSTAGES;
+                    const uint32_t ph = (it / TSTAGES) & 1;
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint64_t a_hi = make_desc(smem_u32(st));
+                    const uint64_t b_hi = make_desc(smem_u32(st + NT_A * A_TILE_BYTES));
 #pragma unroll
-                for (int k = 0; k < TBK / 16; ++k) {
-                    // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-                    tc_mma_bf16(tmem_base, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < TBK / 16; ++k) {
+                        // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+                        tc_mma_bf16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    if constexpr (SPLIT) {
+                        // a b ~ a_hi b_hi + a_lo b_hi + a_hi b_lo  (lo x lo is below fp32 rounding)
+                        const uint64_t a_lo = make_desc(smem_u32(st + A_TILE_BYTES));
+                        const uint64_t b_lo = make_desc(smem_u32(st + NT_A * A_TILE_BYTES + B_TILE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                    }
+                    tc_commit(&empty[s]);
                 }
-                if constexpr (SPLIT) {
-                    // a b ~ a_hi b_hi + a_lo b_hi + a_hi b_lo  (lo x lo is below fp32 rounding)
-                    const uint64_t a_lo = make_desc(smem_u32(st + A_TILE_BYTES));
-                    const uint64_t b_lo = make_desc(smem_u32(st + NT_A * A_TILE_BYTES + B_TILE_BYTES));
-#pragma unroll
-                    for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tmem_base, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-                    for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tmem_base, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                }
-                tc_commit(&empty[s]);
+                tc_commit(&tmem_full[as]);
             }
-            tc_commit(tmem_full);
         }
     } else {
-        // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4 =====
-        // stage this tile's bias slice while the main loop runs
-        {
-            const int e = threadIdx.x - 64;   // 0..255
-            if (e < TBN) sbias[e] = (g.bias && n0 + e < g.N) ? __ldg(g.bias + n0 + e) : 0.f;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        }
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        // two warps per TMEM lane quarter, each taking half of the columns
+        // ===== epilogue: warps 2..9, TMEM lane quarter = warp % 4, two warps per quarter (half the columns each) =====
         const int q = warp & 3;
         const int chalf = (warp - 2) >> 2;
-        const int m = m0 + q * 32 + lane;
-        const bool row_ok = m < g.M;
         const int pitch = SPLIT ? g.lo_o : g.ldo;   // columns of one half
-        float rowsum = 0.f;
-        for (int c0 = chalf * (TBN / 2); c0 < (chalf + 1) * (TBN / 2); c0 += 32) {
-            if (n0 + c0 >= g.N) break;   // warp-uniform
-            uint32_t r[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-            if (!row_ok) continue;
-            const int nb = n0 + c0;
-            const size_t row_off = (size_t)m * g.ldo;
-            if (g.ep == TEP_ACT) {
-                float hv[32], dv[32];
+        int i = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+            const int as = i & 1;
+            const int m0 = (tile / ntn) * TBM, n0 = (tile % ntn) * TBN;
+            float* sb = sbias + as * TBN;
+            {   // stage this tile's bias slice (double-buffered: tile i - 1 may still be read by a slower warp)
+                const int e = threadIdx.x - 64;   // 0..255
+                if (e < TBN) sb[e] = (g.bias && n0 + e < g.N) ? __ldg(g.bias + n0 + e) : 0.f;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            mbar_wait(&tmem_full[as], (i >> 1) & 1);
+            tc_fence_after();
+            const int m = m0 + q * 32 + lane;
+            const bool row_ok = m < g.M;
+            float rowsum = 0.f;
+            for (int c0 = chalf * (TBN / 2); c0 < (chalf + 1) * (TBN / 2); c0 += 32) {
+                if (n0 + c0 >= g.N) break;   // warp-uniform
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TBN + c0), r);
+                if (!row_ok) continue;
+                const int nb = n0 + c0;
+                const size_t row_off = (size_t)m * g.ldo;
+                if (g.ep == TEP_ACT) {
+                    float hv[32], dv[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    hv[j] = 0.f; dv[j] = 0.f;
-                    if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + sbias[c0 + j], hv[j], dv[j]);
-                }
-                store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, hv);
-                store_row32<SPLIT>(g.out1, row_off, nb, pitch, g.lo_o, dv);
-            } else if (g.ep == TEP_MULD) {
-                float dv[32], gv[32];
-                load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
+                    for (int j = 0; j < 32; ++j) {
+                        hv[j] = 0.f; dv[j] = 0.f;
+                        if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + sb[c0 + j], hv[j], dv[j]);
+                    }
+                    store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, hv);
+                    store_row32<SPLIT>(g.out1, row_off, nb, pitch, g.lo_o, dv);
+                } else if (g.ep == TEP_MULD) {
+                    float dv[32], gv[32];
+                    load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) gv[j] = (nb + j < g.N) ? __uint_as_float(r[j]) * dv[j] : 0.f;
-                store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, gv);
-            } else if (g.ep == TEP_TRACE) {
-                float dv[32];
-                load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
+                    for (int j = 0; j < 32; ++j) gv[j] = (nb + j < g.N) ? __uint_as_float(r[j]) * dv[j] : 0.f;
+                    store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, gv);
+                } else if (g.ep == TEP_TRACE) {
+                    float dv[32];
+                    load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (nb + j < g.N) rowsum = fmaf(__uint_as_float(r[j]), dv[j], rowsum);
-            } else {
+                    for (int j = 0; j < 32; ++j)
+                        if (nb + j < g.N) rowsum = fmaf(__uint_as_float(r[j]), dv[j], rowsum);
+                } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = nb + j;
-                    if (n < g.N && n < g.n_limit) {
-                        float v = __uint_as_float(r[j]);
-                        if (g.ep == TEP_LIN_SOA) v += sbias[c0 + j];
-                        g.out_f32[(size_t)n * g.M + m] = v;
+                    for (int j = 0; j < 32; ++j) {
+                        const int n = nb + j;
+                        if (n < g.N && n < g.n_limit) {
+                            float v = __uint_as_float(r[j]);
+                            if (g.ep == TEP_LIN_SOA) v += sb[c0 + j];
+                            g.out_f32[(size_t)n * g.M + m] = v;
+                        }
                     }
                 }
             }
+            // this warp's TMEM reads of the tile are complete (tcgen05.wait::ld in tmem_ld32): hand the buffer back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (g.ep == TEP_TRACE && row_ok) atomicAdd(g.out_f32 + m, rowsum);   // two column halves (and unit tiles) per row
         }
-        if (g.ep == TEP_TRACE && row_ok) atomicAdd(g.out_f32 + m, rowsum);   // two column halves (and unit tiles) per row
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TBN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TBN));
     }
 }
 
