@@ -301,10 +301,18 @@ __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
                 const size_t row_off = (size_t)m * g.ldo;
                 if (g.ep == TEP_ACT) {
                     float hv[32], dv[32];
+                    if (g.act == ICNF_ACT_SOFTPLUS) {   // the default activation without a per-element switch
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        hv[j] = 0.f; dv[j] = 0.f;
-                        if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + sb[c0 + j], hv[j], dv[j]);
+                        for (int j = 0; j < 32; ++j) {
+                            hv[j] = 0.f; dv[j] = 0.f;
+                            if (nb + j < g.N) act_eval<ICNF_ACT_SOFTPLUS>(__uint_as_float(r[j]) + sb[c0 + j], hv[j], dv[j]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            hv[j] = 0.f; dv[j] = 0.f;
+                            if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + sb[c0 + j], hv[j], dv[j]);
+                        }
                     }
                     store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, hv);
                     store_row32<SPLIT>(g.out1, row_off, nb, pitch, g.lo_o, dv);
