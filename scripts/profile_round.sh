@@ -23,4 +23,8 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 200 --csv --
 python scripts/time_wide.py fp32 > gpurun_out/time_wide.txt 2>&1
 python scripts/time_wide.py bf16_tc >> gpurun_out/time_wide.txt 2>&1
 python scripts/time_wide.py bf16x3_tc >> gpurun_out/time_wide.txt 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file gpurun_out/launches_c3.csv \
+    python scripts/time_config3.py fp32 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:gemm_ws -s 41 -c 1 -o gpurun_out/prof_generic_ws \
+    python scripts/time_config3.py fp32 > /dev/null 2>&1
 ls -la gpurun_out
