@@ -204,6 +204,32 @@ def logp_extras(m, local, dev, flush_buf):
                      "mode": repr(mode), "solver_steps": st.naccept, "rhs_calls": st.nf,
                      "algorithmic_tflops": flop_rhs * st.nf * B / (ms / K * 1e-3) / 1e12}
         del icnf
+    # BASELINE config 4 as a TRAINING step (loss + gradient, RNODE regularisers, adaptive Tsit5): fp32 family, and the
+    # split-precision tensor-core forward with the fp32 reverse sweep
+    for name, prec in (("config4_ffjord784_B8192_train_fp32", "fp32"), ("config4_ffjord784_B8192_train_bf16x3tc", "bf16x3_tc")):
+        B = 8192
+        icnf = m.ICNF(device=local, epsdist="rademacher", nvariables=784, naugments=0, nn=ffjord, precision=prec)
+        rng = np.random.default_rng(7)
+        theta, _ = m.setup(rng, icnf)
+        theta_d = torch.from_numpy(theta).to(dev)
+        xs = torch.from_numpy(rng.standard_normal((B, 784)).astype(np.float32)).to(dev)
+        for _ in range(2):
+            m.loss_and_gradient(icnf, m.TrainMode(True), xs.t(), theta_d, {}, seed=3)
+        torch.cuda.synchronize()
+        K, ms = 3, 0.0
+        for _ in range(K):
+            flush_buf.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            m.loss_and_gradient(icnf, m.TrainMode(True), xs.t(), theta_d, {}, seed=3)
+            b.record()
+            torch.cuda.synchronize()
+            ms += a.elapsed_time(b)
+        st = icnf.last_stats
+        out[name] = {"train_samples_per_sec": B * K / (ms * 1e-3), "ms_per_call": ms / K, "kernel_family": icnf.kernel_family,
+                     "mode": "TrainMode(True) loss + gradient", "solver_steps": st.naccept, "rhs_calls": st.nf,
+                     "logp_evals_per_sec": 0.0, "algorithmic_tflops": 0.0}
+        del icnf
     return out
 
 

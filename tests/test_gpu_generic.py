@@ -108,6 +108,30 @@ def test_config3_exact_trace_at_a_larger_batch(m):
     assert np.isfinite(logp).all()
 
 
+@pytest.mark.parametrize("shape", ["config3_gmm16", "cond_generic"])
+@pytest.mark.parametrize("B", [2048, 2051])
+def test_weights_stationary_gemm_paths(m, shape, B):
+    """Batches >= 2048 route the narrow layers through the weights-stationary persistent SGEMM: vector
+    (B % 4 == 0) and scalar tile loads / epilogues, the gathered [z; t; ys] operand, and every epilogue
+    the reverse sweep uses."""
+    from tests.helpers import norm_rel_err
+    icnf = make_icnf(m, shape)
+    om, theta, xs, eps, ys = make_inputs(icnf, B)
+    args = (xs,) if ys is None else (xs, ys)
+    sol = dict(adaptive=False, dt=0.25)
+    opts = O.SolverOpts(adaptive=False, dt=0.25)
+    for mode, omode in [(m.TrainMode(True), O.TRAIN_REG), (m.TestMode(), O.TEST)]:
+        logp, regs = m.inference(icnf, mode, *args, theta, {}, eps=eps, tspan=icnf.tspan, **sol)
+        for sub in (slice(0, 40), slice(B - 40, B)):
+            ref, rr = O.inference(om, omode, t64(xs[:, sub]), t64(theta), t64(eps[:, sub]) if eps is not None else None,
+                                  t64(ys[:, sub]) if ys is not None else None, opts=opts)
+            np.testing.assert_allclose(logp[sub], ref.detach().numpy(), rtol=RTOL, atol=2e-5)
+    l, g = m.loss_and_gradient(icnf, m.TrainMode(True), *args, theta, {}, eps=eps, tspan=icnf.tspan, **sol)
+    rl, rg = O.loss_grad(om, O.TRAIN_REG, t64(xs), t64(theta), t64(eps), t64(ys), opts=opts)[:2]
+    assert abs(l - float(rl)) <= RTOL * abs(float(rl)) + 1e-6
+    assert norm_rel_err(g, rg.numpy()) < RTOL
+
+
 @pytest.mark.parametrize("shape", list(GENERIC_SHAPES))
 @pytest.mark.parametrize("adaptive", [False, True])
 def test_loss_and_gradient_match_oracle(m, shape, adaptive):
