@@ -148,6 +148,8 @@ struct icnf_handle {
         lossterm, scalar, dtheta, dxs;
     DevStats* stats_host = nullptr;  // pinned
     float* scalar_host = nullptr;    // pinned
+    float* grad_host = nullptr;      // pinned staging for the gradient: a copy into the caller's pageable buffer would block per copy
+    size_t grad_host_cap = 0;
     long long launches = 0;
     bool profiling = false;
     cudaEvent_t prof_ev[4][2] = {};
@@ -460,6 +462,7 @@ void icnf_destroy(icnf_handle* h) {
     for (DevBuf* b : bufs) b->release();
     if (h->stats_host) cudaFreeHost(h->stats_host);
     if (h->scalar_host) cudaFreeHost(h->scalar_host);
+    if (h->grad_host) cudaFreeHost(h->grad_host);
     for (auto& pr : h->prof_ev)
         for (cudaEvent_t ev : pr)
             if (ev) cudaEventDestroy(ev);
@@ -804,10 +807,20 @@ static int loss_grad_host(icnf_handle* h, int mode, const icnf_solver* sol, floa
                                global_batch, h->stream)))
         return rc;
     CK(h, cudaMemcpyAsync(h->scalar_host, h->scalar.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    if (dtheta) CK(h, cudaMemcpyAsync(dtheta, h->dtheta.p, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+    if (dtheta) {
+        if (h->grad_host_cap < (size_t)np) {
+            if (h->grad_host) cudaFreeHost(h->grad_host);
+            h->grad_host = nullptr;
+            h->grad_host_cap = 0;
+            CK(h, cudaMallocHost((void**)&h->grad_host, sizeof(float) * (size_t)np));
+            h->grad_host_cap = (size_t)np;
+        }
+        CK(h, cudaMemcpyAsync(h->grad_host, h->dtheta.p, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+    }
     if (dxs) CK(h, cudaMemcpyAsync(dxs, h->dxs.p, sizeof(float) * (size_t)h->cfg.nvars * B, cudaMemcpyDeviceToHost, h->stream));
-    rc = finish_stats(h, stats, h->stream);
+    rc = finish_stats(h, stats, h->stream);   // one synchronisation for loss, gradient and statistics
     *loss = h->scalar_host[0];
+    if (dtheta) memcpy(dtheta, h->grad_host, sizeof(float) * (size_t)np);
     return rc;
 }
 
