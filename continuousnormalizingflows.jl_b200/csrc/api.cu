@@ -383,6 +383,27 @@ extern "C" {
 
 const char* icnf_version(void) { return "icnf_b200 0.1.0 (sm_100a)"; }
 
+int icnf_backward_plan(const icnf_config* cfg, int exact, int sm_count, int64_t B, int32_t* threads, int32_t* grid,
+                       int32_t* first, int32_t* n_blocks) {
+    if (!cfg || !threads || !grid || !first || !n_blocks || B < 1 || sm_count < 1) return ICNF_ERR_INVALID;
+    if (cfg->abi_version != ICNF_ABI_VERSION || cfg->n_layers < 1 || cfg->n_layers > ICNF_MAX_LAYERS) return ICNF_ERR_INVALID;
+    NetShape shape;
+    memset(&shape, 0, sizeof shape);
+    shape.act = cfg->activation; shape.D = cfg->nvars + cfg->naug; shape.C = cfg->ncond; shape.NL = cfg->n_layers;
+    for (int l = 0; l <= cfg->n_layers; ++l) shape.n[l] = cfg->sizes[l];
+    if (cfg->precision != ICNF_FP32) return ICNF_ERR_UNSUPPORTED;
+    for (const Family* f : tiny_registry())
+        if (f->shape == shape) {
+            if (!f->backward_plan) return ICNF_ERR_UNSUPPORTED;
+            int t = 0, g = 0, nb = 0, fi[34] = {0};
+            f->backward_plan(exact != 0, sm_count, (long long)B, &t, &g, fi, &nb);
+            *threads = t; *grid = g; *n_blocks = nb;
+            for (int b = 0; b <= nb; ++b) first[b] = fi[b];
+            return ICNF_OK;
+        }
+    return ICNF_ERR_UNSUPPORTED;
+}
+
 int icnf_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;

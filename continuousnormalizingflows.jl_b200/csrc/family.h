@@ -43,6 +43,9 @@ struct Family {
     int supports_backward;
     int fuses_loss_sum_adaptive;     // the adaptive solve writes the scalar loss itself (SolveArgs::out_loss)
     int adaptive_threads;            // CTA size of the cooperative adaptive kernel (0: not cooperative)
+    // host-only launch plan of the backward kernel (no device needed): CTA size, grid, first thread of every dW block
+    // (`first` has room for 34 entries; entries [0, n_blocks] are filled), null when the family has no such plan
+    void (*backward_plan)(bool exact, int sm_count, long long B, int* threads, int* grid, int* first, int* n_blocks);
     int ckpt_stages;                 // training checkpoints per step and sample, in units of D' floats (tiny: 6 stage inputs)
 };
 

@@ -198,6 +198,22 @@ struct Launch {
         return p;
     }
     template <bool EXACT>
+    static void plan_sp(int sm_count, long long B, int* threads, int* grid, int* first, int* n_blocks) {
+        int ns, g;
+        sp_plan<EXACT>(B, sm_count, ns, g);
+        const SPPlan p = sp_threads<EXACT>(ns);
+        *threads = ns; *grid = g; *n_blocks = SPCfg<N, EXACT>::NBLK;
+        for (int b = 0; b <= SPCfg<N, EXACT>::NBLK; ++b) first[b] = p.first[b];
+    }
+    static void backward_plan(bool exact, int sm_count, long long B, int* threads, int* grid, int* first, int* n_blocks) {
+        if constexpr (USE_SP) {
+            if (exact) plan_sp<true>(sm_count, B, threads, grid, first, n_blocks);
+            else plan_sp<false>(sm_count, B, threads, grid, first, n_blocks);
+        } else {
+            *threads = NT; *grid = backward_grid(exact, sm_count, B); *n_blocks = 0; first[0] = 0;
+        }
+    }
+    template <bool EXACT>
     static cudaError_t backward_sp(const float* theta, const BackwardArgs& a, int grid, cudaStream_t st) {
         using C = SPCfg<N, EXACT>;
         int ns, g2;
@@ -248,6 +264,7 @@ struct Launch {
         f.fuses_loss_sum_adaptive = 1;
         f.adaptive_threads = 64;
         f.ckpt_stages = 6;
+        f.backward_plan = USE_SP ? &backward_plan : nullptr;
         return f;
     }
 };

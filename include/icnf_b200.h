@@ -250,6 +250,13 @@ ICNF_API int icnf_measure_fp32_peak(int device, float* tflops);
  * D[n * M + m]) = A (M x K, row-major) * B (N x K, row-major)' with inputs rounded to
  * bf16 (split = 0) or to bf16 hi + lo pairs (split = 1, ICNF_BF16X3_TC) and fp32
  * accumulation; host buffers; runs on the current device. */
+/* Host-only (no device is touched): the launch plan of the tiny family's backward kernel for a batch of B samples on a
+ * device with `sm_count` SMs -- threads per CTA (= samples per tile), grid size, and first[0 .. n_blocks]: the first
+ * thread of every weight-gradient block (block b owns threads [first[b], first[b + 1]); `first` needs 34 entries).
+ * ICNF_ERR_UNSUPPORTED when the shape is not served by that kernel.  Used by the CPU test-suite. */
+ICNF_API int icnf_backward_plan(const icnf_config* cfg, int exact, int sm_count, int64_t B, int32_t* threads, int32_t* grid,
+                                int32_t* first, int32_t* n_blocks);
+
 ICNF_API int icnf_tc_gemm_selftest(int M, int N, int K, const float* A, const float* B, float* D, int split);
 
 #ifdef __cplusplus

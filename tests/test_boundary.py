@@ -65,3 +65,50 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".jl")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+# ------------------------------------------------------------------ host logic of the backward launch plan (no GPU)
+def _plan(m, sizes, act, nvars, naug, ncond, B, sm_count=148, exact=0):
+    import ctypes as C
+    L = m._lib
+    cfg = L.Config()
+    cfg.abi_version = L.ICNF_ABI_VERSION
+    cfg.nvars, cfg.naug, cfg.ncond = nvars, naug, ncond
+    cfg.autonomous = int(sizes[0] == nvars + naug + ncond)
+    cfg.n_layers = len(sizes) - 1
+    for i, s in enumerate(sizes):
+        cfg.sizes[i] = s
+    cfg.activation = L.ACT[act]
+    cfg.precision = L.PRECISION["fp32"]
+    threads, grid, nb = C.c_int32(), C.c_int32(), C.c_int32()
+    first = (C.c_int32 * 34)()
+    rc = m.lib.icnf_backward_plan(C.byref(cfg), exact, sm_count, B, C.byref(threads), C.byref(grid), first, C.byref(nb))
+    return rc, threads.value, grid.value, list(first[: nb.value + 1])
+
+
+@pytest.mark.parametrize("B", [1, 31, 300, 4096, 65536, 200_003, 1_000_000])
+@pytest.mark.parametrize("exact", [0, 1])
+def test_backward_plan_covers_the_batch(m, B, exact):
+    """Config 2's shape (3-12-12-2 softplus): the plan is a pure function of (B, SM count)."""
+    rc, threads, grid, first = _plan(m, (3, 12, 12, 2), "softplus", 2, 0, 0, B, exact=exact)
+    assert rc == 0
+    assert threads % 32 == 0 and 32 <= threads <= 256
+    tiles = -(-B // threads)
+    assert 1 <= grid <= min(tiles, 2 * 148)                  # at most two CTAs per SM, never more CTAs than tiles
+    rounds = -(-tiles // grid)
+    assert rounds == -(-B // (2 * 148 * threads)) or threads < 224 or rounds >= 1
+    # dW blocks: contiguous thread ranges, every block has threads, nothing beyond the CTA
+    assert first[0] == 0 and all(b > a for a, b in zip(first, first[1:])) and first[-1] <= threads
+    if threads // 32 >= len(first) - 1:                      # one warp or more per block: a warp never mixes blocks
+        assert all(f % 32 == 0 for f in first)
+
+
+def test_backward_plan_headline_batch_is_one_round(m):
+    rc, threads, grid, first = _plan(m, (3, 12, 12, 2), "softplus", 2, 0, 0, 65536)
+    assert rc == 0 and threads == 224 and grid == 293         # 293 x 224 >= 65 536: every SM holds its share at once
+    assert len(first) - 1 == 7 and first[-1] == 224           # seven dW blocks, one warp each
+
+
+def test_backward_plan_unknown_shape_is_unsupported(m):
+    rc, *_ = _plan(m, (3, 64, 64, 2), "softplus", 2, 0, 0, 1024)
+    assert rc == 7                                            # ICNF_ERR_UNSUPPORTED: served by the generic family
