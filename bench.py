@@ -262,7 +262,9 @@ def main():
 
     import cnf_b200 as m
     B = args.batch
-    icnf = m.ICNF(nvariables=2, naugments=0, device=local, epsdist="rademacher", rng=1234 + rank)
+    # the STEER stream is seeded identically on every rank: the unsharded solve draws ONE t1 for the whole batch
+    # (base_icnf.jl:23-43), so the shards of a data-parallel step must integrate to the same t1
+    icnf = m.ICNF(nvariables=2, naugments=0, device=local, epsdist="rademacher", rng=1234)
     assert icnf.kernel_family == "tiny"
     theta = init_theta()
     xs_all = two_moons(B * world, seed=1)
