@@ -230,6 +230,25 @@ def test_gradient_large_batch_several_tiles_per_cta(m):
     assert norm_rel_err(ga + gb, g) < 2e-5
 
 
+def test_full_size_training_step_directional_derivative(m):
+    """BASELINE config 2 at its full batch (65 536): instead of an oracle run, a size-independent property --
+    the gradient predicts the loss change along a random direction (central difference, fixed step so the
+    discretisation is the same function of theta)."""
+    icnf = make_icnf(m, "config2_moons")
+    B = 65536
+    om, theta, xs, _, _ = make_inputs(icnf, B)
+    kw = dict(seed=11, tspan=icnf.tspan, adaptive=False, dt=0.125)
+    l, g = m.loss_and_gradient(icnf, m.TrainMode(True), xs, theta, {}, **kw)
+    v = np.random.default_rng(2).standard_normal(theta.shape).astype(np.float32)
+    v /= np.linalg.norm(v)
+    h = 2e-2
+    lp = m.loss(icnf, m.TrainMode(True), xs, (theta + h * v).astype(np.float32), {}, **kw)
+    lm = m.loss(icnf, m.TrainMode(True), xs, (theta - h * v).astype(np.float32), {}, **kw)
+    fd = (lp - lm) / (2 * h)
+    an = float(np.dot(g.astype(np.float64), v.astype(np.float64)))
+    assert abs(fd - an) <= 5e-3 * max(abs(an), 1e-3) + 2e-4, (fd, an)
+
+
 @pytest.mark.parametrize("B", [1, 2, 31, 33])
 def test_gradient_tiny_batches(m, B):
     icnf = make_icnf(m, "config2_moons")
