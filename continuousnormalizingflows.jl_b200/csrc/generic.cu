@@ -183,10 +183,59 @@ __global__ void __launch_bounds__(GT, 2) gemm128_kernel(GemmArgs g) {
             *reinterpret_cast<float4*>(&Bs[buf][kk0 + 8 * h][c4]) = rb[h];
         }
     };
+    const int nchunk = (g.K + LK - 1) / LK;
+    // interior tiles of plain (non-gathered) operands: cp.async straight into shared memory, no staging registers
+    const bool fast = !g.gather && m0 + LM <= g.M && n0 + LN <= g.N && ((g.lda & 3) == 0) && ((g.ldb & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.Bm) & 15) == 0);
+    auto issue_chunk = [&](int k0, int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int kr = kk0 + 8 * h, k = k0 + kr;
+            float* da = &As[buf][kr][c4];
+            float* db = &Bs[buf][kr][c4];
+            if (k < g.K) {
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(da)),
+                             "l"(g.A + (long long)k * g.lda + m0 + c4) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(db)),
+                             "l"(g.Bm + (long long)k * g.ldb + n0 + c4) : "memory");
+            } else {
+                *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(db) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    if (fast) {
+        issue_chunk(0, 0);
+        for (int c = 0; c < nchunk; ++c) {
+            const int buf = c & 1;
+            if (c + 1 < nchunk) {
+                issue_chunk((c + 1) * LK, buf ^ 1);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < LK; ++kk) {
+                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+                const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+                const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                      make_float2(b1.z, b1.w)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(av[i], av[i]), bp[j], acc[i][j]);
+            }
+            __syncthreads();   // the buffer just read is the next cp.async target
+        }
+    } else {
     load_chunk(0);
     store_chunk(0);
     __syncthreads();
-    const int nchunk = (g.K + LK - 1) / LK;
     for (int c = 0; c < nchunk; ++c) {
         const int buf = c & 1;
         if (c + 1 < nchunk) load_chunk((c + 1) * LK);
@@ -206,6 +255,7 @@ __global__ void __launch_bounds__(GT, 2) gemm128_kernel(GemmArgs g) {
         }
         if (c + 1 < nchunk) store_chunk(buf ^ 1);
         __syncthreads();
+    }
     }
     float colpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
