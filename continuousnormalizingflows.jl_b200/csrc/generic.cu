@@ -126,6 +126,57 @@ __device__ __forceinline__ float gemm_epilogue(const GemmArgs& g, int m, long lo
     return 0.f;
 }
 
+// epilogue of four consecutive samples (n .. n + 3) of one output row: float4 accesses when `vec` (row pitch and n
+// multiples of 4, all four samples in range), the scalar epilogue otherwise
+__device__ __forceinline__ void gemm_epilogue4(const GemmArgs& g, int m, long long n, const float (&v4)[4], bool vec,
+                                               float (&colpart)[4]) {
+    const long long o = (long long)m * g.N + n;
+    if (vec && (g.ep == EP_ACT || g.ep == EP_LIN || g.ep == EP_PLAIN || g.ep == EP_MULD || g.ep == EP_TRACE ||
+                g.ep == EP_MULADD)) {
+        if (g.ep == EP_ACT) {
+            const float bm = g.bias[m];
+            float4 h, d;
+            if (g.act == ICNF_ACT_SOFTPLUS) {   // the common case without a per-element switch
+                act_eval<ICNF_ACT_SOFTPLUS>(v4[0] + bm, h.x, d.x);
+                act_eval<ICNF_ACT_SOFTPLUS>(v4[1] + bm, h.y, d.y);
+                act_eval<ICNF_ACT_SOFTPLUS>(v4[2] + bm, h.z, d.z);
+                act_eval<ICNF_ACT_SOFTPLUS>(v4[3] + bm, h.w, d.w);
+            } else {
+                act_eval_rt(g.act, v4[0] + bm, h.x, d.x);
+                act_eval_rt(g.act, v4[1] + bm, h.y, d.y);
+                act_eval_rt(g.act, v4[2] + bm, h.z, d.z);
+                act_eval_rt(g.act, v4[3] + bm, h.w, d.w);
+            }
+            *reinterpret_cast<float4*>(g.out0 + o) = h;
+            *reinterpret_cast<float4*>(g.out1 + o) = d;
+        } else if (g.ep == EP_LIN) {
+            const float bm = g.bias[m];
+            *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0] + bm, v4[1] + bm, v4[2] + bm, v4[3] + bm);
+        } else if (g.ep == EP_PLAIN) {
+            *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+        } else if (g.ep == EP_MULD) {
+            const float4 x = *reinterpret_cast<const float4*>(g.aux0 + o);
+            if (g.out1) *reinterpret_cast<float4*>(g.out1 + o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
+            *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0] * x.x, v4[1] * x.y, v4[2] * x.z, v4[3] * x.w);
+        } else if (g.ep == EP_MULADD) {
+            const float4 x = *reinterpret_cast<const float4*>(g.aux0 + o);
+            const float4 y = *reinterpret_cast<const float4*>(g.aux1 + o);
+            *reinterpret_cast<float4*>(g.out0 + o) =
+                make_float4(fmaf(v4[0], x.x, y.x), fmaf(v4[1], x.y, y.y), fmaf(v4[2], x.z, y.z), fmaf(v4[3], x.w, y.w));
+        } else {
+            const float4 x = *reinterpret_cast<const float4*>(g.aux0 + o);
+            colpart[0] = fmaf(v4[0], x.x, colpart[0]);
+            colpart[1] = fmaf(v4[1], x.y, colpart[1]);
+            colpart[2] = fmaf(v4[2], x.z, colpart[2]);
+            colpart[3] = fmaf(v4[3], x.w, colpart[3]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (n + j < g.N) colpart[j] += gemm_epilogue(g, m, n + j, v4[j]);
+    }
+}
+
 // 128 x 128 x 16 tiles, 8 x 8 outputs per thread (as 4 + 4 rows / columns 64 apart, so that every
 // 128-bit shared-memory read of a half-warp is contiguous), register-prefetched double buffering.
 constexpr int LM = 128, LN = 128, LK = 16;
@@ -258,16 +309,20 @@ __global__ void __launch_bounds__(GT, 2) gemm128_kernel(GemmArgs g) {
     }
     }
     float colpart[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool nvec = (g.N & 3) == 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
         if (m >= g.M) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const long long n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        for (int jh = 0; jh < 2; ++jh) {
+            const long long n = n0 + jh * 64 + tx * 4;
             if (n >= g.N) continue;
-            const float2 a2 = acc[i][j >> 1];
-            colpart[j] += gemm_epilogue(g, m, n, (j & 1) ? a2.y : a2.x);
+            const float v4[4] = {acc[i][2 * jh].x, acc[i][2 * jh].y, acc[i][2 * jh + 1].x, acc[i][2 * jh + 1].y};
+            float cp4[4] = {0.f, 0.f, 0.f, 0.f};
+            gemm_epilogue4(g, m, n, v4, nvec && n + 3 < g.N, cp4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) colpart[jh * 4 + j] += cp4[j];
         }
     }
     if (g.ep == EP_TRACE) {
@@ -516,45 +571,7 @@ __global__ void __launch_bounds__(512) gemm_ws_kernel(GemmArgs g, int nty, int n
                 const int m = 4 * ty + i;
                 if (m >= g.M) continue;
                 const float v4[4] = {acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y};
-                const long long o = (long long)m * g.N + n0;
-                if (vec && (g.ep == EP_ACT || g.ep == EP_LIN || g.ep == EP_PLAIN || g.ep == EP_MULD || g.ep == EP_TRACE)) {
-                    if (g.ep == EP_ACT) {
-                        const float bm = g.bias[m];
-                        float4 h, d;
-                        if (g.act == ICNF_ACT_SOFTPLUS) {   // the common case without a per-element switch
-                            act_eval<ICNF_ACT_SOFTPLUS>(v4[0] + bm, h.x, d.x);
-                            act_eval<ICNF_ACT_SOFTPLUS>(v4[1] + bm, h.y, d.y);
-                            act_eval<ICNF_ACT_SOFTPLUS>(v4[2] + bm, h.z, d.z);
-                            act_eval<ICNF_ACT_SOFTPLUS>(v4[3] + bm, h.w, d.w);
-                        } else {
-                            act_eval_rt(g.act, v4[0] + bm, h.x, d.x);
-                            act_eval_rt(g.act, v4[1] + bm, h.y, d.y);
-                            act_eval_rt(g.act, v4[2] + bm, h.z, d.z);
-                            act_eval_rt(g.act, v4[3] + bm, h.w, d.w);
-                        }
-                        *reinterpret_cast<float4*>(g.out0 + o) = h;
-                        *reinterpret_cast<float4*>(g.out1 + o) = d;
-                    } else if (g.ep == EP_LIN) {
-                        const float bm = g.bias[m];
-                        *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0] + bm, v4[1] + bm, v4[2] + bm, v4[3] + bm);
-                    } else if (g.ep == EP_PLAIN) {
-                        *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-                    } else if (g.ep == EP_MULD) {
-                        const float4 x = *reinterpret_cast<const float4*>(g.aux0 + o);
-                        if (g.out1) *reinterpret_cast<float4*>(g.out1 + o) = make_float4(v4[0], v4[1], v4[2], v4[3]);
-                        *reinterpret_cast<float4*>(g.out0 + o) = make_float4(v4[0] * x.x, v4[1] * x.y, v4[2] * x.z, v4[3] * x.w);
-                    } else {
-                        const float4 x = *reinterpret_cast<const float4*>(g.aux0 + o);
-                        colpart[0] = fmaf(v4[0], x.x, colpart[0]);
-                        colpart[1] = fmaf(v4[1], x.y, colpart[1]);
-                        colpart[2] = fmaf(v4[2], x.z, colpart[2]);
-                        colpart[3] = fmaf(v4[3], x.w, colpart[3]);
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (n0 + j < g.N) colpart[j] += gemm_epilogue(g, m, n0 + j, v4[j]);
-                }
+                gemm_epilogue4(g, m, n0, v4, vec, colpart);
             }
         }
         if (g.ep == EP_TRACE) {
