@@ -236,8 +236,11 @@ __global__ void __launch_bounds__(GT, 2) gemm128_kernel(GemmArgs g) {
     };
     const int nchunk = (g.K + LK - 1) / LK;
     // interior tiles of plain (non-gathered) operands: cp.async straight into shared memory, no staging registers
-    const bool fast = !g.gather && m0 + LM <= g.M && n0 + LN <= g.N && ((g.lda & 3) == 0) && ((g.ldb & 3) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0) && ((reinterpret_cast<uintptr_t>(g.Bm) & 15) == 0);
+    const bool b_ok = g.gather ? (((g.N & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.zi) & 15) == 0) &&
+                                  (!g.C || (reinterpret_cast<uintptr_t>(g.ys) & 15) == 0))
+                               : (((g.ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.Bm) & 15) == 0));
+    const bool fast = b_ok && m0 + LM <= g.M && n0 + LN <= g.N && ((g.lda & 3) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
     auto issue_chunk = [&](int k0, int buf) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -247,8 +250,16 @@ __global__ void __launch_bounds__(GT, 2) gemm128_kernel(GemmArgs g) {
             if (k < g.K) {
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(da)),
                              "l"(g.A + (long long)k * g.lda + m0 + c4) : "memory");
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(db)),
-                             "l"(g.Bm + (long long)k * g.ldb + n0 + c4) : "memory");
+                // B row k: a plain matrix row, or a row of the gathered [z; t; ys] input
+                const float* brow = nullptr;
+                if (!g.gather) brow = g.Bm + (long long)k * g.ldb;
+                else if (k < g.D) brow = g.zi + (long long)k * g.N;
+                else if (!(g.tin && k == g.D)) brow = g.ys + (long long)(k - g.D - g.tin) * g.N;
+                if (brow)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(db)),
+                                 "l"(brow + n0 + c4) : "memory");
+                else
+                    *reinterpret_cast<float4*>(db) = make_float4(tnow, tnow, tnow, tnow);
             } else {
                 *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4*>(db) = make_float4(0.f, 0.f, 0.f, 0.f);
