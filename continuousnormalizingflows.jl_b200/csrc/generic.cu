@@ -1200,6 +1200,134 @@ __global__ void __launch_bounds__(GT) wgrad_kernel(WgradArgs g) {
     }
 }
 
+// Wide layers: the same split-K weight gradient with 128 x 128 tiles, 8 x 8 outputs per thread and packed FFMA2
+// (the 64 x 64 scalar kernel above reached 16 TFLOP/s and was 41 % of a config-4 training step).  Both operands
+// are contiguous along the samples (the reduction), so tiles are transposed on their way into shared memory;
+// the next chunk is fetched into registers while the current one is being multiplied.
+__global__ void __launch_bounds__(GT, 2) wgrad128_kernel(WgradArgs g) {
+    constexpr int PW = LM + 4;
+    __shared__ __align__(16) float Xs[2][LK][PW];
+    __shared__ __align__(16) float Ys[2][LK][PW];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int j0 = blockIdx.y * LM, k0 = blockIdx.x * LN;
+    const long long b_lo = (long long)blockIdx.z * g.chunk, b_hi = min(g.B, b_lo + g.chunk);
+    float2 acc[8][4];
+    float bacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        bacc[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    }
+    const int lr = threadIdx.x >> 2, s4 = (threadIdx.x & 3) * 4;   // loader role: rows lr and lr + 64, samples s4 .. s4 + 3
+    const bool b4 = (g.B & 3) == 0;
+    const int npass = (g.X2 && k0 < g.K2) ? 2 : 1;
+    float4 rx[2], ry[2];
+    auto row_ptr_y = [&](int pass, int k) -> const float* {   // null: zero row or the constant time row
+        if (pass == 1) return (k < g.K2) ? g.Y2 + (long long)k * g.B : nullptr;
+        if (k >= g.nin) return nullptr;
+        if (!g.gather) return g.Y1 + (long long)k * g.B;
+        if (k < g.D) return g.zi + (long long)k * g.B;
+        if (g.tin && k == g.D) return nullptr;
+        return g.ys + (long long)(k - g.D - g.tin) * g.B;
+    };
+    auto load4 = [&](const float* row, long long b, float fill) {
+        float4 v = make_float4(fill, fill, fill, fill);
+        if (row) {
+            if (b4 && b + 3 < b_hi && ((reinterpret_cast<uintptr_t>(row + b) & 15) == 0)) {
+                v = *reinterpret_cast<const float4*>(row + b);
+            } else {
+                v.x = (b + 0 < b_hi) ? row[b + 0] : 0.f;
+                v.y = (b + 1 < b_hi) ? row[b + 1] : 0.f;
+                v.z = (b + 2 < b_hi) ? row[b + 2] : 0.f;
+                v.w = (b + 3 < b_hi) ? row[b + 3] : 0.f;
+            }
+        } else if (fill != 0.f) {
+            v.x = (b + 0 < b_hi) ? fill : 0.f;
+            v.y = (b + 1 < b_hi) ? fill : 0.f;
+            v.z = (b + 2 < b_hi) ? fill : 0.f;
+            v.w = (b + 3 < b_hi) ? fill : 0.f;
+        }
+        return v;
+    };
+    auto fetch = [&](int pass, long long bb) {
+        const float* X = pass == 0 ? g.X1 : g.X2;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = j0 + lr + 64 * h, k = k0 + lr + 64 * h;
+            rx[h] = load4(j < g.nout ? X + (long long)j * g.B : nullptr, bb + s4, 0.f);
+            const bool trow = pass == 0 && g.gather && g.tin && k == g.D;
+            ry[h] = load4(row_ptr_y(pass, k), bb + s4, trow ? g.tval : 0.f);
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int r = lr + 64 * h;
+            Xs[buf][s4 + 0][r] = rx[h].x; Xs[buf][s4 + 1][r] = rx[h].y; Xs[buf][s4 + 2][r] = rx[h].z; Xs[buf][s4 + 3][r] = rx[h].w;
+            Ys[buf][s4 + 0][r] = ry[h].x; Ys[buf][s4 + 1][r] = ry[h].y; Ys[buf][s4 + 2][r] = ry[h].z; Ys[buf][s4 + 3][r] = ry[h].w;
+        }
+    };
+    const long long nch = (b_hi > b_lo) ? (b_hi - b_lo + LK - 1) / LK : 0;
+    const long long total = nch * (npass - g.first_pass);
+    if (total > 0) {
+        fetch(g.first_pass, b_lo);
+        stash(0);
+        __syncthreads();
+    }
+    for (long long it = 0; it < total; ++it) {
+        const int buf = (int)(it & 1);
+        const int pass = g.first_pass + (int)(it / nch);
+        if (it + 1 < total) fetch(g.first_pass + (int)((it + 1) / nch), b_lo + ((it + 1) % nch) * LK);
+#pragma unroll
+        for (int sidx = 0; sidx < LK; ++sidx) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&Xs[buf][sidx][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&Xs[buf][sidx][64 + ty * 4]);
+            const float4 c0 = *reinterpret_cast<const float4*>(&Ys[buf][sidx][tx * 4]);
+            const float4 c1 = *reinterpret_cast<const float4*>(&Ys[buf][sidx][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float2 bp[4] = {make_float2(c0.x, c0.y), make_float2(c0.z, c0.w), make_float2(c1.x, c1.y), make_float2(c1.z, c1.w)};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(av[i], av[i]), bp[j], acc[i][j]);
+                if (pass == 0 && tx == 0) bacc[i] += av[i];
+            }
+        }
+        if (it + 1 < total) stash(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int j = j0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (j >= g.nout) continue;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int k = k0 + (jj < 4 ? tx * 4 + jj : 64 + tx * 4 + (jj - 4));
+            const float2 a2 = acc[i][jj >> 1];
+            if (k < g.nin) atomicAdd(g.dW + (long long)k * g.nout + j, (jj & 1) ? a2.y : a2.x);
+        }
+        if (g.db && tx == 0 && blockIdx.x == 0) atomicAdd(g.db + j, bacc[i]);
+    }
+}
+
+// launch the weight-gradient kernel that fits the layer; `ncols` = columns of dW that receive a product
+static void launch_wgrad(WgradArgs& wg, int ncols, long long B, cudaStream_t st) {
+    if (wg.nout >= 96 && ncols >= 96) {
+        const int gx = (ncols + LN - 1) / LN, gy = (wg.nout + LM - 1) / LM;
+        int gz = (int)std::min<long long>((B + 255) / 256, std::max(1, 592 / (gx * gy)));
+        wg.chunk = ((B + gz - 1) / gz + LK - 1) / LK * LK;
+        gz = (int)((B + wg.chunk - 1) / wg.chunk);
+        wgrad128_kernel<<<dim3(gx, gy, gz), GT, 0, st>>>(wg);
+        return;
+    }
+    const int gx = (ncols + BN - 1) / BN, gy = (wg.nout + BM - 1) / BM;
+    int gz = (int)std::min<long long>((B + 255) / 256, std::max(1, 592 / (gx * gy)));
+    wg.chunk = ((B + gz - 1) / gz + BK - 1) / BK * BK;
+    gz = (int)((B + wg.chunk - 1) / wg.chunk);
+    wgrad_kernel<<<dim3(gx, gy, gz), GT, 0, st>>>(wg);
+}
+
 // W' (transposed copy) for the VJP GEMMs: WT(k, j) at j * nin + k
 __global__ void g_transpose_w_kernel(const float* W, float* WT, int nout, int nin) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1924,11 +2052,7 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
                         wg.Y2 = wv_ptr(l); wg.K2 = (l == 0) ? D : w->n[l];
                         wg.nout = w->n[l + 1]; wg.nin = w->n[l]; wg.B = B;
                         wg.dW = a.gpartial + w->woff[l]; wg.db = nullptr;
-                        const int gx = (wg.K2 + BN - 1) / BN, gy = (wg.nout + BM - 1) / BM;
-                        int gz = (int)std::min<long long>((B + 255) / 256, std::max(1, 592 / (gx * gy)));
-                        wg.chunk = ((B + gz - 1) / gz + BK - 1) / BK * BK;
-                        gz = (int)((B + wg.chunk - 1) / wg.chunk);
-                        wgrad_kernel<<<dim3(gx, gy, gz), GT, 0, st>>>(wg);
+                        launch_wgrad(wg, wg.K2, B, st);
                         w->launches++;
                     }
                 }
@@ -1944,11 +2068,7 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
                 if (l == 0) { wg.gather = 1; wg.D = D; wg.tin = w->tin; wg.C = w->C; wg.zi = zi; wg.ys = w->YS.as<float>(); wg.tval = ti; }
                 else wg.Y1 = H + w->hoff[l - 1] * B;
                 wg.dW = a.gpartial + w->woff[l]; wg.db = a.gpartial + w->boff[l];
-                const int gx = (wg.nin + BN - 1) / BN, gy = (wg.nout + BM - 1) / BM;
-                int gz = (int)std::min<long long>((B + 255) / 256, std::max(1, 592 / (gx * gy)));
-                wg.chunk = ((B + gz - 1) / gz + BK - 1) / BK * BK;
-                gz = (int)((B + wg.chunk - 1) / wg.chunk);
-                wgrad_kernel<<<dim3(gx, gy, gz), GT, 0, st>>>(wg);
+                launch_wgrad(wg, wg.nin, B, st);
                 w->launches++;
                 GemmArgs g;
                 memset(&g, 0, sizeof g);
