@@ -1315,7 +1315,7 @@ __global__ void __launch_bounds__(GT, 2) wgrad128_kernel(WgradArgs g) {
 static void launch_wgrad(WgradArgs& wg, int ncols, long long B, cudaStream_t st) {
     if (wg.nout >= 96 && ncols >= 96) {
         const int gx = (ncols + LN - 1) / LN, gy = (wg.nout + LM - 1) / LM;
-        int gz = (int)std::min<long long>((B + 255) / 256, std::max(1, 592 / (gx * gy)));
+        int gz = (int)std::min<long long>((B + 255) / 256, std::max(1, 296 / (gx * gy)));   // one wave of 2 CTAs per SM
         wg.chunk = ((B + gz - 1) / gz + LK - 1) / LK * LK;
         gz = (int)((B + wg.chunk - 1) / wg.chunk);
         wgrad128_kernel<<<dim3(gx, gy, gz), GT, 0, st>>>(wg);
