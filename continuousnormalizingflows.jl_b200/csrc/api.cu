@@ -326,7 +326,11 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
     a.wk[0] = h->wk0.as<float>(); a.wk[1] = h->wk1.as<float>();
     a.partials = h->partials.as<double>();
     if (r.want_ckpt) {
-        a.max_ckpt_steps = std::min(a.ctl.max_steps, 256);
+        // room for 256 accepted steps, less for very large batches (16 GB cap): a solve that needs more reports
+        // ICNF_ERR_MAX_STEPS instead of exhausting the device
+        const size_t per_step = sizeof(float) * (size_t)r.B * D * std::max(1, h->fam->ckpt_stages);
+        const int mem_cap = (int)std::max<size_t>(8, ((size_t)16 << 30) / std::max<size_t>(per_step, 1));
+        a.max_ckpt_steps = std::min(std::min(a.ctl.max_steps, 256), mem_cap);
         CK(h, h->ckpt.reserve(sizeof(float) * (size_t)(a.max_ckpt_steps + 1) * r.B * D * std::max(1, h->fam->ckpt_stages)));
         CK(h, h->steps.reserve(sizeof(StepRec) * (size_t)(a.max_ckpt_steps + 1)));
         a.ckpt = h->ckpt.as<float>();
