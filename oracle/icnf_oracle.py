@@ -15,7 +15,8 @@ bounds only in /root/reference/Project.toml:35-63, no Manifest).  This file is
 therefore a from-scratch restatement, validated by its own known-answer tests
 (tests/test_oracle_*.py): closed-form log-density of a linear field, autograd
 VJP vs full jacobian, Hutchinson mean -> exact trace, Tsit5 order of
-convergence and tableau identities, gradients vs float64 finite differences.
+convergence and tableau identities, the augmented solve vs scipy's DOP853,
+gradients vs float64 finite differences.
 
 Two independent statements of the RHS are kept on purpose:
   * ``rhs_ad``      mirrors HOW the reference computes it: network forward, then

@@ -112,3 +112,29 @@ def test_readout_and_loss_definitions():
     assert float(A0) == 0.0
     assert O.steer_t1(m, O.TRAIN_REG, 0.5) == pytest.approx(1.5)
     assert O.steer_t1(m, O.TEST, 0.5) == 1.0
+
+
+@pytest.mark.parametrize("mode", [O.TEST, O.TRAIN_REG])
+def test_solve_agrees_with_an_independent_integrator(mode):
+    """The oracle's own Tsit5 + controller against scipy's DOP853 (a different method, a third-party
+    implementation) on the full augmented ODE of a nonlinear flow: both must converge to the same state."""
+    from scipy.integrate import solve_ivp
+    m = O.OracleICNF(nvars=1, naug=2)                       # config 1: 4-16-16-3 softplus
+    theta = torch.tensor(1.5 * O.init_params(m, seed=4, dtype=np.float64, bias_scale=0.1), dtype=F64)
+    B = 5
+    rng = np.random.default_rng(9)
+    xs = torch.tensor(rng.standard_normal((1, B)), dtype=F64)
+    eps = None if mode == O.TEST else torch.tensor(rng.standard_normal((m.d, B)), dtype=F64)
+    u0 = O.make_u0(m, xs)
+    mine = O.solve(m, mode, u0, theta, eps, opts=O.SolverOpts(reltol=1e-10, abstol=1e-10))
+
+    def f(t, y):
+        u = torch.tensor(y.reshape(m.n_state, B), dtype=F64)
+        return O.rhs_closed(m, mode, u, theta, t, eps, None).numpy().reshape(-1)
+
+    ref = solve_ivp(f, (0.0, 1.0), u0.numpy().reshape(-1), method="DOP853", rtol=1e-11, atol=1e-12)
+    assert ref.success
+    np.testing.assert_allclose(mine.numpy().reshape(-1), ref.y[:, -1], rtol=1e-7, atol=1e-8)
+    # and the default tolerance (1e-4, what the reference and the kernels run at) stays within it
+    loose = O.solve(m, mode, u0, theta, eps, opts=O.SolverOpts())
+    np.testing.assert_allclose(loose.numpy().reshape(-1), ref.y[:, -1], rtol=2e-3, atol=2e-4)
