@@ -39,7 +39,7 @@ namespace tiny {
 #define ICNF_SP_MINB 2
 #endif
 #ifndef ICNF_SP_MAXREG
-#define ICNF_SP_MAXREG 128   // 2 CTAs x 224 threads x 144 registers = 63 K of the SM's 64 K registers
+#define ICNF_SP_MAXREG 128   // 136 and 144 registers measured slower (225 vs 193 us: the second CTA no longer fits the SM)
 #endif
 
 template <class N, bool EXACT>
