@@ -534,3 +534,66 @@ def steer_t1(model: OracleICNF, mode: int, r: float) -> float:
     if mode == TRAIN_REG and model.steer_rate != 0:
         return t1 + abs(t1 - t0) * r
     return t1
+
+
+# --------------------------------------------------------------------------
+# continuous adjoint: what the reference's sensealg computes
+
+def loss_grad_continuous(model: OracleICNF, mode: int, xs, theta, eps, ys=None, t1=None,
+                         opts: Optional[SolverOpts] = None, adj_opts: Optional[SolverOpts] = None,
+                         want_dxs: bool = False, stats: Optional[SolveStats] = None):
+    """Loss and its gradient by the CONTINUOUS adjoint -- the semantics of the
+    reference's ``sensealg = QuadratureAdjoint(autojacvec = ZygoteVJP())``
+    (/root/reference/src/core/icnf.jl:90-99) [3P]: solve u forward, then integrate
+
+        d lam / dt = -(df/du)' lam,        lam(t1) = dL/du(t1)
+        d mu  / dt = -(df/dtheta)' lam,    mu(t1)  = 0
+
+    from t1 back to t0; dL/dtheta = mu(t0), dL/dxs = lam(t0)[1:nvars].  The
+    vector-Jacobian products go THROUGH ``rhs_ad`` (second-order reverse mode, as
+    Zygote-over-Lux.vector_jacobian_product does in the reference).
+
+    QuadratureAdjoint interpolates the stored forward solution and evaluates the
+    theta integral by Gauss-Kronrod quadrature; here u is re-integrated backwards
+    together with (lam, mu) in one Tsit5 solve (``adj_opts``, default = ``opts``).
+    Both discretise the same continuous equations, so they agree to their solver
+    tolerances; with tight tolerances this function returns the exact gradient of
+    the exact flow, which is what tests/test_oracle_adjoint.py uses it for: it
+    measures how far the product's discretise-then-optimise gradient is from it.
+    """
+    opts = opts or SolverOpts()
+    adj_opts = adj_opts or opts
+    theta = theta.detach()
+    t0 = model.tspan[0]
+    t_end = model.tspan[1] if t1 is None else t1
+    with torch.no_grad():
+        u1 = solve(model, mode, make_u0(model, xs.detach()), theta, eps, ys, t0, t_end, opts, closed=True, stats=stats)
+    u1 = u1.detach().clone().requires_grad_(True)
+    logpx, (E, n, Adot) = readout(model, mode, u1)
+    val = (-logpx + model.lam1 * E + model.lam2 * n + model.lam3 * Adot).mean()
+    (lam1_,) = torch.autograd.grad(val, u1)
+    S, B = u1.shape
+    P = theta.numel()
+
+    def pack(u, lam, mu):
+        return torch.cat([u.reshape(-1), lam.reshape(-1), mu.reshape(-1)])
+
+    def g(y, t):
+        u = y[: S * B].reshape(S, B).detach().clone().requires_grad_(True)
+        lam = y[S * B: 2 * S * B].reshape(S, B).detach()
+        th = theta.clone().requires_grad_(True)
+        with torch.enable_grad():
+            fu = rhs_ad(model, mode, u, th, t, eps, ys, create_graph=True)
+            gu, gth = torch.autograd.grad(fu, [u, th], lam, allow_unused=True)
+        gu = torch.zeros_like(u) if gu is None else gu
+        gth = torch.zeros_like(th) if gth is None else gth
+        return pack(fu.detach(), -gu.detach(), -gth.detach())
+
+    y1 = pack(u1.detach(), lam1_.detach(), torch.zeros(P, dtype=theta.dtype))
+    adj_stats = SolveStats()
+    y0 = tsit5_solve(g, y1, t_end, t0, adj_opts, adj_stats)
+    lam0 = y0[S * B: 2 * S * B].reshape(S, B)
+    mu0 = y0[2 * S * B:]
+    if stats is not None:
+        stats.nf += adj_stats.nf
+    return val.detach(), mu0, (lam0[: model.nvars, :] if want_dxs else None)
