@@ -179,7 +179,8 @@ class ICNF:
         if rc != _lib.OK:
             raise ICNFError(rc, lib.icnf_last_error(None).decode())
         self._params_key = None
-        self.last_stats = SolverStats()
+        self._last_stats = SolverStats()
+        self._pending_stats = None    # device-resident icnf_stats of the last asynchronous (_dev) loss/gradient call
 
     # -- helpers
     @staticmethod
@@ -215,6 +216,31 @@ class ICNF:
             except Exception:
                 pass
             self._h = C.c_void_p()
+
+    # -- solver statistics.  Host-pointer calls return them synchronously.  The device-pointer loss/gradient call is
+    # asynchronous: its icnf_stats record stays on the device until somebody asks (reading it synchronises the
+    # stream).  `last_stats` reads it lazily; `check_last()` raises if the device loop failed (max_steps, dt
+    # underflow, non-finite state) -- the backward kernels return a NaN gradient in that case, never a stale one.
+    @property
+    def last_stats(self) -> "SolverStats":
+        if self._pending_stats is not None:
+            ds, self._pending_stats = self._pending_stats, None
+            raw = ds.cpu().numpy()
+            f = raw.view(np.float32)
+            self._last_stats = SolverStats(int(raw[0]), int(raw[1]), int(raw[2]), int(raw[3]), float(f[4]), float(f[5]))
+        return self._last_stats
+
+    @last_stats.setter
+    def last_stats(self, st: "SolverStats"):
+        self._pending_stats = None
+        self._last_stats = st
+
+    def check_last(self) -> "SolverStats":
+        """Statistics of the most recent solve; raises ``ICNFError`` if its device loop did not reach t1."""
+        st = self.last_stats
+        if st.status != _lib.OK:
+            raise ICNFError(st.status, f"tsit5 device loop failed (t = {st.t_final}, accepted {st.naccept}, rejected {st.nreject})")
+        return st
 
     @property
     def kernel_family(self) -> str:
@@ -269,6 +295,7 @@ class ICNF:
                                                     torch.cuda.current_stream(p.device).cuda_stream))
                 self._params_key = None
                 return
+            ps = p
         p = np.ascontiguousarray(np.asarray(ps, dtype=np.float32).reshape(-1))
         key = ("n", p.tobytes())
         if key != self._params_key:

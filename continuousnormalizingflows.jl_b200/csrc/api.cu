@@ -152,6 +152,11 @@ struct icnf_handle {
     size_t grad_host_cap = 0;
     long long launches = 0;
     bool profiling = false;
+    // ordering between the two kinds of entry points: `_dev` calls run on the caller's stream, host-pointer calls on
+    // the handle's private stream, and both use the handle's work buffers.  Every `_dev` call records `dev_done`;
+    // every host-pointer call makes the private stream wait for it first.
+    cudaEvent_t dev_done = nullptr;
+    bool dev_pending = false;
     cudaEvent_t prof_ev[4][2] = {};
     bool prof_used[4] = {false, false, false, false};
     std::string err;
@@ -221,6 +226,22 @@ ModeFlags mode_flags(const icnf_config& c, int mode) {
     f.reg_n = reg && c.lambda2 != 0.0f;
     f.reg_a = reg && c.lambda3 != 0.0f && c.naug != 0;
     return f;
+}
+
+// end of a `_dev` entry point: later host-pointer calls must not touch the work buffers before this point
+int mark_dev(icnf_handle* h, cudaStream_t st) {
+    if (st == h->stream) return ICNF_OK;   // host entry points reuse the `_dev` bodies on the private stream
+    if (!h->dev_done) CK(h, cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming));
+    CK(h, cudaEventRecord(h->dev_done, st));
+    h->dev_pending = true;
+    return ICNF_OK;
+}
+// start of a host-pointer entry point
+int join_dev(icnf_handle* h) {
+    if (!h->dev_pending) return ICNF_OK;
+    CK(h, cudaStreamWaitEvent(h->stream, h->dev_done, 0));
+    h->dev_pending = false;
+    return ICNF_OK;
 }
 
 int validate_common(icnf_handle* h, int mode, int64_t B) {
@@ -488,6 +509,7 @@ void icnf_destroy(icnf_handle* h) {
     if (h->stats_host) cudaFreeHost(h->stats_host);
     if (h->scalar_host) cudaFreeHost(h->scalar_host);
     if (h->grad_host) cudaFreeHost(h->grad_host);
+    if (h->dev_done) cudaEventDestroy(h->dev_done);
     for (auto& pr : h->prof_ev)
         for (cudaEvent_t ev : pr)
             if (ev) cudaEventDestroy(ev);
@@ -573,6 +595,7 @@ int icnf_set_params(icnf_handle* h, const float* theta, int64_t n) {
     if (!h || !theta) return ICNF_ERR_INVALID;
     if (n != icnf_n_params(h)) return h->fail(ICNF_ERR_INVALID, "theta has %lld entries, network has %lld", (long long)n, (long long)icnf_n_params(h));
     CK(h, cudaSetDevice(h->device));
+    { int rcj = join_dev(h); if (rcj) return rcj; }
     h->theta_host.assign(theta, theta + n);
     CK(h, h->theta_dev.reserve(sizeof(float) * n));
     CK(h, cudaMemcpyAsync(h->theta_dev.p, h->theta_host.data(), sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
@@ -616,12 +639,13 @@ int icnf_rhs_dev(icnf_handle* h, int mode, float t, const float* u, const float*
     cudaError_t e = h->fam->rhs(h->ws, h->theta_host.data(), a, mf.exact, h->sm_count, pick_stream(h, stream));
     if (e != cudaSuccess) return h->cuda_fail(e, "rhs launch");
     h->launches++;
-    return ICNF_OK;
+    return mark_dev(h, pick_stream(h, stream));
 }
 
 int icnf_rhs(icnf_handle* h, int mode, float t, const float* u, const float* eps, const float* ys, float* du, int64_t B) {
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
+    if ((rc = join_dev(h))) return rc;
     if (!u || !du) return h->fail(ICNF_ERR_INVALID, "null u/du");
     const int D = h->D(), S = h->S();
     const float *du_, *de_, *dy_;
@@ -646,13 +670,14 @@ int icnf_solve_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, f
     SolveRequest r{mode, sol, t0, t1, u0, IN_U0, noise, eps, ys, u_final, nullptr, nullptr, nullptr, nullptr, false, B};
     if ((rc = enqueue_solve(h, r, st))) return rc;
     if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
-    return ICNF_OK;
+    return mark_dev(h, st);
 }
 
 int icnf_solve(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* u0,
                const icnf_noise* noise, const float* eps, const float* ys, float* u_final, icnf_stats* stats, int64_t B) {
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
+    if ((rc = join_dev(h))) return rc;
     if (!u0 || !u_final) return h->fail(ICNF_ERR_INVALID, "null u0/u_final");
     const int D = h->D(), S = h->S();
     const float *d_in, *d_eps, *d_ys;
@@ -677,7 +702,7 @@ int icnf_inference_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t
     SolveRequest r{mode, sol, t0, t1, xs, IN_XS, noise, eps, ys, nullptr, logp, regs, nullptr, nullptr, false, B};
     if ((rc = enqueue_solve(h, r, st))) return rc;
     if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
-    return ICNF_OK;
+    return mark_dev(h, st);
 }
 
 int icnf_inference(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
@@ -685,6 +710,7 @@ int icnf_inference(icnf_handle* h, int mode, const icnf_solver* sol, float t0, f
                    icnf_stats* stats, int64_t B) {
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
+    if ((rc = join_dev(h))) return rc;
     if (!xs || !logp) return h->fail(ICNF_ERR_INVALID, "null xs/logp");
     const int D = h->D();
     const float *d_in, *d_eps, *d_ys;
@@ -716,13 +742,14 @@ int icnf_generate_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0
                    nullptr, false, n};
     if ((rc = enqueue_solve(h, r, st))) return rc;
     if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
-    return ICNF_OK;
+    return mark_dev(h, st);
 }
 
 int icnf_generate(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* z0,
                   const icnf_noise* noise, const float* eps, const float* ys, float* xs_out, icnf_stats* stats, int64_t n) {
     int rc = validate_common(h, mode, n);
     if (rc) return rc;
+    if ((rc = join_dev(h))) return rc;
     if (!xs_out) return h->fail(ICNF_ERR_INVALID, "null xs_out");
     if (!z0 && !noise) return h->fail(ICNF_ERR_INVALID, "generate needs z0 or a noise seed to draw it");
     const int D = h->D();
@@ -809,7 +836,7 @@ int icnf_loss_grad_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t
     cudaStream_t st = pick_stream(h, stream);
     if ((rc = loss_grad_device(h, mode, sol, t0, t1, xs, noise, eps, ys, loss, dtheta, dxs, B, global_batch, st))) return rc;
     if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
-    return ICNF_OK;
+    return mark_dev(h, st);
 }
 
 static int loss_grad_host(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
@@ -817,6 +844,7 @@ static int loss_grad_host(icnf_handle* h, int mode, const icnf_solver* sol, floa
                           float* dxs, icnf_stats* stats, int64_t B, int64_t global_batch) {
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
+    if ((rc = join_dev(h))) return rc;
     if (!xs || !loss) return h->fail(ICNF_ERR_INVALID, "null xs/loss");
     const int D = h->D();
     const int np = (int)icnf_n_params(h);

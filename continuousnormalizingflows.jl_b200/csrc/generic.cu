@@ -1967,7 +1967,11 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
     size_t np = 0;
     for (int l = 0; l < NL; ++l) np += (size_t)w->n[l] * w->n[l + 1] + w->n[l + 1];
     GCK(cudaMemsetAsync(a.gpartial, 0, sizeof(float) * np, st));
-    if (hs.status != ICNF_OK) return cudaSuccess;   // the caller reports the solver status
+    if (hs.status != ICNF_OK) {   // no gradient of a failed solve: NaN (all-ones bit pattern), the caller reports the status
+        GCK(cudaMemsetAsync(a.gpartial, 0xFF, sizeof(float) * np, st));
+        if (a.dxs) GCK(cudaMemsetAsync(a.dxs, 0xFF, sizeof(float) * (size_t)a.nvars * B, st));
+        return cudaSuccess;
+    }
     const int nsteps = hs.naccept;
     std::vector<StepRec> steps(std::max(nsteps, 1));
     if (nsteps) GCK(cudaMemcpy(steps.data(), a.steps, sizeof(StepRec) * nsteps, cudaMemcpyDeviceToHost));

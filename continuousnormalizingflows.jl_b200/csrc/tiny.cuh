@@ -963,7 +963,10 @@ template <class N, bool EXACT>
 __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_BWD) backward_kernel(const __grid_constant__ WBlock<N> sw, BackwardArgs a) {
     extern __shared__ __align__(16) float smem[];
     StageMem KB{smem};                 // stage cotangents Kbar_i, 6 x D'
-    const int nsteps = a.stats->naccept;
+    // a failed forward solve (max_steps, dt underflow, non-finite state) has no gradient: the sweep is skipped and
+    // the partial gradient is NaN, so that an optimiser step on it cannot pass for a valid one
+    const bool solve_ok = a.stats->status == ICNF_OK;
+    const int nsteps = solve_ok ? a.stats->naccept : 0;
     float gacc[N::NCHUNK];
 #pragma unroll
     for (int c = 0; c < N::NCHUNK; ++c) gacc[c] = 0.0f;
@@ -1052,7 +1055,7 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_BWD) backward_kernel(const 
         if (a.dxs && valid) {
 #pragma unroll
             for (int j = 0; j < N::D; ++j)
-                if (j < a.nvars) a.dxs[b * a.nvars + j] = zbar[j];
+                if (j < a.nvars) a.dxs[b * a.nvars + j] = solve_ok ? zbar[j] : __int_as_float(0x7fc00000);
         }
     }
     // per-CTA partial gradient in native ComponentArray order: the 4 warps' accumulators are
@@ -1074,7 +1077,7 @@ __global__ void __launch_bounds__(NT, ICNF_TINY_MINB_BWD) backward_kernel(const 
         float s = 0.0f;
 #pragma unroll
         for (int w = 0; w < NT / 32; ++w) s += sg[w * N::NP + p];
-        gp[p] = s;
+        gp[p] = solve_ok ? s : __int_as_float(0x7fc00000);
     }
 }
 

@@ -5,7 +5,6 @@
 
 #include "family.h"
 #include "tiny.cuh"
-#include "tiny_ub.cuh"
 #include "tiny_sp.cuh"
 
 namespace icnf {
@@ -110,25 +109,12 @@ struct Launch {
         void* args[] = {(void*)&w, (void*)&aa, (void*)&nv};
         return cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(bs), args, smem, st);
     }
-    // networks with at least one hidden layer use the unit-parallel backward (tiny_ub.cuh)
-    static constexpr bool USE_UB = (N::NL >= 2);
-    static constexpr size_t ub_floats() {
-        if constexpr (USE_UB) {
-            using C = UBCfg<N>;
-            size_t a = (size_t)C::WSM + 6 * N::D * C::SPB, b = (size_t)(NT / 32) * N::NP;
-            return a > b ? a : b;
-        } else {
-            return 0;
-        }
-    }
-    static constexpr size_t smem_ub = sizeof(float) * ub_floats();
-    // sample-parallel backward (tiny_sp.cuh): CTA size (= samples per tile) and grid for a batch.
+    // networks with at least one hidden layer use the sample-parallel backward (tiny_sp.cuh); the thread-per-sample
+    // backward_kernel of tiny.cuh serves networks without a hidden layer (a linear field)
+    static constexpr bool USE_SP = (N::NL >= 2);
+    // sample-parallel backward: CTA size (= samples per tile) and grid for a batch.
     // The CTA size is the smallest multiple of 32 that lets the batch finish in the fewest
     // rounds of ICNF_SP_MINB CTAs per SM, capped by ICNF_SP_MAXT and by shared memory.
-#ifndef ICNF_TINY_BWD
-#define ICNF_TINY_BWD 2   // 1: unit-parallel (tiny_ub.cuh), 2: sample-parallel (tiny_sp.cuh)
-#endif
-    static constexpr bool USE_SP = USE_UB && (ICNF_TINY_BWD == 2);
     template <bool EXACT>
     static void sp_plan(long long B, int sm_count, int& ns, int& grid) {
         using C = SPCfg<N, EXACT>;
@@ -140,13 +126,11 @@ struct Launch {
         ns = (int)std::min<long long>(cap, std::max<long long>(lo, ((per + 31) / 32) * 32));
         grid = (int)std::max(1LL, std::min(slots, (B + ns - 1) / ns));
     }
-    static int cached_sm_count() {
-        static int n = 0;
-        if (!n) {
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        }
+    // SM count of the CURRENT device (a process may hold handles on several devices)
+    static int current_sm_count() {
+        int dev = 0, n = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         return n;
     }
     static int backward_grid(bool exact, int sm_count, long long B) {
@@ -155,12 +139,6 @@ struct Launch {
             if (exact) sp_plan<true>(B, sm_count, ns, grid);
             else sp_plan<false>(B, sm_count, ns, grid);
             return grid;
-        } else if constexpr (USE_UB) {
-            auto k = exact ? backward_ub_kernel<N, true> : backward_ub_kernel<N, false>;
-            const long long spb = UBCfg<N>::SPB;
-            long long need = (B + spb - 1) / spb;
-            long long cap = (long long)std::max(occupancy(k, smem_ub), 1) * sm_count;
-            return (int)std::max(1LL, std::min(need, cap));
         } else {
             auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
             return grid_for(B, occupancy(k, smem_bwd), sm_count);
@@ -217,7 +195,7 @@ struct Launch {
     static cudaError_t backward_sp(const float* theta, const BackwardArgs& a, int grid, cudaStream_t st) {
         using C = SPCfg<N, EXACT>;
         int ns, g2;
-        sp_plan<EXACT>(a.B, cached_sm_count(), ns, g2);
+        sp_plan<EXACT>(a.B, current_sm_count(), ns, g2);
         auto k = backward_sp_kernel<N, EXACT>;
         const SPPlan plan = sp_threads<EXACT>(ns);
         const size_t smem = C::smem_bytes(plan.max_groups);
@@ -231,12 +209,6 @@ struct Launch {
     static cudaError_t backward(void*, const float* theta, const BackwardArgs& a, bool exact, int grid, cudaStream_t st) {
         if constexpr (USE_SP) {
             return exact ? backward_sp<true>(theta, a, grid, st) : backward_sp<false>(theta, a, grid, st);
-        } else if constexpr (USE_UB) {
-            auto k = exact ? backward_ub_kernel<N, true> : backward_ub_kernel<N, false>;
-            cudaError_t e = prep(k, smem_ub);
-            if (e != cudaSuccess) return e;
-            k<<<grid, NT, smem_ub, st>>>(a);
-            return cudaGetLastError();
         } else {
             auto k = exact ? backward_kernel<N, true> : backward_kernel<N, false>;
             cudaError_t e = prep(k, smem_bwd);

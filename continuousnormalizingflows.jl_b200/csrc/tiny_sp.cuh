@@ -171,7 +171,8 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
     const float4* rec4 = reinterpret_cast<const float4*>(smem);
-    const int nsteps = a.stats->naccept;
+    // a failed forward solve has no gradient: skip the sweep, return NaN (see tiny::backward_kernel)
+    const int nsteps = (a.stats->status == ICNF_OK) ? a.stats->naccept : 0;
 
     // ---- dW-phase role of this thread: block `blk`, sample group `grp` of NG
     static_assert(C::NBLK <= 33, "dW blocks per CTA");
@@ -453,7 +454,7 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
         if (a.dxs && valid) {
 #pragma unroll
             for (int j = 0; j < D; ++j)
-                if (j < a.nvars) a.dxs[b * a.nvars + j] = zbar[j];
+                if (j < a.nvars) a.dxs[b * a.nvars + j] = (a.stats->status == ICNF_OK) ? zbar[j] : __int_as_float(0x7fc00000);
         }
     }
 
@@ -498,7 +499,7 @@ __global__ void __maxnreg__(ICNF_SP_MAXREG)
     for (int p = tid; p < N::NP; p += NT_) {
         float s = 0.f;
         for (int w = 0; w < NGM; ++w) s += red[w * N::NP + p];
-        gp[p] = s;
+        gp[p] = (a.stats->status == ICNF_OK) ? s : __int_as_float(0x7fc00000);
     }
 }
 

@@ -103,13 +103,14 @@ class ICNFModel:
         x = np.ascontiguousarray(np.asarray(X, dtype=np.float32).T)       # permutedims(matrix(X)), core_icnf.jl:33
         y = None if Y is None else np.ascontiguousarray(np.asarray(Y, dtype=np.float32).T)
         ps, st = setup(self.icnf.rng, self.icnf)
-        it, last = 0, float("nan")
+        it, last, stop = 0, float("nan"), False
         if self.device_optimiser:
             import torch
             dev = f"cuda:{self.icnf.device}"
             opt = _DeviceOptimiserChain(self.weight_decay, self.adam, ps, self.icnf.device)
             xd = torch.tensor(x.T.copy(), device=dev)                      # (n, nvars) records
             yd = None if y is None else torch.tensor(y.T.copy(), device=dev)
+            l = None
             for _ in range(self.epochs):
                 for idx in self._batches(x.shape[1]):
                     it += 1
@@ -119,9 +120,17 @@ class ICNFModel:
                     opt.step(g)
                     if self.callback:
                         last = float(l)
-                        if self.callback(it, last):
-                            break
-            last = float(l)
+                        self.icnf.check_last()           # the loss was read anyway: the stream is already drained
+                        stop = bool(self.callback(it, last))
+                    elif it % 64 == 0:
+                        self.icnf.check_last()           # a failed solve returns a NaN gradient: stop instead of training on it
+                    if stop:
+                        break
+                if stop:                                 # the reference's callback halts the whole optimisation (core.jl:96-105)
+                    break
+            if l is not None:
+                last = float(l)
+                self.icnf.check_last()
             ps = opt.theta.cpu().numpy()
         else:
             opt = _OptimiserChain(self.weight_decay, self.adam, ps.size)
@@ -132,7 +141,10 @@ class ICNFModel:
                     last, g = loss_and_gradient(self.icnf, TrainMode(True), *args, ps, st)
                     ps = opt.step(ps, g)
                     if self.callback and self.callback(it, last):
+                        stop = True
                         break
+                if stop:
+                    break
         self.fitresult = (ps, st)
         self.report = {"iterations": it, "final_loss": last}
         return self

@@ -4,7 +4,10 @@ columns, parameters replicated.
 The path has exactly one exchange step: the training gradient (and the scalar
 loss) are summed over ranks.  Each shard is told its global column offset (so the
 in-kernel Philox noise is the one the unsharded batch would draw) and the global
-batch size (so the shards' losses and gradients SUM to the unsharded result);
+batch size (so the shards' losses and gradients SUM to the unsharded result --
+exactly for fixed-step solves; with adaptive stepping every rank's controller sees
+its own shard's error norm unless the communicator of ``icnf_group_*`` is attached,
+so the shards then agree with the unsharded solve to solver tolerance only);
 inference and generate need no communication at all.  STEER draws one t1 per solve
 for the whole batch (base_icnf.jl:23-43): seed ``ICNF(rng=...)`` identically on every
 rank so that all shards integrate to the same t1.  The collective is
