@@ -99,6 +99,7 @@ SYMBOLS = [
     ("icnf_adam_step_dev", C.c_int, [_F, _F, _F, _F, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float,
                                      C.c_float, _P]),
     ("icnf_tc_gemm_selftest", C.c_int, [C.c_int, C.c_int, C.c_int, _F, _F, _F, C.c_int]),
+    ("icnf_tc_wgrad_selftest", C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _F, _F, _F, _F, _F, C.c_int, C.c_int]),
     ("icnf_backward_plan", C.c_int, [C.POINTER(Config), C.c_int, C.c_int, C.c_int64, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
 ]

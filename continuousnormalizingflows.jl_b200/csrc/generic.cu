@@ -673,7 +673,20 @@ struct StageArgs {
     int cur_fixed;
     float reltol, abstol;
     int kind;              // 0: solve stage; 1: initial-dt probe (ZI = u + dt0 k1)
+    // training checkpoints: the input of stage i (< 6) of the step being attempted goes to
+    // ckpt[slot][i][D][B], slot = accepted steps so far (an attempt that is rejected is overwritten by the next)
+    float* ckpt;
+    int ckpt_slot_fixed, ckpt_max_slot;
 };
+
+__device__ __forceinline__ long long ckpt_off(long long slot, int stage, long long DB) { return (slot * 6 + stage) * DB; }
+// destination of this stage's checkpoint, or null
+__device__ __forceinline__ float* stage_ckpt(const StageArgs& a) {
+    if (!a.ckpt || a.kind != 0 || a.stage >= 6) return nullptr;
+    const int slot = a.ctrl ? a.ctrl->naccept : a.ckpt_slot_fixed;
+    if (slot > a.ckpt_max_slot) return nullptr;   // capacity exhausted: g_ctrl_end_kernel reports ICNF_ERR_MAX_STEPS
+    return a.ckpt + ckpt_off(slot, a.stage, (long long)a.D * a.B);
+}
 
 __device__ __forceinline__ float* stage_k(const StageArgs& a, int j, int cur) {
     // k_j for j = 0..6: k_0 = KF[cur], k_1..k_5 = Kst[j-1], k_6 = KF[cur^1]
@@ -702,6 +715,7 @@ __global__ void g_stage_input_kernel(StageArgs a) {
             if (j < a.stage) v = fmaf(h * g_a[a.stage][j], kv[j], v);
     }
     a.ZI[idx] = v;
+    if (float* ck = stage_ckpt(a)) ck[idx] = v;
 }
 
 // Tensor-core precisions: the stage input goes straight into the GEMM operand layout -- bf16 (or hi | lo
@@ -723,6 +737,7 @@ __global__ void __launch_bounds__(256) g_stage_input_pack_kernel(StageArgs a, Pa
     const float h = a.ctrl ? a.ctrl->tdir * a.ctrl->dt : a.dt_fixed;
     const float tnow = a.ctrl ? fmaf(p.c_i, a.ctrl->tdir * a.ctrl->dt, a.ctrl->t) : p.t_fixed;
     const long long b = b0 + lane;
+    float* ck = stage_ckpt(a);
     float coef[6];
 #pragma unroll
     for (int j = 0; j < 6; ++j) coef[j] = (a.kind == 0 && j < a.stage) ? h * g_a[a.stage][j] : 0.f;
@@ -746,6 +761,7 @@ __global__ void __launch_bounds__(256) g_stage_input_pack_kernel(StageArgs a, Pa
 #pragma unroll
                     for (int j = 0; j < 6; ++j) v = fmaf(coef[j], kv[j], v);
                 }
+                if (ck) ck[idx] = v;   // fp32 stage input for the reverse sweep
             } else if (p.tin && k == a.D) {
                 v = tnow;
             } else if (k < a.D + p.tin + p.C) {
@@ -1014,7 +1030,7 @@ __global__ void g_ckpt_kernel(const Ctrl* ctrl, const float* U0, const float* U1
     const int slot = ctrl ? ctrl->naccept + (use_trial ? 1 : 0) : slot_fixed;
     if (slot > max_slot) return;   // capacity exhausted: g_ctrl_end_kernel reports ICNF_ERR_MAX_STEPS
     const float* U = (ctrl ? ((cur ^ use_trial) ? U1 : U0) : U0);
-    ckpt[(long long)slot * DB + idx] = U[idx];
+    ckpt[ckpt_off(slot, 0, DB) + idx] = U[idx];   // stage 0 of the slot = the state at the start of the step
 }
 
 // ---- backward (discretise-then-optimise) element-wise pieces ----------------------------
@@ -1026,8 +1042,6 @@ struct BwArgs {
     float lam3, wgt;
     const float* zfinal;      // D x B
     float* zbar;              // D x B
-    float* ZS;                // [6][D][B] stage inputs
-    float* KZ;                // [5][D][B] stage derivatives (z rows) of stages 1..5
     float* KB;                // [6][D][B] stage cotangents
     const float* zn;          // D x B checkpoint
     const float* ZD; const float* Q; const float* E;
@@ -1047,15 +1061,6 @@ __global__ void bw_init_kernel(BwArgs a) {
         const float z = a.zfinal[(long long)r * a.B + b];
         a.zbar[(long long)r * a.B + b] = a.wgt * (r >= a.nvars ? fmaf(s, z, z) : z);
     }
-}
-// ZS[i] = z_n + h sum_{j<i} a_ij KZ[j]
-__global__ void bw_stage_input_kernel(BwArgs a) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long DB = (long long)a.D * a.B;
-    if (idx >= DB) return;
-    float v = a.zn[idx];
-    for (int j = 0; j < a.i; ++j) v = fmaf(a.h * g_a[a.i][j], a.KZ[(long long)j * DB + idx], v);
-    a.ZS[(long long)a.i * DB + idx] = v;
 }
 // KB[i] = h b_i zbar, i = 0..5
 __global__ void bw_kbar_init_kernel(BwArgs a) {
@@ -1408,9 +1413,16 @@ struct Workspace {
     std::vector<size_t> wtoff;        // offsets in thetaT
     Buf thetaT, amat, gvec;
     Buf U0, U1, KF0, KF1, Kst, ZI, EPS, YS, ZD, Q, TR, F1, Hb, Db, Gb, ctrl;
-    Buf bZS, bKZ, bKB, bzbar, bV, bWv, bAEX, bAB, bSB;   // backward
+    Buf bKB, bzbar, bV, bWv, bAEX, bAB, bSB;   // backward (fp32 family)
+    // backward on tensor cores: bf16 [sample][unit] cotangents (AB), tangents (WV, WV0), second-order extras (AEX);
+    // [unit][sample] transposed copies for the weight-gradient GEMMs; per-slice fp32 weight-gradient partials
+    Buf AB16, WV16, WV016, AEX16, XT16, ET16, HT16, GT16, ABT16, WVT16, WV0T16, tZB, tQB, wpart;
+    long long t16_B = -1;        // batch the transposed buffers were last zero-padded for
     // precision = ICNF_BF16_TC: bf16 operands for the tcgen05 GEMM, [sample][unit] activations
     bool tc = false;
+    // the exact trace of networks with three or more hidden layers has no closed form: it is D' one-hot chains
+    // (utils.jl:35-54), which stay on the fp32 SGEMMs in every precision
+    bool use_tc(bool exact) const { return tc && !(exact && NL >= 4); }
     int split = 0;   // ICNF_BF16X3_TC: every bf16 row is [hi | lo], three MMAs per K step
     bool e16_valid = false;   // E16 holds the packed probe of the current solve (eps is constant over a solve)
     int rs(int cols) const { return (split ? 2 : 1) * pad8(cols); }   // row stride of a bf16 matrix with `cols` columns
@@ -1687,7 +1699,7 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
             GCK(cudaMemsetAsync(TR, 0, sizeof(float) * B, p.st));
             GCK(tc::gemm(act_ptr(Dv, 0), w->rs(w->n[1]), w->a16.as<__nv_bfloat16>(), w->rs(w->n[1]), g, p.st));
         } else {
-            return cudaErrorNotSupported;   // exact trace of deeper networks: fp32 families only
+            return cudaErrorNotSupported;   // unreachable: use_tc() routes deeper exact traces to the fp32 chains
         }
         w->launches++;
         return cudaGetLastError();
@@ -1715,7 +1727,7 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
 // forward, then trace / VJP chain -> TR or Q
 static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
     Workspace* w = p.w;
-    if (w->tc) return tc_rhs_core(p, c_i);
+    if (w->use_tc(p.exact)) return tc_rhs_core(p, c_i);
     const long long B = p.B;
     const int NL = w->NL, D = w->D;
     float* Dv = w->Db.as<float>();
@@ -1844,7 +1856,7 @@ static cudaError_t enqueue_stage(Workspace* w, const SolveArgs& a, StageArgs s, 
                                  float t_step, float h_fixed, int cur_fixed, cudaStream_t st) {
     s.ctrl = ctrl; s.stage = stage; s.dt_fixed = h_fixed; s.cur_fixed = cur_fixed; s.kind = 0;
     RhsPlan p{w, a.theta, a.B, exact, a.reg_e, a.reg_n, a.squared, ctrl, t_step + g_c_host(stage) * h_fixed, st};
-    if (w->tc) {
+    if (w->use_tc(exact)) {
         GCK(tc_reserve(w, a.B));
         PackArgs pk{w->X16.as<__nv_bfloat16>(), w->YS.as<float>(), w->tin, w->C, Workspace::pad8(w->n[0]), w->split,
                     p.t_fixed, g_c_host(stage)};
@@ -1877,6 +1889,7 @@ static cudaError_t solve_fixed(void* wsp, const float*, const SolveArgs& a, int 
         const float tb = fminf(span, step * a.dt);
         h = tdir * fminf(a.dt, span - tb);
         const float t = a.t0 + tdir * tb;
+        s.ckpt = a.ckpt; s.ckpt_slot_fixed = step; s.ckpt_max_slot = a.max_ckpt_steps;
         for (int stage = 0; stage < 6; ++stage) GCK(enqueue_stage(w, a, s, stage, exact, nullptr, t, h, cur, st));
         s.ctrl = nullptr; s.dt_fixed = h; s.cur_fixed = cur;
         g_advance_kernel<<<blocks_for((long long)w->S * a.B), 256, 0, st>>>(s);
@@ -1908,6 +1921,7 @@ static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, i
     if (a.ckpt) { g_ckpt_kernel<<<blocks_for(DB), 256, 0, st>>>(nullptr, w->U0.as<float>(), nullptr, a.ckpt, DB, 0, 0, a.max_ckpt_steps); w->launches++; }
     StageArgs s = make_stage_args(w, a.B, exact, a.reg_e, a.reg_n, a.squared);
     s.reltol = a.ctl.reltol; s.abstol = a.ctl.abstol;
+    s.ckpt = a.ckpt; s.ckpt_max_slot = a.max_ckpt_steps;
     const int sb = blocks_for((long long)w->S * a.B);
     // k1 = f(u0, t0)
     GCK(enqueue_stage(w, a, s, 0, exact, ctrl, 0.f, 0.f, 0, st));
@@ -1953,11 +1967,183 @@ static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, i
 }
 
 static int adaptive_max_grid(bool, int sm_count) { return sm_count; }   // not a cooperative kernel; any value > 0
-// Reverse sweep over the recorded steps (discretise-then-optimise; derivation in tiny.cuh).
+static inline long long ckpt_off_h(long long slot, int stage, long long DB) { return (slot * 6 + stage) * DB; }
+
+// out[p] = sum over slices of part[s][p], fixed order
+__global__ void bw_reduce_slices_kernel(const float* part, int nsl, long long np, float* out) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= np) return;
+    float s = 0.f;
+    for (int i = 0; i < nsl; ++i) s += part[(long long)i * np + p];
+    out[p] = s;
+}
+
+// Reverse sweep on the tensor cores (precision = bf16_tc / bf16x3_tc, Hutchinson modes).  Per stage: forward and VJP
+// chain as in tc_rhs_core (their epilogues also leave [unit][sample] copies of h and g), the cotangents of zdot and
+// eps'J, the tangent GEMMs (second-order terms), then per layer, top down: the weight gradient
+//     dW_l += ABAR_l' H_{l-1} + G_l' W_{l-1}        (K = samples: both operands transposed, two operand pairs
+//                                                     accumulated in TMEM, split-K slices, no atomics)
+// the bias gradient (row sums of ABAR_l') and the backprop GEMM ABAR_{l-1} = (ABAR_l W_l) .* d + AEX.
+static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, const std::vector<StepRec>& steps, size_t np,
+                               cudaStream_t st) {
+    const long long B = a.B;
+    const int NL = w->NL, D = w->D, split = w->split;
+    const long long DB = (long long)D * B;
+    auto P8 = [](int x) { return Workspace::pad8(x); };
+    const long long Bp = (B + 7) & ~7LL;
+    const long long rsT = (split ? 2 : 1) * Bp;     // row pitch of a transposed matrix
+    const int loT = (int)Bp;
+    const size_t f = sizeof(float);
+    GCK(tc_reserve(w, B));
+    GCK(w->AB16.reserve((size_t)B * w->h16_cols * 2)); GCK(w->WV16.reserve((size_t)B * w->h16_cols * 2));
+    GCK(w->AEX16.reserve((size_t)B * w->h16_cols * 2)); GCK(w->WV016.reserve((size_t)B * w->rs(w->n[0]) * 2));
+    const size_t tr = (size_t)rsT * 2;   // bytes per transposed row
+    GCK(w->XT16.reserve(tr * w->n[0])); GCK(w->ET16.reserve(tr * D)); GCK(w->WV0T16.reserve(tr * D));
+    GCK(w->HT16.reserve(tr * w->hrows)); GCK(w->GT16.reserve(tr * w->hrows)); GCK(w->ABT16.reserve(tr * w->hrows));
+    GCK(w->WVT16.reserve(tr * w->hrows));
+    GCK(w->tZB.reserve(f * DB)); GCK(w->tQB.reserve(f * DB));
+    GCK(w->bKB.reserve(f * 6 * DB)); GCK(w->bzbar.reserve(f * DB)); GCK(w->bSB.reserve(f * DB));
+    if (Bp != B && w->t16_B != B) {   // the K padding of the transposed operands must read as zero
+        Buf* tb[] = {&w->XT16, &w->ET16, &w->WV0T16, &w->HT16, &w->GT16, &w->ABT16, &w->WVT16};
+        for (Buf* b : tb) GCK(cudaMemsetAsync(b->p, 0, b->cap, st));
+    }
+    w->t16_B = B;
+    // split-K slices of the weight gradient: fill the SMs, at most one slice per K block
+    int sms = 0, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nkb = (int)((B + tc::TBK - 1) / tc::TBK);
+    std::vector<int> nsl(NL);
+    int nsl_max = 1;
+    for (int l = 0; l < NL; ++l) {
+        const int bn = w->n[l] > 160 ? 256 : 128;
+        const int tiles = ((w->n[l + 1] + tc::TBM - 1) / tc::TBM) * ((w->n[l] + bn - 1) / bn);
+        nsl[l] = std::max(1, std::min(std::min(nkb, 32), sms / tiles));
+        nsl_max = std::max(nsl_max, nsl[l]);
+    }
+    GCK(w->wpart.reserve(f * np * nsl_max));
+    GCK(cudaMemsetAsync(w->wpart.p, 0, f * np * nsl_max, st));
+
+    __nv_bfloat16* X = w->X16.as<__nv_bfloat16>();
+    __nv_bfloat16* E16 = w->E16.as<__nv_bfloat16>();
+    __nv_bfloat16* H = w->H16.as<__nv_bfloat16>();
+    __nv_bfloat16* Dv = w->D16.as<__nv_bfloat16>();
+    __nv_bfloat16* G = w->G16.as<__nv_bfloat16>();
+    __nv_bfloat16* AB = w->AB16.as<__nv_bfloat16>();
+    __nv_bfloat16* WV = w->WV16.as<__nv_bfloat16>();
+    __nv_bfloat16* WV0 = w->WV016.as<__nv_bfloat16>();
+    __nv_bfloat16* AEX = w->AEX16.as<__nv_bfloat16>();
+    __nv_bfloat16* XT = w->XT16.as<__nv_bfloat16>();
+    __nv_bfloat16* ET = w->ET16.as<__nv_bfloat16>();
+    __nv_bfloat16* WV0T = w->WV0T16.as<__nv_bfloat16>();
+    __nv_bfloat16* HT = w->HT16.as<__nv_bfloat16>();
+    __nv_bfloat16* GT = w->GT16.as<__nv_bfloat16>();
+    __nv_bfloat16* ABT = w->ABT16.as<__nv_bfloat16>();
+    __nv_bfloat16* WVT = w->WVT16.as<__nv_bfloat16>();
+    auto rm = [&](__nv_bfloat16* base, int l) { return base + w->h16_off[l] * (size_t)B; };   // row-major slot of layer l's output
+    auto tp = [&](__nv_bfloat16* base, int l) { return base + (size_t)w->hoff[l] * rsT; };    // transposed slot (rows = units)
+    float* wpart = w->wpart.as<float>();
+
+    BwArgs b;
+    memset(&b, 0, sizeof b);
+    b.B = B; b.D = D; b.nvars = a.nvars; b.squared = a.squared; b.reg_a = a.reg_a; b.lam3 = a.lam3; b.wgt = a.inv_denominator;
+    b.zfinal = a.ckpt + ckpt_off_h(nsteps, 0, DB); b.zbar = w->bzbar.as<float>(); b.KB = w->bKB.as<float>();
+    b.ZD = w->ZD.as<float>(); b.Q = w->Q.as<float>(); b.E = w->EPS.as<float>();
+    b.ZB = w->tZB.as<float>(); b.QB = w->tQB.as<float>(); b.sbar = w->bSB.as<float>(); b.dxs = a.dxs;
+    const int db_blocks = blocks_for(DB), b_blocks = blocks_for(B);
+    bw_init_kernel<<<b_blocks, 256, 0, st>>>(b);
+    const float lbar = a.inv_denominator;
+    const float Ebar = a.reg_e ? a.lam1 * a.inv_denominator : 0.f, nbar = a.reg_n ? a.lam2 * a.inv_denominator : 0.f;
+    // the probe: row-major for the chain, transposed for the top layer's weight gradient (constant over the solve)
+    GCK(tc::pack_soa(w->EPS.as<float>(), E16, B, D, P8(D), nullptr, split, st, ET, rsT, loT));
+    w->e16_valid = true;
+    w->launches += 2;
+    auto base_args = [&](int M, int N, int K, int a_cols, int b_cols, int o_cols) {
+        tc::TcArgs g;
+        memset(&g, 0, sizeof g);
+        g.M = M; g.N = N; g.K = K; g.act = w->cfg.activation;
+        g.split = split; g.lo_a = P8(a_cols); g.lo_b = P8(b_cols); g.lo_o = P8(o_cols);
+        g.ldo = w->rs(o_cols); g.ldT = rsT; g.lo_T = loT;
+        return g;
+    };
+    const __nv_bfloat16* w16t = w->w16t.as<__nv_bfloat16>();
+    const __nv_bfloat16* w16n = w->w16n.as<__nv_bfloat16>();
+
+    for (int step = nsteps - 1; step >= 0; --step) {
+        const float t = steps[step].t, h = steps[step].dt;
+        b.h = h;
+        bw_kbar_init_kernel<<<db_blocks, 256, 0, st>>>(b);
+        w->launches++;
+        for (int i = 5; i >= 0; --i) {
+            const float* zi = a.ckpt + ckpt_off_h(step, i, DB);
+            const float ti = t + g_c_host(i) * h;
+            const float hb = h * g_b_host(i);
+            b.i = i; b.cl = hb * lbar; b.cE = hb * Ebar; b.cn = hb * nbar;
+            // ---- forward at the checkpointed stage input (h, sigma' row-major; h transposed)
+            GCK(tc::pack_input(zi, w->YS.as<float>(), X, B, D, w->tin, w->C, P8(w->n[0]), ti, nullptr, 0.f, nullptr, split, st,
+                               XT, rsT, loT));
+            for (int l = 0; l < NL; ++l) {
+                tc::TcArgs g = base_args((int)B, w->n[l + 1], w->n[l], w->n[l], w->n[l], w->n[l + 1]);
+                g.bias = a.theta + w->boff[l];
+                if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = rm(H, l); g.out1 = rm(Dv, l); g.outT = tp(HT, l); }
+                else { g.ep = tc::TEP_LIN_SOA; g.out_f32 = w->ZD.as<float>(); g.n_limit = D; }
+                GCK(tc::gemm(l == 0 ? X : rm(H, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, st));
+            }
+            // ---- VJP chain of the probe (g row-major and transposed), q = eps'J
+            for (int l = NL - 1; l >= 0; --l) {
+                const int nout = (l == 0) ? D : w->n[l];
+                tc::TcArgs g = base_args((int)B, nout, w->n[l + 1], w->n[l + 1], w->n[l + 1], w->n[l]);
+                if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = rm(G, l - 1); g.aux = rm(Dv, l - 1); g.outT = tp(GT, l - 1); }
+                else { g.ep = tc::TEP_PLAIN_SOA; g.out_f32 = w->Q.as<float>(); g.n_limit = D; }
+                GCK(tc::gemm(l == NL - 1 ? E16 : rm(G, l), w->rs(w->n[l + 1]), w16n + w->w16n_off[l], w->rs(w->n[l + 1]), g, st));
+            }
+            // ---- cotangents: zb on zdot (output of the top layer), qb on eps'J (the tangent that enters layer 0)
+            bw_cotangent_kernel<<<blocks_for(B, 32), 256, 0, st>>>(b, -1);
+            GCK(tc::pack_soa(b.ZB, rm(AB, NL - 1), B, D, P8(D), nullptr, split, st, tp(ABT, NL - 1), rsT, loT));
+            // the tangent that enters layer 0 is laid out like the network input (zeros in the t / ys columns), so that
+            // its K blocks line up with W_1's: hi and lo halves of both operands then sit at the same column offsets
+            GCK(tc::pack_soa(b.QB, WV0, B, D, P8(w->n[0]), nullptr, split, st, WV0T, rsT, loT));
+            // ---- tangent pass: r = W_l w_l;  w_{l+1} = r .* d_l;  aex_l = r .* g_l .* sigma''/sigma'
+            for (int l = 0; l < NL - 1; ++l) {
+                tc::TcArgs g = base_args((int)B, w->n[l + 1], w->n[l], w->n[l], w->n[l], w->n[l + 1]);
+                g.ep = tc::TEP_TANGENT;
+                g.out0 = rm(WV, l); g.outT = tp(WVT, l); g.out1 = rm(AEX, l);
+                g.aux = rm(Dv, l); g.aux1 = rm(G, l); g.aux2 = rm(H, l);
+                GCK(tc::gemm(l == 0 ? WV0 : rm(WV, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, st));
+            }
+            // ---- top down: weight gradient, bias gradient, backprop
+            for (int l = NL - 1; l >= 0; --l) {
+                const int nout = w->n[l + 1], nin = w->n[l], kz = (l == 0) ? D : nin;
+                tc::TcArgs g = base_args(nout, nin, (int)B, 0, 0, 0);
+                g.lo_a = loT; g.lo_b = loT; g.lo_a2 = loT; g.lo_b2 = loT;
+                g.ep = tc::TEP_WGRAD; g.K2 = (int)B; g.N2 = kz;
+                g.nslices = nsl[l]; g.slice_stride = (long long)np; g.ldw = nout;
+                g.out_f32 = wpart + w->woff[l];
+                GCK(tc::gemm(tp(ABT, l), rsT, l == 0 ? XT : tp(HT, l - 1), rsT, g, st,
+                             l == NL - 1 ? ET : tp(GT, l), rsT, l == 0 ? WV0T : tp(WVT, l - 1), rsT));
+                GCK(tc::row_sums(tp(ABT, l), rsT, loT, split, nout, B, wpart + w->boff[l], st));
+                const int nprev = (l == 0) ? D : nin;
+                tc::TcArgs p = base_args((int)B, nprev, nout, nout, nout, nin);
+                if (l > 0) {
+                    p.ep = tc::TEP_MULADD; p.out0 = rm(AB, l - 1); p.outT = tp(ABT, l - 1);
+                    p.aux = rm(Dv, l - 1); p.aux1 = rm(AEX, l - 1);
+                } else { p.ep = tc::TEP_PLAIN_SOA; p.out_f32 = w->bSB.as<float>(); p.n_limit = D; }
+                GCK(tc::gemm(rm(AB, l), w->rs(nout), w16n + w->w16n_off[l], w->rs(nout), p, st));
+            }
+            bw_accumulate_kernel<<<db_blocks, 256, 0, st>>>(b);
+            w->launches += 5 + 2 * NL + (NL - 1) + 3 * NL;
+        }
+    }
+    bw_reduce_slices_kernel<<<blocks_for((long long)np), 256, 0, st>>>(wpart, nsl_max, (long long)np, a.gpartial);
+    w->launches++;
+    if (a.dxs) { bw_dxs_kernel<<<b_blocks, 256, 0, st>>>(b); w->launches++; }
+    return cudaGetLastError();
+}
+
+// Reverse sweep over the recorded steps (discretise-then-optimise; derivation in tiny.cuh).  Stage inputs come from
+// the forward solve's checkpoints (ckpt[slot][stage][D][B]), so no step is re-integrated.
 static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
-    // tensor-core precisions: the forward solve (and its checkpoints) ran on tcgen05; the reverse sweep below
-    // is the fp32 one (FFMA2 SGEMMs), evaluated at those checkpoints
     const long long B = a.B;
     const int NL = w->NL, D = w->D;
     const long long DB = (long long)D * B;
@@ -1966,7 +2152,6 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
     GCK(cudaMemcpy(&hs, a.stats, sizeof hs, cudaMemcpyDeviceToHost));
     size_t np = 0;
     for (int l = 0; l < NL; ++l) np += (size_t)w->n[l] * w->n[l + 1] + w->n[l + 1];
-    GCK(cudaMemsetAsync(a.gpartial, 0, sizeof(float) * np, st));
     if (hs.status != ICNF_OK) {   // no gradient of a failed solve: NaN (all-ones bit pattern), the caller reports the status
         GCK(cudaMemsetAsync(a.gpartial, 0xFF, sizeof(float) * np, st));
         if (a.dxs) GCK(cudaMemsetAsync(a.dxs, 0xFF, sizeof(float) * (size_t)a.nvars * B, st));
@@ -1975,8 +2160,12 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
     const int nsteps = hs.naccept;
     std::vector<StepRec> steps(std::max(nsteps, 1));
     if (nsteps) GCK(cudaMemcpy(steps.data(), a.steps, sizeof(StepRec) * nsteps, cudaMemcpyDeviceToHost));
+    // tensor-core precisions: the Hutchinson reverse sweep runs on tcgen05 as well; the exact-trace gradient
+    // (D' one-hot probes per stage) stays on the fp32 SGEMMs
+    if (w->tc && !exact) return backward_tc(w, a, nsteps, steps, np, st);
+    GCK(cudaMemsetAsync(a.gpartial, 0, sizeof(float) * np, st));
     const size_t f = sizeof(float);
-    GCK(w->bZS.reserve(f * 6 * DB)); GCK(w->bKZ.reserve(f * 5 * DB)); GCK(w->bKB.reserve(f * 6 * DB));
+    GCK(w->bKB.reserve(f * 6 * DB));
     GCK(w->bzbar.reserve(f * DB)); GCK(w->bSB.reserve(f * DB));
     GCK(w->bV.reserve(f * w->hrows * B)); GCK(w->bWv.reserve(f * (w->hrows + D) * B));
     GCK(w->bAEX.reserve(f * w->hrows * B)); GCK(w->bAB.reserve(f * w->hrows * B));
@@ -1989,8 +2178,8 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
     BwArgs b;
     memset(&b, 0, sizeof b);
     b.B = B; b.D = D; b.nvars = a.nvars; b.squared = a.squared; b.reg_a = a.reg_a; b.lam3 = a.lam3; b.wgt = a.inv_denominator;
-    b.zfinal = a.ckpt + (long long)nsteps * DB; b.zbar = w->bzbar.as<float>();
-    b.ZS = w->bZS.as<float>(); b.KZ = w->bKZ.as<float>(); b.KB = w->bKB.as<float>();
+    b.zfinal = a.ckpt + ckpt_off_h(nsteps, 0, DB); b.zbar = w->bzbar.as<float>();
+    b.KB = w->bKB.as<float>();
     b.ZD = w->ZD.as<float>(); b.Q = w->Q.as<float>(); b.E = w->EPS.as<float>();
     b.ZB = AB + w->hoff[NL - 1] * B; b.QB = wv_ptr(0); b.sbar = w->bSB.as<float>(); b.dxs = a.dxs;
     const int db_blocks = blocks_for(DB), b_blocks = blocks_for(B);
@@ -2001,19 +2190,11 @@ static cudaError_t backward(void* wsp, const float*, const BackwardArgs& a, bool
 
     for (int step = nsteps - 1; step >= 0; --step) {
         const float t = steps[step].t, h = steps[step].dt;
-        b.h = h; b.zn = a.ckpt + (long long)step * DB;
-        for (int i = 0; i < 6; ++i) {
-            b.i = i;
-            bw_stage_input_kernel<<<db_blocks, 256, 0, st>>>(b);
-            if (i < 5) {
-                p.t_fixed = t + g_c_host(i) * h;
-                GCK(enqueue_forward(p, 0.f, b.ZS + (long long)i * DB, b.KZ + (long long)i * DB));
-            }
-        }
+        b.h = h;
         bw_kbar_init_kernel<<<db_blocks, 256, 0, st>>>(b);
-        w->launches += 7;
+        w->launches++;
         for (int i = 5; i >= 0; --i) {
-            const float* zi = b.ZS + (long long)i * DB;
+            const float* zi = a.ckpt + ckpt_off_h(step, i, DB);
             const float ti = t + g_c_host(i) * h;
             const float hb = h * g_b_host(i);
             b.i = i; b.cl = hb * lbar; b.cE = hb * Ebar; b.cn = hb * nbar;
@@ -2112,6 +2293,7 @@ const Family* generic_family() {
         g.backward_grid = &generic::backward_grid;
         g.backward_partials_per_block = 1;
         g.supports_backward = 1;
+        g.ckpt_stages = 6;   // the inputs of all six Tsit5 stages of every accepted step: ckpt[slot][stage][D'][B]
         return g;
     }();
     return &f;

@@ -4,6 +4,7 @@
 #include "tc_gemm.cuh"
 
 #include <cstring>
+#include <vector>
 
 namespace icnf {
 namespace tc {
@@ -35,34 +36,60 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// per-device launch state: shared-memory attribute set, SM count (a process may drive several devices)
+struct DevState { bool attr_set = false; int sms = 0; };
+static DevState& dev_state() {
+    static DevState st[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return st[dev & 63];
+}
+
+template <bool SPLIT, int BN>
+static cudaError_t launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2, const CUtensorMap& mB2,
+                          const TcArgs& g, int sms, cudaStream_t st) {
+    const long long ntiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
+    const long long nwork = ntiles * (g.nslices > 1 ? g.nslices : 1);
+    const dim3 grid((unsigned)std::min<long long>(nwork, (long long)sms));
+    tc_gemm_kernel<SPLIT, BN><<<grid, TTHREADS, smem_bytes(SPLIT, BN), st>>>(mA, mB, mA2, mB2, g);
+    return cudaGetLastError();
+}
+
 // lda / ldb are the full row pitches; with g.split every row is [hi | lo] and the tensor map's inner
 // extent covers both halves (the zero padding between K and the pitch keeps the hi tiles clean)
-cudaError_t gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, TcArgs g, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, TcArgs g, cudaStream_t st,
+                 const __nv_bfloat16* A2, long long lda2, const __nv_bfloat16* B2, long long ldb2) {
+    DevState& ds = dev_state();
+    if (!ds.attr_set) {
+        cudaError_t e;
+#define ICNF_TC_ATTR(S, N)                                                                                          \
+        e = cudaFuncSetAttribute(tc_gemm_kernel<S, N>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(S, N)); \
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(tc_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_SPLIT);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    CUtensorMap mapA, mapB;
-    const uint64_t ka = g.split ? (uint64_t)g.lo_a + g.K : (uint64_t)g.K;
-    const uint64_t kb = g.split ? (uint64_t)g.lo_b + g.K : (uint64_t)g.K;
-    if (!make_map(&mapA, A, (uint64_t)g.M, ka, (uint64_t)lda, TBM) || !make_map(&mapB, B, (uint64_t)g.N, kb, (uint64_t)ldb, TBN))
-        return cudaErrorInvalidValue;
-    static int sms = 0;
-    if (!sms) {
+        ICNF_TC_ATTR(false, 128) ICNF_TC_ATTR(false, 256) ICNF_TC_ATTR(true, 128) ICNF_TC_ATTR(true, 256)
+#undef ICNF_TC_ATTR
         int dev = 0;
         cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&ds.sms, cudaDevAttrMultiProcessorCount, dev);
+        ds.attr_set = true;
     }
-    // persistent grid: one (split) or two CTAs per SM, each walking tiles blockIdx.x, + gridDim.x, ...
-    const long long ntiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + TBN - 1) / TBN);
-    const dim3 grid((unsigned)std::min<long long>(ntiles, (long long)sms * (g.split ? 1 : 2)));
-    if (g.split) tc_gemm_kernel<true><<<grid, TTHREADS, SMEM_BYTES_SPLIT, st>>>(mapA, mapB, g);
-    else tc_gemm_kernel<false><<<grid, TTHREADS, SMEM_BYTES, st>>>(mapA, mapB, g);
-    return cudaGetLastError();
+    // wide outputs: 128 x 256 tiles (half the operand bytes per MAC through L2); narrow ones: 128 x 128
+    const int bn = (g.N > 160) ? 256 : 128;
+    CUtensorMap mapA, mapB, mapA2, mapB2;
+    const uint64_t ka = g.split ? (uint64_t)g.lo_a + g.K : (uint64_t)g.K;
+    const uint64_t kb = g.split ? (uint64_t)g.lo_b + g.K : (uint64_t)g.K;
+    if (!make_map(&mapA, A, (uint64_t)g.M, ka, (uint64_t)lda, TBM) || !make_map(&mapB, B, (uint64_t)g.N, kb, (uint64_t)ldb, bn))
+        return cudaErrorInvalidValue;
+    if (g.K2 > 0) {
+        const uint64_t ka2 = g.split ? (uint64_t)g.lo_a2 + g.K2 : (uint64_t)g.K2;
+        const uint64_t kb2 = g.split ? (uint64_t)g.lo_b2 + g.K2 : (uint64_t)g.K2;
+        if (!A2 || !B2 || !make_map(&mapA2, A2, (uint64_t)g.M, ka2, (uint64_t)lda2, TBM) ||
+            !make_map(&mapB2, B2, (uint64_t)g.N2, kb2, (uint64_t)ldb2, bn))
+            return cudaErrorInvalidValue;
+    } else {
+        mapA2 = mapA; mapB2 = mapB;
+    }
+    if (g.split) return bn == 256 ? launch<true, 256>(mapA, mapB, mapA2, mapB2, g, ds.sms, st) : launch<true, 128>(mapA, mapB, mapA2, mapB2, g, ds.sms, st);
+    return bn == 256 ? launch<false, 256>(mapA, mapB, mapA2, mapB2, g, ds.sms, st) : launch<false, 128>(mapA, mapB, mapA2, mapB2, g, ds.sms, st);
 }
 
 // ---- packing kernels ------------------------------------------------------------------------
@@ -91,7 +118,7 @@ cudaError_t pack_matrix(const float* src, long long rs, long long cs, __nv_bfloa
 // then `ys`; pack_soa is the special case tin = 0, C = 0.
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* zi, const float* ys, __nv_bfloat16* X, long long B, int D,
                                                         int tin, int C, int pitch, float t_fixed, const float* ctrl_f, float c_i,
-                                                        const int* done, int split) {
+                                                        const int* done, int split, __nv_bfloat16* XT, long long ldT, int lo_T) {
     if (done && *done) return;
     __shared__ float tile[32][33];
     const long long b0 = (long long)blockIdx.x * 32;
@@ -106,6 +133,11 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* zi, const f
             if (k < D) v = zi[(long long)k * B + b];
             else if (tin && k == D) v = tnow;
             else if (k < D + tin + C) v = ys[(long long)(k - D - tin) * B + b];
+            if (XT && k < D + tin + C) {   // transposed operand of the weight-gradient GEMM: [input][sample], coalesced along b
+                const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                XT[(long long)k * ldT + b] = hi;
+                if (split) XT[(long long)k * ldT + lo_T + b] = __float2bfloat16_rn(v - __bfloat162float(hi));
+            }
         }
         tile[kk][tx] = v;
     }
@@ -123,15 +155,41 @@ __global__ void __launch_bounds__(256) pack_rows_kernel(const float* zi, const f
     }
 }
 cudaError_t pack_input(const float* zi, const float* ys, __nv_bfloat16* X, long long B, int D, int tin, int C, int pitch,
-                       float t_fixed, const float* ctrl_f, float c_i, const int* done, int split, cudaStream_t st) {
+                       float t_fixed, const float* ctrl_f, float c_i, const int* done, int split, cudaStream_t st,
+                       __nv_bfloat16* XT, long long ldT, int lo_T) {
     dim3 grid((unsigned)((B + 31) / 32), (unsigned)((pitch + 31) / 32));
-    pack_rows_kernel<<<grid, 256, 0, st>>>(zi, ys, X, B, D, tin, C, pitch, t_fixed, ctrl_f, c_i, done, split);
+    pack_rows_kernel<<<grid, 256, 0, st>>>(zi, ys, X, B, D, tin, C, pitch, t_fixed, ctrl_f, c_i, done, split, XT, ldT, lo_T);
     return cudaGetLastError();
 }
 cudaError_t pack_soa(const float* src, __nv_bfloat16* dst, long long B, int rows, int pitch, const int* done, int split,
-                     cudaStream_t st) {
+                     cudaStream_t st, __nv_bfloat16* XT, long long ldT, int lo_T) {
     dim3 grid((unsigned)((B + 31) / 32), (unsigned)((pitch + 31) / 32));
-    pack_rows_kernel<<<grid, 256, 0, st>>>(src, nullptr, dst, B, rows, 0, 0, pitch, 0.f, nullptr, 0.f, done, split);
+    pack_rows_kernel<<<grid, 256, 0, st>>>(src, nullptr, dst, B, rows, 0, 0, pitch, 0.f, nullptr, 0.f, done, split, XT, ldT, lo_T);
+    return cudaGetLastError();
+}
+
+// db[j] += sum over samples of XT[j][.] (hi + lo): one CTA per row, per-thread strided partial sums combined in a
+// fixed order (bit-reproducible)
+__global__ void __launch_bounds__(256) row_sums_kernel(const __nv_bfloat16* XT, long long ldT, int lo_T, int split, long long B,
+                                                       float* db) {
+    __shared__ float sh[256];
+    const __nv_bfloat16* row = XT + (long long)blockIdx.x * ldT;
+    float s = 0.f;
+    for (long long b = threadIdx.x; b < B; b += 256) {
+        float v = __bfloat162float(row[b]);
+        if (split) v += __bfloat162float(row[lo_T + b]);
+        s += v;
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) db[blockIdx.x] += sh[0];
+}
+cudaError_t row_sums(const __nv_bfloat16* XT, long long ldT, int lo_T, int split, int rows, long long B, float* db, cudaStream_t st) {
+    row_sums_kernel<<<rows, 256, 0, st>>>(XT, ldT, lo_T, split, B, db);
     return cudaGetLastError();
 }
 
@@ -187,5 +245,52 @@ extern "C" __attribute__((visibility("default"))) int icnf_tc_gemm_selftest(int 
         ok(cudaMemcpy(D, dD, sizeof(float) * M * N, cudaMemcpyDeviceToHost));
     }
     cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(a16); cudaFree(b16);
+    return rc;
+}
+
+// Self-test of the weight-gradient form of the GEMM: D[n * M + m] = sum_k A[m][k] B[n][k] + sum_k A2[m][k] B2[n][k]
+// (B2 has N2 <= N rows), K cut into `nslices` split-K slices that are summed on the host in slice order.
+extern "C" __attribute__((visibility("default"))) int icnf_tc_wgrad_selftest(int M, int N, int N2, int K, const float* A,
+                                                                            const float* B, const float* A2, const float* B2,
+                                                                            float* D, int split, int nslices) {
+    using namespace icnf::tc;
+    const int kp = (K + 7) & ~7;
+    const int rp = split ? 2 * kp : kp;
+    float *dA = nullptr, *dB = nullptr, *dA2 = nullptr, *dB2 = nullptr, *dD = nullptr;
+    __nv_bfloat16 *a16 = nullptr, *b16 = nullptr, *a216 = nullptr, *b216 = nullptr;
+    int rc = 0;
+    auto ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == 0) rc = 2; return e == cudaSuccess; };
+    const size_t fm = sizeof(float);
+    if (ok(cudaMalloc(&dA, fm * M * K)) && ok(cudaMalloc(&dB, fm * N * K)) && ok(cudaMalloc(&dA2, fm * M * K)) &&
+        ok(cudaMalloc(&dB2, fm * std::max(N2, 1) * K)) && ok(cudaMalloc(&dD, fm * (size_t)M * N * nslices)) &&
+        ok(cudaMalloc(&a16, 2 * (size_t)M * rp)) && ok(cudaMalloc(&b16, 2 * (size_t)N * rp)) &&
+        ok(cudaMalloc(&a216, 2 * (size_t)M * rp)) && ok(cudaMalloc(&b216, 2 * (size_t)std::max(N2, 1) * rp))) {
+        ok(cudaMemcpy(dA, A, fm * M * K, cudaMemcpyHostToDevice));
+        ok(cudaMemcpy(dB, B, fm * N * K, cudaMemcpyHostToDevice));
+        ok(cudaMemcpy(dA2, A2, fm * M * K, cudaMemcpyHostToDevice));
+        if (N2) ok(cudaMemcpy(dB2, B2, fm * N2 * K, cudaMemcpyHostToDevice));
+        ok(cudaMemset(dD, 0, fm * (size_t)M * N * nslices));
+        ok(pack_matrix(dA, K, 1, a16, M, K, kp, split, 0));
+        ok(pack_matrix(dB, K, 1, b16, N, K, kp, split, 0));
+        ok(pack_matrix(dA2, K, 1, a216, M, K, kp, split, 0));
+        if (N2) ok(pack_matrix(dB2, K, 1, b216, N2, K, kp, split, 0));
+        TcArgs g;
+        memset(&g, 0, sizeof g);
+        g.M = M; g.N = N; g.K = K; g.ep = TEP_WGRAD; g.out_f32 = dD;
+        g.split = split; g.lo_a = kp; g.lo_b = kp; g.lo_a2 = kp; g.lo_b2 = kp;
+        g.K2 = N2 ? K : 0; g.N2 = N2;
+        g.nslices = nslices; g.slice_stride = (long long)M * N; g.ldw = M;
+        ok(gemm(a16, rp, b16, rp, g, 0, a216, rp, b216, rp));
+        ok(cudaDeviceSynchronize());
+        std::vector<float> host((size_t)M * N * nslices);
+        ok(cudaMemcpy(host.data(), dD, fm * host.size(), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < (size_t)M * N; ++i) {
+            float s = 0.f;
+            for (int sl = 0; sl < nslices; ++sl) s += host[(size_t)sl * M * N + i];
+            D[i] = s;
+        }
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dA2); cudaFree(dB2); cudaFree(dD);
+    cudaFree(a16); cudaFree(b16); cudaFree(a216); cudaFree(b216);
     return rc;
 }

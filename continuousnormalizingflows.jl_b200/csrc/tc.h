@@ -1,5 +1,5 @@
 // tc.h -- host interface of the tensor-core GEMM (tc.cu) used by the generic family when
-// precision = ICNF_BF16_TC.
+// precision = ICNF_BF16_TC / ICNF_BF16X3_TC: the forward RHS and the whole reverse sweep.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -7,47 +7,76 @@
 namespace icnf {
 namespace tc {
 
-// 3 stages = 96 KB of operand ring per CTA, so two CTAs share an SM and one CTA's epilogue
-// overlaps the other's main loop
-constexpr int TBM = 128, TBN = 128, TBK = 64, TSTAGES = 3, TTHREADS = 320;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int A_TILE_BYTES = TBM * TBK * 2, B_TILE_BYTES = TBN * TBK * 2;
-constexpr int SMEM_BYTES = TSTAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + 2 * TBN * 4 /*bias, double-buffered*/;
-// split precision (bf16 x 3: every operand is hi + lo, three MMAs per K step): four tiles per stage
-constexpr int SMEM_BYTES_SPLIT = TSTAGES * 2 * (A_TILE_BYTES + B_TILE_BYTES) + 1024 + 256 + 2 * TBN * 4;
+// CTA tile: 128 rows of the A operand (the TMEM lanes) x BN rows of the B operand (TMEM columns), K blocks of 64.
+// BN = 256 halves the operand bytes per MAC that a CTA pulls through L2 (the limiter of these GEMMs: the SM's
+// share of L2 bandwidth, not the tensor pipe) and turns a 512-unit layer at 8192 samples into ONE wave of
+// 128 CTAs; BN = 128 serves narrow outputs.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue.
+constexpr int TBM = 128, TBK = 64, TTHREADS = 320;
+constexpr int A_TILE_BYTES = TBM * TBK * 2;
+__host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * TBK * 2; }
+// shared-memory ring depth: as many stages as fit next to the barriers and the bias slice
+__host__ __device__ constexpr int stages(bool split, int bn) { return split ? (bn == 256 ? 2 : 3) : (bn == 256 ? 4 : 6); }
+__host__ __device__ constexpr int stage_bytes(bool split, int bn) { return (split ? 2 : 1) * (A_TILE_BYTES + b_tile_bytes(bn)); }
+__host__ __device__ constexpr int smem_bytes(bool split, int bn) {
+    return stages(split, bn) * stage_bytes(split, bn) + 1024 /*align*/ + 256 /*barriers*/ + 2 * bn * 4 /*bias, double-buffered*/;
+}
 
 enum TcEpilogue {
-    TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)
+    TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)  [+ H transposed]
     TEP_LIN_SOA = 1,    // out_f32[n * M + m] = acc + bias[n]              (fp32, [unit][sample])
-    TEP_MULD = 2,       // G[m][n] = acc * aux[m][n]                        (bf16)
+    TEP_MULD = 2,       // G[m][n] = acc * aux[m][n]                        (bf16)                 [+ G transposed]
     TEP_PLAIN_SOA = 3,  // out_f32[n * M + m] = acc
-    TEP_TRACE = 4       // rowsum[m] (+)= sum_n acc * aux[m][n]
+    TEP_TRACE = 4,      // rowsum[m] (+)= sum_n acc * aux[m][n]
+    // reverse sweep (derivation: tiny.cuh rhs_reverse / DESIGN.md):
+    TEP_TANGENT = 5,    // out0 = acc * aux (sigma');  out1 = acc * aux1 (chain g) * phi(aux2 (h), aux),  phi = sigma''/sigma'
+    TEP_MULADD = 6,     // out0 = acc * aux (sigma') + aux1                                         [+ out0 transposed]
+    TEP_WGRAD = 7       // out_f32[slice * slice_stride + n * ldw + m] += acc      (weight gradient, column-major n_out x n_in)
 };
 
 struct TcArgs {
-    int M, N, K;               // samples, units, reduction
+    int M, N, K;               // rows of A (TMEM lanes), rows of B (TMEM columns), reduction length of segment 0
     int ep, act;
     const float* bias;         // N
-    __nv_bfloat16* out0;       // H or G
-    __nv_bfloat16* out1;       // Dv
-    const __nv_bfloat16* aux;  // D (same pitch as out0)
-    int ldo;                   // row pitch (elements) of out0/out1/aux
-    float* out_f32;            // SoA output / row sums
+    __nv_bfloat16* out0;       // H / G / Wv / AB
+    __nv_bfloat16* out1;       // Dv / AEX
+    const __nv_bfloat16* aux;  // sigma' (same pitch as out0)
+    const __nv_bfloat16* aux1; // TANGENT: chain g;  MULADD: AEX
+    const __nv_bfloat16* aux2; // TANGENT: h
+    int ldo;                   // row pitch (elements) of out0/out1/aux*
+    float* out_f32;            // SoA output / row sums / weight-gradient slices
     int n_limit;               // SoA: only units < n_limit are written
     int atomic_rowsum;         // TEP_TRACE with several unit tiles
     const int* done;
     // split precision: every bf16 matrix row is [hi (pitch) | lo (pitch)]; lo_* = column offset of the
     // lo half in A, B and in out0/out1/aux (ldo is then the full row pitch, 2 x lo_o)
     int split, lo_a, lo_b, lo_o;
+    // transposed copy of out0 for the weight-gradient GEMMs: outT[n * ldT + m] (hi) and outT[n * ldT + lo_T + m] (lo)
+    __nv_bfloat16* outT;
+    long long ldT;
+    int lo_T;
+    // second operand pair accumulated into the same tile (weight gradient: abar h' + g w'): K2 = its reduction
+    // length (0: none), N2 = valid rows of its B operand (tiles at n0 >= N2 skip the segment)
+    int K2, N2, lo_a2, lo_b2;
+    // split-K: the K blocks of every segment are cut into nslices ranges, one work item per (tile, slice)
+    int nslices;
+    long long slice_stride;
+    int ldw;
 };
 
-cudaError_t gemm(const __nv_bfloat16* A, int lda, const __nv_bfloat16* B, int ldb, TcArgs g, cudaStream_t st);
+// A (M x K) and B (N x K), both K contiguous; A2/B2: the optional second segment
+cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, TcArgs g, cudaStream_t st,
+                 const __nv_bfloat16* A2 = nullptr, long long lda2 = 0, const __nv_bfloat16* B2 = nullptr, long long ldb2 = 0);
 cudaError_t pack_matrix(const float* src, long long rs, long long cs, __nv_bfloat16* dst, int rows, int cols, int pitch,
                         int split, cudaStream_t st);
+// SoA fp32 rows [zi (D); t; ys (C)] -> bf16 rows X[b][pitch] and, when XT != null, the transposed copy XT[k][ldT]
 cudaError_t pack_input(const float* zi, const float* ys, __nv_bfloat16* X, long long B, int D, int tin, int C, int pitch,
-                       float t_fixed, const float* ctrl_f, float c_i, const int* done, int split, cudaStream_t st);
+                       float t_fixed, const float* ctrl_f, float c_i, const int* done, int split, cudaStream_t st,
+                       __nv_bfloat16* XT = nullptr, long long ldT = 0, int lo_T = 0);
 cudaError_t trace_dot(const float* gvec, const __nv_bfloat16* D1, float* TR, int n1, int pitch, long long B, const int* done,
                       int split, cudaStream_t st);
 cudaError_t pack_soa(const float* src, __nv_bfloat16* dst, long long B, int rows, int pitch, const int* done, int split,
-                     cudaStream_t st);
+                     cudaStream_t st, __nv_bfloat16* XT = nullptr, long long ldT = 0, int lo_T = 0);
+// db[j] += sum_b XT[j][b] (hi + lo), one CTA per row, fixed summation order
+cudaError_t row_sums(const __nv_bfloat16* XT, long long ldT, int lo_T, int split, int rows, long long B, float* db, cudaStream_t st);
 }  // namespace tc
 }  // namespace icnf

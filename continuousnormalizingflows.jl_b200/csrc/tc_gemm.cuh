@@ -1,15 +1,20 @@
 // tc_gemm.cuh -- tcgen05 / TMEM / TMA GEMM with fused epilogues for wide MLPs (sm_100a).
 //
-//   D[m][n] = sum_k A[m][k] * B[n][k]        A: samples x K  (bf16, K contiguous)
-//                                            B: units   x K  (bf16, K contiguous)
+//   D[m][n] = sum_k A[m][k] * B[n][k]  (+ sum_k A2[m][k] * B2[n][k])      all operands bf16, K contiguous
 //
-// One CTA computes a 128 (samples) x 128 (units) tile: warp 0 streams 64-wide K blocks of
-// both operands into a 4-stage shared-memory ring with TMA (cp.async.bulk.tensor, 128-byte
-// swizzle), one elected thread of warp 1 issues tcgen05.mma (M = 128, N = 128, K = 16,
-// bf16 x bf16 -> fp32) into a 128-column TMEM accumulator and releases ring slots with
-// tcgen05.commit, and warps 2..9 run the epilogue straight out of TMEM (tcgen05.ld, one
-// sample row and half of the columns per thread) -- bias + activation + sigma', the VJP's ".* d", or the
-// exact-trace contraction -- so activations go to HBM once, in bf16.
+// Forward / VJP chain / tangent / backprop GEMMs: A = activations (samples x K), B = weights (units x K).
+// Weight-gradient GEMMs: A = cotangents transposed (n_out x samples), B = layer inputs transposed
+// (n_in x samples), K = the sample index, two operand pairs (abar h' + g w') accumulated into one tile and
+// the sample range cut into split-K slices whose tiles are added into per-slice fp32 buffers (no atomics:
+// one CTA owns a (tile, slice) pair, so the sum order is fixed).
+//
+// One CTA computes a 128 x BN tile (BN = 128 or 256): warp 0 streams 64-wide K blocks of both operands into a
+// shared-memory ring with TMA (cp.async.bulk.tensor, 128-byte swizzle), one elected thread of warp 1 issues
+// tcgen05.mma (M = 128, N = BN, K = 16, bf16 x bf16 -> fp32) into a BN-column TMEM accumulator and releases
+// ring slots with tcgen05.commit, and warps 2..9 run the epilogue straight out of TMEM (tcgen05.ld, one
+// row and half of the columns per thread) -- bias + activation + sigma', the VJP's ".* d", the exact-trace
+// contraction, the second-order tangent terms, the backprop ".* d + extra" -- so activations go to HBM once,
+// in bf16, row-major for the next GEMM and (reverse sweep) transposed for the weight gradient.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -175,40 +180,77 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Persistent: the grid is one or two CTAs per SM and every CTA walks tiles blockIdx.x, + gridDim.x, ...
-// (unit tiles fastest, so concurrently running CTAs share the same sample rows of A in L2).  The
-// accumulator is double-buffered in TMEM (2 x 128 columns): while the epilogue warps drain tile i
-// the MMA warp already accumulates tile i + 1, and the TMA warp runs ahead across tile boundaries.
+// sigma'' / sigma' from (h, d): v .* sigma'' = g .* phi for the chain cotangent g = v .* sigma'
+__device__ __forceinline__ float act_ratio_rt(int act, float h, float d) {
+    switch (act) {
+        case ICNF_ACT_SOFTPLUS: return 1.0f - d;
+        case ICNF_ACT_TANH: return -2.0f * h;
+        case ICNF_ACT_SIGMOID: return 1.0f - 2.0f * h;
+        default: return 0.0f;
+    }
+}
+
+// transposed copy of 32 consecutive columns of row m: outT[(nb + j) * ldT + m]; a warp writes 32 consecutive
+// rows m, i.e. 64 contiguous bytes per column
 template <bool SPLIT>
-__global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                          const __grid_constant__ CUtensorMap mapB, TcArgs g) {
+__device__ __forceinline__ void store_col32T(__nv_bfloat16* outT, long long ldT, int lo_T, int nb, int N, int m,
+                                             const float (&v)[32]) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        if (nb + j < N) {
+            const __nv_bfloat16 hi = __float2bfloat16_rn(v[j]);
+            __nv_bfloat16* p = outT + (long long)(nb + j) * ldT + m;
+            p[0] = hi;
+            if constexpr (SPLIT) p[lo_T] = __float2bfloat16_rn(v[j] - __bfloat162float(hi));
+        }
+    }
+}
+
+// Persistent: the grid is one CTA per SM and every CTA walks work items blockIdx.x, + gridDim.x, ...
+// A work item is a (tile, split-K slice) pair; tiles are ordered with the B-operand tiles fastest, so
+// concurrently running CTAs share the same A rows in L2.  The accumulator is double-buffered in TMEM
+// (2 x BN columns): while the epilogue warps drain item i the MMA warp already accumulates item i + 1, and
+// the TMA warp runs ahead across item boundaries.
+template <bool SPLIT, int BN>
+__global__ void __launch_bounds__(TTHREADS, 1)
+    tc_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                   const __grid_constant__ CUtensorMap mapA2, const __grid_constant__ CUtensorMap mapB2, TcArgs g) {
     if (g.done && *g.done) return;
     constexpr int NT_A = SPLIT ? 2 : 1;   // tiles per operand and stage
-    constexpr int STAGE_BYTES = NT_A * (A_TILE_BYTES + B_TILE_BYTES);
+    constexpr int NSTAGE = stages(SPLIT, BN);
+    constexpr int BTB = b_tile_bytes(BN);
+    constexpr int STAGE_BYTES = stage_bytes(SPLIT, BN);
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     // stage s: [A_hi | A_lo? | B_hi | B_lo?]
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + TSTAGES * STAGE_BYTES);
-    uint64_t* empty = full + TSTAGES;
-    uint64_t* tmem_full = empty + TSTAGES;     // [2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
+    uint64_t* empty = full + NSTAGE;
+    uint64_t* tmem_full = empty + NSTAGE;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;      // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* sbias = reinterpret_cast<float*>(smem + TSTAGES * STAGE_BYTES + 256);   // [2][TBN]
+    float* sbias = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES + 256);   // [2][BN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nkb = (g.K + TBK - 1) / TBK;
-    const int ntn = (g.N + TBN - 1) / TBN;
+    const int nkb0 = (g.K + TBK - 1) / TBK;
+    const int nkb1 = g.K2 > 0 ? (g.K2 + TBK - 1) / TBK : 0;
+    const int ntn = (g.N + BN - 1) / BN;
     const int ntiles = ((g.M + TBM - 1) / TBM) * ntn;
+    const int nsl = g.nslices > 1 ? g.nslices : 1;
+    const int nwork = ntiles * nsl;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
-        for (int s = 0; s < TSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        if (nkb1) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA2) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB2) : "memory");
+        }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(2 * TBN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(2 * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -220,54 +262,72 @@ __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
         // ===== TMA producer =====
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                const int m0 = (tile / ntn) * TBM, n0 = (tile % ntn) * TBN;
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % TSTAGES;
-                    const uint32_t ph = (it / TSTAGES) & 1;
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_wait(&empty[s], ph ^ 1);
-                    mbar_expect_tx(&full[s], STAGE_BYTES);
-                    tma_load_2d(st, &mapA, &full[s], kb * TBK, m0);
-                    if constexpr (SPLIT) tma_load_2d(st + A_TILE_BYTES, &mapA, &full[s], g.lo_a + kb * TBK, m0);
-                    tma_load_2d(st + NT_A * A_TILE_BYTES, &mapB, &full[s], kb * TBK, n0);
-                    if constexpr (SPLIT) tma_load_2d(st + NT_A * A_TILE_BYTES + B_TILE_BYTES, &mapB, &full[s], g.lo_b + kb * TBK, n0);
+            for (int work = blockIdx.x; work < nwork; work += gridDim.x) {
+                const int tile = work / nsl, sl = work - tile * nsl;
+                const int m0 = (tile / ntn) * TBM, n0 = (tile % ntn) * BN;
+                const int nseg = (nkb1 && n0 < g.N2) ? 2 : 1;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    const CUtensorMap* ma = seg ? &mapA2 : &mapA;
+                    const CUtensorMap* mb = seg ? &mapB2 : &mapB;
+                    const int nkb = seg ? nkb1 : nkb0;
+                    const int lo_a = seg ? g.lo_a2 : g.lo_a, lo_b = seg ? g.lo_b2 : g.lo_b;
+                    const int kbe = (int)((long long)nkb * (sl + 1) / nsl);
+                    for (int kb = (int)((long long)nkb * sl / nsl); kb < kbe; ++kb, ++it) {
+                        const int s = it % NSTAGE;
+                        const uint32_t ph = (it / NSTAGE) & 1;
+                        uint8_t* st = smem + s * STAGE_BYTES;
+                        mbar_wait(&empty[s], ph ^ 1);
+                        mbar_expect_tx(&full[s], STAGE_BYTES);
+                        tma_load_2d(st, ma, &full[s], kb * TBK, m0);
+                        if constexpr (SPLIT) tma_load_2d(st + A_TILE_BYTES, ma, &full[s], lo_a + kb * TBK, m0);
+                        tma_load_2d(st + NT_A * A_TILE_BYTES, mb, &full[s], kb * TBK, n0);
+                        if constexpr (SPLIT) tma_load_2d(st + NT_A * A_TILE_BYTES + BTB, mb, &full[s], lo_b + kb * TBK, n0);
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TBM, TBN);
+            constexpr uint32_t idesc = make_idesc(TBM, BN);
             int it = 0, i = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+            for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++i) {
+                const int tile = work / nsl, sl = work - tile * nsl;
+                const int n0 = (tile % ntn) * BN;
+                const int nseg = (nkb1 && n0 < g.N2) ? 2 : 1;
                 const int as = i & 1;
                 mbar_wait(&tmem_empty[as], ((i >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t tacc = tmem_base + (uint32_t)(as * TBN);
-                for (int kb = 0; kb < nkb; ++kb, ++it) {
-                    const int s = it % TSTAGES;
-                    const uint32_t ph = (it / TSTAGES) & 1;
-                    uint8_t* st = smem + s * STAGE_BYTES;
-                    mbar_wait(&full[s], ph);
-                    tc_fence_after();
-                    const uint64_t a_hi = make_desc(smem_u32(st));
-                    const uint64_t b_hi = make_desc(smem_u32(st + NT_A * A_TILE_BYTES));
+                const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
+                uint32_t started = 0;
+                for (int seg = 0; seg < nseg; ++seg) {
+                    const int nkb = seg ? nkb1 : nkb0;
+                    const int kbe = (int)((long long)nkb * (sl + 1) / nsl);
+                    for (int kb = (int)((long long)nkb * sl / nsl); kb < kbe; ++kb, ++it) {
+                        const int s = it % NSTAGE;
+                        const uint32_t ph = (it / NSTAGE) & 1;
+                        uint8_t* st = smem + s * STAGE_BYTES;
+                        mbar_wait(&full[s], ph);
+                        tc_fence_after();
+                        const uint64_t a_hi = make_desc(smem_u32(st));
+                        const uint64_t b_hi = make_desc(smem_u32(st + NT_A * A_TILE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < TBK / 16; ++k) {
-                        // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
-                        tc_mma_bf16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, (kb | k) != 0);
+                        for (int k = 0; k < TBK / 16; ++k) {
+                            // advance 16 bf16 = 32 bytes inside the 128-byte swizzle atom: +2 in the (addr >> 4) field
+                            tc_mma_bf16(tacc, a_hi + 2 * k, b_hi + 2 * k, idesc, started | (uint32_t)k);
+                        }
+                        started = 1;
+                        if constexpr (SPLIT) {
+                            // a b ~ a_hi b_hi + a_lo b_hi + a_hi b_lo  (lo x lo is below fp32 rounding)
+                            const uint64_t a_lo = make_desc(smem_u32(st + A_TILE_BYTES));
+                            const uint64_t b_lo = make_desc(smem_u32(st + NT_A * A_TILE_BYTES + BTB));
+#pragma unroll
+                            for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+#pragma unroll
+                            for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+                        }
+                        tc_commit(&empty[s]);
                     }
-                    if constexpr (SPLIT) {
-                        // a b ~ a_hi b_hi + a_lo b_hi + a_hi b_lo  (lo x lo is below fp32 rounding)
-                        const uint64_t a_lo = make_desc(smem_u32(st + A_TILE_BYTES));
-                        const uint64_t b_lo = make_desc(smem_u32(st + NT_A * A_TILE_BYTES + B_TILE_BYTES));
-#pragma unroll
-                        for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tacc, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
-#pragma unroll
-                        for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
-                    }
-                    tc_commit(&empty[s]);
                 }
                 tc_commit(&tmem_full[as]);
             }
@@ -278,13 +338,14 @@ __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
         const int chalf = (warp - 2) >> 2;
         const int pitch = SPLIT ? g.lo_o : g.ldo;   // columns of one half
         int i = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++i) {
+        for (int work = blockIdx.x; work < nwork; work += gridDim.x, ++i) {
+            const int tile = work / nsl, sl = work - tile * nsl;
             const int as = i & 1;
-            const int m0 = (tile / ntn) * TBM, n0 = (tile % ntn) * TBN;
-            float* sb = sbias + as * TBN;
-            {   // stage this tile's bias slice (double-buffered: tile i - 1 may still be read by a slower warp)
+            const int m0 = (tile / ntn) * TBM, n0 = (tile % ntn) * BN;
+            float* sb = sbias + as * BN;
+            {   // stage this tile's bias slice (double-buffered: item i - 1 may still be read by a slower warp)
                 const int e = threadIdx.x - 64;   // 0..255
-                if (e < TBN) sb[e] = (g.bias && n0 + e < g.N) ? __ldg(g.bias + n0 + e) : 0.f;
+                if (e < BN) sb[e] = (g.bias && n0 + e < g.N) ? __ldg(g.bias + n0 + e) : 0.f;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             mbar_wait(&tmem_full[as], (i >> 1) & 1);
@@ -292,10 +353,10 @@ __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
             const int m = m0 + q * 32 + lane;
             const bool row_ok = m < g.M;
             float rowsum = 0.f;
-            for (int c0 = chalf * (TBN / 2); c0 < (chalf + 1) * (TBN / 2); c0 += 32) {
+            for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
                 if (n0 + c0 >= g.N) break;   // warp-uniform
                 uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * TBN + c0), r);
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), r);
                 if (!row_ok) continue;
                 const int nb = n0 + c0;
                 const size_t row_off = (size_t)m * g.ldo;
@@ -316,12 +377,55 @@ __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
                     }
                     store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, hv);
                     store_row32<SPLIT>(g.out1, row_off, nb, pitch, g.lo_o, dv);
+                    if (g.outT) store_col32T<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, hv);
                 } else if (g.ep == TEP_MULD) {
                     float dv[32], gv[32];
                     load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) gv[j] = (nb + j < g.N) ? __uint_as_float(r[j]) * dv[j] : 0.f;
                     store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, gv);
+                    if (g.outT) store_col32T<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, gv);
+                } else if (g.ep == TEP_TANGENT) {
+                    float dv[32], gv[32], o0[32], o1[32];
+                    load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
+                    load_row32<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, gv);
+                    if (g.act == ICNF_ACT_SOFTPLUS) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float rr = (nb + j < g.N) ? __uint_as_float(r[j]) : 0.f;
+                            o0[j] = rr * dv[j];
+                            o1[j] = rr * gv[j] * (1.0f - dv[j]);
+                        }
+                    } else {
+                        float hv[32];
+                        load_row32<SPLIT>(g.aux2, row_off, nb, pitch, g.lo_o, hv);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float rr = (nb + j < g.N) ? __uint_as_float(r[j]) : 0.f;
+                            o0[j] = rr * dv[j];
+                            o1[j] = rr * gv[j] * act_ratio_rt(g.act, hv[j], dv[j]);
+                        }
+                    }
+                    store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, o0);
+                    store_row32<SPLIT>(g.out1, row_off, nb, pitch, g.lo_o, o1);
+                    if (g.outT) store_col32T<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, o0);
+                } else if (g.ep == TEP_MULADD) {
+                    float dv[32], ax[32], o0[32];
+                    load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
+                    load_row32<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, ax);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) o0[j] = (nb + j < g.N) ? fmaf(__uint_as_float(r[j]), dv[j], ax[j]) : 0.f;
+                    store_row32<SPLIT>(g.out0, row_off, nb, pitch, g.lo_o, o0);
+                    if (g.outT) store_col32T<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, o0);
+                } else if (g.ep == TEP_WGRAD) {
+                    float* base = g.out_f32 + (long long)sl * g.slice_stride + m;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (nb + j < g.N) {
+                            float* p = base + (long long)(nb + j) * g.ldw;   // a warp covers 32 consecutive m: coalesced
+                            *p += __uint_as_float(r[j]);
+                        }
+                    }
                 } else if (g.ep == TEP_TRACE) {
                     float dv[32];
                     load_row32<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
@@ -351,7 +455,7 @@ __global__ void __launch_bounds__(TTHREADS, SPLIT ? 1 : 2) tc_gemm_kernel(const 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * TBN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
     }
 }
 

@@ -258,6 +258,11 @@ ICNF_API int icnf_backward_plan(const icnf_config* cfg, int exact, int sm_count,
                                 int32_t* first, int32_t* n_blocks);
 
 ICNF_API int icnf_tc_gemm_selftest(int M, int N, int K, const float* A, const float* B, float* D, int split);
+/* Self-test of the weight-gradient form of the same kernel (K = the sample index, two operand pairs accumulated
+ * into one tile, `nslices` split-K slices summed in slice order): D[n * M + m] = sum_k A[m][k] B[n][k] +
+ * sum_k A2[m][k] B2[n][k], A, A2: M x K, B: N x K, B2: N2 x K (N2 <= N, 0 = no second pair), row-major host buffers. */
+ICNF_API int icnf_tc_wgrad_selftest(int M, int N, int N2, int K, const float* A, const float* B, const float* A2,
+                                    const float* B2, float* D, int split, int nslices);
 
 #ifdef __cplusplus
 }

@@ -45,6 +45,27 @@ def test_tcgen05_gemm_selftest(m, shape):
     assert np.abs(D3 - exact).max() < 0.02 * np.abs(D - exact).max()
 
 
+@pytest.mark.parametrize("shape", [(128, 128, 0, 64, 1), (512, 513, 512, 1000, 3), (784, 512, 512, 515, 4), (100, 785, 784, 300, 2),
+                                   (388, 97, 64, 4096, 16)])
+def test_tcgen05_wgrad_selftest(m, shape):
+    """the weight-gradient form of the kernel: K = samples, two operand pairs in one accumulator, split-K slices"""
+    torch.zeros(1, device="cuda")
+    M, N, N2, K, nsl = shape
+    rng = np.random.default_rng(1)
+    A, A2 = (rng.standard_normal((M, K)).astype(np.float32) for _ in range(2))
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    B2 = rng.standard_normal((max(N2, 1), K)).astype(np.float32)
+    exact = B.astype(np.float64) @ A.astype(np.float64).T
+    if N2:
+        exact[:N2] += B2[:N2].astype(np.float64) @ A2.astype(np.float64).T
+    for split, tol in ((1, 3e-5), (0, 2e-2)):
+        D = np.zeros((N, M), np.float32)
+        rc = m.lib.icnf_tc_wgrad_selftest(M, N, N2, K, A.ctypes.data, B.ctypes.data, A2.ctypes.data, B2.ctypes.data,
+                                          D.ctypes.data, split, nsl)
+        assert rc == 0
+        assert np.abs(D - exact).max() / np.abs(exact).max() < tol, (split, np.abs(D - exact).max() / np.abs(exact).max())
+
+
 WIDE = {
     "cond64": dict(nvariables=64, naugments=0, nconditions=32, n_hidden=256),          # config 5 (97-256-256-64)
     "ffjord_small": dict(nvariables=96, naugments=0, nn=("softplus", (97, 128, 160, 128, 96))),   # config-4-like, 4 layers
@@ -143,8 +164,8 @@ def test_solve_bf16x3_tc_matches_oracle_and_step_count(m):
 
 @pytest.mark.parametrize("prec,tol", [("bf16x3_tc", 2e-4), ("bf16_tc", BF16_TOL)])
 def test_tc_training_gradient(m, prec, tol):
-    """Training through the tensor-core precisions: the forward solve runs on tcgen05, the reverse
-    sweep is the fp32 one over the forward's checkpoints."""
+    """Training through the tensor-core precisions: forward solve AND reverse sweep on tcgen05 (chain / tangent /
+    backprop GEMMs with fused epilogues, weight gradient as a split-K GEMM over the samples)."""
     icnf = _make(m, "cond64", precision=prec)
     B = 96
     om, theta, xs, eps, ys = make_inputs(icnf, B)
@@ -156,3 +177,31 @@ def test_tc_training_gradient(m, prec, tol):
     assert abs(l - float(rl)) <= tol * abs(float(rl)) + 1e-5
     assert norm_rel_err(g, rg.numpy()) < tol, norm_rel_err(g, rg.numpy())
     assert norm_rel_err(gx, rgx.numpy()) < tol, norm_rel_err(gx, rgx.numpy())
+
+
+@pytest.mark.parametrize("name,B", [("ffjord_small", 333), ("cond64", 1000)])
+def test_tc_training_gradient_ragged_and_adaptive(m, name, B):
+    """four-layer network, ragged batch (not a multiple of 8: zero-padded K of the transposed operands), adaptive steps"""
+    icnf = _make(m, name, precision="bf16x3_tc")
+    om, theta, xs, eps, ys = make_inputs(icnf, B)
+    theta = (0.5 * theta).astype(np.float32)
+    args = (xs, ys) if ys is not None else (xs,)
+    l, g, gx = m.loss_and_gradient(icnf, m.TrainMode(True), *args, theta, {}, want_dxs=True, eps=eps, tspan=icnf.tspan)
+    st = icnf.last_stats
+    # the oracle differentiates its own discrete solve at the product's accepted steps
+    rl, rg, rgx = O.loss_grad(om, O.TRAIN_REG, t64(xs), t64(theta), t64(eps), t64(ys), want_dxs=True)
+    assert st.naccept >= 1
+    assert abs(l - float(rl)) <= 2e-4 * abs(float(rl)) + 1e-5
+    assert norm_rel_err(g, rg.numpy()) < 1e-3, norm_rel_err(g, rg.numpy())      # adaptive: solver tolerance, not rounding
+    assert norm_rel_err(gx, rgx.numpy()) < 1e-3
+
+
+def test_tc_gradient_is_bit_reproducible(m):
+    """no atomics anywhere in the tensor-core reverse sweep: two runs give identical bits"""
+    icnf = _make(m, "cond64", precision="bf16x3_tc")
+    B = 500
+    om, theta, xs, eps, ys = make_inputs(icnf, B)
+    sol = dict(adaptive=False, dt=0.5)
+    a = m.loss_and_gradient(icnf, m.TrainMode(True), xs, ys, theta, {}, eps=eps, tspan=icnf.tspan, **sol)
+    b = m.loss_and_gradient(icnf, m.TrainMode(True), xs, ys, theta, {}, eps=eps, tspan=icnf.tspan, **sol)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1])
