@@ -9,10 +9,11 @@ CPU or PyTorch fallback for any numeric result.
 from ._lib import ICNFError, LIB_PATH, lib  # noqa: F401  (loads the shared library)
 from .api import (  # noqa: F401
     B200MatrixMode, Chain, ComputeMode, Dense, ICNF, MatrixMode, Mode, SolverStats, TestMode, TrainMode,
-    augmented_f, base_sol, generate, inference, loss, loss_and_gradient, measure_fp32_peak, setup,
+    augmented_f, base_sol, create_group, generate, group_info, group_join_id, group_unique_id, inference, loss,
+    loss_and_gradient, measure_fp32_peak, setup,
 )
 from .dist import CondICNFDist, ICNFDist  # noqa: F401
-from .parallel import all_reduce_sum, dp_loss_and_gradient, shard_bounds  # noqa: F401
+from .parallel import all_reduce_sum, dp_loss_and_gradient, group_join, shard_bounds  # noqa: F401
 from .mlj import Adam, CondICNFModel, ICNFModel, WeightDecay, make_opt_callback  # noqa: F401
 
 __all__ = [

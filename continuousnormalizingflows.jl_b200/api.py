@@ -539,7 +539,7 @@ def generate(icnf: ICNF, mode: Mode, *args, z0=None, eps=None, seed=None, tspan=
 
 
 def _loss_impl(icnf: ICNF, mode: Mode, xs, ys, ps, want_grad: bool, want_dxs: bool, eps, seed, tspan,
-               sample_offset: int, global_batch: int, sol: dict):
+               sample_offset: int, global_batch: int, sol: dict, dp: bool = False):
     icnf._set_params(ps)
     dev = _on_device(xs, eps, ys)
     d = icnf.nvariables + icnf.naugments
@@ -562,10 +562,10 @@ def _loss_impl(icnf: ICNF, mode: Mode, xs, ys, ps, want_grad: bool, want_dxs: bo
         icnf._grad_loss_buf = buf if want_grad else None
         dxs = torch.empty((xa.B, icnf.nvariables), dtype=torch.float32, device=device) if want_dxs else None
         ds = _dev_stats(icnf)
-        icnf._check(lib.icnf_loss_grad_dev(icnf._h, mode.code, C.byref(solver), t0, t1, xa.ptr, C.byref(noise), ea.ptr,
-                                           ya.ptr, lossv.data_ptr(), dth.data_ptr() if want_grad else None,
-                                           dxs.data_ptr() if want_dxs else None, ds.data_ptr(), xa.B, int(global_batch),
-                                           _stream(icnf)))
+        fn = lib.icnf_loss_grad_dp_dev if (dp and want_grad) else lib.icnf_loss_grad_dev
+        icnf._check(fn(icnf._h, mode.code, C.byref(solver), t0, t1, xa.ptr, C.byref(noise), ea.ptr,
+                       ya.ptr, lossv.data_ptr(), dth.data_ptr() if want_grad else None,
+                       dxs.data_ptr() if want_dxs else None, ds.data_ptr(), xa.B, int(global_batch), _stream(icnf)))
         icnf._pending_stats = ds
         return lossv[0], dth, (dxs.t() if want_dxs else None)
     lossv = C.c_float()
@@ -573,9 +573,10 @@ def _loss_impl(icnf: ICNF, mode: Mode, xs, ys, ps, want_grad: bool, want_dxs: bo
     if want_grad:
         dth = np.empty(npar, dtype=np.float32)
         dxs = np.empty((icnf.nvariables, xa.B), dtype=np.float32, order="F") if want_dxs else None
-        rc = lib.icnf_loss_grad(icnf._h, mode.code, C.byref(solver), t0, t1, xa.ptr, C.byref(noise), ea.ptr, ya.ptr,
-                                C.byref(lossv), dth.ctypes.data, dxs.ctypes.data if want_dxs else None, C.byref(stt),
-                                xa.B, int(global_batch))
+        fn = lib.icnf_loss_grad_dp if dp else lib.icnf_loss_grad
+        rc = fn(icnf._h, mode.code, C.byref(solver), t0, t1, xa.ptr, C.byref(noise), ea.ptr, ya.ptr,
+                C.byref(lossv), dth.ctypes.data, dxs.ctypes.data if want_dxs else None, C.byref(stt),
+                xa.B, int(global_batch))
     else:
         dth = dxs = None
         rc = lib.icnf_loss(icnf._h, mode.code, C.byref(solver), t0, t1, xa.ptr, C.byref(noise), ea.ptr, ya.ptr,
@@ -593,10 +594,45 @@ def loss(icnf: ICNF, mode: Mode, xs, *args, eps=None, seed=None, tspan=None, sam
 
 
 def loss_and_gradient(icnf: ICNF, mode: Mode, xs, *args, want_dxs: bool = False, eps=None, seed=None, tspan=None,
-                      sample_offset: int = 0, global_batch: int = 0, **sol):
+                      sample_offset: int = 0, global_batch: int = 0, data_parallel: bool = False, **sol):
     """What ``Zygote.gradient(p -> loss(icnf, mode, xs, [ys,] p, st), ps)`` (and the
     gradient w.r.t. ``xs``, smoke_tests.jl:132-133) gives the reference's callers:
-    returns ``(loss, dtheta)`` or ``(loss, dtheta, dxs)``."""
+    returns ``(loss, dtheta)`` or ``(loss, dtheta, dxs)``.  ``data_parallel=True`` (a handle that joined a
+    group, ``group_join``): ``xs`` is this rank's shard and the returned loss / gradient are those of the
+    global batch, summed inside the library (``icnf_loss_grad_dp``)."""
     ys, ps, st = _split(args, 2, "loss_and_gradient")
-    l, g, gx = _loss_impl(icnf, mode, xs, ys, ps, True, want_dxs, eps, seed, tspan, sample_offset, global_batch, sol)
+    l, g, gx = _loss_impl(icnf, mode, xs, ys, ps, True, want_dxs, eps, seed, tspan, sample_offset, global_batch, sol,
+                          dp=data_parallel)
     return (l, g, gx) if want_dxs else (l, g)
+
+
+# ---------------------------------------------------------------- multi-GPU groups (include/icnf_b200.h, SURVEY 8(e))
+def group_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib.icnf_group_unique_id(buf)
+    if rc != _lib.OK:
+        raise ICNFError(rc, lib.icnf_last_error(None).decode())
+    return buf.raw
+
+
+def group_join_id(icnf: ICNF, uid: bytes, rank: int, world: int):
+    """``icnf_group_join``: collective over the ``world`` processes that hold ``uid``."""
+    buf = C.create_string_buffer(uid, 128)
+    icnf._check(lib.icnf_group_join(icnf._h, buf, int(world), int(rank)))
+    icnf._group = (int(rank), int(world))
+
+
+def group_info(icnf: ICNF):
+    n, r, p = C.c_int32(), C.c_int32(), C.c_int32()
+    icnf._check(lib.icnf_group_info(icnf._h, C.byref(n), C.byref(r), C.byref(p)))
+    return {"n_ranks": n.value, "rank": r.value, "peer_memory": bool(p.value)}
+
+
+def create_group(icnfs: Sequence[ICNF]):
+    """``icnf_create_group``: the handles of ONE process, one per device."""
+    arr = (C.c_void_p * len(icnfs))(*[i._h.value for i in icnfs])
+    rc = lib.icnf_create_group(arr, len(icnfs))
+    if rc != _lib.OK:
+        raise ICNFError(rc, lib.icnf_last_error(icnfs[0]._h).decode())
+    for r, i in enumerate(icnfs):
+        i._group = (r, len(icnfs))

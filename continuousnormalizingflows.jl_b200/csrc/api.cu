@@ -3,6 +3,7 @@
 // kernels (loss mean, partial-gradient sum).  No CPU fallback lives here: every
 // entry point either launches CUDA kernels or returns an error code.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -51,6 +52,79 @@ __global__ void __launch_bounds__(256) reduce_grad_kernel(const float* __restric
         for (int i = 0; i < 8; ++i) s += sh[i][lane];
         out[p] = s;
     }
+}
+
+// ---- data-parallel exchange through NVLink peer memory (small gradients) -------------------------------------------
+// Every rank owns one exchange buffer; `peers[r]` is rank r's buffer mapped into this process (CUDA IPC between
+// processes, direct peer access inside one process).  Layout (bytes):
+//   [0, 64)                       header (reserved: sequence counter of the in-solve error-norm exchange)
+//   XG_OFF   + ((par * R + r) * XG_FLOATS + p) * 4     gradient slice of rank r, parity par
+//   XF_OFF   + ((par * R + r) * XG_CTAS + c) * 4       flag of CTA c of rank r, parity par (= epoch when the slice is complete)
+constexpr int XG_FLOATS = 4096, XG_CTAS = XG_FLOATS / 32, XG_MAXR = 16;
+constexpr size_t XG_OFF = 64;
+constexpr size_t XF_OFF = XG_OFF + (size_t)2 * XG_MAXR * XG_FLOATS * 4;
+constexpr size_t XBUF_BYTES = XF_OFF + (size_t)2 * XG_MAXR * XG_CTAS * 4 + 4096;
+
+struct PeerTable { unsigned char* p[XG_MAXR]; };
+
+// One kernel = the local gradient reduction AND the all-reduce: CTA c sums parameters [32 c, 32 c + 32) over the
+// partial rows (fixed order), stores the slice into EVERY rank's exchange buffer (remote stores over NVLink), raises
+// its flag there, waits for the same slice of every other rank to land in its own buffer and adds the slices in rank
+// order -- every rank ends with bit-identical sums.  Element np of the vector is the scalar loss.
+__global__ void __launch_bounds__(256) reduce_grad_xchg_kernel(const float* __restrict__ partial, int nrows, int np,
+                                                             const float* __restrict__ loss_in, float* __restrict__ dtheta,
+                                                             float* __restrict__ loss_out, PeerTable peers, int nranks, int rank,
+                                                             unsigned epoch, int* __restrict__ timeout_flag) {
+    __shared__ float sh[8][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x, p = c * 32 + lane;
+    const int par = (int)(epoch & 1u);
+    const int per = (nrows + 7) / 8;
+    const int r0 = w * per, r1 = min(nrows, r0 + per);
+    float s0 = 0.f, s1 = 0.f;
+    if (p < np) {
+        int r = r0;
+        for (; r + 1 < r1; r += 2) {
+            s0 += partial[(size_t)r * np + p];
+            s1 += partial[(size_t)(r + 1) * np + p];
+        }
+        if (r < r1) s0 += partial[(size_t)r * np + p];
+    }
+    sh[w][lane] = s0 + s1;
+    __syncthreads();
+    if (w != 0) return;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += sh[i][lane];
+    if (p == np) s = loss_in ? loss_in[0] : 0.f;
+    // publish this slice to every rank (own buffer included), then the flag
+    const size_t goff = XG_OFF + ((size_t)(par * nranks + rank) * XG_FLOATS + p) * 4;
+    const size_t foff = XF_OFF + ((size_t)(par * nranks + rank) * XG_CTAS + c) * 4;
+    if (p <= np)
+        for (int r = 0; r < nranks; ++r) *reinterpret_cast<volatile float*>(peers.p[r] + goff) = s;
+    __threadfence_system();
+    __syncwarp();
+    if (lane < nranks) *reinterpret_cast<volatile unsigned*>(peers.p[lane] + foff) = epoch;
+    // wait for every rank's slice in MY buffer
+    unsigned char* mine = peers.p[rank];
+    bool ok = true;
+    if (lane < nranks) {
+        const volatile unsigned* f = reinterpret_cast<const volatile unsigned*>(mine + XF_OFF + ((size_t)(par * nranks + lane) * XG_CTAS + c) * 4);
+        long long spins = 0;
+        while (*f != epoch) {
+            if (++spins > (1LL << 26)) { ok = false; break; }   // a peer never arrived (~ seconds): report, do not hang the GPU
+            __nanosleep(64);
+        }
+    }
+    ok = __all_sync(0xffffffffu, ok);
+    __threadfence_system();
+    float tot = 0.f;
+    if (p <= np)
+        for (int r = 0; r < nranks; ++r)
+            tot += *reinterpret_cast<const volatile float*>(mine + XG_OFF + ((size_t)(par * nranks + r) * XG_FLOATS + p) * 4);
+    if (!ok) { tot = __int_as_float(0x7fc00000); if (lane == 0 && timeout_flag) *timeout_flag = 1; }
+    if (p < np) dtheta[p] = tot;
+    else if (p == np && loss_out) loss_out[0] = tot;
 }
 
 // out[0] = scale * sum(x[0..n)) with a fixed reduction tree; single CTA, double accumulation
@@ -150,6 +224,10 @@ struct icnf_handle {
     float* scalar_host = nullptr;    // pinned
     float* grad_host = nullptr;      // pinned staging for the gradient: a copy into the caller's pageable buffer would block per copy
     size_t grad_host_cap = 0;
+    struct Group* grp = nullptr;     // data-parallel communicator (icnf_group_join / icnf_create_group), or null
+    bool dp_defer_reduce = false;    // the data-parallel step fuses the partial-gradient reduction with the exchange
+    int dp_nrows = 0;                // rows of gpartial left by the last backward launch
+    DevBuf dpbuf;                    // [dtheta; loss] of the data-parallel step
     long long launches = 0;
     bool profiling = false;
     // ordering between the two kinds of entry points: `_dev` calls run on the caller's stream, host-pointer calls on
@@ -497,14 +575,16 @@ int icnf_create(const icnf_config* cfg, icnf_handle** out) {
     return ICNF_OK;
 }
 
+static void group_free_fwd(icnf_handle* h);
 void icnf_destroy(icnf_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    group_free_fwd(h);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->ws && h->fam && h->fam->ws_destroy) h->fam->ws_destroy(h->ws);
     DevBuf* bufs[] = {&h->theta_dev, &h->in, &h->eps, &h->ys, &h->out0, &h->out1, &h->out2, &h->wu0, &h->wu1, &h->wk0,
                       &h->wk1, &h->partials, &h->ckpt, &h->steps, &h->stats, &h->gpartial, &h->lossterm, &h->scalar,
-                      &h->dtheta, &h->dxs};
+                      &h->dtheta, &h->dxs, &h->dpbuf};
     for (DevBuf* b : bufs) b->release();
     if (h->stats_host) cudaFreeHost(h->stats_host);
     if (h->scalar_host) cudaFreeHost(h->scalar_host);
@@ -817,7 +897,8 @@ static int loss_grad_device(icnf_handle* h, int mode, const icnf_solver* sol, fl
     h->prof_end(2, st);
     if (e != cudaSuccess) return h->cuda_fail(e, "backward launch");
     h->launches++;
-    if (dtheta) {
+    h->dp_nrows = nrows;
+    if (dtheta && !h->dp_defer_reduce) {
         h->prof_begin(3, st);
         reduce_grad_kernel<<<(np + 31) / 32, 256, 0, st>>>(h->gpartial.as<float>(), nrows, np, dtheta);
         h->prof_end(3, st);
@@ -888,6 +969,295 @@ int icnf_loss_grad(icnf_handle* h, int mode, const icnf_solver* sol, float t0, f
                    icnf_stats* stats, int64_t B, int64_t global_batch) {
     if (h && !dtheta) return h->fail(ICNF_ERR_INVALID, "null dtheta");
     return loss_grad_host(h, mode, sol, t0, t1, xs, noise, eps, ys, loss, dtheta, dxs, stats, B, global_batch);
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- data-parallel group
+// NCCL is bound at run time (dlopen): the library loads without it, and inside a process that already holds an NCCL
+// (PyTorch's) the same copy is picked up by its SONAME.
+namespace {
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, icnf_group_id, int) = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+    bool ok = false;
+};
+Nccl& nccl() {
+    static Nccl n;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) {
+            n.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (n.lib) break;
+        }
+        if (!n.lib) { n.err = std::string("cannot load libnccl.so.2: ") + (dlerror() ? dlerror() : "?"); return; }
+        auto sym = [&](const char* s) { void* p = dlsym(n.lib, s); if (!p) n.err = std::string("libnccl lacks ") + s; return p; };
+        n.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+        n.CommInitRank = (int (*)(void**, int, icnf_group_id, int))sym("ncclCommInitRank");
+        n.CommInitAll = (int (*)(void**, int, const int*))sym("ncclCommInitAll");
+        n.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+        n.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+        n.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
+        n.GroupStart = (int (*)())sym("ncclGroupStart");
+        n.GroupEnd = (int (*)())sym("ncclGroupEnd");
+        n.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+        n.ok = n.err.empty();
+    });
+    return n;
+}
+constexpr int NCCL_FLOAT = 7, NCCL_UINT8 = 1, NCCL_SUM = 0;
+}  // namespace
+
+struct Group {
+    void* comm = nullptr;
+    int nranks = 1, rank = 0;
+    // NVLink peer-memory exchange for small payloads
+    unsigned char* xbuf = nullptr;
+    icnf::PeerTable peers{};
+    bool peer_ok = false, ipc = false;
+    unsigned epoch = 0;
+    int* timeout_flag = nullptr;   // device
+};
+
+namespace {
+#define NCK(h, call)                                                                                         \
+    do {                                                                                                     \
+        int r__ = (call);                                                                                    \
+        if (r__ != 0) return (h)->fail(ICNF_ERR_CUDA, "%s: %s", #call, nccl().GetErrorString ? nccl().GetErrorString(r__) : "nccl error"); \
+    } while (0)
+
+void group_free(icnf_handle* h) {
+    Group* g = h->grp;
+    if (!g) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    if (g->ipc)
+        for (int r = 0; r < g->nranks; ++r)
+            if (r != g->rank && g->peers.p[r]) cudaIpcCloseMemHandle(g->peers.p[r]);
+    if (g->comm && nccl().ok) nccl().CommDestroy(g->comm);
+    if (g->xbuf) cudaFree(g->xbuf);
+    if (g->timeout_flag) cudaFree(g->timeout_flag);
+    delete g;
+    h->grp = nullptr;
+}
+
+int group_alloc_xbuf(icnf_handle* h, Group* g) {
+    CK(h, cudaMalloc((void**)&g->xbuf, XBUF_BYTES));
+    CK(h, cudaMemset(g->xbuf, 0, XBUF_BYTES));
+    CK(h, cudaMalloc((void**)&g->timeout_flag, sizeof(int)));
+    CK(h, cudaMemset(g->timeout_flag, 0, sizeof(int)));
+    return ICNF_OK;
+}
+}  // namespace
+
+static void group_free_fwd(icnf_handle* h) { group_free(h); }
+
+extern "C" {
+
+int icnf_group_unique_id(icnf_group_id* id) {
+    if (!id) return ICNF_ERR_INVALID;
+    if (!nccl().ok) { g_create_error = nccl().err; return ICNF_ERR_UNSUPPORTED; }
+    return nccl().GetUniqueId(id) == 0 ? ICNF_OK : ICNF_ERR_CUDA;
+}
+
+int icnf_group_join(icnf_handle* h, const icnf_group_id* id, int32_t n_ranks, int32_t rank) {
+    if (!h || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return ICNF_ERR_INVALID;
+    if (n_ranks > XG_MAXR) return h->fail(ICNF_ERR_UNSUPPORTED, "at most %d ranks per group", XG_MAXR);
+    if (!nccl().ok) return h->fail(ICNF_ERR_UNSUPPORTED, "%s", nccl().err.c_str());
+    CK(h, cudaSetDevice(h->device));
+    group_free(h);
+    Group* g = new Group();
+    g->nranks = n_ranks; g->rank = rank;
+    h->grp = g;
+    NCK(h, nccl().CommInitRank(&g->comm, n_ranks, *id, rank));
+    int rc = group_alloc_xbuf(h, g);
+    if (rc) return rc;
+    // exchange the CUDA IPC handles of the exchange buffers with one all-gather, then map every peer's buffer
+    cudaIpcMemHandle_t mine;
+    std::vector<cudaIpcMemHandle_t> all(n_ranks);
+    bool have = cudaIpcGetMemHandle(&mine, g->xbuf) == cudaSuccess;
+    if (!have) { memset(&mine, 0, sizeof mine); cudaGetLastError(); }
+    unsigned char* stage = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t) + 8;   // handle + "valid" byte, padded
+    CK(h, cudaMalloc((void**)&stage, hb * (size_t)(n_ranks + 1)));
+    std::vector<unsigned char> rec(hb, 0);
+    memcpy(rec.data(), &mine, sizeof mine);
+    rec[sizeof mine] = have ? 1 : 0;
+    CK(h, cudaMemcpy(stage, rec.data(), hb, cudaMemcpyHostToDevice));
+    NCK(h, nccl().AllGather(stage, stage + hb, hb, NCCL_UINT8, g->comm, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    std::vector<unsigned char> got(hb * (size_t)n_ranks);
+    CK(h, cudaMemcpy(got.data(), stage + hb, got.size(), cudaMemcpyDeviceToHost));
+    cudaFree(stage);
+    bool all_ok = true;
+    for (int r = 0; r < n_ranks; ++r) {
+        if (!got[(size_t)r * hb + sizeof(cudaIpcMemHandle_t)]) all_ok = false;
+        memcpy(&all[r], &got[(size_t)r * hb], sizeof(cudaIpcMemHandle_t));
+    }
+    g->peers.p[rank] = g->xbuf;
+    if (all_ok) {
+        g->ipc = true;
+        for (int r = 0; r < n_ranks && all_ok; ++r) {
+            if (r == rank) continue;
+            void* pp = nullptr;
+            if (cudaIpcOpenMemHandle(&pp, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { all_ok = false; cudaGetLastError(); }
+            g->peers.p[r] = (unsigned char*)pp;
+        }
+    }
+    // every rank must take the same path: agree on peer_ok with a one-float all-reduce
+    float* flag = nullptr;
+    CK(h, cudaMalloc((void**)&flag, sizeof(float)));
+    const float mineok = all_ok ? 0.f : 1.f;
+    CK(h, cudaMemcpy(flag, &mineok, sizeof(float), cudaMemcpyHostToDevice));
+    NCK(h, nccl().AllReduce(flag, flag, 1, NCCL_FLOAT, NCCL_SUM, g->comm, h->stream));
+    CK(h, cudaStreamSynchronize(h->stream));
+    float bad = 1.f;
+    CK(h, cudaMemcpy(&bad, flag, sizeof(float), cudaMemcpyDeviceToHost));
+    cudaFree(flag);
+    g->peer_ok = (bad == 0.f);
+    return ICNF_OK;
+}
+
+int icnf_create_group(icnf_handle** handles, int32_t n) {
+    if (!handles || n < 1) return ICNF_ERR_INVALID;
+    for (int i = 0; i < n; ++i)
+        if (!handles[i]) return ICNF_ERR_INVALID;
+    icnf_handle* h0 = handles[0];
+    if (n > XG_MAXR) return h0->fail(ICNF_ERR_UNSUPPORTED, "at most %d ranks per group", XG_MAXR);
+    if (!nccl().ok) return h0->fail(ICNF_ERR_UNSUPPORTED, "%s", nccl().err.c_str());
+    std::vector<int> devs(n);
+    std::vector<void*> comms(n, nullptr);
+    for (int i = 0; i < n; ++i) {
+        devs[i] = handles[i]->device;
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return h0->fail(ICNF_ERR_INVALID, "icnf_create_group: two handles on device %d", devs[i]);
+    }
+    NCK(h0, nccl().CommInitAll(comms.data(), n, devs.data()));
+    bool peer_ok = true;
+    for (int i = 0; i < n; ++i) {
+        icnf_handle* h = handles[i];
+        CK(h, cudaSetDevice(h->device));
+        group_free(h);
+        Group* g = new Group();
+        g->nranks = n; g->rank = i; g->comm = comms[i];
+        h->grp = g;
+        int rc = group_alloc_xbuf(h, g);
+        if (rc) return rc;
+        for (int j = 0; j < n; ++j) {
+            if (j == i) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devs[i], devs[j]);
+            if (!can) { peer_ok = false; continue; }
+            cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) peer_ok = false;
+            cudaGetLastError();
+        }
+    }
+    for (int i = 0; i < n; ++i) {
+        Group* g = handles[i]->grp;
+        for (int j = 0; j < n; ++j) g->peers.p[j] = handles[j]->grp->xbuf;
+        g->peer_ok = peer_ok;
+    }
+    return ICNF_OK;
+}
+
+int icnf_group_leave(icnf_handle* h) {
+    if (!h) return ICNF_ERR_INVALID;
+    group_free(h);
+    return ICNF_OK;
+}
+
+int icnf_group_info(const icnf_handle* h, int32_t* n_ranks, int32_t* rank, int32_t* peer_memory) {
+    if (!h) return ICNF_ERR_INVALID;
+    if (n_ranks) *n_ranks = h->grp ? h->grp->nranks : 1;
+    if (rank) *rank = h->grp ? h->grp->rank : 0;
+    if (peer_memory) *peer_memory = (h->grp && h->grp->peer_ok) ? 1 : 0;
+    return ICNF_OK;
+}
+
+int icnf_group_start(void) { return (nccl().ok && nccl().GroupStart() == 0) ? ICNF_OK : ICNF_ERR_UNSUPPORTED; }
+int icnf_group_end(void) { return (nccl().ok && nccl().GroupEnd() == 0) ? ICNF_OK : ICNF_ERR_UNSUPPORTED; }
+
+// Data-parallel training step: loss and gradient of this rank's columns, then ONE sum over the group of
+// [dtheta; loss], all enqueued on `stream`; every rank receives the gradient of the whole batch.  Small vectors
+// (the narrow-MLP family: <= 4095 parameters) are exchanged inside the gradient-reduction kernel through NVLink peer
+// memory; larger ones go through ncclAllReduce.
+int icnf_loss_grad_dp_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+                          const icnf_noise* noise, const float* eps, const float* ys, float* loss, float* dtheta, float* dxs,
+                          icnf_stats* stats, int64_t B, int64_t global_batch, void* stream) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!xs || !dtheta) return h->fail(ICNF_ERR_INVALID, "null xs/dtheta");
+    Group* g = h->grp;
+    if (!g || g->nranks == 1)
+        return icnf_loss_grad_dev(h, mode, sol, t0, t1, xs, noise, eps, ys, loss, dtheta, dxs, stats, B, global_batch, stream);
+    cudaStream_t st = pick_stream(h, stream);
+    const int np = (int)icnf_n_params(h);
+    CK(h, h->dpbuf.reserve(sizeof(float) * (size_t)(np + 1)));
+    float* buf = h->dpbuf.as<float>();
+    const bool fused = g->peer_ok && (np + 1 <= XG_FLOATS) && h->fam->backward_partials_per_block == 1 &&
+                       std::string(h->fam->name) == "tiny";
+    h->dp_defer_reduce = fused;
+    rc = loss_grad_device(h, mode, sol, t0, t1, xs, noise, eps, ys, buf + np, buf, dxs, B, global_batch, st);
+    h->dp_defer_reduce = false;
+    if (rc) return rc;
+    if (fused) {
+        g->epoch++;
+        reduce_grad_xchg_kernel<<<(np + 1 + 31) / 32, 256, 0, st>>>(h->gpartial.as<float>(), h->dp_nrows, np, buf + np, dtheta, loss,
+                                                                   g->peers, g->nranks, g->rank, g->epoch, g->timeout_flag);
+        CK(h, cudaGetLastError());
+        h->launches++;
+    } else {
+        NCK(h, nccl().AllReduce(buf, buf, (size_t)np + 1, NCCL_FLOAT, NCCL_SUM, g->comm, st));
+        CK(h, cudaMemcpyAsync(dtheta, buf, sizeof(float) * (size_t)np, cudaMemcpyDeviceToDevice, st));
+        if (loss) CK(h, cudaMemcpyAsync(loss, buf + np, sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+    if (stats) CK(h, cudaMemcpyAsync(stats, h->stats.p, sizeof(DevStats), cudaMemcpyDeviceToDevice, st));
+    return mark_dev(h, st);
+}
+
+int icnf_loss_grad_dp(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
+                      const icnf_noise* noise, const float* eps, const float* ys, float* loss, float* dtheta, float* dxs,
+                      icnf_stats* stats, int64_t B, int64_t global_batch) {
+    int rc = validate_common(h, mode, B);
+    if (rc) return rc;
+    if (!xs || !loss || !dtheta) return h->fail(ICNF_ERR_INVALID, "null xs/loss/dtheta");
+    if ((rc = join_dev(h))) return rc;
+    const int D = h->D();
+    const int np = (int)icnf_n_params(h);
+    const float *d_in, *d_eps, *d_ys;
+    if ((rc = upload(h, h->in, xs, (size_t)h->cfg.nvars * B, h->stream, &d_in))) return rc;
+    if ((rc = upload(h, h->eps, mode == ICNF_TEST ? nullptr : eps, (size_t)D * B, h->stream, &d_eps))) return rc;
+    if ((rc = upload(h, h->ys, ys, (size_t)h->cfg.ncond * B, h->stream, &d_ys))) return rc;
+    CK(h, h->scalar.reserve(4 * sizeof(float)));
+    CK(h, h->dtheta.reserve(sizeof(float) * (size_t)np));
+    if (dxs) CK(h, h->dxs.reserve(sizeof(float) * (size_t)h->cfg.nvars * B));
+    if ((rc = icnf_loss_grad_dp_dev(h, mode, sol, t0, t1, d_in, noise, d_eps, d_ys, h->scalar.as<float>(), h->dtheta.as<float>(),
+                                    dxs ? h->dxs.as<float>() : nullptr, nullptr, B, global_batch, h->stream)))
+        return rc;
+    CK(h, cudaMemcpyAsync(h->scalar_host, h->scalar.p, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    if (h->grad_host_cap < (size_t)np) {
+        if (h->grad_host) cudaFreeHost(h->grad_host);
+        h->grad_host = nullptr;
+        h->grad_host_cap = 0;
+        CK(h, cudaMallocHost((void**)&h->grad_host, sizeof(float) * (size_t)np));
+        h->grad_host_cap = (size_t)np;
+    }
+    CK(h, cudaMemcpyAsync(h->grad_host, h->dtheta.p, sizeof(float) * (size_t)np, cudaMemcpyDeviceToHost, h->stream));
+    if (dxs) CK(h, cudaMemcpyAsync(dxs, h->dxs.p, sizeof(float) * (size_t)h->cfg.nvars * B, cudaMemcpyDeviceToHost, h->stream));
+    rc = finish_stats(h, stats, h->stream);
+    *loss = h->scalar_host[0];
+    memcpy(dtheta, h->grad_host, sizeof(float) * (size_t)np);
+    return rc;
 }
 
 }  // extern "C"

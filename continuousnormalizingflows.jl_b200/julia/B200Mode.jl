@@ -12,8 +12,14 @@ const libicnf = "libicnf_b200.so"   # on LD_LIBRARY_PATH, or an absolute path
 
 struct B200MatrixMode{ADBack <: ADTypes.AbstractADType} <: MatrixMode{ADBack}
     adback::ADBack          # unused: gradients come from icnf_loss_grad
+    precision::Int32        # icnf_precision: 0 = fp32, 1 = bf16 tensor cores (2e-2), 2 = split bf16 tensor cores (1e-4)
+    device::Int32           # CUDA ordinal
 end
-B200MatrixMode() = B200MatrixMode(ADTypes.AutoZygote())
+function B200MatrixMode(adback::ADTypes.AbstractADType = ADTypes.AutoZygote(); precision::Symbol = :fp32, device::Integer = 0)
+    codes = Dict(:fp32 => 0, :bf16_tc => 1, :bf16x3_tc => 2)
+    haskey(codes, precision) || error("B200MatrixMode: precision must be :fp32, :bf16_tc or :bf16x3_tc")
+    return B200MatrixMode(adback, Int32(codes[precision]), Int32(device))
+end
 
 # ---- C structs (include/icnf_b200.h) ---------------------------------------------
 struct IcnfConfig
@@ -63,6 +69,15 @@ mode_code(::TrainMode{false}) = Int32(2)
 #      (test/ci_tests/smoke_tests.jl:142) ------------------------------------------
 const HANDLES = IdDict{Any, Ptr{Cvoid}}()
 
+# icnf_activation codes; anything else has no kernel
+function activation_code(f)
+    f === NNlib.softplus && return Int32(0)
+    (f === tanh || f === NNlib.tanh_fast) && return Int32(1)
+    (f === NNlib.sigmoid || f === NNlib.sigmoid_fast) && return Int32(2)
+    f === identity && return Int32(3)
+    error("B200MatrixMode: no kernel for activation $(f); use softplus, tanh, sigmoid or identity")
+end
+
 function dense_sizes(nn::Lux.Chain)
     sizes = Int32[nn.layers[1].in_dims]
     for l in nn.layers
@@ -75,12 +90,17 @@ function handle(icnf::ICNF{Float32, <:B200MatrixMode})
     get!(HANDLES, icnf) do
         sizes = dense_sizes(icnf.nn)
         padded = ntuple(i -> i <= length(sizes) ? sizes[i] : Int32(0), 9)
-        act = icnf.nn.layers[1].activation === NNlib.softplus ? 0 :
-              icnf.nn.layers[1].activation === tanh ? 1 : 2
+        length(sizes) - 1 <= 8 || error("B200MatrixMode: at most 8 Dense layers")
+        all(l -> l isa Lux.Dense, icnf.nn.layers) || error("B200MatrixMode: nn must be a Lux.Chain of Dense layers")
+        act = activation_code(length(icnf.nn.layers) > 1 ? icnf.nn.layers[1].activation : identity)
+        all(l -> activation_code(l.activation) == act, icnf.nn.layers[1:(end - 1)]) ||
+            error("B200MatrixMode: all hidden layers must share one activation")
+        activation_code(icnf.nn.layers[end].activation) == 3 || error("B200MatrixMode: the last Dense layer must be linear")
+        autonomous = icnf isa ICNF{Float32, <:Any, <:Any, <:Any, true}
         cfg = Ref(IcnfConfig(1, icnf.nvariables, icnf.naugments,
-            first(sizes) - icnf.nvariables - icnf.naugments - !(icnf isa ICNF{Float32, <:Any, <:Any, <:Any, true}),
-            icnf isa ICNF{Float32, <:Any, <:Any, <:Any, true}, length(sizes) - 1, padded, act,
-            icnf.λ₁, icnf.λ₂, icnf.λ₃, 0, 0, 0))
+            first(sizes) - icnf.nvariables - icnf.naugments - !autonomous,
+            autonomous, length(sizes) - 1, padded, act,
+            icnf.λ₁, icnf.λ₂, icnf.λ₃, 0, icnf.compute_mode.precision, icnf.compute_mode.device))
         out = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:icnf_create, libicnf), Cint, (Ref{IcnfConfig}, Ref{Ptr{Cvoid}}), cfg, out)
         rc == 0 || error(unsafe_string(ccall((:icnf_last_error, libicnf), Cstring, (Ptr{Cvoid},), C_NULL)))
@@ -95,8 +115,18 @@ function set_params!(h, ps)
     GC.@preserve θ check(h, ccall((:icnf_set_params, libicnf), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int64), h, θ, length(θ)))
 end
 
-tsit5_opts(icnf) = Ref(IcnfSolver(1, 0.0f0, icnf.sol_kwargs.reltol, icnf.sol_kwargs.abstol, 0,
-    0, 0, 0, 0, 0, 0, 0, 0))
+# The library integrates with Tsit5 (and nothing else): the reference's default `alg = VCABM()` (icnf.jl:89) must be
+# replaced by the caller, never silently (SURVEY D1).  Fixed-step solves pass `adaptive = false, dt = ...`.
+function tsit5_opts(icnf)
+    kw = icnf.sol_kwargs
+    alg = get(kw, :alg, nothing)
+    (!isnothing(alg) && nameof(typeof(alg)) === :Tsit5) ||
+        error("B200MatrixMode integrates with Tsit5: construct the ICNF with sol_kwargs = (; alg = Tsit5(), ...); got $(alg)")
+    adaptive = get(kw, :adaptive, true)
+    maxiters = get(kw, :maxiters, 100000)
+    return Ref(IcnfSolver(adaptive ? 1 : 0, Float32(get(kw, :dt, 0.0f0)), Float32(get(kw, :reltol, 1.0f-4)),
+        Float32(get(kw, :abstol, 1.0f-4)), Int32(min(maxiters, typemax(Int32))), 0, 0, 0, 0, 0, 0, 0, 0))
+end
 
 # ---- S2: one ccall per solve (replaces base_sol, src/core/base_icnf.jl:134-140) ---
 function base_sol(
@@ -151,6 +181,12 @@ function loss(icnf::ICNF{Float32, <:B200MatrixMode}, mode::Mode, xs::AbstractMat
     return first(b200_loss_grad(icnf, mode, Matrix{Float32}(xs), nothing, ps))
 end
 
+# conditioned signature, src/core/icnf.jl:639-649
+function loss(icnf::ICNF{Float32, <:B200MatrixMode}, mode::Mode, xs::AbstractMatrix{<:Real}, ys::AbstractMatrix{<:Real},
+              ps::Any, st::NamedTuple)
+    return first(b200_loss_grad(icnf, mode, Matrix{Float32}(xs), Matrix{Float32}(ys), ps))
+end
+
 function ChainRulesCore.rrule(
     ::typeof(loss), icnf::ICNF{Float32, <:B200MatrixMode}, mode::Mode, xs::AbstractMatrix{<:Real}, ps::Any, st::NamedTuple,
 )
@@ -161,3 +197,28 @@ function ChainRulesCore.rrule(
     end
     return l, loss_pullback
 end
+
+function ChainRulesCore.rrule(
+    ::typeof(loss), icnf::ICNF{Float32, <:B200MatrixMode}, mode::Mode, xs::AbstractMatrix{<:Real}, ys::AbstractMatrix{<:Real},
+    ps::Any, st::NamedTuple,
+)
+    l, dθ, dxs = b200_loss_grad(icnf, mode, Matrix{Float32}(xs), Matrix{Float32}(ys), ps; want_dxs = true)
+    function cond_loss_pullback(l̄)
+        NT = ChainRulesCore.NoTangent()
+        # the conditioning input is data: the library returns no gradient for it (neither do the reference's callers ask)
+        return NT, NT, NT, l̄ .* dxs, ChainRulesCore.ZeroTangent(),
+               ComponentArrays.ComponentArray(l̄ .* dθ, ComponentArrays.getaxes(ps)), NT
+    end
+    return l, cond_loss_pullback
+end
+
+# ---- multi-GPU (SURVEY 8(e)): one handle per device, batch columns sharded, ONE all-reduce of [dθ; loss] inside the
+#      library (NCCL over NVLink; tiny gradients go through peer memory in one kernel).  Single process, several GPUs:
+#
+#          hs = [handle(icnf_on_device_g) for g in 0:(G - 1)]
+#          check(C_NULL, ccall((:icnf_create_group, libicnf), Cint, (Ptr{Ptr{Cvoid}}, Int32), hs, G))
+#
+#      then call `icnf_loss_grad_dp` (same arguments as `icnf_loss_grad`, `global_batch` = the unsharded batch,
+#      `noise.sample_offset` = first global column of the shard) once per handle from one task per device; every
+#      shard returns the gradient of the WHOLE batch.  One process per GPU (MPI.jl / Distributed.jl): rank 0 calls
+#      `icnf_group_unique_id`, ships the 128 bytes to the other ranks, every rank calls `icnf_group_join`.

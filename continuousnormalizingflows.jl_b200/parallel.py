@@ -51,16 +51,32 @@ def all_reduce_sum(x, group=None):
     return x
 
 
+def group_join(icnf, rank: int, world: int, group=None):
+    """Attach the library's own communicator to ``icnf`` (``icnf_group_join``): rank 0 draws the id, torch.distributed
+    (whatever backend is initialised) only ships its 128 bytes.  After this, ``dp_loss_and_gradient`` sums
+    [gradient; loss] inside the library -- in the gradient-reduction kernel over NVLink peer memory for small
+    networks, with ncclAllReduce on the same stream for large ones -- and torch.distributed is out of the step."""
+    if world == 1:
+        return
+    uid = [api.group_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0, group=group)
+    api.group_join_id(icnf, uid[0], rank, world)
+
+
 def dp_loss_and_gradient(icnf, mode, xs_local, *args, rank: int, world: int, global_batch: int,
                          local_fn: Optional[Callable] = None, group=None, **kw):
     """Data-parallel training step: local loss/gradient on this rank's columns, then
     ONE all-reduce of [gradient; loss].  ``xs_local`` holds columns
     ``shard_bounds(global_batch, rank, world)`` of the global batch.  ``local_fn``
     defaults to ``api.loss_and_gradient`` (the CUDA path); tests inject a CPU stand-in
-    to exercise the protocol under gloo."""
+    to exercise the protocol under gloo.  A handle that joined a group (``group_join``) does
+    the exchange inside the library; otherwise ``torch.distributed.all_reduce`` is used."""
     lo, hi = shard_bounds(global_batch, rank, world)
     if xs_local.shape[1] != hi - lo:
         raise ValueError(f"rank {rank} expects {hi - lo} columns, got {xs_local.shape[1]}")
+    if local_fn is None and getattr(icnf, "_group", None) == (rank, world) and world > 1:
+        return api.loss_and_gradient(icnf, mode, xs_local, *args, sample_offset=lo, global_batch=global_batch,
+                                     data_parallel=True, **kw)
     fn = local_fn or api.loss_and_gradient
     l, g = fn(icnf, mode, xs_local, *args, sample_offset=lo, global_batch=global_batch, **kw)
     if torch is not None and isinstance(g, torch.Tensor):

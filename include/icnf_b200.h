@@ -224,6 +224,37 @@ ICNF_API int icnf_loss_grad_dev(icnf_handle* h, int mode, const icnf_solver* sol
                        float* loss, float* dtheta, float* dxs, icnf_stats* stats,
                        int64_t B, int64_t global_batch, void* stream);
 
+/* -- multi-GPU ---------------------------------------------------
+ * The batch is sharded by columns, parameters are replicated, one handle per GPU.  Inference and generate need no
+ * communication.  Training has exactly one exchange: the sum over the group of [dtheta; loss].  It happens INSIDE
+ * icnf_loss_grad_dp*: for small parameter vectors (the narrow-MLP family) in the gradient-reduction kernel itself,
+ * through NVLink peer memory (every rank stores its slice into every peer's exchange buffer and adds the slices in
+ * rank order: bit-identical results on all ranks, no extra launch); for large ones with ncclAllReduce on the same
+ * stream.  NCCL is loaded at run time (libnccl.so.2); without it these entry points return ICNF_ERR_UNSUPPORTED.
+ *
+ * One process per GPU: rank 0 calls icnf_group_unique_id and ships the 128 bytes to the other ranks by any means;
+ * every rank then calls icnf_group_join (collective).  One process, several GPUs: icnf_create_group on all handles
+ * at once; calls that drive several handles from ONE thread must sit between icnf_group_start / icnf_group_end. */
+typedef struct icnf_group_id { char internal[128]; } icnf_group_id;
+ICNF_API int icnf_group_unique_id(icnf_group_id* id);
+ICNF_API int icnf_group_join(icnf_handle* h, const icnf_group_id* id, int32_t n_ranks, int32_t rank);
+ICNF_API int icnf_create_group(icnf_handle** handles, int32_t n);
+ICNF_API int icnf_group_leave(icnf_handle* h);
+/* peer_memory = 1 when the NVLink peer-memory exchange is available to this group */
+ICNF_API int icnf_group_info(const icnf_handle* h, int32_t* n_ranks, int32_t* rank, int32_t* peer_memory);
+ICNF_API int icnf_group_start(void);
+ICNF_API int icnf_group_end(void);
+/* `loss` + gradient of the GLOBAL batch on every rank: arguments as icnf_loss_grad[_dev]; `global_batch` is the
+ * unsharded batch size and noise->sample_offset the first global column of this rank's shard.  dxs stays local. */
+ICNF_API int icnf_loss_grad_dp(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                      const float* xs, const icnf_noise* noise, const float* eps, const float* ys,
+                      float* loss, float* dtheta, float* dxs, icnf_stats* stats,
+                      int64_t B, int64_t global_batch);
+ICNF_API int icnf_loss_grad_dp_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1,
+                          const float* xs, const icnf_noise* noise, const float* eps, const float* ys,
+                          float* loss, float* dtheta, float* dxs, icnf_stats* stats,
+                          int64_t B, int64_t global_batch, void* stream);
+
 /* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
 ICNF_API int64_t icnf_launch_count(const icnf_handle* h);
 
