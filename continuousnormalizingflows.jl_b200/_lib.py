@@ -92,6 +92,7 @@ SYMBOLS = [
                                  C.POINTER(C.c_float), _F, _F, C.POINTER(Stats), C.c_int64, C.c_int64]),
     ("icnf_loss_grad_dev", C.c_int, [_P, C.c_int, C.POINTER(Solver), C.c_float, C.c_float, _F, C.POINTER(Noise), _F, _F,
                                      _F, _F, _F, _P, C.c_int64, C.c_int64, _P]),
+    ("icnf_steer_tspan", C.c_int, [C.c_int, C.c_float, C.c_float, C.c_float, C.c_uint64, C.POINTER(C.c_float)]),
     ("icnf_group_unique_id", C.c_int, [_P]),
     ("icnf_group_join", C.c_int, [_P, _P, C.c_int32, C.c_int32]),
     ("icnf_create_group", C.c_int, [C.POINTER(_P), C.c_int32]),

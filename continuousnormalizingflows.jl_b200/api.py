@@ -315,12 +315,15 @@ class ICNF:
             n.seed = int(self.rng.integers(0, 2 ** 63)) if seed is None else int(seed)
         return n
 
-    def steer_tspan(self, mode: Mode) -> Tuple[float, float]:
-        """``steer_tspan`` (base_icnf.jl:23-43)."""
+    def steer_tspan(self, mode: Mode, seed: Optional[int] = None) -> Tuple[float, float]:
+        """``steer_tspan`` (base_icnf.jl:23-43).  The draw is the library's (``icnf_steer_tspan``: Philox stream
+        "STER" keyed on a seed taken from ``icnf.rng``), so identically seeded ranks steer to the same t1."""
         t0, t1 = self.tspan
         if isinstance(mode, TrainMode) and mode.reg and self.steer_rate != 0.0:
-            r = np.float32(self.rng.uniform(-self.steer_rate, self.steer_rate))
-            t1 = float(np.float32(t1) + np.float32(abs(t1 - t0)) * r)
+            s = int(self.rng.integers(0, 2 ** 63)) if seed is None else int(seed)
+            out = C.c_float()
+            self._check(lib.icnf_steer_tspan(mode.code, t0, t1, self.steer_rate, s, C.byref(out)))
+            t1 = float(out.value)
         return t0, t1
 
     # callable layer (base_icnf.jl:509-523)

@@ -4,6 +4,7 @@
 // entry point either launches CUDA kernels or returns an error code.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -182,6 +183,12 @@ using namespace icnf;
 
 // ---------------------------------------------------------------- handle
 namespace {
+
+// NVTX range over one entry point (tracing): shows up in Nsight timelines, costs nothing without a tool attached
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 thread_local std::string g_create_error;
 
@@ -507,6 +514,26 @@ int icnf_backward_plan(const icnf_config* cfg, int exact, int sm_count, int64_t 
     return ICNF_ERR_UNSUPPORTED;
 }
 
+// STEER end time (steer_tspan, src/core/base_icnf.jl:23-43) from the library's own counter-based stream, so that a
+// caller without an RNG of its own (and every rank of a data-parallel step) draws the SAME t1 from a seed:
+// r = rate * (2 u - 1), u = (w >> 8) * 2^-24, w = philox4x32_10(ctr = (0, 0, 0, "STER"), key = seed)[0]   (oracle/philox.py)
+int icnf_steer_tspan(int mode, float t0, float t1, float steer_rate, uint64_t seed, float* t1_out) {
+    if (!t1_out) return ICNF_ERR_INVALID;
+    *t1_out = t1;
+    if (mode != ICNF_TRAIN_REG || steer_rate == 0.0f) return ICNF_OK;
+    uint32_t c[4] = {0u, 0u, 0u, 0x53544552u}, k[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0], n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1], n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        if (r != 9) { k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }
+    }
+    const float u = (float)(c[0] >> 8) * 5.9604644775390625e-08f;
+    const float r = steer_rate * (2.0f * u - 1.0f);
+    *t1_out = fmaf(fabsf(t1 - t0), r, t1);   // muladd(dt, r, t1), base_icnf.jl:38
+    return ICNF_OK;
+}
+
 int icnf_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -704,6 +731,7 @@ int icnf_set_params_dev(icnf_handle* h, const float* theta, int64_t n, void* str
 // ---------------------------------------------------------------- S1
 int icnf_rhs_dev(icnf_handle* h, int mode, float t, const float* u, const float* eps, const float* ys, float* du,
                  int64_t B, void* stream) {
+    NvtxRange nvtx_("icnf_rhs_dev");
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
     if (!u || !du) return h->fail(ICNF_ERR_INVALID, "null u/du");
@@ -743,6 +771,7 @@ int icnf_rhs(icnf_handle* h, int mode, float t, const float* u, const float* eps
 int icnf_solve_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* u0,
                    const icnf_noise* noise, const float* eps, const float* ys, float* u_final, icnf_stats* stats,
                    int64_t B, void* stream) {
+    NvtxRange nvtx_("icnf_solve_dev");
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
     if (!u0 || !u_final) return h->fail(ICNF_ERR_INVALID, "null u0/u_final");
@@ -775,6 +804,7 @@ int icnf_solve(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float
 int icnf_inference_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
                        const icnf_noise* noise, const float* eps, const float* ys, float* logp, float* regs,
                        icnf_stats* stats, int64_t B, void* stream) {
+    NvtxRange nvtx_("icnf_inference_dev");
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
     if (!xs || !logp) return h->fail(ICNF_ERR_INVALID, "null xs/logp");
@@ -812,6 +842,7 @@ int icnf_inference(icnf_handle* h, int mode, const icnf_solver* sol, float t0, f
 int icnf_generate_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* z0,
                       const icnf_noise* noise, const float* eps, const float* ys, float* xs_out, icnf_stats* stats,
                       int64_t n, void* stream) {
+    NvtxRange nvtx_("icnf_generate_dev");
     int rc = validate_common(h, mode, n);
     if (rc) return rc;
     if (!xs_out) return h->fail(ICNF_ERR_INVALID, "null xs_out");
@@ -911,6 +942,7 @@ static int loss_grad_device(icnf_handle* h, int mode, const icnf_solver* sol, fl
 int icnf_loss_grad_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
                        const icnf_noise* noise, const float* eps, const float* ys, float* loss, float* dtheta, float* dxs,
                        icnf_stats* stats, int64_t B, int64_t global_batch, void* stream) {
+    NvtxRange nvtx_("icnf_loss_grad_dev");
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
     if (!xs) return h->fail(ICNF_ERR_INVALID, "null xs");
@@ -1194,6 +1226,7 @@ int icnf_group_end(void) { return (nccl().ok && nccl().GroupEnd() == 0) ? ICNF_O
 int icnf_loss_grad_dp_dev(icnf_handle* h, int mode, const icnf_solver* sol, float t0, float t1, const float* xs,
                           const icnf_noise* noise, const float* eps, const float* ys, float* loss, float* dtheta, float* dxs,
                           icnf_stats* stats, int64_t B, int64_t global_batch, void* stream) {
+    NvtxRange nvtx_("icnf_loss_grad_dp_dev");
     int rc = validate_common(h, mode, B);
     if (rc) return rc;
     if (!xs || !dtheta) return h->fail(ICNF_ERR_INVALID, "null xs/dtheta");

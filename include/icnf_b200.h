@@ -224,6 +224,11 @@ ICNF_API int icnf_loss_grad_dev(icnf_handle* h, int mode, const icnf_solver* sol
                        float* loss, float* dtheta, float* dxs, icnf_stats* stats,
                        int64_t B, int64_t global_batch, void* stream);
 
+/* `steer_tspan(icnf, mode)`, src/core/base_icnf.jl:23-43: t1 + |t1 - t0| r, r ~ U(-steer_rate, steer_rate), in
+ * TrainMode{true} only; drawn from the library's counter-based Philox stream "STER" keyed on `seed`, so that every
+ * rank of a data-parallel step (and a caller without an RNG) gets the same t1.  Host function, no device work. */
+ICNF_API int icnf_steer_tspan(int mode, float t0, float t1, float steer_rate, uint64_t seed, float* t1_out);
+
 /* -- multi-GPU ---------------------------------------------------
  * The batch is sharded by columns, parameters are replicated, one handle per GPU.  Inference and generate need no
  * communication.  Training has exactly one exchange: the sum over the group of [dtheta; loss].  It happens INSIDE

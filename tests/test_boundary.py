@@ -112,3 +112,24 @@ def test_backward_plan_headline_batch_is_one_round(m):
 def test_backward_plan_unknown_shape_is_unsupported(m):
     rc, *_ = _plan(m, (3, 64, 64, 2), "softplus", 2, 0, 0, 1024)
     assert rc == 7                                            # ICNF_ERR_UNSUPPORTED: served by the generic family
+
+
+def test_steer_tspan_matches_the_draw_spec():
+    """icnf_steer_tspan (host function of the library, runs without a GPU) against the oracle's Philox draw
+    (steer_tspan, /root/reference/src/core/base_icnf.jl:23-43): only TrainMode{true} steers, rate 0 does not."""
+    import ctypes as C
+    import numpy as np
+    import cnf_b200 as m
+    from oracle import icnf_oracle as O
+    from oracle import philox as P
+    out = C.c_float()
+    for seed in (0, 1, 12345, 2 ** 40 + 7, 2 ** 63 - 1):
+        for rate, t0, t1 in ((0.1, 0.0, 1.0), (0.25, 0.5, 2.0), (0.1, 1.0, 0.0)):
+            assert m.lib.icnf_steer_tspan(1, t0, t1, rate, seed, C.byref(out)) == 0
+            om = O.OracleICNF(nvars=1, tspan=(t0, t1), steer_rate=rate)
+            ref = O.steer_t1(om, O.TRAIN_REG, P.uniform_pm(seed, rate))
+            assert abs(out.value - ref) <= 2e-7 * max(1.0, abs(ref)), (seed, rate, out.value, ref)
+            assert abs(out.value - t1) <= rate * abs(t1 - t0) * (1 + 1e-6)
+            for mode in (0, 2):
+                assert m.lib.icnf_steer_tspan(mode, t0, t1, rate, seed, C.byref(out)) == 0 and out.value == np.float32(t1)
+        assert m.lib.icnf_steer_tspan(1, 0.0, 1.0, 0.0, seed, C.byref(out)) == 0 and out.value == 1.0
