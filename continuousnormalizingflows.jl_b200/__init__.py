@@ -9,7 +9,7 @@ CPU or PyTorch fallback for any numeric result.
 from ._lib import ICNFError, LIB_PATH, lib  # noqa: F401  (loads the shared library)
 from .api import (  # noqa: F401
     B200MatrixMode, Chain, ComputeMode, Dense, ICNF, MatrixMode, Mode, SolverStats, TestMode, TrainMode,
-    augmented_f, base_sol, create_group, generate, group_info, group_join_id, group_unique_id, inference, loss,
+    augmented_f, base_sol, create_group, generate, group_info, group_join_id, group_set_global_norm, group_unique_id, inference, loss,
     loss_and_gradient, measure_fp32_peak, setup,
 )
 from .dist import CondICNFDist, ICNFDist  # noqa: F401

@@ -98,6 +98,7 @@ SYMBOLS = [
     ("icnf_create_group", C.c_int, [C.POINTER(_P), C.c_int32]),
     ("icnf_group_leave", C.c_int, [_P]),
     ("icnf_group_info", C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    ("icnf_group_set_global_norm", C.c_int, [_P, C.c_int]),
     ("icnf_group_start", C.c_int, []),
     ("icnf_group_end", C.c_int, []),
     ("icnf_loss_grad_dp", C.c_int, [_P, C.c_int, C.POINTER(Solver), C.c_float, C.c_float, _F, C.POINTER(Noise), _F, _F,

@@ -631,6 +631,12 @@ def group_info(icnf: ICNF):
     return {"n_ranks": n.value, "rank": r.value, "peer_memory": bool(p.value)}
 
 
+def group_set_global_norm(icnf: ICNF, enabled: bool = True):
+    """``icnf_group_set_global_norm``: adaptive data-parallel solves use the error norm of the GLOBAL batch (one
+    scalar pair per step attempt through NVLink peer memory), i.e. exactly the unsharded solve's steps."""
+    icnf._check(lib.icnf_group_set_global_norm(icnf._h, int(bool(enabled))))
+
+
 def create_group(icnfs: Sequence[ICNF]):
     """``icnf_create_group``: the handles of ONE process, one per device."""
     arr = (C.c_void_p * len(icnfs))(*[i._h.value for i in icnfs])

@@ -56,18 +56,8 @@ __global__ void __launch_bounds__(256) reduce_grad_kernel(const float* __restric
 }
 
 // ---- data-parallel exchange through NVLink peer memory (small gradients) -------------------------------------------
-// Every rank owns one exchange buffer; `peers[r]` is rank r's buffer mapped into this process (CUDA IPC between
-// processes, direct peer access inside one process).  Layout (bytes):
-//   [0, 64)                       header (reserved: sequence counter of the in-solve error-norm exchange)
-//   XG_OFF   + ((par * R + r) * XG_FLOATS + p) * 4     gradient slice of rank r, parity par
-//   XF_OFF   + ((par * R + r) * XG_CTAS + c) * 4       flag of CTA c of rank r, parity par (= epoch when the slice is complete)
-constexpr int XG_FLOATS = 4096, XG_CTAS = XG_FLOATS / 32, XG_MAXR = 16;
-constexpr size_t XG_OFF = 64;
-constexpr size_t XF_OFF = XG_OFF + (size_t)2 * XG_MAXR * XG_FLOATS * 4;
-constexpr size_t XBUF_BYTES = XF_OFF + (size_t)2 * XG_MAXR * XG_CTAS * 4 + 4096;
-
-struct PeerTable { unsigned char* p[XG_MAXR]; };
-
+// Every rank owns one exchange buffer (layout: common.cuh); `peers[r]` is rank r's buffer mapped into this process
+// (CUDA IPC between processes, direct peer access inside one process).
 // One kernel = the local gradient reduction AND the all-reduce: CTA c sums parameters [32 c, 32 c + 32) over the
 // partial rows (fixed order), stores the slice into EVERY rank's exchange buffer (remote stores over NVLink), raises
 // its flag there, waits for the same slice of every other rank to land in its own buffer and adds the slices in rank
@@ -232,6 +222,7 @@ struct icnf_handle {
     float* grad_host = nullptr;      // pinned staging for the gradient: a copy into the caller's pageable buffer would block per copy
     size_t grad_host_cap = 0;
     struct Group* grp = nullptr;     // data-parallel communicator (icnf_group_join / icnf_create_group), or null
+    bool dp_active = false;          // inside icnf_loss_grad_dp*
     bool dp_defer_reduce = false;    // the data-parallel step fuses the partial-gradient reduction with the exchange
     int dp_nrows = 0;                // rows of gpartial left by the last backward launch
     DevBuf dpbuf;                    // [dtheta; loss] of the data-parallel step
@@ -345,6 +336,9 @@ int fixed_steps(float t0, float t1, float dt) {
     return (int)std::ceil(span / (double)dt - 1e-6);
 }
 
+bool group_wants_global_norm(const icnf_handle* h);
+void group_fill_xchg(const icnf_handle* h, NormXchg& x);
+
 struct SolveRequest {
     int mode;
     const icnf_solver* sol;
@@ -357,6 +351,7 @@ struct SolveRequest {
     float *out_u, *out_logp, *out_regs, *out_x, *out_lossterm;
     bool want_ckpt;
     int64_t B;
+    int64_t global_B = 0;        // data-parallel step: size of the unsharded batch (error norm of the exact mode)
     float* out_loss = nullptr;   // scalar loss (fused by the family when it can)
     float loss_scale = 0.f;
     bool loss_fused = false;     // set by enqueue_solve
@@ -427,6 +422,11 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
     if (r.out_loss && h->fam->fuses_loss_sum_adaptive) {
         a.out_loss = r.out_loss; a.loss_scale = r.loss_scale; a.out_lossterm = nullptr;
         r.loss_fused = true;
+    }
+    if (group_wants_global_norm(h) && r.global_B > 0) {
+        // exact data-parallel mode: the controller's error norm is taken over the global batch
+        group_fill_xchg(h, a.xg);
+        a.norm_B = r.global_B;
     }
     a.wu[0] = h->wu0.as<float>(); a.wu[1] = h->wu1.as<float>();
     a.wk[0] = h->wk0.as<float>(); a.wk[1] = h->wk1.as<float>();
@@ -891,6 +891,7 @@ static int loss_grad_device(icnf_handle* h, int mode, const icnf_solver* sol, fl
                    h->lossterm.as<float>(), want_grad, B};
     r.out_loss = loss;
     r.loss_scale = 1.0f / (float)denom;
+    r.global_B = h->dp_defer_reduce || h->dp_active ? denom : 0;
     int rc = enqueue_solve(h, r, st);
     if (rc) return rc;
     if (loss && !r.loss_fused) {
@@ -1058,7 +1059,20 @@ struct Group {
     bool peer_ok = false, ipc = false;
     unsigned epoch = 0;
     int* timeout_flag = nullptr;   // device
+    bool global_norm = false;      // adaptive solves of the data-parallel step use the error norm of the GLOBAL batch
 };
+
+namespace {
+bool group_wants_global_norm(const icnf_handle* h) {
+    const Group* g = h->grp;
+    return g && g->global_norm && g->peer_ok && g->nranks > 1 && std::string(h->fam->name) == "tiny";
+}
+void group_fill_xchg(const icnf_handle* h, NormXchg& x) {
+    x.peers = h->grp->peers;
+    x.nranks = h->grp->nranks;
+    x.rank = h->grp->rank;
+}
+}  // namespace
 
 namespace {
 #define NCK(h, call)                                                                                         \
@@ -1216,6 +1230,15 @@ int icnf_group_info(const icnf_handle* h, int32_t* n_ranks, int32_t* rank, int32
     return ICNF_OK;
 }
 
+int icnf_group_set_global_norm(icnf_handle* h, int enabled) {
+    if (!h) return ICNF_ERR_INVALID;
+    if (!h->grp) return h->fail(ICNF_ERR_INVALID, "handle is not in a group");
+    if (enabled && !(h->grp->peer_ok && std::string(h->fam->name) == "tiny"))
+        return h->fail(ICNF_ERR_UNSUPPORTED, "the global error norm needs NVLink peer memory and the single-launch (tiny) solve");
+    h->grp->global_norm = enabled != 0;
+    return ICNF_OK;
+}
+
 int icnf_group_start(void) { return (nccl().ok && nccl().GroupStart() == 0) ? ICNF_OK : ICNF_ERR_UNSUPPORTED; }
 int icnf_group_end(void) { return (nccl().ok && nccl().GroupEnd() == 0) ? ICNF_OK : ICNF_ERR_UNSUPPORTED; }
 
@@ -1240,8 +1263,10 @@ int icnf_loss_grad_dp_dev(icnf_handle* h, int mode, const icnf_solver* sol, floa
     const bool fused = g->peer_ok && (np + 1 <= XG_FLOATS) && h->fam->backward_partials_per_block == 1 &&
                        std::string(h->fam->name) == "tiny";
     h->dp_defer_reduce = fused;
+    h->dp_active = true;
     rc = loss_grad_device(h, mode, sol, t0, t1, xs, noise, eps, ys, buf + np, buf, dxs, B, global_batch, st);
     h->dp_defer_reduce = false;
+    h->dp_active = false;
     if (rc) return rc;
     if (fused) {
         g->epoch++;

@@ -162,6 +162,26 @@ constexpr int IN_XS = 1;      // input has nvars rows; augmented rows and the 3 
 constexpr int IN_Z0 = 2;      // input has D' rows (generate); the 3 extra rows start at 0
 constexpr int IN_Z0_DRAW = 3; // z0 ~ N(0, I) drawn in-kernel (generate without a supplied base sample)
 
+// ---- data-parallel exchange buffers (one per rank, mapped into every peer: CUDA IPC / peer access over NVLink) ----
+// Layout (bytes) of a rank's buffer, R = XG_MAXR rank slots:
+//   [0, 64)                                               header: word 0 = sequence number of the error-norm exchange
+//   XG_OFF + ((par * R + r) * XG_FLOATS + p) * 4          gradient slice of rank r, parity par
+//   XF_OFF + ((par * R + r) * XG_CTAS + c) * 4            flag of CTA c of rank r (= epoch when its slice is complete)
+//   XN_OFF + (par * R + r) * 32                           error-norm record of rank r: {double a, double b, unsigned seq}
+constexpr int XG_FLOATS = 4096, XG_CTAS = XG_FLOATS / 32, XG_MAXR = 16;
+constexpr size_t XG_OFF = 64;
+constexpr size_t XF_OFF = XG_OFF + (size_t)2 * XG_MAXR * XG_FLOATS * 4;
+constexpr size_t XN_OFF = XF_OFF + (size_t)2 * XG_MAXR * XG_CTAS * 4;
+constexpr size_t XBUF_BYTES = XN_OFF + (size_t)2 * XG_MAXR * 32 + 1024;
+
+struct PeerTable { unsigned char* p[XG_MAXR]; };
+
+// in-solve exchange of the adaptive controller's error sums: nranks <= 1 = off
+struct NormXchg {
+    PeerTable peers;
+    int nranks, rank;
+};
+
 struct Controller {
     float reltol, abstol, beta1, beta2, gamma, qmin, qmax, qsteady_min, qsteady_max, qoldinit;
     int max_steps;
@@ -206,6 +226,10 @@ struct SolveArgs {
     float dt;                // |dt| of a fixed step, or initial |dt| when adaptive (0 = automatic)
     int max_ckpt_steps;      // capacity of ckpt/steps
     Controller ctl;
+    // data-parallel exact mode: the error norm is taken over the GLOBAL batch (one scalar pair per step attempt
+    // exchanged through NVLink peer memory inside the device loop), so N shards take the steps of the unsharded solve
+    NormXchg xg;
+    int64_t norm_B;          // batch size in the error norm's mean (0 = B)
 };
 
 struct RhsArgs {

@@ -523,8 +523,45 @@ struct GridReducer {
     double* partials;  // [2 parities][2 values][gridDim.x]
     double* sred;      // shared, 2 * (warps per CTA)
     int parity;
+    const NormXchg* xg;   // data-parallel exact mode: ranks exchange their sums (nranks <= 1: off); points into the kernel parameters
+    unsigned seq;      // sequence number of the next exchange (same on every rank)
+    bool timed_out;
+    // sum over the ranks of the group of (ta, tb), which every thread of this GPU already holds: block 0 stores the
+    // pair into every peer's exchange buffer (remote stores over NVLink), every CTA polls its OWN GPU's copy of all
+    // ranks' records and adds them in rank order -- bit-identical totals, hence identical step decisions, on all ranks
+    __device__ void exchange(double& ta, double& tb) {
+        ++seq;
+        const int par = (int)(seq & 1u);
+        __shared__ double xs[2 * XG_MAXR];
+        __shared__ int xbad;
+        if (threadIdx.x == 0) xbad = 0;
+        __syncthreads();
+        if (blockIdx.x == 0 && (int)threadIdx.x < xg->nranks) {
+            unsigned char* rec = xg->peers.p[threadIdx.x] + XN_OFF + (size_t)(par * XG_MAXR + xg->rank) * 32;
+            reinterpret_cast<volatile double*>(rec)[0] = ta;
+            reinterpret_cast<volatile double*>(rec)[1] = tb;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned*>(rec + 16) = seq;
+        }
+        if ((int)threadIdx.x < xg->nranks) {
+            const unsigned char* rec = xg->peers.p[xg->rank] + XN_OFF + (size_t)(par * XG_MAXR + threadIdx.x) * 32;
+            long long spins = 0;
+            while (*reinterpret_cast<const volatile unsigned*>(rec + 16) != seq) {
+                if (++spins > (1LL << 26)) { xbad = 1; break; }   // a peer never arrived: fail the solve, do not hang
+                __nanosleep(32);
+            }
+            __threadfence_system();
+            xs[threadIdx.x] = reinterpret_cast<const volatile double*>(rec)[0];
+            xs[XG_MAXR + threadIdx.x] = reinterpret_cast<const volatile double*>(rec)[1];
+        }
+        __syncthreads();
+        ta = 0.0; tb = 0.0;
+        for (int r = 0; r < xg->nranks; ++r) { ta += xs[r]; tb += xs[XG_MAXR + r]; }
+        if (xbad) { timed_out = true; ta = __longlong_as_double(0x7ff8000000000000LL); }
+        __syncthreads();
+    }
     // grid-wide sums of two per-thread values with ONE grid synchronisation
-    __device__ void sum2(double a, double b, double& ta, double& tb) {
+    __device__ void sum2(double a, double b, double& ta, double& tb, bool across_ranks = false) {
         const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
         a = warp_sum(a);
         b = warp_sum(b);
@@ -553,6 +590,7 @@ struct GridReducer {
         for (int i = 0; i < nw; ++i) { ta += sred[i]; tb += sred[nw + i]; }
         __syncthreads();
         parity ^= 1;
+        if (across_ranks && xg->nranks > 1) exchange(ta, tb);
     }
 };
 
@@ -560,18 +598,19 @@ struct GridReducer {
 // automatic initial step, then step attempts); each phase evaluates 1 or 6 stages per
 // sample and ends in one grid-wide reduction.
 template <class N, bool EXACT>
-__global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __grid_constant__ WBlock<N> sw, SolveArgs a, int nvars) {
+__global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __grid_constant__ WBlock<N> sw, const __grid_constant__ SolveArgs a, int nvars) {
     extern __shared__ __align__(16) float smem[];
     StageMem K{smem};
     __shared__ double sred[2 * (NTA / 32) + 2];
-    GridReducer red{cg::this_grid(), a.partials, sred, 0};
+    GridReducer red{cg::this_grid(), a.partials, sred, 0, &a.xg, 0u, false};
+    if (a.xg.nranks > 1) red.seq = *reinterpret_cast<const volatile unsigned*>(a.xg.peers.p[a.xg.rank]);   // left by the previous solve
 
     const float tdir = (a.t1 >= a.t0) ? 1.0f : -1.0f;
     const float span = fabsf(a.t1 - a.t0);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t b0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const Controller ctl = a.ctl;
-    const double inv_count = 1.0 / ((double)a.B * (double)N::S);
+    const double inv_count = 1.0 / ((double)(a.norm_B > 0 ? a.norm_B : a.B) * (double)N::S);
     enum { P_INIT = 0, P_PROBE = 1, P_STEP = 2 };
     int phase = P_INIT;
     int cur = 0;
@@ -720,7 +759,7 @@ __global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __g
             }
         }
         double ta, tb;
-        red.sum2(acc_a, acc_b, ta, tb);
+        red.sum2(acc_a, acc_b, ta, tb, true);
         // ---- control (identical arithmetic in every thread)
         if (phase == P_INIT) {
             nf = 1;
@@ -783,6 +822,8 @@ __global__ void __launch_bounds__(NTA, NTA_MINB) solve_adaptive_kernel(const __g
         red.sum2(loss_local, 0.0, tot, unused);
         if (blockIdx.x == 0 && threadIdx.x == 0) a.out_loss[0] = (float)(tot * (double)a.loss_scale);
     }
+    if (a.xg.nranks > 1 && blockIdx.x == 0 && threadIdx.x == 0)
+        *reinterpret_cast<volatile unsigned*>(a.xg.peers.p[a.xg.rank]) = red.seq;   // the next solve continues the sequence
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
         a.stats->naccept = nacc;
         a.stats->nreject = nrej;

@@ -247,6 +247,12 @@ ICNF_API int icnf_create_group(icnf_handle** handles, int32_t n);
 ICNF_API int icnf_group_leave(icnf_handle* h);
 /* peer_memory = 1 when the NVLink peer-memory exchange is available to this group */
 ICNF_API int icnf_group_info(const icnf_handle* h, int32_t* n_ranks, int32_t* rank, int32_t* peer_memory);
+/* Exact data-parallel mode: adaptive solves inside icnf_loss_grad_dp* take the controller's RMS
+ * error norm over the GLOBAL batch -- one pair of doubles per step attempt exchanged through NVLink peer memory
+ * inside the device loop -- so N shards accept and reject exactly the steps of the unsharded solve.  Off by
+ * default (each shard then controls its own dt; results agree to solver tolerance).  Collective setting: every rank
+ * of the group must choose the same value. */
+ICNF_API int icnf_group_set_global_norm(icnf_handle* h, int enabled);
 ICNF_API int icnf_group_start(void);
 ICNF_API int icnf_group_end(void);
 /* `loss` + gradient of the GLOBAL batch on every rank: arguments as icnf_loss_grad[_dev]; `global_batch` is the

@@ -62,10 +62,25 @@ def _worker(rank, world, port, which, out):
     # host-pointer entry point of the same step
     lh, gh = m.loss_and_gradient(icnf, m.TrainMode(True), xs[:, lo:hi], theta, {}, eps=eps[:, lo:hi], tspan=icnf.tspan,
                                  sample_offset=lo, global_batch=B, data_parallel=True, **sol)
+    exact = None
+    if which == "tiny":
+        # exact mode: ADAPTIVE solve with the error norm of the global batch -> the unsharded solve's own steps
+        m.group_set_global_norm(icnf, True)
+        la, ga = m.dp_loss_and_gradient(icnf, m.TrainMode(True), xd, theta, {}, rank=rank, world=world, global_batch=B,
+                                        eps=ed, tspan=icnf.tspan)
+        sa = icnf.check_last()
+        m.group_set_global_norm(icnf, False)
+        lb, gb = m.dp_loss_and_gradient(icnf, m.TrainMode(True), xd, theta, {}, rank=rank, world=world, global_batch=B,
+                                        eps=ed, tspan=icnf.tspan)
+        exact = (float(la), ga.cpu().numpy(), sa.naccept, sa.nreject, sa.t_final, float(lb), gb.cpu().numpy())
     if rank == 0:
         solo, _ = _case(m, which, 0)
         lw, gw = m.loss_and_gradient(solo, m.TrainMode(True), xs, theta, {}, eps=eps, tspan=solo.tspan, **sol)
-        out.put((res, (float(lh), gh), (float(lw), gw), info))
+        if exact is not None:
+            lwa, gwa = m.loss_and_gradient(solo, m.TrainMode(True), xs, theta, {}, eps=eps, tspan=solo.tspan)
+            sw = solo.last_stats
+            exact = exact + (float(lwa), gwa, sw.naccept, sw.nreject)
+        out.put((res, (float(lh), gh), (float(lw), gw), info, exact))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -80,7 +95,7 @@ def test_two_process_group_gradient_equals_unsharded(which):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, which, out)) for r in range(2)]
     for p in procs:
         p.start()
-    res, host, whole, info = out.get(timeout=300)
+    res, host, whole, info, exact = out.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
@@ -94,6 +109,13 @@ def test_two_process_group_gradient_equals_unsharded(which):
         assert np.linalg.norm(g - gw) / np.linalg.norm(gw) < tol
     # the steps are identical, bit for bit (deterministic exchange)
     assert all(np.array_equal(res[0][1], r[1]) for r in res[1:])
+    if exact is not None:
+        la, ga, nacc, nrej, tf, lb, gb, lwa, gwa, nacc_w, nrej_w = exact
+        # global error norm: same accepted / rejected steps as the unsharded adaptive solve, same gradient to rounding
+        assert (nacc, nrej) == (nacc_w, nrej_w)
+        assert abs(la - lwa) <= 1e-5 * abs(lwa) and np.linalg.norm(ga - gwa) / np.linalg.norm(gwa) < 5e-6
+        # shard-local norm (default): agreement to solver tolerance only
+        assert abs(lb - lwa) <= 1e-3 * abs(lwa) and np.linalg.norm(gb - gwa) / np.linalg.norm(gwa) < 1e-2
 
 
 @needs2
