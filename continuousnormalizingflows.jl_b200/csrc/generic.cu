@@ -61,7 +61,7 @@ enum Epilogue {
     EP_LIN = 1,     // out0 = acc + bias
     EP_MULD = 2,    // out1 = acc (optional), out0 = acc .* aux0
     EP_PLAIN = 3,   // out0 = acc
-    EP_TRACE = 4,   // colsum[n] += sum_m acc .* aux0     (exact trace, two hidden layers)
+    EP_TRACE = 4,   // colsum[part][n] = sum_{m in row tile `part`} acc .* aux0   (exact trace, two hidden layers; no atomics)
     EP_TANGENT = 5, // out0 = acc .* aux0 (d); out1 (+)= acc .* aux1 (v) .* sigma''(aux2 (h), aux0 (d))
     EP_MULADD = 6   // out0 = acc .* aux0 + aux1
 };
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(GT, 2) gemm128_kernel(GemmArgs g) {
 #pragma unroll
             for (int r = 0; r < 16; ++r) s += red[r * 128 + threadIdx.x];
             const long long n = n0 + threadIdx.x;
-            if (n < g.N) atomicAdd(g.colsum + n, s);
+            if (n < g.N) g.colsum[(long long)blockIdx.y * g.N + n] = s;   // one part per row tile: summed in order by the reader
         }
     }
 }
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(GT) gemm_kernel(GemmArgs g) {
 #pragma unroll
             for (int r = 0; r < 16; ++r) s += red[r * 64 + threadIdx.x];
             const long long n = n0 + threadIdx.x;
-            if (n < g.N) atomicAdd(g.colsum + n, s);
+            if (n < g.N) g.colsum[(long long)blockIdx.y * g.N + n] = s;
         }
     }
 }
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(512) gemm_ws_kernel(GemmArgs g, int nty, int n
                 float sum = 0.f;
                 for (int r = 0; r < nty; ++r) sum += red[r * TS + c];
                 const long long n = tile * TS + c;
-                if (n < g.N) atomicAdd(g.colsum + n, sum);
+                if (n < g.N) g.colsum[n] = sum;   // the weights-stationary kernel holds all rows: a single part
             }
         }
         __syncthreads();   // the buffer just read is the next cp.async target
@@ -664,7 +664,8 @@ struct StageArgs {
     float* ZI;             // D x B stage input
     const float* Q;        // D x B: eps'J rows (TrainMode) from the chain
     const float* ZD;       // D x B: zdot (last layer output)
-    const float* TR;       // B: exact trace (TestMode)
+    const float* TR;       // [tr_parts][B]: exact trace (TestMode) as per-tile partial sums, added in order here
+    int tr_parts;
     const float* E;        // D x B eps
     long long B;
     int D, S, stage;       // stage 0..6 (6 = FSAL evaluation at the trial state)
@@ -826,7 +827,10 @@ __global__ void __launch_bounds__(256) g_rhs_finish_kernel(StageArgs a, float* K
         zz = qq = s = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { zz += red[0][i][lane]; qq += red[1][i][lane]; s += red[2][i][lane]; }
-        K[(long long)a.D * a.B + b] = a.exact ? -a.TR[b] : -s;
+        float tr = 0.f;
+        if (a.exact)
+            for (int p = 0; p < a.tr_parts; ++p) tr += a.TR[(long long)p * a.B + b];
+        K[(long long)a.D * a.B + b] = a.exact ? -tr : -s;
         K[(long long)(a.D + 1) * a.B + b] = (!a.exact && a.reg_e) ? (a.squared ? zz : sqrtf(zz)) : 0.f;
         K[(long long)(a.D + 2) * a.B + b] = (!a.exact && a.reg_n) ? (a.squared ? qq : sqrtf(qq)) : 0.f;
     }
@@ -1424,6 +1428,7 @@ struct Workspace {
     // (utils.jl:35-54), which stay on the fp32 SGEMMs in every precision
     bool use_tc(bool exact) const { return tc && !(exact && NL >= 4); }
     int split = 0;   // ICNF_BF16X3_TC: every bf16 row is [hi | lo], three MMAs per K step
+    int tr_parts = 1;         // parts of TR written by the last exact-trace evaluation
     bool e16_valid = false;   // E16 holds the packed probe of the current solve (eps is constant over a solve)
     int rs(int cols) const { return (split ? 2 : 1) * pad8(cols); }   // row stride of a bf16 matrix with `cols` columns
     Buf w16t, w16n, a16, X16, E16, H16, D16, G16;
@@ -1553,7 +1558,8 @@ struct RhsPlan {
     bool x_packed = false;   // tensor-core precisions: X16 already holds this evaluation's packed input
 };
 
-static cudaError_t launch_gemm(Workspace* w, GemmArgs& g, cudaStream_t st) {
+static cudaError_t launch_gemm(Workspace* w, GemmArgs& g, cudaStream_t st, int* row_tiles = nullptr) {
+    if (row_tiles) *row_tiles = 1;
     if (g.M <= 128 && g.K <= 128 && g.N >= 2048) {   // narrow layers, large batch: weights-stationary persistent kernel
         static int sms = 0;
         static bool attr_set = false;
@@ -1576,11 +1582,13 @@ static cudaError_t launch_gemm(Workspace* w, GemmArgs& g, cudaStream_t st) {
     }
     if (g.M >= 96) {   // wide layers: 128 x 128 tiles
         dim3 grid((unsigned)((g.N + LN - 1) / LN), (unsigned)((g.M + LM - 1) / LM));
+        if (row_tiles) *row_tiles = (int)grid.y;
         gemm128_kernel<<<grid, GT, 0, st>>>(g);
         w->launches++;
         return cudaGetLastError();
     }
     dim3 grid((unsigned)((g.N + BN - 1) / BN), (unsigned)((g.M + BM - 1) / BM));
+    if (row_tiles) *row_tiles = (int)grid.y;
     gemm_kernel<<<grid, GT, 0, st>>>(g);
     w->launches++;
     return cudaGetLastError();
@@ -1685,6 +1693,7 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
     }
     if (p.exact) {
         float* TR = w->TR.as<float>();
+        w->tr_parts = 1;
         if (NL == 1) {
             g_trace_dot_kernel<<<blocks_for(B), 256, 0, p.st>>>(w->gvec.as<float>(), nullptr, TR, D, B, 0.f, done);
         } else if (NL == 2) {
@@ -1695,8 +1704,8 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
             g.M = (int)B; g.N = w->n[2]; g.K = w->n[1]; g.ep = tc::TEP_TRACE; g.done = done;
             set_split(g, w->n[1], w->n[1], w->n[2]);
             g.aux = act_ptr(Dv, 1); g.ldo = w->rs(w->n[2]); g.out_f32 = TR;
-            g.atomic_rowsum = 1;
-            GCK(cudaMemsetAsync(TR, 0, sizeof(float) * B, p.st));
+            // one part per (unit tile, column half): out_f32[part * M + m], no atomics
+            w->tr_parts = 2 * tc::unit_tiles(w->n[2]);
             GCK(tc::gemm(act_ptr(Dv, 0), w->rs(w->n[1]), w->a16.as<__nv_bfloat16>(), w->rs(w->n[1]), g, p.st));
         } else {
             return cudaErrorNotSupported;   // unreachable: use_tc() routes deeper exact traces to the fp32 chains
@@ -1736,6 +1745,7 @@ static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
     const float* thetaT = w->thetaT.as<float>();
     if (p.exact) {
         float* TR = w->TR.as<float>();
+        w->tr_parts = 1;
         if (NL == 1) {
             g_trace_dot_kernel<<<blocks_for(B), 256, 0, p.st>>>(w->gvec.as<float>(), nullptr, TR, D, B, 0.f, done);
             w->launches++;
@@ -1743,13 +1753,12 @@ static cudaError_t enqueue_rhs_core(const RhsPlan& p, float c_i) {
             g_trace_dot_kernel<<<blocks_for(B), 256, 0, p.st>>>(w->gvec.as<float>(), Dv + w->hoff[0] * B, TR, w->n[1], B, 0.f, done);
             w->launches++;
         } else if (NL == 3) {
-            GCK(cudaMemsetAsync(TR, 0, sizeof(float) * B, p.st));
             GemmArgs g;
             memset(&g, 0, sizeof g);
             g.A = w->amat.as<float>(); g.lda = w->n[2]; g.M = w->n[2]; g.K = w->n[1]; g.N = B;
             g.Bm = Dv + w->hoff[0] * B; g.ldb = B;
             g.ep = EP_TRACE; g.aux0 = Dv + w->hoff[1] * B; g.colsum = TR; g.done = done;
-            GCK(launch_gemm(w, g, p.st));
+            GCK(launch_gemm(w, g, p.st, &w->tr_parts));
         } else {
             // D' one-hot pullbacks (utils.jl:35-54) through the chain GEMMs
             float* G = w->Gb.as<float>();
@@ -1785,7 +1794,7 @@ static cudaError_t reserve_common(Workspace* w, long long B) {
     GCK(w->KF0.reserve(f * w->S * B)); GCK(w->KF1.reserve(f * w->S * B));
     GCK(w->Kst.reserve(f * 5 * w->S * B));
     GCK(w->ZI.reserve(f * w->D * B)); GCK(w->EPS.reserve(f * w->D * B)); GCK(w->YS.reserve(f * std::max(w->C, 1) * B));
-    GCK(w->ZD.reserve(f * w->D * B)); GCK(w->Q.reserve(f * w->D * B)); GCK(w->TR.reserve(f * B));
+    GCK(w->ZD.reserve(f * w->D * B)); GCK(w->Q.reserve(f * w->D * B)); GCK(w->TR.reserve(f * B * (w->NL == 3 ? (size_t)((w->n[2] + 63) / 64 + 2) : 1)));
     GCK(w->F1.reserve(f * w->S * B));
     GCK(w->Hb.reserve(f * w->hrows * B)); GCK(w->Db.reserve(f * w->hrows * B)); GCK(w->Gb.reserve(f * w->hrows * B));
     GCK(w->ctrl.reserve(sizeof(Ctrl)));
@@ -1817,6 +1826,7 @@ static cudaError_t rhs(void* wsp, const float*, const RhsArgs& a, bool exact, in
     RhsPlan p{w, a.theta, B, exact, a.reg_e, a.reg_n, a.squared, nullptr, a.t, st};
     GCK(enqueue_rhs_core(p, 0.f));
     StageArgs s = make_stage_args(w, B, exact, a.reg_e, a.reg_n, a.squared);
+    s.tr_parts = w->tr_parts;
     g_rhs_finish_kernel<<<blocks_for(B, 32), 256, 0, st>>>(s, w->F1.as<float>());
     g_from_soa_kernel<<<blocks_for(B), 256, 0, st>>>(w->F1.as<float>(), a.du, B, w->S);
     w->launches += 5;
@@ -1868,6 +1878,7 @@ static cudaError_t enqueue_stage(Workspace* w, const SolveArgs& a, StageArgs s, 
     }
     w->launches++;
     GCK(enqueue_rhs_core(p, g_c_host(stage)));
+    s.tr_parts = w->tr_parts;
     g_rhs_finish_kernel<<<blocks_for(a.B, 32), 256, 0, st>>>(s, nullptr);
     w->launches++;
     return cudaGetLastError();
@@ -1936,6 +1947,7 @@ static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, i
         g_stage_input_kernel<<<blocks_for((long long)w->D * a.B), 256, 0, st>>>(s1);
         RhsPlan p{w, a.theta, a.B, exact, a.reg_e, a.reg_n, a.squared, ctrl, 0.f, st};
         GCK(enqueue_rhs_core(p, 1.0f));
+        s1.tr_parts = w->tr_parts;
         g_rhs_finish_kernel<<<blocks_for(a.B, 32), 256, 0, st>>>(s1, w->F1.as<float>());
         g_initnorm_kernel<<<sb, 256, 0, st>>>(s, 1, w->F1.as<float>());
         g_ctrl_initdt_kernel<<<1, 1, 0, st>>>(ca, 1);

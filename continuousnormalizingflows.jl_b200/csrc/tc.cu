@@ -73,7 +73,7 @@ cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, 
         ds.attr_set = true;
     }
     // wide outputs: 128 x 256 tiles (half the operand bytes per MAC through L2); narrow ones: 128 x 128
-    const int bn = (g.N > 160) ? 256 : 128;
+    const int bn = (g.N > 160) ? 256 : 128;   // keep in step with unit_tiles() in tc.h
     CUtensorMap mapA, mapB, mapA2, mapB2;
     const uint64_t ka = g.split ? (uint64_t)g.lo_a + g.K : (uint64_t)g.K;
     const uint64_t kb = g.split ? (uint64_t)g.lo_b + g.K : (uint64_t)g.K;

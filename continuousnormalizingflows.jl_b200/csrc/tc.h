@@ -21,12 +21,15 @@ __host__ __device__ constexpr int smem_bytes(bool split, int bn) {
     return stages(split, bn) * stage_bytes(split, bn) + 1024 /*align*/ + 256 /*barriers*/ + 2 * bn * 4 /*bias, double-buffered*/;
 }
 
+// unit (B-operand row) tiles of a GEMM with N output units, as tc::gemm chooses them
+inline int unit_tiles(int N) { const int bn = N > 160 ? 256 : 128; return (N + bn - 1) / bn; }
+
 enum TcEpilogue {
     TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)  [+ H transposed]
     TEP_LIN_SOA = 1,    // out_f32[n * M + m] = acc + bias[n]              (fp32, [unit][sample])
     TEP_MULD = 2,       // G[m][n] = acc * aux[m][n]                        (bf16)                 [+ G transposed]
     TEP_PLAIN_SOA = 3,  // out_f32[n * M + m] = acc
-    TEP_TRACE = 4,      // rowsum[m] (+)= sum_n acc * aux[m][n]
+    TEP_TRACE = 4,      // out_f32[part * M + m] = sum_{n in part} acc * aux[m][n],  part = 2 * unit tile + column half
     // reverse sweep (derivation: tiny.cuh rhs_reverse / DESIGN.md):
     TEP_TANGENT = 5,    // out0 = acc * aux (sigma');  out1 = acc * aux1 (chain g) * phi(aux2 (h), aux),  phi = sigma''/sigma'
     TEP_MULADD = 6,     // out0 = acc * aux (sigma') + aux1                                         [+ out0 transposed]

@@ -448,7 +448,8 @@ __global__ void __launch_bounds__(TTHREADS, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
-            if (g.ep == TEP_TRACE && row_ok) atomicAdd(g.out_f32 + m, rowsum);   // two column halves (and unit tiles) per row
+            // exact trace: one part per (unit tile, column half), added in part order by the reader (no atomics)
+            if (g.ep == TEP_TRACE && row_ok) g.out_f32[(size_t)((tile % ntn) * 2 + chalf) * g.M + m] = rowsum;
         }
     }
     tc_fence_before();
