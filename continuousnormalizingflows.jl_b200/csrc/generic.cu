@@ -1435,7 +1435,9 @@ struct Workspace {
     std::vector<size_t> w16t_off, w16n_off;   // element offsets per layer
     std::vector<size_t> h16_off;              // element offsets / B per layer
     size_t h16_cols = 0;
-    static int pad8(int x) { return (x + 7) & ~7; }
+    // column pitch of a bf16 operand half: a multiple of 16, so that the epilogue's 16-column TMA store boxes never
+    // straddle the boundary between the hi and the lo half of a row
+    static int pad8(int x) { return (x + 15) & ~15; }
     Ctrl* ctrl_host = nullptr;   // pinned, two slots
     std::vector<StepRec> recs;   // fixed-step schedule staged for the backward pass
     cudaEvent_t ev[2] = {nullptr, nullptr};
@@ -1704,8 +1706,8 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
             g.M = (int)B; g.N = w->n[2]; g.K = w->n[1]; g.ep = tc::TEP_TRACE; g.done = done;
             set_split(g, w->n[1], w->n[1], w->n[2]);
             g.aux = act_ptr(Dv, 1); g.ldo = w->rs(w->n[2]); g.out_f32 = TR;
-            // one part per (unit tile, column half): out_f32[part * M + m], no atomics
-            w->tr_parts = 2 * tc::unit_tiles(w->n[2]);
+            // one part per (unit tile, column quarter): out_f32[part * M + m], no atomics
+            w->tr_parts = tc::WQ * tc::unit_tiles(w->n[2]);
             GCK(tc::gemm(act_ptr(Dv, 0), w->rs(w->n[1]), w->a16.as<__nv_bfloat16>(), w->rs(w->n[1]), g, p.st));
         } else {
             return cudaErrorNotSupported;   // unreachable: use_tc() routes deeper exact traces to the fp32 chains
@@ -1794,7 +1796,7 @@ static cudaError_t reserve_common(Workspace* w, long long B) {
     GCK(w->KF0.reserve(f * w->S * B)); GCK(w->KF1.reserve(f * w->S * B));
     GCK(w->Kst.reserve(f * 5 * w->S * B));
     GCK(w->ZI.reserve(f * w->D * B)); GCK(w->EPS.reserve(f * w->D * B)); GCK(w->YS.reserve(f * std::max(w->C, 1) * B));
-    GCK(w->ZD.reserve(f * w->D * B)); GCK(w->Q.reserve(f * w->D * B)); GCK(w->TR.reserve(f * B * (w->NL == 3 ? (size_t)((w->n[2] + 63) / 64 + 2) : 1)));
+    GCK(w->ZD.reserve(f * w->D * B)); GCK(w->Q.reserve(f * w->D * B)); GCK(w->TR.reserve(f * B * (w->NL == 3 ? (size_t)((w->n[2] + 63) / 64 + 4) : 1)));
     GCK(w->F1.reserve(f * w->S * B));
     GCK(w->Hb.reserve(f * w->hrows * B)); GCK(w->Db.reserve(f * w->hrows * B)); GCK(w->Gb.reserve(f * w->hrows * B));
     GCK(w->ctrl.reserve(sizeof(Ctrl)));
@@ -1981,6 +1983,132 @@ static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, i
 static int adaptive_max_grid(bool, int sm_count) { return sm_count; }   // not a cooperative kernel; any value > 0
 static inline long long ckpt_off_h(long long slot, int stage, long long DB) { return (slot * 6 + stage) * DB; }
 
+// ---- fused cotangent kernel of the tensor-core reverse sweep ---------------------------------------------------
+// Per stage i of a step: the stage cotangent is assembled on the fly from the step's output cotangent and the input
+// cotangents of the later stages (so no KB arrays are kept or updated),
+//     kb = h (b_i zbar + sum_{j > i} a_ji sbar_j),
+// then zb = kb + cE zdot / |zdot| (cotangent of the top layer's output) and qb = -cl eps + cn q / |q| (the tangent that
+// enters layer 0), both written straight into the GEMM operand layouts: bf16 (hi | lo) rows [sample][unit] through a
+// 32 x 32 shared-memory transpose, and the [unit][sample] transposed copies for the weight gradient.
+// CTA = 32 samples (lanes) x 32 row groups (warps).
+struct CotArgs {
+    long long B;
+    int D, i, squared, split;
+    float h, cl, cE, cn;
+    const float* ZD; const float* Q; const float* E; const float* zbar;
+    const float* SB6;              // [6][D][B] input cotangents of the stages (entries j > i are valid)
+    __nv_bfloat16* ZBr; int zb_pitch;      // row-major zb: pitch of one half (pad columns are zero-filled)
+    __nv_bfloat16* QBr; int qb_pitch;      // row-major qb, laid out like the network input (zeros beyond D)
+    __nv_bfloat16* ZBt; __nv_bfloat16* QBt; long long ldT; int loT;
+};
+__global__ void __launch_bounds__(1024) bw_cotangent_pack_kernel(CotArgs a) {
+    constexpr int RPT = 4;                       // rows per thread and pass-2 iteration: 4 x 9 independent loads in flight
+    __shared__ float red[2][32 * RPT][33];
+    __shared__ float s_sz[32], s_sq[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long b0 = (long long)blockIdx.x * 32, b = b0 + lane;
+    const long long DB = (long long)a.D * a.B;
+    float zz = 0.f, qq = 0.f;
+    if (b < a.B) {
+        for (int r = w; r < a.D; r += 32 * RPT) {
+            float zd[RPT], q[RPT];
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                const int rr = r + 32 * u;
+                zd[u] = rr < a.D ? a.ZD[(long long)rr * a.B + b] : 0.f;
+                q[u] = rr < a.D ? a.Q[(long long)rr * a.B + b] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) { zz = fmaf(zd[u], zd[u], zz); qq = fmaf(q[u], q[u], qq); }
+        }
+    }
+    red[0][w][lane] = zz; red[1][w][lane] = qq;
+    __syncthreads();
+    if (w == 0) {
+        zz = qq = 0.f;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { zz += red[0][k][lane]; qq += red[1][k][lane]; }
+        s_sz[lane] = (a.cE != 0.f) ? (a.squared ? 2.0f * a.cE : (zz > 0.f ? a.cE * rsqrtf(zz) : 0.f)) : 0.f;
+        s_sq[lane] = (a.cn != 0.f) ? (a.squared ? 2.0f * a.cn : (qq > 0.f ? a.cn * rsqrtf(qq) : 0.f)) : 0.f;
+    }
+    __syncthreads();
+    const float sz = s_sz[lane], sq = s_sq[lane];
+    float coef[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) coef[j] = (j > a.i) ? a.h * g_a[j][a.i] : 0.f;
+    const float cb = a.h * g_a[6][a.i];
+    const int rows_max = max(a.zb_pitch, a.qb_pitch);
+    const int zrs = a.split ? 2 * a.zb_pitch : a.zb_pitch, qrs = a.split ? 2 * a.qb_pitch : a.qb_pitch;
+    for (int r0 = 0; r0 < rows_max; r0 += 32 * RPT) {
+        float zb[RPT], qb[RPT];
+        float zdv[RPT], qv[RPT], ev[RPT], zbv[RPT], sbv[RPT][6];
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {       // every load of the iteration is issued before the first use
+            const int r = r0 + w + 32 * u;
+            const bool in = b < a.B && r < a.D;
+            const long long o = (long long)r * a.B + b;
+            zdv[u] = in ? a.ZD[o] : 0.f; qv[u] = in ? a.Q[o] : 0.f; ev[u] = in ? a.E[o] : 0.f; zbv[u] = in ? a.zbar[o] : 0.f;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) sbv[u][j] = (in && j > a.i) ? a.SB6[(long long)j * DB + o] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < RPT; ++u) {
+            const int r = r0 + w + 32 * u;
+            float kb = cb * zbv[u];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) kb = fmaf(coef[j], sbv[u][j], kb);
+            zb[u] = fmaf(sz, zdv[u], kb);
+            qb[u] = fmaf(sq, qv[u], -a.cl * ev[u]);
+            if (b < a.B && r < a.D) {
+                // transposed operands: same [row][sample] layout as the sources
+                const __nv_bfloat16 zh = __float2bfloat16_rn(zb[u]), qh = __float2bfloat16_rn(qb[u]);
+                a.ZBt[(long long)r * a.ldT + b] = zh;
+                a.QBt[(long long)r * a.ldT + b] = qh;
+                if (a.split) {
+                    a.ZBt[(long long)r * a.ldT + a.loT + b] = __float2bfloat16_rn(zb[u] - __bfloat162float(zh));
+                    a.QBt[(long long)r * a.ldT + a.loT + b] = __float2bfloat16_rn(qb[u] - __bfloat162float(qh));
+                }
+            } else {
+                zb[u] = 0.f; qb[u] = 0.f;
+            }
+            red[0][w + 32 * u][lane] = zb[u]; red[1][w + 32 * u][lane] = qb[u];
+        }
+        __syncthreads();
+        // row-major operands: warp w now serves sample b0 + w, a lane covers rows r0 + lane + 32 u
+        const long long bo = b0 + w;
+        if (bo < a.B) {
+#pragma unroll
+            for (int u = 0; u < RPT; ++u) {
+                const int rr = r0 + lane + 32 * u;
+                const float z = red[0][lane + 32 * u][w], q = red[1][lane + 32 * u][w];
+                if (rr < a.zb_pitch) {
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(z);
+                    a.ZBr[bo * zrs + rr] = hi;
+                    if (a.split) a.ZBr[bo * zrs + a.zb_pitch + rr] = __float2bfloat16_rn(z - __bfloat162float(hi));
+                }
+                if (rr < a.qb_pitch) {
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(q);
+                    a.QBr[bo * qrs + rr] = hi;
+                    if (a.split) a.QBr[bo * qrs + a.qb_pitch + rr] = __float2bfloat16_rn(q - __bfloat162float(hi));
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+// end of a step: zbar += sum of the six stages' input cotangents
+__global__ void bw_zbar_update_kernel(float* zbar, const float* SB6, long long DB) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= DB) return;
+    float v[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) v[j] = SB6[(long long)j * DB + idx];
+    float s = zbar[idx];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) s += v[j];
+    zbar[idx] = s;
+}
+
 // out[p] = sum over slices of part[s][p], fixed order
 __global__ void bw_reduce_slices_kernel(const float* part, int nsl, long long np, float* out) {
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -2013,8 +2141,7 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
     GCK(w->XT16.reserve(tr * w->n[0])); GCK(w->ET16.reserve(tr * D)); GCK(w->WV0T16.reserve(tr * D));
     GCK(w->HT16.reserve(tr * w->hrows)); GCK(w->GT16.reserve(tr * w->hrows)); GCK(w->ABT16.reserve(tr * w->hrows));
     GCK(w->WVT16.reserve(tr * w->hrows));
-    GCK(w->tZB.reserve(f * DB)); GCK(w->tQB.reserve(f * DB));
-    GCK(w->bKB.reserve(f * 6 * DB)); GCK(w->bzbar.reserve(f * DB)); GCK(w->bSB.reserve(f * DB));
+    GCK(w->bzbar.reserve(f * DB)); GCK(w->bSB.reserve(f * 6 * DB));   // zbar; the six stages' input cotangents of a step
     if (Bp != B && w->t16_B != B) {   // the K padding of the transposed operands must read as zero
         Buf* tb[] = {&w->XT16, &w->ET16, &w->WV0T16, &w->HT16, &w->GT16, &w->ABT16, &w->WVT16};
         for (Buf* b : tb) GCK(cudaMemsetAsync(b->p, 0, b->cap, st));
@@ -2028,9 +2155,11 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
     std::vector<int> nsl(NL);
     int nsl_max = 1;
     for (int l = 0; l < NL; ++l) {
-        const int bn = w->n[l] > 160 ? 256 : 128;
-        const int tiles = ((w->n[l + 1] + tc::TBM - 1) / tc::TBM) * ((w->n[l] + bn - 1) / bn);
-        nsl[l] = std::max(1, std::min(std::min(nkb, 32), sms / tiles));
+        const int bn = tc::unit_tile_width(w->n[l]);
+        const int tm = tc::tile_mode(w->n[l]) == 2 ? 2 * tc::TBM : tc::TBM;       // CTA pairs: 256-row tiles, sms / 2 pairs
+        const int tiles = ((w->n[l + 1] + tm - 1) / tm) * ((w->n[l] + bn - 1) / bn);
+        const int slots = tc::tile_mode(w->n[l]) == 2 ? sms / 2 : sms;
+        nsl[l] = std::max(1, std::min(std::min(nkb, 32), slots / tiles));
         nsl_max = std::max(nsl_max, nsl[l]);
     }
     GCK(w->wpart.reserve(f * np * nsl_max));
@@ -2059,9 +2188,9 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
     BwArgs b;
     memset(&b, 0, sizeof b);
     b.B = B; b.D = D; b.nvars = a.nvars; b.squared = a.squared; b.reg_a = a.reg_a; b.lam3 = a.lam3; b.wgt = a.inv_denominator;
-    b.zfinal = a.ckpt + ckpt_off_h(nsteps, 0, DB); b.zbar = w->bzbar.as<float>(); b.KB = w->bKB.as<float>();
-    b.ZD = w->ZD.as<float>(); b.Q = w->Q.as<float>(); b.E = w->EPS.as<float>();
-    b.ZB = w->tZB.as<float>(); b.QB = w->tQB.as<float>(); b.sbar = w->bSB.as<float>(); b.dxs = a.dxs;
+    b.zfinal = a.ckpt + ckpt_off_h(nsteps, 0, DB); b.zbar = w->bzbar.as<float>();
+    b.dxs = a.dxs;
+    float* SB6 = w->bSB.as<float>();
     const int db_blocks = blocks_for(DB), b_blocks = blocks_for(B);
     bw_init_kernel<<<b_blocks, 256, 0, st>>>(b);
     const float lbar = a.inv_denominator;
@@ -2083,14 +2212,10 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
 
     for (int step = nsteps - 1; step >= 0; --step) {
         const float t = steps[step].t, h = steps[step].dt;
-        b.h = h;
-        bw_kbar_init_kernel<<<db_blocks, 256, 0, st>>>(b);
-        w->launches++;
         for (int i = 5; i >= 0; --i) {
             const float* zi = a.ckpt + ckpt_off_h(step, i, DB);
             const float ti = t + g_c_host(i) * h;
             const float hb = h * g_b_host(i);
-            b.i = i; b.cl = hb * lbar; b.cE = hb * Ebar; b.cn = hb * nbar;
             // ---- forward at the checkpointed stage input (h, sigma' row-major; h transposed)
             GCK(tc::pack_input(zi, w->YS.as<float>(), X, B, D, w->tin, w->C, P8(w->n[0]), ti, nullptr, 0.f, nullptr, split, st,
                                XT, rsT, loT));
@@ -2109,12 +2234,19 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
                 else { g.ep = tc::TEP_PLAIN_SOA; g.out_f32 = w->Q.as<float>(); g.n_limit = D; }
                 GCK(tc::gemm(l == NL - 1 ? E16 : rm(G, l), w->rs(w->n[l + 1]), w16n + w->w16n_off[l], w->rs(w->n[l + 1]), g, st));
             }
-            // ---- cotangents: zb on zdot (output of the top layer), qb on eps'J (the tangent that enters layer 0)
-            bw_cotangent_kernel<<<blocks_for(B, 32), 256, 0, st>>>(b, -1);
-            GCK(tc::pack_soa(b.ZB, rm(AB, NL - 1), B, D, P8(D), nullptr, split, st, tp(ABT, NL - 1), rsT, loT));
-            // the tangent that enters layer 0 is laid out like the network input (zeros in the t / ys columns), so that
-            // its K blocks line up with W_1's: hi and lo halves of both operands then sit at the same column offsets
-            GCK(tc::pack_soa(b.QB, WV0, B, D, P8(w->n[0]), nullptr, split, st, WV0T, rsT, loT));
+            // ---- cotangents: zb on zdot (output of the top layer), qb on eps'J (the tangent that enters layer 0).  The
+            // latter is laid out like the network input (zeros in the t / ys columns), so that its K blocks line up with
+            // W_1's: hi and lo halves of both operands then sit at the same column offsets
+            {
+                CotArgs c;
+                memset(&c, 0, sizeof c);
+                c.B = B; c.D = D; c.i = i; c.squared = a.squared; c.split = split;
+                c.h = h; c.cl = hb * lbar; c.cE = hb * Ebar; c.cn = hb * nbar;
+                c.ZD = w->ZD.as<float>(); c.Q = w->Q.as<float>(); c.E = w->EPS.as<float>(); c.zbar = b.zbar; c.SB6 = SB6;
+                c.ZBr = rm(AB, NL - 1); c.zb_pitch = P8(D); c.QBr = WV0; c.qb_pitch = P8(w->n[0]);
+                c.ZBt = tp(ABT, NL - 1); c.QBt = WV0T; c.ldT = rsT; c.loT = loT;
+                bw_cotangent_pack_kernel<<<blocks_for(B, 32), 1024, 0, st>>>(c);
+            }
             // ---- tangent pass: r = W_l w_l;  w_{l+1} = r .* d_l;  aex_l = r .* g_l .* sigma''/sigma'
             for (int l = 0; l < NL - 1; ++l) {
                 tc::TcArgs g = base_args((int)B, w->n[l + 1], w->n[l], w->n[l], w->n[l], w->n[l + 1]);
@@ -2139,12 +2271,13 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
                 if (l > 0) {
                     p.ep = tc::TEP_MULADD; p.out0 = rm(AB, l - 1); p.outT = tp(ABT, l - 1);
                     p.aux = rm(Dv, l - 1); p.aux1 = rm(AEX, l - 1);
-                } else { p.ep = tc::TEP_PLAIN_SOA; p.out_f32 = w->bSB.as<float>(); p.n_limit = D; }
+                } else { p.ep = tc::TEP_PLAIN_SOA; p.out_f32 = SB6 + (long long)i * DB; p.n_limit = D; }   // sbar_i, kept for the earlier stages
                 GCK(tc::gemm(rm(AB, l), w->rs(nout), w16n + w->w16n_off[l], w->rs(nout), p, st));
             }
-            bw_accumulate_kernel<<<db_blocks, 256, 0, st>>>(b);
-            w->launches += 5 + 2 * NL + (NL - 1) + 3 * NL;
+            w->launches += 2 + 2 * NL + (NL - 1) + 3 * NL;
         }
+        bw_zbar_update_kernel<<<db_blocks, 256, 0, st>>>(b.zbar, SB6, DB);
+        w->launches++;
     }
     bw_reduce_slices_kernel<<<blocks_for((long long)np), 256, 0, st>>>(wpart, nsl_max, (long long)np, a.gpartial);
     w->launches++;

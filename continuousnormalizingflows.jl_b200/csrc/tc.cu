@@ -36,6 +36,19 @@ static bool make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t K
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// row-major bf16 output (M rows, `cols` columns incl. the lo half, row pitch ldo): box = 16 columns x 32 rows, dense
+static bool make_out_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t pitch) {
+    EncodeFn fn = encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {pitch * 2};
+    cuuint32_t box[2] = {16, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // per-device launch state: shared-memory attribute set, SM count (a process may drive several devices)
 struct DevState { bool attr_set = false; int sms = 0; };
 static DevState& dev_state() {
@@ -45,13 +58,23 @@ static DevState& dev_state() {
     return st[dev & 63];
 }
 
+template <bool SPLIT>
+static cudaError_t launch_pair(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2, const CUtensorMap& mB2,
+                               const CUtensorMap& mO0, const CUtensorMap& mO1, const TcArgs& g, int sms, cudaStream_t st) {
+    const long long ntiles = (long long)((g.M + 2 * TBM - 1) / (2 * TBM)) * ((g.N + 255) / 256);
+    const long long nwork = ntiles * (g.nslices > 1 ? g.nslices : 1);
+    const long long pairs = std::max<long long>(1, std::min<long long>(nwork, sms / 2));
+    tc_gemm_pair_kernel<SPLIT><<<dim3((unsigned)(2 * pairs)), TTHREADS, smem_bytes(SPLIT, 128), st>>>(mA, mB, mA2, mB2, mO0, mO1, g);
+    return cudaGetLastError();
+}
+
 template <bool SPLIT, int BN>
 static cudaError_t launch(const CUtensorMap& mA, const CUtensorMap& mB, const CUtensorMap& mA2, const CUtensorMap& mB2,
-                          const TcArgs& g, int sms, cudaStream_t st) {
+                          const CUtensorMap& mO0, const CUtensorMap& mO1, const TcArgs& g, int sms, cudaStream_t st) {
     const long long ntiles = (long long)((g.M + TBM - 1) / TBM) * ((g.N + BN - 1) / BN);
     const long long nwork = ntiles * (g.nslices > 1 ? g.nslices : 1);
     const dim3 grid((unsigned)std::min<long long>(nwork, (long long)sms));
-    tc_gemm_kernel<SPLIT, BN><<<grid, TTHREADS, smem_bytes(SPLIT, BN), st>>>(mA, mB, mA2, mB2, g);
+    tc_gemm_kernel<SPLIT, BN><<<grid, TTHREADS, smem_bytes(SPLIT, BN), st>>>(mA, mB, mA2, mB2, mO0, mO1, g);
     return cudaGetLastError();
 }
 
@@ -67,13 +90,19 @@ cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, 
         if (e != cudaSuccess) return e;
         ICNF_TC_ATTR(false, 128) ICNF_TC_ATTR(false, 256) ICNF_TC_ATTR(true, 128) ICNF_TC_ATTR(true, 256)
 #undef ICNF_TC_ATTR
+        e = cudaFuncSetAttribute(tc_gemm_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(false, 128));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tc_gemm_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true, 128));
+        if (e != cudaSuccess) return e;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&ds.sms, cudaDevAttrMultiProcessorCount, dev);
         ds.attr_set = true;
     }
     // wide outputs: 128 x 256 tiles (half the operand bytes per MAC through L2); narrow ones: 128 x 128
-    const int bn = (g.N > 160) ? 256 : 128;   // keep in step with unit_tiles() in tc.h
+    const int mode = tile_mode(g.N);
+    // TMA box of the B operand: a CTA of a pair loads 128 of the tile's 256 unit rows
+    const int bn = mode == 3 ? 256 : 128;
     CUtensorMap mapA, mapB, mapA2, mapB2;
     const uint64_t ka = g.split ? (uint64_t)g.lo_a + g.K : (uint64_t)g.K;
     const uint64_t kb = g.split ? (uint64_t)g.lo_b + g.K : (uint64_t)g.K;
@@ -88,8 +117,16 @@ cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, 
     } else {
         mapA2 = mapA; mapB2 = mapB;
     }
-    if (g.split) return bn == 256 ? launch<true, 256>(mapA, mapB, mapA2, mapB2, g, ds.sms, st) : launch<true, 128>(mapA, mapB, mapA2, mapB2, g, ds.sms, st);
-    return bn == 256 ? launch<false, 256>(mapA, mapB, mapA2, mapB2, g, ds.sms, st) : launch<false, 128>(mapA, mapB, mapA2, mapB2, g, ds.sms, st);
+    // row-major bf16 outputs go out through TMA (16-column boxes: the row pitch of a half must be a multiple of 16)
+    CUtensorMap mapO0 = mapA, mapO1 = mapA;
+    const uint64_t ocols = g.split ? 2 * (uint64_t)g.lo_o : (uint64_t)g.ldo;
+    if (g.out0 && (((g.split ? g.lo_o : g.ldo) & 15) || !make_out_map(&mapO0, g.out0, (uint64_t)g.M, ocols, (uint64_t)g.ldo))) return cudaErrorInvalidValue;
+    if (g.out1 && !make_out_map(&mapO1, g.out1, (uint64_t)g.M, ocols, (uint64_t)g.ldo)) return cudaErrorInvalidValue;
+#define ICNF_TC_MAPS mapA, mapB, mapA2, mapB2, mapO0, mapO1
+    if (mode == 2) return g.split ? launch_pair<true>(ICNF_TC_MAPS, g, ds.sms, st) : launch_pair<false>(ICNF_TC_MAPS, g, ds.sms, st);
+    if (g.split) return bn == 256 ? launch<true, 256>(ICNF_TC_MAPS, g, ds.sms, st) : launch<true, 128>(ICNF_TC_MAPS, g, ds.sms, st);
+    return bn == 256 ? launch<false, 256>(ICNF_TC_MAPS, g, ds.sms, st) : launch<false, 128>(ICNF_TC_MAPS, g, ds.sms, st);
+#undef ICNF_TC_MAPS
 }
 
 // ---- packing kernels ------------------------------------------------------------------------
@@ -292,5 +329,38 @@ extern "C" __attribute__((visibility("default"))) int icnf_tc_wgrad_selftest(int
     }
     cudaFree(dA); cudaFree(dB); cudaFree(dA2); cudaFree(dB2); cudaFree(dD);
     cudaFree(a16); cudaFree(b16); cudaFree(a216); cudaFree(b216);
+    return rc;
+}
+
+
+// Development aid: timeline (clock64 of CTA 0's TMA, MMA and first epilogue warp) of one GEMM of the forward kind
+// (TEP_ACT epilogue, split or plain operands) on synthetic operands.  `out` receives 3 x 8192 long longs (see TcArgs::trace).
+extern "C" __attribute__((visibility("default"))) int icnf_tc_gemm_timeline(int M, int N, int K, int split, int ep, long long* out) {
+    using namespace icnf::tc;
+    const int kp = (K + 7) & ~7, np_ = (N + 15) & ~15;
+    const int rpa = split ? 2 * kp : kp, rpo = split ? 2 * np_ : np_;
+    __nv_bfloat16 *a16 = nullptr, *b16 = nullptr, *o0 = nullptr, *o1 = nullptr;
+    float *bias = nullptr, *of = nullptr;
+    long long* tr = nullptr;
+    int rc = 0;
+    auto ok = [&](cudaError_t e) { if (e != cudaSuccess && rc == 0) rc = 2; return e == cudaSuccess; };
+    if (ok(cudaMalloc(&a16, 2 * (size_t)M * rpa)) && ok(cudaMalloc(&b16, 2 * (size_t)N * rpa)) && ok(cudaMalloc(&o0, 2 * (size_t)M * rpo)) &&
+        ok(cudaMalloc(&o1, 2 * (size_t)M * rpo)) && ok(cudaMalloc(&bias, 4 * (size_t)N)) && ok(cudaMalloc(&of, 4 * (size_t)M * N)) &&
+        ok(cudaMalloc(&tr, 8 * 3 * 8192))) {
+        ok(cudaMemset(a16, 0, 2 * (size_t)M * rpa)); ok(cudaMemset(b16, 0, 2 * (size_t)N * rpa)); ok(cudaMemset(bias, 0, 4 * (size_t)N));
+        TcArgs g;
+        memset(&g, 0, sizeof g);
+        g.M = M; g.N = N; g.K = K; g.ep = ep; g.act = 0; g.bias = bias; g.out0 = o0; g.out1 = o1; g.aux = o1; g.ldo = rpo;
+        g.out_f32 = of; g.n_limit = N;
+        g.split = split; g.lo_a = kp; g.lo_b = kp; g.lo_o = np_;
+        for (int rep = 0; rep < 3; ++rep) {   // the last (warm) run is the one reported
+            ok(cudaMemset(tr, 0, 8 * 3 * 8192));
+            g.trace = tr;
+            ok(gemm(a16, rpa, b16, rpa, g, 0));
+            ok(cudaDeviceSynchronize());
+        }
+        ok(cudaMemcpy(out, tr, 8 * 3 * 8192, cudaMemcpyDeviceToHost));
+    }
+    cudaFree(a16); cudaFree(b16); cudaFree(o0); cudaFree(o1); cudaFree(bias); cudaFree(of); cudaFree(tr);
     return rc;
 }

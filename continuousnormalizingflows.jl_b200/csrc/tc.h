@@ -4,32 +4,55 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 namespace icnf {
 namespace tc {
 
 // CTA tile: 128 rows of the A operand (the TMEM lanes) x BN rows of the B operand (TMEM columns), K blocks of 64.
 // BN = 256 halves the operand bytes per MAC that a CTA pulls through L2 (the limiter of these GEMMs: the SM's
 // share of L2 bandwidth, not the tensor pipe) and turns a 512-unit layer at 8192 samples into ONE wave of
-// 128 CTAs; BN = 128 serves narrow outputs.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2..9 = epilogue.
-constexpr int TBM = 128, TBK = 64, TTHREADS = 320;
+// 128 CTAs; BN = 128 serves narrow outputs.  Warp 0 = TMA producer, warp 1 = MMA issuer, warps 2.. = epilogue, WQ per TMEM lane quarter (the
+// epilogue -- activation, hi/lo split, uncoalesced row stores -- is latency-bound: 8 warps left it at twice the main loop).
+#ifndef ICNF_TC_WQ
+#define ICNF_TC_WQ 3
+#endif
+constexpr int WQ = ICNF_TC_WQ;                      // epilogue warps per TMEM lane quarter
+constexpr int EPI_THREADS = 4 * WQ * 32;
+// Warp roles: warps 0 .. 4 WQ - 1 = epilogue, then the MMA issuer, then the TMA producer.  The two single-thread
+// roles sit at the HIGHEST warp ids on purpose: the warp scheduler favours high ids, and with the roles the other way
+// round the MMA thread needed 3000 cycles instead of 900 to issue a K block while the epilogue warps were busy.
+constexpr int TBM = 128, TBK = 64, TTHREADS = EPI_THREADS + 64;
+constexpr int MMA_WARP = 4 * WQ, TMA_WARP = 4 * WQ + 1;
+constexpr int EPI_STAGE_BYTES = 2048;      // per epilogue warp: one 32-row x 16-column bf16 box, hi and lo halves
 constexpr int A_TILE_BYTES = TBM * TBK * 2;
 __host__ __device__ constexpr int b_tile_bytes(int bn) { return bn * TBK * 2; }
 // shared-memory ring depth: as many stages as fit next to the barriers and the bias slice
 __host__ __device__ constexpr int stages(bool split, int bn) { return split ? (bn == 256 ? 2 : 3) : (bn == 256 ? 4 : 6); }
 __host__ __device__ constexpr int stage_bytes(bool split, int bn) { return (split ? 2 : 1) * (A_TILE_BYTES + b_tile_bytes(bn)); }
 __host__ __device__ constexpr int smem_bytes(bool split, int bn) {
-    return stages(split, bn) * stage_bytes(split, bn) + 1024 /*align*/ + 256 /*barriers*/ + 2 * bn * 4 /*bias, double-buffered*/;
+    return stages(split, bn) * stage_bytes(split, bn) + 1024 /*align*/ + 256 /*barriers*/ + 2 * 256 * 4 /*bias, double-buffered*/ +
+           4 * WQ * EPI_STAGE_BYTES /*store staging*/;
 }
 
-// unit (B-operand row) tiles of a GEMM with N output units, as tc::gemm chooses them
-inline int unit_tiles(int N) { const int bn = N > 160 ? 256 : 128; return (N + bn - 1) / bn; }
+// Tile mode of the GEMM: 2 = CTA pairs (cta_group::2, 256 x 256 tiles; the default for wide outputs), 1 = one CTA
+// per 128 x 128 tile, 3 = one CTA per 128 x 256 tile.  ICNF_TC_MODE=1|2|3 in the environment forces one (a tuning
+// knob for measurements; every mode computes the same products in the same order per output element).
+inline int tile_mode(int N) {
+    static const int forced = [] { const char* e = getenv("ICNF_TC_MODE"); return e ? atoi(e) : 0; }();
+    if (forced >= 1 && forced <= 3) return (forced != 1 && N <= 128) ? 1 : forced;
+    return N > 128 ? 2 : 1;
+}
+// width of the unit (B-operand row) tiles for a GEMM with N output units
+inline int unit_tile_width(int N) { return tile_mode(N) == 1 ? 128 : 256; }
+inline int unit_tiles(int N) { const int bn = unit_tile_width(N); return (N + bn - 1) / bn; }
 
 enum TcEpilogue {
     TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)  [+ H transposed]
     TEP_LIN_SOA = 1,    // out_f32[n * M + m] = acc + bias[n]              (fp32, [unit][sample])
     TEP_MULD = 2,       // G[m][n] = acc * aux[m][n]                        (bf16)                 [+ G transposed]
     TEP_PLAIN_SOA = 3,  // out_f32[n * M + m] = acc
-    TEP_TRACE = 4,      // out_f32[part * M + m] = sum_{n in part} acc * aux[m][n],  part = 2 * unit tile + column half
+    TEP_TRACE = 4,      // out_f32[part * M + m] = sum_{n in part} acc * aux[m][n],  part = WQ * unit tile + epilogue warp of the lane quarter
     // reverse sweep (derivation: tiny.cuh rhs_reverse / DESIGN.md):
     TEP_TANGENT = 5,    // out0 = acc * aux (sigma');  out1 = acc * aux1 (chain g) * phi(aux2 (h), aux),  phi = sigma''/sigma'
     TEP_MULADD = 6,     // out0 = acc * aux (sigma') + aux1                                         [+ out0 transposed]
@@ -64,6 +87,10 @@ struct TcArgs {
     int nslices;
     long long slice_stride;
     int ldw;
+    // optional timeline of CTA 0 (development aid, icnf_tc_gemm_timeline): trace[0] = event count, then (tag, clock64) pairs.
+    // tags: 1000 + it = TMA issued for K block it; 2000 + it = operands of K block it landed (MMA thread);
+    //       3000 + it = MMAs of K block it issued; 4000 + i = accumulator i complete (epilogue warp 2); 5000 + i = epilogue of item i done
+    long long* trace;
 };
 
 // A (M x K) and B (N x K), both K contiguous; A2/B2: the optional second segment

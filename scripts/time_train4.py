@@ -10,9 +10,9 @@ rng = np.random.default_rng(7)
 theta, _ = m.setup(rng, icnf)
 theta_d = torch.from_numpy(theta).cuda()
 xs = torch.from_numpy(rng.standard_normal((B, 784)).astype(np.float32)).cuda()
-for i in range(3):
+for i in range(4):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     m.loss_and_gradient(icnf, m.TrainMode(True), xs.t(), theta_d, {}, seed=3, adaptive=False, dt=0.25)
     b.record(); torch.cuda.synchronize()
-    print(prec, "config 4 training step, 4 fixed steps:", a.elapsed_time(b), "ms", flush=True)
+    print(prec, "config 4 training step, 4 fixed steps:", a.elapsed_time(b), "ms", os.environ.get("ICNF_TC_MODE", "auto"), flush=True)
