@@ -1687,7 +1687,8 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
         g.M = (int)B; g.N = w->n[l + 1]; g.K = w->n[l];
         g.bias = p.theta + w->boff[l]; g.act = w->cfg.activation; g.done = done;
         set_split(g, w->n[l], w->n[l], w->n[l + 1]);
-        if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = act_ptr(H, l); g.out1 = act_ptr(Dv, l); g.ldo = w->rs(w->n[l + 1]); }
+        // sigma' is written only for the exact trace (its GEMM takes D_1 as an operand); the Hutchinson chain derives it from h
+        if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = act_ptr(H, l); g.out1 = p.exact ? act_ptr(Dv, l) : nullptr; g.ldo = w->rs(w->n[l + 1]); }
         else { g.ep = tc::TEP_LIN_SOA; g.out_f32 = w->ZD.as<float>(); g.n_limit = D; }
         const __nv_bfloat16* A = (l == 0) ? X : act_ptr(H, l - 1);
         GCK(tc::gemm(A, w->rs(w->n[l]), w->w16t.as<__nv_bfloat16>() + w->w16t_off[l], w->rs(w->n[l]), g, p.st));
@@ -1726,7 +1727,7 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
         memset(&g, 0, sizeof g);
         g.M = (int)B; g.N = (l == 0) ? D : w->n[l]; g.K = w->n[l + 1]; g.done = done;
         set_split(g, w->n[l + 1], w->n[l + 1], w->n[l]);
-        if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = act_ptr(G, l - 1); g.aux = act_ptr(Dv, l - 1); g.ldo = w->rs(w->n[l]); }
+        if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = act_ptr(G, l - 1); g.aux = act_ptr(H, l - 1); g.aux_is_h = 1; g.ldo = w->rs(w->n[l]); }
         else { g.ep = tc::TEP_PLAIN_SOA; g.out_f32 = w->Q.as<float>(); g.n_limit = D; }
         const __nv_bfloat16* A = (l == NL - 1) ? E : act_ptr(G, l);
         GCK(tc::gemm(A, w->rs(w->n[l + 1]), w->w16n.as<__nv_bfloat16>() + w->w16n_off[l], w->rs(w->n[l + 1]), g, p.st));
@@ -2222,7 +2223,7 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
             for (int l = 0; l < NL; ++l) {
                 tc::TcArgs g = base_args((int)B, w->n[l + 1], w->n[l], w->n[l], w->n[l], w->n[l + 1]);
                 g.bias = a.theta + w->boff[l];
-                if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = rm(H, l); g.out1 = rm(Dv, l); g.outT = tp(HT, l); }
+                if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = rm(H, l); g.outT = tp(HT, l); }   // no sigma' array: derived from h
                 else { g.ep = tc::TEP_LIN_SOA; g.out_f32 = w->ZD.as<float>(); g.n_limit = D; }
                 GCK(tc::gemm(l == 0 ? X : rm(H, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, st));
             }
@@ -2230,7 +2231,7 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
             for (int l = NL - 1; l >= 0; --l) {
                 const int nout = (l == 0) ? D : w->n[l];
                 tc::TcArgs g = base_args((int)B, nout, w->n[l + 1], w->n[l + 1], w->n[l + 1], w->n[l]);
-                if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = rm(G, l - 1); g.aux = rm(Dv, l - 1); g.outT = tp(GT, l - 1); }
+                if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = rm(G, l - 1); g.aux = rm(H, l - 1); g.aux_is_h = 1; g.outT = tp(GT, l - 1); }
                 else { g.ep = tc::TEP_PLAIN_SOA; g.out_f32 = w->Q.as<float>(); g.n_limit = D; }
                 GCK(tc::gemm(l == NL - 1 ? E16 : rm(G, l), w->rs(w->n[l + 1]), w16n + w->w16n_off[l], w->rs(w->n[l + 1]), g, st));
             }
@@ -2252,7 +2253,7 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
                 tc::TcArgs g = base_args((int)B, w->n[l + 1], w->n[l], w->n[l], w->n[l], w->n[l + 1]);
                 g.ep = tc::TEP_TANGENT;
                 g.out0 = rm(WV, l); g.outT = tp(WVT, l); g.out1 = rm(AEX, l);
-                g.aux = rm(Dv, l); g.aux1 = rm(G, l); g.aux2 = rm(H, l);
+                g.aux = rm(H, l); g.aux_is_h = 1; g.aux1 = rm(G, l); g.aux2 = rm(H, l);
                 GCK(tc::gemm(l == 0 ? WV0 : rm(WV, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, st));
             }
             // ---- top down: weight gradient, bias gradient, backprop
@@ -2270,7 +2271,7 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
                 tc::TcArgs p = base_args((int)B, nprev, nout, nout, nout, nin);
                 if (l > 0) {
                     p.ep = tc::TEP_MULADD; p.out0 = rm(AB, l - 1); p.outT = tp(ABT, l - 1);
-                    p.aux = rm(Dv, l - 1); p.aux1 = rm(AEX, l - 1);
+                    p.aux = rm(H, l - 1); p.aux_is_h = 1; p.aux1 = rm(AEX, l - 1);
                 } else { p.ep = tc::TEP_PLAIN_SOA; p.out_f32 = SB6 + (long long)i * DB; p.n_limit = D; }   // sbar_i, kept for the earlier stages
                 GCK(tc::gemm(rm(AB, l), w->rs(nout), w16n + w->w16n_off[l], w->rs(nout), p, st));
             }

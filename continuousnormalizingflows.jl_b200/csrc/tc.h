@@ -35,20 +35,22 @@ __host__ __device__ constexpr int smem_bytes(bool split, int bn) {
            4 * WQ * EPI_STAGE_BYTES /*store staging*/;
 }
 
-// Tile mode of the GEMM: 2 = CTA pairs (cta_group::2, 256 x 256 tiles; the default for wide outputs), 1 = one CTA
-// per 128 x 128 tile, 3 = one CTA per 128 x 256 tile.  ICNF_TC_MODE=1|2|3 in the environment forces one (a tuning
-// knob for measurements; every mode computes the same products in the same order per output element).
+// Tile mode of the GEMM: 1 = one CTA per 128 x 128 tile (the default: measured fastest at the batch sizes of
+// BASELINE.json, where a layer is one or two tiles per CTA and the epilogue's write traffic, not the operand loads,
+// sets the pace), 2 = CTA pairs (cta_group::2, 256 x 256 tiles: half the operand bytes per MAC), 3 = one CTA per
+// 128 x 256 tile.  ICNF_TC_MODE=1|2|3 in the environment forces one (a tuning knob for measurements; every mode
+// computes the same products in the same order per output element).
 inline int tile_mode(int N) {
     static const int forced = [] { const char* e = getenv("ICNF_TC_MODE"); return e ? atoi(e) : 0; }();
     if (forced >= 1 && forced <= 3) return (forced != 1 && N <= 128) ? 1 : forced;
-    return N > 128 ? 2 : 1;
+    return 1;
 }
 // width of the unit (B-operand row) tiles for a GEMM with N output units
 inline int unit_tile_width(int N) { return tile_mode(N) == 1 ? 128 : 256; }
 inline int unit_tiles(int N) { const int bn = unit_tile_width(N); return (N + bn - 1) / bn; }
 
 enum TcEpilogue {
-    TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act'   (bf16, row pitch ldo)  [+ H transposed]
+    TEP_ACT = 0,        // H[m][n] = act(acc + bias[n]), Dv[m][n] = act' (only when out1 != null)   (bf16, row pitch ldo)  [+ H transposed]
     TEP_LIN_SOA = 1,    // out_f32[n * M + m] = acc + bias[n]              (fp32, [unit][sample])
     TEP_MULD = 2,       // G[m][n] = acc * aux[m][n]                        (bf16)                 [+ G transposed]
     TEP_PLAIN_SOA = 3,  // out_f32[n * M + m] = acc
@@ -65,7 +67,9 @@ struct TcArgs {
     const float* bias;         // N
     __nv_bfloat16* out0;       // H / G / Wv / AB
     __nv_bfloat16* out1;       // Dv / AEX
-    const __nv_bfloat16* aux;  // sigma' (same pitch as out0)
+    const __nv_bfloat16* aux;  // sigma' (same pitch as out0), or h when aux_is_h (sigma' is then derived from it)
+    int aux_is_h;              // sigma' = f(h) for every supported activation (softplus: 1 - exp(-h), tanh: 1 - h^2,
+                               // sigmoid: h (1 - h)): the Hutchinson paths never write or read a sigma' array
     const __nv_bfloat16* aux1; // TANGENT: chain g;  MULADD: AEX
     const __nv_bfloat16* aux2; // TANGENT: h
     int ldo;                   // row pitch (elements) of out0/out1/aux*

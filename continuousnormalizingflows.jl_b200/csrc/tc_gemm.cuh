@@ -218,6 +218,30 @@ __device__ __forceinline__ float act_ratio_rt(int act, float h, float d) {
     }
 }
 
+// sigma'(a) from h = sigma(a)
+__device__ __forceinline__ float act_deriv_from_h(int act, float h) {
+    switch (act) {
+        case ICNF_ACT_SOFTPLUS: return 1.0f - __expf(-h);     // h = log(1 + e^a)  =>  e^-h = 1 - sigmoid(a)
+        case ICNF_ACT_TANH: return 1.0f - h * h;
+        case ICNF_ACT_SIGMOID: return h * (1.0f - h);
+        default: return 1.0f;
+    }
+}
+// the sigma' values of a chunk: loaded, or derived from the loaded h
+template <bool SPLIT>
+__device__ __forceinline__ void load_deriv(const TcArgs& g, size_t row_off, int nb, int pitch, float (&dv)[NC]) {
+    load_row<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
+    if (g.aux_is_h) {
+        if (g.act == ICNF_ACT_SOFTPLUS) {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) dv[j] = 1.0f - __expf(-dv[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) dv[j] = act_deriv_from_h(g.act, dv[j]);
+        }
+    }
+}
+
 // transposed copy of NC consecutive columns of row m: outT[(nb + j) * ldT + m]; a warp writes 32 consecutive
 // rows m, i.e. 64 contiguous bytes per column
 template <bool SPLIT>
@@ -260,19 +284,23 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& g, const CUtensorMap* 
             }
         }
         store_rows<SPLIT>(es, mapO0, nb, hv);
-        store_rows<SPLIT>(es, mapO1, nb, dv);
+        if (g.out1) store_rows<SPLIT>(es, mapO1, nb, dv);
         if (g.outT && row_ok) store_colT<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, hv);
     } else if (g.ep == TEP_MULD) {
         float dv[NC], gv[NC];
-        if (row_ok) load_row<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv); else zero(dv);
+        if (row_ok) load_deriv<SPLIT>(g, row_off, nb, pitch, dv); else zero(dv);
 #pragma unroll
         for (int j = 0; j < NC; ++j) gv[j] = (nb + j < g.N) ? __uint_as_float(r[j]) * dv[j] : 0.f;
         store_rows<SPLIT>(es, mapO0, nb, gv);
         if (g.outT && row_ok) store_colT<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, gv);
     } else if (g.ep == TEP_TANGENT) {
         float dv[NC], gv[NC], o0[NC], o1[NC];
-        if (row_ok) { load_row<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv); load_row<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, gv); }
-        else { zero(dv); zero(gv); }
+        float hv[NC];
+        if (row_ok) {
+            load_row<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, gv);
+            if (g.act != ICNF_ACT_SOFTPLUS) load_row<SPLIT>(g.aux2, row_off, nb, pitch, g.lo_o, hv);   // phi needs h itself
+            load_deriv<SPLIT>(g, row_off, nb, pitch, dv);
+        } else { zero(dv); zero(gv); zero(hv); }
         if (g.act == ICNF_ACT_SOFTPLUS) {
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
@@ -281,8 +309,6 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& g, const CUtensorMap* 
                 o1[j] = rr * gv[j] * (1.0f - dv[j]);
             }
         } else {
-            float hv[NC];
-            if (row_ok) load_row<SPLIT>(g.aux2, row_off, nb, pitch, g.lo_o, hv); else zero(hv);
 #pragma unroll
             for (int j = 0; j < NC; ++j) {
                 const float rr = (nb + j < g.N) ? __uint_as_float(r[j]) : 0.f;
@@ -295,7 +321,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& g, const CUtensorMap* 
         if (g.outT && row_ok) store_colT<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, o0);
     } else if (g.ep == TEP_MULADD) {
         float dv[NC], ax[NC], o0[NC];
-        if (row_ok) { load_row<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv); load_row<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, ax); }
+        if (row_ok) { load_row<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, ax); load_deriv<SPLIT>(g, row_off, nb, pitch, dv); }
         else { zero(dv); zero(ax); }
 #pragma unroll
         for (int j = 0; j < NC; ++j) o0[j] = (nb + j < g.N) ? fmaf(__uint_as_float(r[j]), dv[j], ax[j]) : 0.f;
@@ -653,6 +679,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TTHREADS, 1)
                         const uint32_t ph = (it / NSTAGE) & 1;
                         uint8_t* st = smem + s * STAGE_BYTES;
                         mbar_wait(&empty[s], ph ^ 1);
+                        trace_event(g.trace, 0, 1000 + it);
                         if (leader) mbar_expect_tx(&full[s], 2 * STAGE_BYTES);   // both CTAs' bytes land on the leader's barrier
                         tma_load_2d_pair(st, ma, &full[s], kb * TBK, m0);
                         if constexpr (SPLIT) tma_load_2d_pair(st + A_TILE_BYTES, ma, &full[s], lo_a + kb * TBK, m0);
@@ -685,6 +712,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TTHREADS, 1)
                         uint8_t* st = smem + s * STAGE_BYTES;
                         mbar_wait(&full[s], ph);
                         tc_fence_after();
+                        trace_event(g.trace, 8192, 2000 + it);
                         const uint64_t a_hi = make_desc(smem_u32(st));
                         const uint64_t b_hi = make_desc(smem_u32(st + NT_A * A_TILE_BYTES));
 #pragma unroll
@@ -699,6 +727,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TTHREADS, 1)
                             for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16_pair(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                         }
                         tc_commit_pair(&empty[s]);     // frees slot s in both CTAs
+                        trace_event(g.trace, 8192, 3000 + it);
                     }
                 }
                 tc_commit_pair(&tmem_full[as]);        // wakes the epilogue warps of both CTAs
@@ -724,6 +753,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TTHREADS, 1)
             }
             mbar_wait(&tmem_full[as], (i >> 1) & 1);
             tc_fence_after();
+            if (threadIdx.x == 0) trace_event(g.trace, 16384, 4000 + i);
             const int m = m0 + q * 32 + lane;
             const bool row_ok = m < g.M;
             es.m_warp = m0 + q * 32;
@@ -753,6 +783,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TTHREADS, 1)
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_leader(&tmem_empty[as]);
+            if (threadIdx.x == 0) trace_event(g.trace, 16384, 5000 + i);
             if (g.ep == TEP_TRACE && row_ok) g.out_f32[(size_t)((tile % ntn) * WQ + cq) * g.M + m] = rowsum;
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's bulk stores have completed
