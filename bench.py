@@ -533,7 +533,8 @@ def main():
     achieved_gbs = bwd_bytes / (bwd_ms * 1e-3) / 1e9
     traffic = None
     try:   # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["tiny::backward_sp_kernel"]
+        import glob
+        tr = json.load(open(sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json")))[-1]))["tiny::backward_sp_kernel"]
         traffic = tr["dram_bytes_per_launch"] * (B / tr["batch"])
     except Exception:
         pass

@@ -1432,6 +1432,7 @@ struct Workspace {
     bool e16_valid = false;   // E16 holds the packed probe of the current solve (eps is constant over a solve)
     int rs(int cols) const { return (split ? 2 : 1) * pad8(cols); }   // row stride of a bf16 matrix with `cols` columns
     Buf w16t, w16n, a16, X16, E16, H16, D16, G16;
+    tc::ChainState* chain = nullptr;          // dependent GEMMs of an evaluation run as one persistent launch (tc.h)
     std::vector<size_t> w16t_off, w16n_off;   // element offsets per layer
     std::vector<size_t> h16_off;              // element offsets / B per layer
     size_t h16_cols = 0;
@@ -1485,6 +1486,7 @@ static void* ws_create(const icnf_config* cfg) {
         }
         w->h16_cols = oh;
     }
+    if (w->tc) w->chain = tc::chain_state_create();
     cudaMallocHost((void**)&w->ctrl_host, 2 * sizeof(Ctrl));
     cudaEventCreateWithFlags(&w->ev[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&w->ev[1], cudaEventDisableTiming);
@@ -1495,6 +1497,7 @@ static void ws_destroy(void* p) {
     if (!w) return;
     if (w->ctrl_host) cudaFreeHost(w->ctrl_host);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    tc::chain_state_destroy(w->chain);
     delete w;
 }
 
@@ -1681,6 +1684,18 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
                            (const float*)p.ctrl, c_i, done, w->split, p.st));
         w->launches++;
     }
+    // the GEMMs of the evaluation as ONE persistent launch (tc.h, gemm_chain): forward layers, then the trace GEMM or
+    // the VJP chain; each step waits, row tile by row tile, on the steps whose outputs it reads
+    const int nchain = p.exact ? (NL == 3 ? NL + 1 : NL) : 2 * NL;
+    const bool chained = tc::chain_enabled() && w->chain && nchain <= tc::CHAIN_MAXG && NL >= 1;
+    tc::ChainStep cst[tc::CHAIN_MAXG];
+    int ncs = 0;
+    memset(cst, 0, sizeof cst);
+    auto add_step = [&](const __nv_bfloat16* A, long long lda, const __nv_bfloat16* Bm, long long ldb, const tc::TcArgs& g, int d0, int d1) {
+        tc::ChainStep& s = cst[ncs++];
+        s.A = A; s.lda = lda; s.B = Bm; s.ldb = ldb; s.g = g; s.g.done = nullptr;
+        s.dep_row[0] = d0; s.dep_row[1] = d1; s.dep_all[0] = -1; s.dep_all[1] = -1;
+    };
     for (int l = 0; l < NL; ++l) {
         tc::TcArgs g;
         memset(&g, 0, sizeof g);
@@ -1691,12 +1706,17 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
         if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = act_ptr(H, l); g.out1 = p.exact ? act_ptr(Dv, l) : nullptr; g.ldo = w->rs(w->n[l + 1]); }
         else { g.ep = tc::TEP_LIN_SOA; g.out_f32 = w->ZD.as<float>(); g.n_limit = D; }
         const __nv_bfloat16* A = (l == 0) ? X : act_ptr(H, l - 1);
+        if (chained) { add_step(A, w->rs(w->n[l]), w->w16t.as<__nv_bfloat16>() + w->w16t_off[l], w->rs(w->n[l]), g, l - 1, -1); continue; }
         GCK(tc::gemm(A, w->rs(w->n[l]), w->w16t.as<__nv_bfloat16>() + w->w16t_off[l], w->rs(w->n[l]), g, p.st));
         w->launches++;
     }
     if (p.exact) {
         float* TR = w->TR.as<float>();
         w->tr_parts = 1;
+        if (chained && NL != 3) {   // the trace kernels of shallow networks read the forward GEMMs' output: launch those first
+            GCK(tc::gemm_chain(w->chain, 0, cst, ncs, done, p.st));
+            w->launches++;
+        }
         if (NL == 1) {
             g_trace_dot_kernel<<<blocks_for(B), 256, 0, p.st>>>(w->gvec.as<float>(), nullptr, TR, D, B, 0.f, done);
         } else if (NL == 2) {
@@ -1709,10 +1729,12 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
             g.aux = act_ptr(Dv, 1); g.ldo = w->rs(w->n[2]); g.out_f32 = TR;
             // one part per (unit tile, column quarter): out_f32[part * M + m], no atomics
             w->tr_parts = tc::WQ * tc::unit_tiles(w->n[2]);
-            GCK(tc::gemm(act_ptr(Dv, 0), w->rs(w->n[1]), w->a16.as<__nv_bfloat16>(), w->rs(w->n[1]), g, p.st));
+            if (chained) add_step(act_ptr(Dv, 0), w->rs(w->n[1]), w->a16.as<__nv_bfloat16>(), w->rs(w->n[1]), g, 0, 1);
+            else GCK(tc::gemm(act_ptr(Dv, 0), w->rs(w->n[1]), w->a16.as<__nv_bfloat16>(), w->rs(w->n[1]), g, p.st));
         } else {
             return cudaErrorNotSupported;   // unreachable: use_tc() routes deeper exact traces to the fp32 chains
         }
+        if (chained && NL == 3) GCK(tc::gemm_chain(w->chain, 0, cst, ncs, done, p.st));
         w->launches++;
         return cudaGetLastError();
     }
@@ -1730,7 +1752,17 @@ static cudaError_t tc_rhs_core(const RhsPlan& p, float c_i) {
         if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = act_ptr(G, l - 1); g.aux = act_ptr(H, l - 1); g.aux_is_h = 1; g.ldo = w->rs(w->n[l]); }
         else { g.ep = tc::TEP_PLAIN_SOA; g.out_f32 = w->Q.as<float>(); g.n_limit = D; }
         const __nv_bfloat16* A = (l == NL - 1) ? E : act_ptr(G, l);
+        if (chained) {
+            // reads G_l (the previous step of the chain, unless it starts from the probe) and h_{l-1} (forward step l - 1)
+            add_step(A, w->rs(w->n[l + 1]), w->w16n.as<__nv_bfloat16>() + w->w16n_off[l], w->rs(w->n[l + 1]), g,
+                     l == NL - 1 ? -1 : ncs - 1, l > 0 ? l - 1 : -1);
+            continue;
+        }
         GCK(tc::gemm(A, w->rs(w->n[l + 1]), w->w16n.as<__nv_bfloat16>() + w->w16n_off[l], w->rs(w->n[l + 1]), g, p.st));
+        w->launches++;
+    }
+    if (chained) {
+        GCK(tc::gemm_chain(w->chain, 1, cst, ncs, done, p.st));
         w->launches++;
     }
     return cudaSuccess;
@@ -2220,12 +2252,29 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
             // ---- forward at the checkpointed stage input (h, sigma' row-major; h transposed)
             GCK(tc::pack_input(zi, w->YS.as<float>(), X, B, D, w->tin, w->C, P8(w->n[0]), ti, nullptr, 0.f, nullptr, split, st,
                                XT, rsT, loT));
+            // The GEMMs of the stage run as two persistent launches (tc.h, gemm_chain) around the cotangent kernel:
+            //   A: forward layers, VJP chain                      (row-tile dependencies only)
+            //   B: tangent pass, then per layer backprop + weight gradient (the weight gradients reduce over the samples:
+            //      they wait for whole earlier GEMMs, and are listed one GEMM late so that the wait is rarely exposed)
+            const bool chained = tc::chain_enabled() && w->chain && 2 * NL <= tc::CHAIN_MAXG && (NL - 1) + 2 * NL <= tc::CHAIN_MAXG;
+            tc::ChainStep cst[tc::CHAIN_MAXG];
+            int ncs = 0;
+            memset(cst, 0, sizeof cst);
+            auto add_step = [&](const __nv_bfloat16* A, long long lda, const __nv_bfloat16* Bm, long long ldb, const tc::TcArgs& g,
+                                int d0, int d1, int a0 = -1, int a1 = -1, const __nv_bfloat16* A2 = nullptr, long long lda2 = 0,
+                                const __nv_bfloat16* B2 = nullptr, long long ldb2 = 0) {
+                tc::ChainStep& s = cst[ncs];
+                s.A = A; s.lda = lda; s.B = Bm; s.ldb = ldb; s.A2 = A2; s.lda2 = lda2; s.B2 = B2; s.ldb2 = ldb2; s.g = g;
+                s.dep_row[0] = d0; s.dep_row[1] = d1; s.dep_all[0] = a0; s.dep_all[1] = a1;
+                return ncs++;
+            };
             for (int l = 0; l < NL; ++l) {
                 tc::TcArgs g = base_args((int)B, w->n[l + 1], w->n[l], w->n[l], w->n[l], w->n[l + 1]);
                 g.bias = a.theta + w->boff[l];
                 if (l < NL - 1) { g.ep = tc::TEP_ACT; g.out0 = rm(H, l); g.outT = tp(HT, l); }   // no sigma' array: derived from h
                 else { g.ep = tc::TEP_LIN_SOA; g.out_f32 = w->ZD.as<float>(); g.n_limit = D; }
-                GCK(tc::gemm(l == 0 ? X : rm(H, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, st));
+                if (chained) add_step(l == 0 ? X : rm(H, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, l - 1, -1);
+                else GCK(tc::gemm(l == 0 ? X : rm(H, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, st));
             }
             // ---- VJP chain of the probe (g row-major and transposed), q = eps'J
             for (int l = NL - 1; l >= 0; --l) {
@@ -2233,8 +2282,11 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
                 tc::TcArgs g = base_args((int)B, nout, w->n[l + 1], w->n[l + 1], w->n[l + 1], w->n[l]);
                 if (l > 0) { g.ep = tc::TEP_MULD; g.out0 = rm(G, l - 1); g.aux = rm(H, l - 1); g.aux_is_h = 1; g.outT = tp(GT, l - 1); }
                 else { g.ep = tc::TEP_PLAIN_SOA; g.out_f32 = w->Q.as<float>(); g.n_limit = D; }
-                GCK(tc::gemm(l == NL - 1 ? E16 : rm(G, l), w->rs(w->n[l + 1]), w16n + w->w16n_off[l], w->rs(w->n[l + 1]), g, st));
+                if (chained) add_step(l == NL - 1 ? E16 : rm(G, l), w->rs(w->n[l + 1]), w16n + w->w16n_off[l], w->rs(w->n[l + 1]), g,
+                                      l == NL - 1 ? -1 : ncs - 1, l > 0 ? l - 1 : -1);
+                else GCK(tc::gemm(l == NL - 1 ? E16 : rm(G, l), w->rs(w->n[l + 1]), w16n + w->w16n_off[l], w->rs(w->n[l + 1]), g, st));
             }
+            if (chained) GCK(tc::gemm_chain(w->chain, 2, cst, ncs, nullptr, st));
             // ---- cotangents: zb on zdot (output of the top layer), qb on eps'J (the tangent that enters layer 0).  The
             // latter is laid out like the network input (zeros in the t / ys columns), so that its K blocks line up with
             // W_1's: hi and lo halves of both operands then sit at the same column offsets
@@ -2248,32 +2300,64 @@ static cudaError_t backward_tc(Workspace* w, const BackwardArgs& a, int nsteps, 
                 c.ZBt = tp(ABT, NL - 1); c.QBt = WV0T; c.ldT = rsT; c.loT = loT;
                 bw_cotangent_pack_kernel<<<blocks_for(B, 32), 1024, 0, st>>>(c);
             }
+            ncs = 0;
+            memset(cst, 0, sizeof cst);
             // ---- tangent pass: r = W_l w_l;  w_{l+1} = r .* d_l;  aex_l = r .* g_l .* sigma''/sigma'
+            std::vector<int> tan_idx(NL, -1), bp_idx(NL + 1, -1);   // chain positions of tangent l / of the backprop that produces AB_{l-1}
             for (int l = 0; l < NL - 1; ++l) {
                 tc::TcArgs g = base_args((int)B, w->n[l + 1], w->n[l], w->n[l], w->n[l], w->n[l + 1]);
                 g.ep = tc::TEP_TANGENT;
                 g.out0 = rm(WV, l); g.outT = tp(WVT, l); g.out1 = rm(AEX, l);
                 g.aux = rm(H, l); g.aux_is_h = 1; g.aux1 = rm(G, l); g.aux2 = rm(H, l);
-                GCK(tc::gemm(l == 0 ? WV0 : rm(WV, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, st));
+                if (chained) tan_idx[l] = add_step(l == 0 ? WV0 : rm(WV, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g,
+                                                   l == 0 ? -1 : tan_idx[l - 1], -1);
+                else GCK(tc::gemm(l == 0 ? WV0 : rm(WV, l - 1), w->rs(w->n[l]), w16t + w->w16t_off[l], w->rs(w->n[l]), g, st));
             }
             // ---- top down: weight gradient, bias gradient, backprop
-            for (int l = NL - 1; l >= 0; --l) {
+            auto wgrad_args = [&](int l) {
                 const int nout = w->n[l + 1], nin = w->n[l], kz = (l == 0) ? D : nin;
                 tc::TcArgs g = base_args(nout, nin, (int)B, 0, 0, 0);
                 g.lo_a = loT; g.lo_b = loT; g.lo_a2 = loT; g.lo_b2 = loT;
                 g.ep = tc::TEP_WGRAD; g.K2 = (int)B; g.N2 = kz;
                 g.nslices = nsl[l]; g.slice_stride = (long long)np; g.ldw = nout;
                 g.out_f32 = wpart + w->woff[l];
-                GCK(tc::gemm(tp(ABT, l), rsT, l == 0 ? XT : tp(HT, l - 1), rsT, g, st,
-                             l == NL - 1 ? ET : tp(GT, l), rsT, l == 0 ? WV0T : tp(WVT, l - 1), rsT));
-                GCK(tc::row_sums(tp(ABT, l), rsT, loT, split, nout, B, wpart + w->boff[l], st));
+                return g;
+            };
+            int pending_wgrad = -1;   // chained: the weight gradient of layer `pending_wgrad` is listed after the next backprop GEMM
+            auto add_wgrad = [&](int l) {
+                // reads ABT_l (backprop of layer l + 1, or the cotangent kernel for the top layer), HT_{l-1} (chain A),
+                // GT_l (chain A) and WVT_{l-1} (tangent l - 1; WV0T from the cotangent kernel for l = 0): whole-GEMM dependencies
+                add_step(tp(ABT, l), rsT, l == 0 ? XT : tp(HT, l - 1), rsT, wgrad_args(l), -1, -1, l == NL - 1 ? -1 : bp_idx[l + 1],
+                         l == 0 ? -1 : tan_idx[l - 1], l == NL - 1 ? ET : tp(GT, l), rsT, l == 0 ? WV0T : tp(WVT, l - 1), rsT);
+            };
+            for (int l = NL - 1; l >= 0; --l) {
+                const int nout = w->n[l + 1], nin = w->n[l];
+                if (!chained) {
+                    tc::TcArgs g = wgrad_args(l);
+                    GCK(tc::gemm(tp(ABT, l), rsT, l == 0 ? XT : tp(HT, l - 1), rsT, g, st,
+                                 l == NL - 1 ? ET : tp(GT, l), rsT, l == 0 ? WV0T : tp(WVT, l - 1), rsT));
+                    GCK(tc::row_sums(tp(ABT, l), rsT, loT, split, nout, B, wpart + w->boff[l], st));
+                }
                 const int nprev = (l == 0) ? D : nin;
                 tc::TcArgs p = base_args((int)B, nprev, nout, nout, nout, nin);
                 if (l > 0) {
                     p.ep = tc::TEP_MULADD; p.out0 = rm(AB, l - 1); p.outT = tp(ABT, l - 1);
                     p.aux = rm(H, l - 1); p.aux_is_h = 1; p.aux1 = rm(AEX, l - 1);
                 } else { p.ep = tc::TEP_PLAIN_SOA; p.out_f32 = SB6 + (long long)i * DB; p.n_limit = D; }   // sbar_i, kept for the earlier stages
-                GCK(tc::gemm(rm(AB, l), w->rs(nout), w16n + w->w16n_off[l], w->rs(nout), p, st));
+                if (chained) {
+                    // backprop of layer l: A = AB_l (backprop l + 1 / cotangent kernel), aux1 = AEX_{l-1} (tangent l - 1)
+                    bp_idx[l] = add_step(rm(AB, l), w->rs(nout), w16n + w->w16n_off[l], w->rs(nout), p, l == NL - 1 ? -1 : bp_idx[l + 1],
+                                         l > 0 ? tan_idx[l - 1] : -1);
+                    if (pending_wgrad >= 0) add_wgrad(pending_wgrad);
+                    pending_wgrad = l;
+                } else {
+                    GCK(tc::gemm(rm(AB, l), w->rs(nout), w16n + w->w16n_off[l], w->rs(nout), p, st));
+                }
+            }
+            if (chained) {
+                add_wgrad(pending_wgrad);
+                GCK(tc::gemm_chain(w->chain, 3, cst, ncs, nullptr, st));
+                for (int l = NL - 1; l >= 0; --l) GCK(tc::row_sums(tp(ABT, l), rsT, loT, split, w->n[l + 1], B, wpart + w->boff[l], st));
             }
             w->launches += 2 + 2 * NL + (NL - 1) + 3 * NL;
         }

@@ -2,6 +2,7 @@
 // bf16 packing kernels, and a self-test entry point.
 #include <algorithm>
 #include "tc_gemm.cuh"
+#include "tc_chain.cuh"
 
 #include <cstring>
 #include <vector>
@@ -127,6 +128,134 @@ cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, 
     if (g.split) return bn == 256 ? launch<true, 256>(ICNF_TC_MAPS, g, ds.sms, st) : launch<true, 128>(ICNF_TC_MAPS, g, ds.sms, st);
     return bn == 256 ? launch<false, 256>(ICNF_TC_MAPS, g, ds.sms, st) : launch<false, 128>(ICNF_TC_MAPS, g, ds.sms, st);
 #undef ICNF_TC_MAPS
+}
+
+// ---- GEMM chains (tc_chain.cuh) -------------------------------------------------------------------------------
+struct ChainSlot {
+    bool valid = false;
+    int n = 0;
+    ChainStep steps[CHAIN_MAXG];
+    ChainParams P;
+};
+struct ChainState {
+    unsigned* flags = nullptr;   // two counter sets
+    int nflags = 0;              // counters per set
+    int row_stride = 0;
+    unsigned parity = 0;
+    ChainSlot slot[8];
+    int dev = -1;
+};
+ChainState* chain_state_create() { return new ChainState(); }
+void chain_state_destroy(ChainState* cs) {
+    if (!cs) return;
+    if (cs->flags) cudaFree(cs->flags);
+    delete cs;
+}
+
+static long long* g_chain_trace = nullptr;
+static bool build_chain_gemm(const ChainStep& s, ChainGemm& o) {
+    const TcArgs& g = s.g;
+    const uint64_t ka = g.split ? (uint64_t)g.lo_a + g.K : (uint64_t)g.K;
+    const uint64_t kb = g.split ? (uint64_t)g.lo_b + g.K : (uint64_t)g.K;
+    if (!make_map(&o.mapA, s.A, (uint64_t)g.M, ka, (uint64_t)s.lda, TBM) || !make_map(&o.mapB, s.B, (uint64_t)g.N, kb, (uint64_t)s.ldb, 128))
+        return false;
+    if (g.K2 > 0) {
+        const uint64_t ka2 = g.split ? (uint64_t)g.lo_a2 + g.K2 : (uint64_t)g.K2;
+        const uint64_t kb2 = g.split ? (uint64_t)g.lo_b2 + g.K2 : (uint64_t)g.K2;
+        if (!s.A2 || !s.B2 || !make_map(&o.mapA2, s.A2, (uint64_t)g.M, ka2, (uint64_t)s.lda2, TBM) ||
+            !make_map(&o.mapB2, s.B2, (uint64_t)g.N2, kb2, (uint64_t)s.ldb2, 128))
+            return false;
+    } else {
+        o.mapA2 = o.mapA; o.mapB2 = o.mapB;
+    }
+    o.mapO0 = o.mapA; o.mapO1 = o.mapA;
+    const uint64_t ocols = g.split ? 2 * (uint64_t)g.lo_o : (uint64_t)g.ldo;
+    if (g.out0 && (((g.split ? g.lo_o : g.ldo) & 15) || !make_out_map(&o.mapO0, g.out0, (uint64_t)g.M, ocols, (uint64_t)g.ldo))) return false;
+    if (g.out1 && !make_out_map(&o.mapO1, g.out1, (uint64_t)g.M, ocols, (uint64_t)g.ldo)) return false;
+    o.g = g;
+    return true;
+}
+
+cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, const int* done, cudaStream_t st, long long* trace) {
+    if (!cs || slot < 0 || slot >= 8 || n < 1 || n > CHAIN_MAXG) return cudaErrorInvalidValue;
+    DevState& ds = dev_state();
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(tc_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(false, 128));
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tc_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true, 128));
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    if (!ds.sms) cudaDeviceGetAttribute(&ds.sms, cudaDevAttrMultiProcessorCount, dev);
+    ChainSlot& sl = cs->slot[slot];
+    const bool same = sl.valid && sl.n == n && memcmp(sl.steps, steps, sizeof(ChainStep) * n) == 0;
+    if (!same) {
+        sl.valid = false;
+        memset(&sl.P, 0, sizeof sl.P);
+        int work = 0, max_rows = 1;
+        const int split = steps[0].g.split;
+        for (int i = 0; i < n; ++i) {
+            const ChainStep& s = steps[i];
+            if (s.g.split != split) return cudaErrorInvalidValue;
+            ChainGemm& o = sl.P.gm[i];
+            if (!build_chain_gemm(s, o)) return cudaErrorInvalidValue;
+            const int ntm = (s.g.M + TBM - 1) / TBM;
+            o.ntn = (s.g.N + 127) / 128;
+            o.nsl = s.g.nslices > 1 ? s.g.nslices : 1;
+            o.nwork = ntm * o.ntn * o.nsl;
+            o.work_begin = work;
+            work += o.nwork;
+            max_rows = std::max(max_rows, ntm);
+            for (int k = 0; k < 2; ++k) {
+                o.dep_row[k] = s.dep_row[k]; o.dep_all[k] = s.dep_all[k];
+                if (s.dep_row[k] >= i || s.dep_all[k] >= i) return cudaErrorInvalidValue;   // only earlier steps
+                if (s.dep_row[k] >= 0) {
+                    const ChainGemm& d = sl.P.gm[s.dep_row[k]];
+                    if ((d.g.M + TBM - 1) / TBM != ntm) return cudaErrorInvalidValue;          // row tiles must correspond
+                    o.row_target[k] = (unsigned)(d.ntn * d.nsl * 4 * WQ);
+                }
+                if (s.dep_all[k] >= 0) o.all_target[k] = (unsigned)(sl.P.gm[s.dep_all[k]].nwork * 4 * WQ);
+            }
+        }
+        sl.P.ngemm = n; sl.P.nwork = work;
+        sl.P.row_stride = max_rows;
+        memcpy(sl.steps, steps, sizeof(ChainStep) * n);
+        sl.n = n;
+        sl.valid = true;
+    }
+    // counters: one allocation serves every slot (launches of a workspace are ordered on its stream)
+    const int need = CHAIN_MAXG * sl.P.row_stride + CHAIN_MAXG;
+    if (need > cs->nflags || cs->dev != dev) {
+        if (cs->flags) { cudaStreamSynchronize(st); cudaFree(cs->flags); cs->flags = nullptr; }
+        const int cap = std::max(need, CHAIN_MAXG * 2048 + CHAIN_MAXG);
+        cudaError_t e = cudaMalloc(&cs->flags, sizeof(unsigned) * 2 * (size_t)cap);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(cs->flags, 0, sizeof(unsigned) * 2 * (size_t)cap, st);
+        if (e != cudaSuccess) return e;
+        cs->nflags = cap; cs->dev = dev; cs->parity = 0;
+    }
+    // development aid: ICNF_CHAIN_TRACE=<slot> records the timeline of CTA 0 of every launch of that slot (the last one
+    // stays readable through icnf_tc_chain_trace_fetch)
+    static const int trace_slot = [] { const char* e = getenv("ICNF_CHAIN_TRACE"); return e ? atoi(e) : -1; }();
+    if (!trace && trace_slot == slot) {
+        if (!g_chain_trace) cudaMalloc(&g_chain_trace, 8 * 3 * 8192);
+        if (g_chain_trace) { cudaMemsetAsync(g_chain_trace, 0, 8 * 3 * 8192, st); trace = g_chain_trace; }
+    }
+    ChainParams& P = sl.P;
+    P.flags = cs->flags + (size_t)(cs->parity & 1u) * cs->nflags;
+    P.flags_next = cs->flags + (size_t)((cs->parity + 1u) & 1u) * cs->nflags;
+    P.nflags = cs->nflags;
+    P.done = done;
+    P.trace = trace;
+    { static const int dbg = [] { const char* e = getenv("ICNF_CHAIN_DBG"); return e ? atoi(e) : 0; }(); P.dbg = dbg; }
+    cs->parity++;
+    const dim3 grid((unsigned)std::min<long long>(P.nwork, (long long)ds.sms));
+    if (steps[0].g.split) tc_chain_kernel<true><<<grid, TTHREADS, smem_bytes(true, 128), st>>>(P);
+    else tc_chain_kernel<false><<<grid, TTHREADS, smem_bytes(false, 128), st>>>(P);
+    return cudaGetLastError();
 }
 
 // ---- packing kernels ------------------------------------------------------------------------
@@ -332,6 +461,12 @@ extern "C" __attribute__((visibility("default"))) int icnf_tc_wgrad_selftest(int
     return rc;
 }
 
+
+extern "C" __attribute__((visibility("default"))) int icnf_tc_chain_trace_fetch(long long* out) {
+    if (!icnf::tc::g_chain_trace) return 1;
+    cudaDeviceSynchronize();
+    return cudaMemcpy(out, icnf::tc::g_chain_trace, 8 * 3 * 8192, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 2;
+}
 
 // Development aid: timeline (clock64 of CTA 0's TMA, MMA and first epilogue warp) of one GEMM of the forward kind
 // (TEP_ACT epilogue, split or plain operands) on synthetic operands.  `out` receives 3 x 8192 long longs (see TcArgs::trace).

@@ -97,6 +97,32 @@ struct TcArgs {
     long long* trace;
 };
 
+// ---- GEMM chains: several dependent GEMMs in ONE persistent launch ------------------------------------------------
+// The GEMMs of an RHS evaluation (forward layers, VJP chain) or of a reverse-sweep stage (tangent pass, weight
+// gradients, backprop) depend on each other only through the row tile (128 samples) they share, or -- the weight
+// gradients, whose reduction runs over the samples -- through a whole earlier GEMM.  gemm_chain() runs such a list as
+// one kernel: every CTA walks the concatenated work list in order, the TMA producer of a work item waits on device-side
+// counters until the items it reads have been published, and the epilogue warps publish theirs once their stores have
+// completed.  The epilogue of one GEMM's last tiles then overlaps the main loop of the next GEMM's first ones, and the
+// launch gaps and per-launch pipeline fills of a layer-by-layer sequence disappear.
+constexpr int CHAIN_MAXG = 12;
+struct ChainStep {
+    const __nv_bfloat16 *A, *B, *A2, *B2;
+    long long lda, ldb, lda2, ldb2;
+    TcArgs g;
+    int dep_row[2];   // earlier steps of the chain whose outputs this step reads by row tile (A operand, aux arrays); -1 = none
+    int dep_all[2];   // earlier steps that must be complete before any tile of this one starts (operands with K = samples); -1 = none
+};
+struct ChainState;   // device counters + cached launch parameters (tensor maps) of the chains of one workspace
+ChainState* chain_state_create();
+void chain_state_destroy(ChainState*);
+// slot: which cached parameter block to compare against / refill (one per call site, < 8)
+cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, const int* done, cudaStream_t st, long long* trace = nullptr);
+inline bool chain_enabled() {
+    static const int on = [] { const char* e = getenv("ICNF_TC_CHAIN"); return e ? atoi(e) : 1; }();
+    return on != 0 && tile_mode(512) == 1;   // chains run 128 x 128 tiles
+}
+
 // A (M x K) and B (N x K), both K contiguous; A2/B2: the optional second segment
 cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, TcArgs g, cudaStream_t st,
                  const __nv_bfloat16* A2 = nullptr, long long lda2 = 0, const __nv_bfloat16* B2 = nullptr, long long ldb2 = 0);

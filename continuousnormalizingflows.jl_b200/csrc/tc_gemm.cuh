@@ -125,6 +125,13 @@ struct EpiStore {
     int lane;
     int m_warp;              // first row of this warp
     int lo_o;                // column offset of the lo half in the output rows
+    // direct mode (GEMM chains): every lane stores its row's NC columns straight from registers -- one full 32-byte
+    // sector per half.  A bulk tensor store queues behind the producer's operand loads in the SM's TMA unit, so a warp
+    // that recycles one staging box per chunk waits out that queue for every chunk: measured, the epilogue of a tile
+    // then takes twice as long as its main loop and sets the pace of the whole chain.
+    bool direct = false;
+    bool row_ok = false;
+    long long row_off = 0;   // m * ldo
 };
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)),
@@ -132,7 +139,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                  : "memory");
 }
 template <bool SPLIT>
-__device__ __forceinline__ void store_rows(const EpiStore& es, const CUtensorMap* map, int nb, const float (&v)[NC]) {
+__device__ __forceinline__ void store_rows(const EpiStore& es, const CUtensorMap* map, __nv_bfloat16* base, int nb, const float (&v)[NC]) {
     uint32_t hp[NC / 2], lp[NC / 2];
 #pragma unroll
     for (int j = 0; j < NC; j += 2) {
@@ -145,6 +152,19 @@ __device__ __forceinline__ void store_rows(const EpiStore& es, const CUtensorMap
         } else {
             hp[j / 2] = pack_bf16(v[j], v[j + 1]);
         }
+    }
+    if (es.direct) {
+        if (es.row_ok) {
+            uint4* hrow = reinterpret_cast<uint4*>(base + es.row_off + nb);
+#pragma unroll
+            for (int q = 0; q < NC / 8; ++q) __stcg(hrow + q, make_uint4(hp[4 * q], hp[4 * q + 1], hp[4 * q + 2], hp[4 * q + 3]));
+            if constexpr (SPLIT) {
+                uint4* lrow = reinterpret_cast<uint4*>(base + es.row_off + es.lo_o + nb);
+#pragma unroll
+                for (int q = 0; q < NC / 8; ++q) __stcg(lrow + q, make_uint4(lp[4 * q], lp[4 * q + 1], lp[4 * q + 2], lp[4 * q + 3]));
+            }
+        }
+        return;
     }
     // the previous boxes of this warp have been read out of the staging buffer
     if (es.lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -171,11 +191,11 @@ __device__ __forceinline__ void load_row(const __nv_bfloat16* base, size_t row_o
 #pragma unroll
     for (int q = 0; q < NC / 8; ++q) {
         if (nb + q * 8 < pitch) {
-            const uint4 a4 = *reinterpret_cast<const uint4*>(base + row_off + nb + q * 8);
+            const uint4 a4 = __ldcg(reinterpret_cast<const uint4*>(base + row_off + nb + q * 8));   // L2: another SM may have written it in this launch (chains)
             const uint32_t aw[4] = {a4.x, a4.y, a4.z, a4.w};
             uint32_t lw[4] = {0u, 0u, 0u, 0u};
             if constexpr (SPLIT) {
-                const uint4 l4 = *reinterpret_cast<const uint4*>(base + row_off + lo_o + nb + q * 8);
+                const uint4 l4 = __ldcg(reinterpret_cast<const uint4*>(base + row_off + lo_o + nb + q * 8));
                 lw[0] = l4.x; lw[1] = l4.y; lw[2] = l4.z; lw[3] = l4.w;
             }
 #pragma unroll
@@ -193,6 +213,36 @@ __device__ __forceinline__ void load_row(const __nv_bfloat16* base, size_t row_o
         } else {
 #pragma unroll
             for (int e = 0; e < 8; ++e) v[q * 8 + e] = 0.f;
+        }
+    }
+}
+
+// the same NC columns as raw bf16 pairs (x[0..1] = hi half, x[2..3] = lo half), for a load issued one chunk ahead of its use
+struct RawRow { uint4 x[4]; };
+template <bool SPLIT>
+__device__ __forceinline__ void load_row_raw(const __nv_bfloat16* base, size_t row_off, int nb, int pitch, int lo_o, RawRow& o) {
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+        o.x[q] = make_uint4(0u, 0u, 0u, 0u);
+        o.x[2 + q] = make_uint4(0u, 0u, 0u, 0u);
+        if (nb + q * 8 < pitch) {
+            o.x[q] = __ldcg(reinterpret_cast<const uint4*>(base + row_off + nb + q * 8));
+            if constexpr (SPLIT) o.x[2 + q] = __ldcg(reinterpret_cast<const uint4*>(base + row_off + lo_o + nb + q * 8));
+        }
+    }
+}
+template <bool SPLIT>
+__device__ __forceinline__ void raw_to_f32(const RawRow& o, float (&v)[NC]) {
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) {
+        const uint32_t aw[4] = {o.x[q].x, o.x[q].y, o.x[q].z, o.x[q].w};
+        const uint32_t lw[4] = {o.x[2 + q].x, o.x[2 + q].y, o.x[2 + q].z, o.x[2 + q].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            float x0 = __uint_as_float(aw[e] << 16), x1 = __uint_as_float(aw[e] & 0xffff0000u);
+            if constexpr (SPLIT) { x0 += __uint_as_float(lw[e] << 16); x1 += __uint_as_float(lw[e] & 0xffff0000u); }
+            v[q * 8 + e * 2] = x0;
+            v[q * 8 + e * 2 + 1] = x1;
         }
     }
 }
@@ -229,8 +279,9 @@ __device__ __forceinline__ float act_deriv_from_h(int act, float h) {
 }
 // the sigma' values of a chunk: loaded, or derived from the loaded h
 template <bool SPLIT>
-__device__ __forceinline__ void load_deriv(const TcArgs& g, size_t row_off, int nb, int pitch, float (&dv)[NC]) {
-    load_row<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
+__device__ __forceinline__ void load_deriv(const TcArgs& g, size_t row_off, int nb, int pitch, float (&dv)[NC], const RawRow* pre = nullptr) {
+    if (pre) raw_to_f32<SPLIT>(*pre, dv);
+    else load_row<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
     if (g.aux_is_h) {
         if (g.act == ICNF_ACT_SOFTPLUS) {
 #pragma unroll
@@ -262,7 +313,7 @@ __device__ __forceinline__ void store_colT(__nv_bfloat16* outT, long long ldT, i
 template <bool SPLIT>
 __device__ __forceinline__ void tc_epilogue(const TcArgs& g, const CUtensorMap* mapO0, const CUtensorMap* mapO1, const EpiStore& es,
                                             const uint32_t (&r)[NC], bool row_ok, int m, int nb, const float* sbc, int sl, int pitch,
-                                            float& rowsum) {
+                                            float& rowsum, const RawRow* pre = nullptr) {   // pre: g.aux's columns of this chunk, already loaded
     const size_t row_off = (size_t)m * g.ldo;
     auto zero = [](float (&v)[NC]) {
 #pragma unroll
@@ -283,15 +334,15 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& g, const CUtensorMap* 
                 if (nb + j < g.N) act_eval_rt(g.act, __uint_as_float(r[j]) + sbc[j], hv[j], dv[j]);
             }
         }
-        store_rows<SPLIT>(es, mapO0, nb, hv);
-        if (g.out1) store_rows<SPLIT>(es, mapO1, nb, dv);
+        store_rows<SPLIT>(es, mapO0, g.out0, nb, hv);
+        if (g.out1) store_rows<SPLIT>(es, mapO1, g.out1, nb, dv);
         if (g.outT && row_ok) store_colT<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, hv);
     } else if (g.ep == TEP_MULD) {
         float dv[NC], gv[NC];
-        if (row_ok) load_deriv<SPLIT>(g, row_off, nb, pitch, dv); else zero(dv);
+        if (row_ok) load_deriv<SPLIT>(g, row_off, nb, pitch, dv, pre); else zero(dv);
 #pragma unroll
         for (int j = 0; j < NC; ++j) gv[j] = (nb + j < g.N) ? __uint_as_float(r[j]) * dv[j] : 0.f;
-        store_rows<SPLIT>(es, mapO0, nb, gv);
+        store_rows<SPLIT>(es, mapO0, g.out0, nb, gv);
         if (g.outT && row_ok) store_colT<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, gv);
     } else if (g.ep == TEP_TANGENT) {
         float dv[NC], gv[NC], o0[NC], o1[NC];
@@ -299,7 +350,7 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& g, const CUtensorMap* 
         if (row_ok) {
             load_row<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, gv);
             if (g.act != ICNF_ACT_SOFTPLUS) load_row<SPLIT>(g.aux2, row_off, nb, pitch, g.lo_o, hv);   // phi needs h itself
-            load_deriv<SPLIT>(g, row_off, nb, pitch, dv);
+            load_deriv<SPLIT>(g, row_off, nb, pitch, dv, pre);
         } else { zero(dv); zero(gv); zero(hv); }
         if (g.act == ICNF_ACT_SOFTPLUS) {
 #pragma unroll
@@ -316,16 +367,16 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& g, const CUtensorMap* 
                 o1[j] = rr * gv[j] * act_ratio_rt(g.act, hv[j], dv[j]);
             }
         }
-        store_rows<SPLIT>(es, mapO0, nb, o0);
-        store_rows<SPLIT>(es, mapO1, nb, o1);
+        store_rows<SPLIT>(es, mapO0, g.out0, nb, o0);
+        store_rows<SPLIT>(es, mapO1, g.out1, nb, o1);
         if (g.outT && row_ok) store_colT<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, o0);
     } else if (g.ep == TEP_MULADD) {
         float dv[NC], ax[NC], o0[NC];
-        if (row_ok) { load_row<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, ax); load_deriv<SPLIT>(g, row_off, nb, pitch, dv); }
+        if (row_ok) { load_row<SPLIT>(g.aux1, row_off, nb, pitch, g.lo_o, ax); load_deriv<SPLIT>(g, row_off, nb, pitch, dv, pre); }
         else { zero(dv); zero(ax); }
 #pragma unroll
         for (int j = 0; j < NC; ++j) o0[j] = (nb + j < g.N) ? fmaf(__uint_as_float(r[j]), dv[j], ax[j]) : 0.f;
-        store_rows<SPLIT>(es, mapO0, nb, o0);
+        store_rows<SPLIT>(es, mapO0, g.out0, nb, o0);
         if (g.outT && row_ok) store_colT<SPLIT>(g.outT, g.ldT, g.lo_T, nb, g.N, m, o0);
     } else if (!row_ok) {
         return;
@@ -341,7 +392,8 @@ __device__ __forceinline__ void tc_epilogue(const TcArgs& g, const CUtensorMap* 
             if (nb + j < g.N) __stcg(base + (long long)(nb + j) * g.ldw, old[j] + __uint_as_float(r[j]));   // a warp covers 32 consecutive m: coalesced
     } else if (g.ep == TEP_TRACE) {
         float dv[NC];
-        load_row<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
+        if (pre) raw_to_f32<SPLIT>(*pre, dv);
+        else load_row<SPLIT>(g.aux, row_off, nb, pitch, g.lo_o, dv);
 #pragma unroll
         for (int j = 0; j < NC; ++j)
             if (nb + j < g.N) rowsum = fmaf(__uint_as_float(r[j]), dv[j], rowsum);
@@ -529,12 +581,16 @@ __global__ void __launch_bounds__(TTHREADS, 1)
                 if (n0 + c0 >= g.N) break;   // warp-uniform
                 const bool more1 = (ci + 1 < nch) && (n0 + c0 + NC < g.N);
                 if (more1) tmem_ld16(trow + (uint32_t)(c0 + NC), rb);
+                if (threadIdx.x == 0) trace_event(g.trace, 16384, 6000 + ci);
                 tc_epilogue<SPLIT>(g, &mapO0, &mapO1, es, ra, row_ok, m, n0 + c0, sb + c0, sl, pitch, rowsum);
+                if (threadIdx.x == 0) trace_event(g.trace, 16384, 7000 + ci);
                 if (!more1) break;
                 tmem_wait_ld();
                 const bool more2 = (ci + 2 < nch) && (n0 + c0 + 2 * NC < g.N);
                 if (more2) tmem_ld16(trow + (uint32_t)(c0 + 2 * NC), ra);
+                if (threadIdx.x == 0) trace_event(g.trace, 16384, 6000 + ci + 1);
                 tc_epilogue<SPLIT>(g, &mapO0, &mapO1, es, rb, row_ok, m, n0 + c0 + NC, sb + c0 + NC, sl, pitch, rowsum);
+                if (threadIdx.x == 0) trace_event(g.trace, 16384, 7000 + ci + 1);
                 if (more2) tmem_wait_ld();
             }
             // this warp's TMEM reads of the tile are complete (tcgen05.wait::ld above): hand the buffer back

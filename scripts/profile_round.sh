@@ -27,4 +27,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --l
     python scripts/time_config3.py fp32 > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm_ws -s 41 -c 1 -o gpurun_out/prof_generic_ws \
     python scripts/time_config3.py fp32 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 700 --csv --log-file gpurun_out/launches_train4.csv \
+    python scripts/time_train4.py bf16x3_tc > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 520 -c 6 -o gpurun_out/prof_tc_train \
+    python scripts/time_train4.py bf16x3_tc > /dev/null 2>&1
+python scripts/time_train4.py bf16x3_tc > gpurun_out/time_train4.txt 2>&1
 ls -la gpurun_out

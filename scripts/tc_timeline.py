@@ -20,6 +20,6 @@ for r in range(3):
 ev.sort()
 t0 = ev[0][0]
 print(f"GEMM {M}x{N}x{K} split={split} ep={ep} mode={os.environ.get('ICNF_TC_MODE','auto')}: {len(ev)} events, span {ev[-1][0]-t0} cycles")
-names = {1: "tma", 2: "landed", 3: "mma", 4: "acc_ready", 5: "epi_done"}
+names = {1: "tma", 2: "landed", 3: "mma", 4: "acc_ready", 5: "epi_done", 6: "chunk_begin", 7: "chunk_end"}
 for t, tag in ev:
     print(f"{t - t0:8d}  {names[tag // 1000]:10s} {tag % 1000}")
