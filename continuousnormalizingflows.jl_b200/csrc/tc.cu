@@ -130,10 +130,18 @@ cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, 
 #undef ICNF_TC_MAPS
 }
 
+int& knob(int which) {
+    static int v[4] = {[] { const char* e = getenv("ICNF_TC_CHAIN"); return e ? atoi(e) : 1; }(),
+                       [] { const char* e = getenv("ICNF_CHAIN_DIRECT"); return e ? atoi(e) : -1; }(),
+                       [] { const char* e = getenv("ICNF_CHAIN_SG"); return e ? atoi(e) : 1; }(), 0};
+    return v[which & 3];
+}
+
 // ---- GEMM chains (tc_chain.cuh) -------------------------------------------------------------------------------
 struct ChainSlot {
     bool valid = false;
     int n = 0;
+    int sg_knob = -1;
     ChainStep steps[CHAIN_MAXG];
     ChainParams P;
 };
@@ -191,7 +199,7 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
     }
     if (!ds.sms) cudaDeviceGetAttribute(&ds.sms, cudaDevAttrMultiProcessorCount, dev);
     ChainSlot& sl = cs->slot[slot];
-    const bool same = sl.valid && sl.n == n && memcmp(sl.steps, steps, sizeof(ChainStep) * n) == 0;
+    const bool same = sl.valid && sl.n == n && sl.sg_knob == knob(2) && memcmp(sl.steps, steps, sizeof(ChainStep) * n) == 0;
     if (!same) {
         sl.valid = false;
         memset(&sl.P, 0, sizeof sl.P);
@@ -222,8 +230,26 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
         }
         sl.P.ngemm = n; sl.P.nwork = work;
         sl.P.row_stride = max_rows;
+        // super-groups of row tiles (see ChainParams): every GEMM over the same rows, no whole-GEMM dependency, and more row
+        // tiles than three rounds of the grid can hold
+        {
+            bool uniform = true;
+            int row_items = 0, max_ntn = 1;
+            const int ntm0 = (steps[0].g.M + TBM - 1) / TBM;
+            for (int i = 0; i < n; ++i) {
+                const ChainGemm& o = sl.P.gm[i];
+                if ((steps[i].g.M + TBM - 1) / TBM != ntm0 || steps[i].dep_all[0] >= 0 || steps[i].dep_all[1] >= 0) uniform = false;
+                row_items += o.ntn * o.nsl;
+                max_ntn = std::max(max_ntn, o.ntn * o.nsl);
+            }
+            const int rg = std::max(1, 3 * ds.sms / max_ntn);
+            const int sg_on = knob(2);
+            if (uniform && sg_on && ntm0 > rg) { sl.P.rg = rg; sl.P.ntm = ntm0; sl.P.row_items = row_items; }
+            else { sl.P.rg = 0; sl.P.ntm = ntm0; sl.P.row_items = row_items; }
+        }
         memcpy(sl.steps, steps, sizeof(ChainStep) * n);
         sl.n = n;
+        sl.sg_knob = knob(2);
         sl.valid = true;
     }
     // counters: one allocation serves every slot (launches of a workspace are ordered on its stream)
@@ -250,6 +276,9 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
     P.nflags = cs->nflags;
     P.done = done;
     P.trace = trace;
+    // row-major outputs leave through bulk tensor stores; 16-byte stores straight from the registers (knob 1) measured
+    // equal on the 8192-sample shapes and 10 % slower on the large-batch ones (scripts/ab_chain.py)
+    P.direct_stores = knob(1) > 0 ? 1 : 0;
     { static const int dbg = [] { const char* e = getenv("ICNF_CHAIN_DBG"); return e ? atoi(e) : 0; }(); P.dbg = dbg; }
     cs->parity++;
     const dim3 grid((unsigned)std::min<long long>(P.nwork, (long long)ds.sms));
@@ -461,6 +490,8 @@ extern "C" __attribute__((visibility("default"))) int icnf_tc_wgrad_selftest(int
     return rc;
 }
 
+
+extern "C" __attribute__((visibility("default"))) void icnf_tc_knob_set(int which, int value) { icnf::tc::knob(which) = value; }
 
 extern "C" __attribute__((visibility("default"))) int icnf_tc_chain_trace_fetch(long long* out) {
     if (!icnf::tc::g_chain_trace) return 1;

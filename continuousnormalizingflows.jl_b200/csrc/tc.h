@@ -118,10 +118,10 @@ ChainState* chain_state_create();
 void chain_state_destroy(ChainState*);
 // slot: which cached parameter block to compare against / refill (one per call site, < 8)
 cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, const int* done, cudaStream_t st, long long* trace = nullptr);
-inline bool chain_enabled() {
-    static const int on = [] { const char* e = getenv("ICNF_TC_CHAIN"); return e ? atoi(e) : 1; }();
-    return on != 0 && tile_mode(512) == 1;   // chains run 128 x 128 tiles
-}
+// tuning knobs (environment at first use; icnf_tc_knob_set changes them at run time for A/B measurements in one process):
+// 0 = chains on/off (ICNF_TC_CHAIN), 1 = direct row stores: -1 auto / 0 / 1 (ICNF_CHAIN_DIRECT), 2 = row-tile super-groups (ICNF_CHAIN_SG)
+int& knob(int which);
+inline bool chain_enabled() { return knob(0) != 0 && tile_mode(512) == 1; }   // chains run 128 x 128 tiles
 
 // A (M x K) and B (N x K), both K contiguous; A2/B2: the optional second segment
 cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, long long ldb, TcArgs g, cudaStream_t st,

@@ -8,7 +8,7 @@ icnf = m.ICNF(nvariables=16, naugments=0, precision=prec)
 rng = np.random.default_rng(7)
 theta, _ = m.setup(rng, icnf)
 xs = torch.from_numpy(rng.standard_normal((B, 16)).astype(np.float32)).cuda()
-for i in range(3):
+for i in range(6):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     m.inference(icnf, m.TestMode(), xs.t(), theta, {}, adaptive=False, dt=0.25)

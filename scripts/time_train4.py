@@ -10,7 +10,7 @@ rng = np.random.default_rng(7)
 theta, _ = m.setup(rng, icnf)
 theta_d = torch.from_numpy(theta).cuda()
 xs = torch.from_numpy(rng.standard_normal((B, 784)).astype(np.float32)).cuda()
-for i in range(4):
+for i in range(6):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     m.loss_and_gradient(icnf, m.TrainMode(True), xs.t(), theta_d, {}, seed=3, adaptive=False, dt=0.25)

@@ -9,7 +9,7 @@ icnf = m.ICNF(nvariables=784, naugments=0, nn=ffjord, precision=prec, epsdist="r
 rng = np.random.default_rng(7)
 theta, _ = m.setup(rng, icnf)
 xs = torch.from_numpy(rng.standard_normal((B, 784)).astype(np.float32)).cuda()
-for i in range(3):
+for i in range(6):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     m.inference(icnf, m.TrainMode(False), xs.t(), theta, {}, seed=3, adaptive=False, dt=0.25)
