@@ -1,539 +1,16 @@
-// narrow.cu -- "narrow" fast path of the generic family: the whole exact-trace (TestMode) Tsit5 solve of a narrow MLP
-// with two hidden layers (every width <= 128, D' <= 32: BASELINE config 3, ICNF(nvariables = 3..7), 3-64-64-2) in ONE
-// persistent cooperative kernel, any widths at run time.
-//
-// What it computes (reference, paths relative to the reference root): augmented_f in TestMode, src/core/icnf.jl:297-316,
-// with the exact trace that utils.jl:35-54 obtains from D' one-hot pullbacks, here in closed form
-//     tr J = d2' (W2 .* (W1z W3)') d1                      (the matrix comes from generic.cu's on_params)
-// integrated by Tsit5 (base_sol, src/core/base_icnf.jl:134-140) with the whole-batch RMS error norm, fused with
-// inference_prob (:247-296), inference_sol (:158-172), reg_z_aug (:106-132) and generate_sol (:185-194).
-//
-// Design.  A CTA of 8 warps owns a tile of 128 samples for a whole step attempt: all six Tsit5 stages of the tile run
-// out of shared memory and registers, and only the state and the FSAL derivative cross HBM (2 x 2 x S floats per
-// sample and attempt).  The weights (transposed, padded) stay in shared memory for the life of the kernel.  A layer is a
-// small SGEMM: warp w owns output units [w jt, (w + 1) jt), lane l owns samples 4 l .. 4 l + 3; per input k the warp
-// reads its units' weights with broadcast 128-bit loads and its samples' activations with one conflict-free 128-bit load,
-// and issues packed FP32 FMAs (fma.rn.f32x2) on (unit pair) x sample accumulators.  The second hidden layer accumulates
-// the trace contraction (A d1) next to (W2 h1) in the same k loop.  The thread that computes a z-row's derivative also
-// owns that row's Tsit5 state (k1..k5, the solution and error sums) in registers, so stage combination, error norm and
-// accept / reject never leave the kernel; the controller is the tiny family's (one grid-wide reduction per attempt).
-#include <cooperative_groups.h>
-
+// narrow.cu -- host side of the narrow fast path (kernel: narrow_kernel.cuh; instantiations: narrow_inst_*.cu)
 #include <algorithm>
 #include <cstring>
 
-#include "tiny.cuh"
-#include "narrow.h"
+#include "narrow_kernel.cuh"
 
 namespace icnf {
 namespace narrow {
 
-namespace cg = cooperative_groups;
-using tiny::c_a;
-using tiny::c_bt;
-using tiny::c_c;
-
-constexpr int NW = 8, NTHR = NW * 32, SPT = 4, NS = 32 * SPT;
-
-struct Layout {            // shared-memory offsets in floats
-    int n0, n1, n2, D, C, tin, act;
-    int jt1, jt2, jt3;     // output units per warp of layers 1..3
-    int ld12, ld3;         // padded row length of the transposed weights: 8 * JP / 8 * JP3
-    int w1, b1, w2, at, b2, w3, b3, x, h1, d1, h2, red, total;
-};
-
-struct Params {
-    SolveArgs a;
-    const float* amat;     // exact-trace matrix, (j, k) at k * n2 + j  (generic.cu g_trace_matrix_kernel)
-    Layout L;
-    int nvars, adaptive;
-    long long woff[3], boff[3];
-};
-
-__device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
-
-// acc[jp][s] (+)= sum_k Wt[k][warp slot 2 jp, 2 jp + 1] * act[k][4 lane + s];  DUAL: the same for (Wt2, act2) -> acc2
-template <int JP, bool DUAL>
-__device__ __forceinline__ void layer_mm(const float* __restrict__ wt, const float* __restrict__ wt2, int ldw,
-                                         const float* __restrict__ act, const float* __restrict__ act2, int nin, int lane,
-                                         float2 (&acc)[JP / 2][SPT], float2 (&acc2)[JP / 2][SPT]) {
-#pragma unroll
-    for (int p = 0; p < JP / 2; ++p)
-#pragma unroll
-        for (int s = 0; s < SPT; ++s) { acc[p][s] = f2(0.f, 0.f); if (DUAL) acc2[p][s] = f2(0.f, 0.f); }
-    const float* ap = act + 4 * lane;
-    const float* ap2 = act2 + 4 * lane;
-#pragma unroll 2
-    for (int k = 0; k < nin; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(ap + k * NS);
-        const float2 as[SPT] = {f2(a.x, a.x), f2(a.y, a.y), f2(a.z, a.z), f2(a.w, a.w)};
-        if constexpr (JP >= 4) {
-#pragma unroll
-            for (int q = 0; q < JP / 4; ++q) {
-                const float4 wv = *reinterpret_cast<const float4*>(wt + k * ldw + 4 * q);
-#pragma unroll
-                for (int s = 0; s < SPT; ++s) {
-                    acc[2 * q][s] = __ffma2_rn(f2(wv.x, wv.y), as[s], acc[2 * q][s]);
-                    acc[2 * q + 1][s] = __ffma2_rn(f2(wv.z, wv.w), as[s], acc[2 * q + 1][s]);
-                }
-            }
-        } else {
-            const float2 wv = *reinterpret_cast<const float2*>(wt + k * ldw);
-#pragma unroll
-            for (int s = 0; s < SPT; ++s) acc[0][s] = __ffma2_rn(wv, as[s], acc[0][s]);
-        }
-        if constexpr (DUAL) {
-            const float4 b = *reinterpret_cast<const float4*>(ap2 + k * NS);
-            const float2 bs[SPT] = {f2(b.x, b.x), f2(b.y, b.y), f2(b.z, b.z), f2(b.w, b.w)};
-#pragma unroll
-            for (int q = 0; q < JP / 4; ++q) {
-                const float4 wv = *reinterpret_cast<const float4*>(wt2 + k * ldw + 4 * q);
-#pragma unroll
-                for (int s = 0; s < SPT; ++s) {
-                    acc2[2 * q][s] = __ffma2_rn(f2(wv.x, wv.y), bs[s], acc2[2 * q][s]);
-                    acc2[2 * q + 1][s] = __ffma2_rn(f2(wv.z, wv.w), bs[s], acc2[2 * q + 1][s]);
-                }
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ float comp(const float2& v, int odd) { return odd ? v.y : v.x; }
-
-// One RHS evaluation of the tile whose network input sits in sm[L.x].  zd[r][s] = derivative of z-row (warp jt3 + r) for
-// sample 4 lane + s (owner layout); the per-sample trace is left in sm[L.red + sample] by warp 0 (read it after the call's
-// final barrier).  Three CTA barriers.
-template <int JP, int JP3>
-__device__ __forceinline__ void rhs_tile(const Layout& L, float* sm, int warp, int lane, float (&zd)[JP3][SPT]) {
-    float2 acc[JP / 2][SPT], acc2[JP / 2][SPT];
-    // ---- layer 1: h1, d1
-    layer_mm<JP, false>(sm + L.w1 + warp * JP, nullptr, L.ld12, sm + L.x, nullptr, L.n0, lane, acc, acc2);
-#pragma unroll
-    for (int r = 0; r < JP; ++r) {
-        const int j = warp * L.jt1 + r;
-        if (r < L.jt1 && j < L.n1) {
-            const float b = sm[L.b1 + warp * JP + r];
-            float h[SPT], d[SPT];
-#pragma unroll
-            for (int s = 0; s < SPT; ++s) act_eval_rt(L.act, comp(acc[r >> 1][s], r & 1) + b, h[s], d[s]);
-            *reinterpret_cast<float4*>(sm + L.h1 + j * NS + 4 * lane) = make_float4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<float4*>(sm + L.d1 + j * NS + 4 * lane) = make_float4(d[0], d[1], d[2], d[3]);
-        }
-    }
-    __syncthreads();
-    // ---- layer 2 with the trace contraction: a2 = W2 h1 + b2, t = A d1;  h2 = act(a2), trace partial += act'(a2) .* t
-    layer_mm<JP, true>(sm + L.w2 + warp * JP, sm + L.at + warp * JP, L.ld12, sm + L.h1, sm + L.d1, L.n1, lane, acc, acc2);
-    float trp[SPT] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int r = 0; r < JP; ++r) {
-        const int j = warp * L.jt2 + r;
-        if (r < L.jt2 && j < L.n2) {
-            const float b = sm[L.b2 + warp * JP + r];
-            float h[SPT], d[SPT];
-#pragma unroll
-            for (int s = 0; s < SPT; ++s) {
-                act_eval_rt(L.act, comp(acc[r >> 1][s], r & 1) + b, h[s], d[s]);
-                trp[s] = fmaf(d[s], comp(acc2[r >> 1][s], r & 1), trp[s]);
-            }
-            *reinterpret_cast<float4*>(sm + L.h2 + j * NS + 4 * lane) = make_float4(h[0], h[1], h[2], h[3]);
-        }
-    }
-    *reinterpret_cast<float4*>(sm + L.red + (1 + warp) * NS + 4 * lane) = make_float4(trp[0], trp[1], trp[2], trp[3]);
-    __syncthreads();
-    // ---- layer 3 (linear): zdot rows of this warp; warp 0 also adds up the trace partials (fixed order)
-    float2 acc3[JP3 / 2][SPT], dummy[JP3 / 2][SPT];
-    layer_mm<JP3, false>(sm + L.w3 + warp * JP3, nullptr, L.ld3, sm + L.h2, nullptr, L.n2, lane, acc3, dummy);
-#pragma unroll
-    for (int r = 0; r < JP3; ++r) {
-        const float b = sm[L.b3 + warp * JP3 + r];
-#pragma unroll
-        for (int s = 0; s < SPT; ++s) zd[r][s] = comp(acc3[r >> 1][s], r & 1) + b;
-    }
-    if (warp == 0) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int w = 0; w < NW; ++w) {
-            const float4 v = *reinterpret_cast<const float4*>(sm + L.red + (1 + w) * NS + 4 * lane);
-            t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
-        }
-        *reinterpret_cast<float4*>(sm + L.red + 4 * lane) = t;
-    }
-    __syncthreads();
-}
-
-template <int JP, int JP3>
-__global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ Params P) {
-    extern __shared__ __align__(16) float sm[];
-    __shared__ double sred[2 * NW + 2];
-    const SolveArgs& a = P.a;
-    const Layout& L = P.L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int D = L.D, S = D + 3;
-    const long long B = a.B;
-    tiny::GridReducer red{cg::this_grid(), a.partials, sred, 0, &a.xg, 0u, false};
-    if (P.adaptive && a.xg.nranks > 1) red.seq = *reinterpret_cast<const volatile unsigned*>(a.xg.peers.p[a.xg.rank]);
-
-    // ---- weights -> shared memory (transposed, padded per warp; the padding reads as zero)
-    for (int i = threadIdx.x; i < L.x; i += NTHR) sm[i] = 0.f;
-    __syncthreads();
-    {
-        const float* th = a.theta;
-        for (int i = threadIdx.x; i < L.n0 * L.n1; i += NTHR) {       // W1 (j, k) at k * n1 + j
-            const int k = i / L.n1, j = i - k * L.n1;
-            sm[L.w1 + k * L.ld12 + (j / L.jt1) * JP + (j % L.jt1)] = th[P.woff[0] + i];
-        }
-        for (int i = threadIdx.x; i < L.n1 * L.n2; i += NTHR) {
-            const int k = i / L.n2, j = i - k * L.n2;
-            const int col = (j / L.jt2) * JP + (j % L.jt2);
-            sm[L.w2 + k * L.ld12 + col] = th[P.woff[1] + i];
-            sm[L.at + k * L.ld12 + col] = P.amat[i];
-        }
-        for (int i = threadIdx.x; i < L.n2 * D; i += NTHR) {
-            const int k = i / D, j = i - k * D;
-            sm[L.w3 + k * L.ld3 + (j / L.jt3) * JP3 + (j % L.jt3)] = th[P.woff[2] + i];
-        }
-        for (int j = threadIdx.x; j < L.n1; j += NTHR) sm[L.b1 + (j / L.jt1) * JP + (j % L.jt1)] = th[P.boff[0] + j];
-        for (int j = threadIdx.x; j < L.n2; j += NTHR) sm[L.b2 + (j / L.jt2) * JP + (j % L.jt2)] = th[P.boff[1] + j];
-        for (int j = threadIdx.x; j < D; j += NTHR) sm[L.b3 + (j / L.jt3) * JP3 + (j % L.jt3)] = th[P.boff[2] + j];
-    }
-    __syncthreads();
-
-    const float tdir = (a.t1 >= a.t0) ? 1.0f : -1.0f;
-    const float span = fabsf(a.t1 - a.t0);
-    const Controller ctl = a.ctl;
-    const double inv_count = 1.0 / ((double)(a.norm_B > 0 ? a.norm_B : B) * (double)S);
-    const long long ntiles = (B + NS - 1) / NS;
-    enum { P_INIT = 0, P_PROBE = 1, P_STEP = 2 };
-    int phase = P_INIT, cur = 0;
-    int nacc = 0, nrej = 0, nf = 0, status = ICNF_OK, attempts = 0, fixed_step = 0;
-    float t = a.t0, dt = (a.dt > 0.0f) ? fminf(a.dt, span) : 0.0f, dt0 = 0.0f, d1n = 0.0f;
-    float qold = ctl.qoldinit, dt_last = 0.0f, hmag = 0.0f;
-    bool last = false;
-    // rows of the state this thread owns: j = warp * jt3 + r, r < jt3 (and j < D); samples 4 lane .. 4 lane + 3 of the tile
-    bool own[JP3];
-#pragma unroll
-    for (int r = 0; r < JP3; ++r) own[r] = r < L.jt3 && warp * L.jt3 + r < D;
-
-    while (span > 0.0f) {
-        float h = 0.0f;
-        if (phase == P_STEP) {
-            if (P.adaptive) {
-                const float remaining = fabsf(a.t1 - t);
-                if (remaining <= 1e-7f * fmaxf(1.0f, fabsf(a.t1))) break;
-                last = dt >= remaining * (1.0f - 1e-6f);
-                hmag = last ? remaining : dt;
-                h = tdir * hmag;
-                if (!(hmag > 0.0f) || t + h == t) { status = ICNF_ERR_DT_UNDERFLOW; break; }
-                if (++attempts > ctl.max_steps) { status = ICNF_ERR_MAX_STEPS; break; }
-            } else {
-                if (fixed_step >= a.nsteps) break;
-                const float tb = fminf(span, fixed_step * a.dt);
-                hmag = fminf(a.dt, span - tb);
-                h = tdir * hmag;
-                t = a.t0 + tdir * tb;
-                last = false;
-            }
-        } else if (phase == P_PROBE) {
-            h = tdir * dt0;
-        }
-        const int nstage = (phase == P_STEP) ? 6 : 1;
-        double acc_a = 0.0, acc_b = 0.0;
-        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const long long b0 = tile * NS + 4 * lane;          // first of this lane's four samples
-            const bool in4 = b0 + 3 < B;                        // all four exist (B is not required to be a multiple of 4)
-            auto ld4 = [&](const float* base, int row) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                const float* p = base + (long long)row * B + b0;
-                if (in4 && ((B & 3) == 0)) v = *reinterpret_cast<const float4*>(p);
-                else { if (b0 < B) v.x = p[0]; if (b0 + 1 < B) v.y = p[1]; if (b0 + 2 < B) v.z = p[2]; if (b0 + 3 < B) v.w = p[3]; }
-                return v;
-            };
-            auto st4 = [&](float* base, int row, float4 v) {
-                float* p = base + (long long)row * B + b0;
-                if (in4 && ((B & 3) == 0)) *reinterpret_cast<float4*>(p) = v;
-                else { if (b0 < B) p[0] = v.x; if (b0 + 1 < B) p[1] = v.y; if (b0 + 2 < B) p[2] = v.z; if (b0 + 3 < B) p[3] = v.w; }
-            };
-            // ---- state of the tile: z rows (owners), l (warp 0)
-            float z[JP3][SPT], k1[JP3][SPT], K[4][JP3][SPT], zs[JP3][SPT], ze[JP3][SPT];
-            float lv[SPT] = {0.f, 0.f, 0.f, 0.f}, kl1[SPT] = {0.f, 0.f, 0.f, 0.f}, sl[SPT], el[SPT];
-            if (phase == P_INIT) {
-#pragma unroll
-                for (int r = 0; r < JP3; ++r) {
-                    const int j = warp * L.jt3 + r;
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        const long long b = b0 + s;
-                        float v = 0.f;
-                        if (own[r] && b < B) {
-                            if (a.in_kind == IN_U0) v = __ldg(a.in + b * S + j);
-                            else if (a.in_kind == IN_XS) v = (j < P.nvars) ? __ldg(a.in + b * P.nvars + j) : 0.f;
-                            else if (a.in_kind == IN_Z0) v = __ldg(a.in + b * D + j);
-                            else {
-                                float o[4];
-                                philox_draw4(ICNF_EPS_GAUSSIAN, a.seed, PHILOX_STREAM_BASE, a.sample_offset + b, j >> 2, o);
-                                v = o[j & 3];
-                            }
-                        }
-                        z[r][s] = v;
-                    }
-                }
-                if (warp == 0 && a.in_kind == IN_U0) {
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) if (b0 + s < B) lv[s] = __ldg(a.in + (b0 + s) * S + D);
-                }
-            } else {
-#pragma unroll
-                for (int r = 0; r < JP3; ++r) {
-                    const int j = warp * L.jt3 + r;
-                    float4 u = make_float4(0.f, 0.f, 0.f, 0.f), k = u;
-                    if (own[r]) { u = ld4(a.wu[cur], j); k = ld4(a.wk[cur], j); }
-                    z[r][0] = u.x; z[r][1] = u.y; z[r][2] = u.z; z[r][3] = u.w;
-                    k1[r][0] = k.x; k1[r][1] = k.y; k1[r][2] = k.z; k1[r][3] = k.w;
-                }
-                if (warp == 0) {
-                    const float4 u = ld4(a.wu[cur], D), k = ld4(a.wk[cur], D);
-                    lv[0] = u.x; lv[1] = u.y; lv[2] = u.z; lv[3] = u.w;
-                    kl1[0] = k.x; kl1[1] = k.y; kl1[2] = k.z; kl1[3] = k.w;
-                }
-            }
-            // conditioning rows of the network input are constant over the stages
-            for (int i = threadIdx.x; i < L.C * NS; i += NTHR) {
-                const int c = i / NS, s = i - c * NS;
-                const long long b = tile * NS + s;
-                sm[L.x + (D + L.tin + c) * NS + s] = b < B ? __ldg(a.ys + b * L.C + c) : 0.f;
-            }
-            if (phase == P_STEP) {
-#pragma unroll
-                for (int r = 0; r < JP3; ++r)
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) { zs[r][s] = c_a[6][0] * k1[r][s]; ze[r][s] = c_bt[0] * k1[r][s]; }
-#pragma unroll
-                for (int s = 0; s < SPT; ++s) { sl[s] = c_a[6][0] * kl1[s]; el[s] = c_bt[0] * kl1[s]; }
-            }
-            float zd[JP3][SPT], kl[SPT] = {0.f, 0.f, 0.f, 0.f};
-            for (int sidx = 0; sidx < nstage; ++sidx) {
-                const int i = sidx + 1;   // Tsit5 stage (1..6) when stepping
-                // ---- stage input -> shared memory
-                float tt = t;
-                if (phase == P_PROBE) tt = t + h;
-                else if (phase == P_STEP) tt = (i == 6 && last) ? a.t1 : fmaf(c_c[i], h, t);
-#pragma unroll
-                for (int r = 0; r < JP3; ++r) {
-                    if (!own[r]) continue;
-                    float xi[SPT];
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        float v = z[r][s];
-                        if (phase == P_PROBE) v = fmaf(h, k1[r][s], v);
-                        else if (phase == P_STEP) {
-                            if (i == 6) v = fmaf(h, zs[r][s], v);      // u_new (b = a7: the FSAL stage)
-                            else {
-                                v = fmaf(h * c_a[i][0], k1[r][s], v);
-#pragma unroll
-                                for (int jj = 1; jj < 5; ++jj)
-                                    if (jj < i) v = fmaf(h * c_a[i][jj], K[jj - 1][r][s], v);
-                            }
-                        }
-                        xi[s] = v;
-                    }
-                    *reinterpret_cast<float4*>(sm + L.x + (warp * L.jt3 + r) * NS + 4 * lane) = make_float4(xi[0], xi[1], xi[2], xi[3]);
-                }
-                if (L.tin && warp == 1) *reinterpret_cast<float4*>(sm + L.x + D * NS + 4 * lane) = make_float4(tt, tt, tt, tt);
-                __syncthreads();
-                rhs_tile<JP, JP3>(L, sm, warp, lane, zd);
-                if (warp == 0) {
-                    const float4 tr = *reinterpret_cast<const float4*>(sm + L.red + 4 * lane);
-                    kl[0] = -tr.x; kl[1] = -tr.y; kl[2] = -tr.z; kl[3] = -tr.w;
-                }
-                // ---- stage bookkeeping (stages 1..5 of a step: k2..k6)
-                if (phase == P_STEP && i < 6) {
-                    const float bi = c_a[6][i], bti = c_bt[i];
-#pragma unroll
-                    for (int r = 0; r < JP3; ++r)
-#pragma unroll
-                        for (int s = 0; s < SPT; ++s) {
-                            if (i < 5) K[i - 1][r][s] = zd[r][s];
-                            zs[r][s] = fmaf(bi, zd[r][s], zs[r][s]);
-                            ze[r][s] = fmaf(bti, zd[r][s], ze[r][s]);
-                        }
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) { sl[s] = fmaf(bi, kl[s], sl[s]); el[s] = fmaf(bti, kl[s], el[s]); }
-                }
-            }
-            // ---- epilogue of the phase for this tile
-            if (phase == P_INIT) {
-#pragma unroll
-                for (int r = 0; r < JP3; ++r) {
-                    if (!own[r]) continue;
-                    const int j = warp * L.jt3 + r;
-                    st4(a.wu[0], j, make_float4(z[r][0], z[r][1], z[r][2], z[r][3]));
-                    st4(a.wk[0], j, make_float4(zd[r][0], zd[r][1], zd[r][2], zd[r][3]));
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        if (b0 + s >= B) continue;
-                        const float sk = ctl.abstol + fabsf(z[r][s]) * ctl.reltol;
-                        acc_a += (double)((z[r][s] / sk) * (z[r][s] / sk));
-                        acc_b += (double)((zd[r][s] / sk) * (zd[r][s] / sk));
-                    }
-                }
-                if (warp == 0) {
-                    st4(a.wu[0], D, make_float4(lv[0], lv[1], lv[2], lv[3]));
-                    st4(a.wk[0], D, make_float4(kl[0], kl[1], kl[2], kl[3]));
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        if (b0 + s >= B) continue;
-                        const float sk = ctl.abstol + fabsf(lv[s]) * ctl.reltol;
-                        acc_a += (double)((lv[s] / sk) * (lv[s] / sk));
-                        acc_b += (double)((kl[s] / sk) * (kl[s] / sk));
-                    }
-                }
-            } else if (phase == P_PROBE) {
-#pragma unroll
-                for (int r = 0; r < JP3; ++r) {
-                    if (!own[r]) continue;
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        if (b0 + s >= B) continue;
-                        const float sk = ctl.abstol + fabsf(z[r][s]) * ctl.reltol;
-                        const float df = (zd[r][s] - k1[r][s]) / sk;
-                        acc_a += (double)(df * df);
-                    }
-                }
-                if (warp == 0) {
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        if (b0 + s >= B) continue;
-                        const float sk = ctl.abstol + fabsf(lv[s]) * ctl.reltol;
-                        const float df = (kl[s] - kl1[s]) / sk;
-                        acc_a += (double)(df * df);
-                    }
-                }
-            } else {
-                // zd / kl hold the FSAL stage k7 = f(u_new)
-#pragma unroll
-                for (int r = 0; r < JP3; ++r) {
-                    if (!own[r]) continue;
-                    const int j = warp * L.jt3 + r;
-                    float zn[SPT];
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        zn[s] = fmaf(h, zs[r][s], z[r][s]);
-                        if (b0 + s < B) {
-                            const float e = h * fmaf(c_bt[6], zd[r][s], ze[r][s]);
-                            const float sk = ctl.abstol + fmaxf(fabsf(z[r][s]), fabsf(zn[s])) * ctl.reltol;
-                            const float q = e / sk;
-                            acc_a += (double)(q * q);
-                        }
-                    }
-                    st4(a.wu[cur ^ 1], j, make_float4(zn[0], zn[1], zn[2], zn[3]));
-                    st4(a.wk[cur ^ 1], j, make_float4(zd[r][0], zd[r][1], zd[r][2], zd[r][3]));
-                }
-                if (warp == 0) {
-                    float ln[SPT];
-#pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        ln[s] = fmaf(h, sl[s], lv[s]);
-                        if (b0 + s < B) {
-                            const float e = h * fmaf(c_bt[6], kl[s], el[s]);
-                            const float sk = ctl.abstol + fmaxf(fabsf(lv[s]), fabsf(ln[s])) * ctl.reltol;
-                            const float q = e / sk;
-                            acc_a += (double)(q * q);
-                        }
-                    }
-                    st4(a.wu[cur ^ 1], D, make_float4(ln[0], ln[1], ln[2], ln[3]));
-                    st4(a.wk[cur ^ 1], D, make_float4(kl[0], kl[1], kl[2], kl[3]));
-                }
-            }
-        }
-        // ---- control (identical arithmetic in every thread; the two extra rows E, n of the state are identically zero
-        // in TestMode: they contribute nothing to the sums but count in the mean, as in the other families)
-        if (!P.adaptive) {
-            // fixed steps: a tile's state is written and read by the same threads of the same CTA (tile -> CTA is static),
-            // so the steps need no grid-wide synchronisation at all
-            if (phase == P_INIT) { nf = 1; phase = P_STEP; continue; }
-            nf += 6; nacc++; dt_last = h; fixed_step++; cur ^= 1;
-            t = (fixed_step >= a.nsteps) ? a.t1 : t + h;
-            continue;
-        }
-        double ta, tb;
-        red.sum2(acc_a, acc_b, ta, tb, true);
-        if (phase == P_INIT) {
-            nf = 1;
-            if (a.dt > 0.0f) phase = P_STEP;
-            else {
-                const float d0 = (float)sqrt(ta * inv_count);
-                d1n = (float)sqrt(tb * inv_count);
-                dt0 = (d0 < 1e-5f || d1n < 1e-5f) ? 1e-6f : 0.01f * d0 / d1n;
-                dt0 = fminf(dt0, span);
-                phase = P_PROBE;
-            }
-        } else if (phase == P_PROBE) {
-            nf += 1;
-            const float d2 = (float)sqrt(ta * inv_count) / dt0;
-            const float dm = fmaxf(d1n, d2);
-            const float dt1 = (dm <= 1e-15f) ? fmaxf(1e-6f, dt0 * 1e-3f) : exp10f(-(2.0f + log10f(dm)) / 6.0f);
-            dt = fminf(fminf(100.0f * dt0, dt1), span);
-            phase = P_STEP;
-        } else {
-            nf += 6;
-            const float eest = (float)sqrt(ta * inv_count);
-            if (!isfinite(eest)) { status = ICNF_ERR_NONFINITE; break; }
-            const float q11 = eest > 0.0f ? powf(eest, ctl.beta1) : 0.0f;
-            float q = q11 / powf(qold, ctl.beta2);
-            q = fmaxf(1.0f / ctl.qmax, fminf(1.0f / ctl.qmin, q / ctl.gamma));
-            if (eest <= 1.0f) {
-                nacc++;
-                dt_last = h;
-                t = last ? a.t1 : t + h;
-                cur ^= 1;
-                if (q >= ctl.qsteady_min && q <= ctl.qsteady_max) q = 1.0f;
-                qold = fmaxf(eest, ctl.qoldinit);
-                dt = hmag / q;
-            } else {
-                nrej++;
-                dt = hmag / fminf(1.0f / ctl.qmin, q11 / ctl.gamma);
-            }
-        }
-    }
-
-    // ---- readout: one thread per sample (inference_sol, reg_z_aug, generate_sol); E = n = 0 in TestMode
-    __threadfence();
-    red.grid.sync();
-    for (long long b = (long long)blockIdx.x * NTHR + threadIdx.x; b < B; b += (long long)gridDim.x * NTHR) {
-        float zz = 0.f, za = 0.f, l = 0.f;
-        const bool moved = span > 0.0f;
-        for (int j = 0; j < D; ++j) {
-            float v;
-            if (moved) v = a.wu[cur][(long long)j * B + b];
-            else if (a.in_kind == IN_U0) v = a.in[b * S + j];
-            else if (a.in_kind == IN_XS) v = j < P.nvars ? a.in[b * P.nvars + j] : 0.f;
-            else if (a.in_kind == IN_Z0) v = a.in[b * D + j];
-            else { float o[4]; philox_draw4(ICNF_EPS_GAUSSIAN, a.seed, PHILOX_STREAM_BASE, a.sample_offset + b, j >> 2, o); v = o[j & 3]; }
-            zz = fmaf(v, v, zz);
-            if (j >= P.nvars) za = fmaf(v, v, za);
-            if (a.out_u) a.out_u[b * S + j] = v;
-            if (a.out_x && j < P.nvars) a.out_x[b * P.nvars + j] = v;
-        }
-        if (moved) l = a.wu[cur][(long long)D * B + b];
-        else if (a.in_kind == IN_U0) l = a.in[b * S + D];
-        if (a.out_u) { a.out_u[b * S + D] = l; a.out_u[b * S + D + 1] = 0.f; a.out_u[b * S + D + 2] = 0.f; }
-        const float logp = -0.91893853320467274178f * (float)D - 0.5f * zz - l;
-        const float Aa = a.reg_a ? tiny::vec_norm(za, a.squared) : 0.0f;
-        if (a.out_logp) a.out_logp[b] = logp;
-        if (a.out_regs) { a.out_regs[b * 3] = 0.f; a.out_regs[b * 3 + 1] = 0.f; a.out_regs[b * 3 + 2] = Aa; }
-        if (a.out_lossterm) a.out_lossterm[b] = -logp + a.lam3 * Aa;
-    }
-    if (P.adaptive && a.xg.nranks > 1 && blockIdx.x == 0 && threadIdx.x == 0)
-        *reinterpret_cast<volatile unsigned*>(a.xg.peers.p[a.xg.rank]) = red.seq;
-    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
-        a.stats->naccept = nacc;
-        a.stats->nreject = nrej;
-        a.stats->nf = nf;
-        a.stats->status = status;
-        a.stats->t_final = span > 0.0f ? t : a.t1;
-        a.stats->dt_last = dt_last;
-    }
-}
+cudaError_t launch_o2_softplus(const Params& P, int JP, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_o2_any(const Params& P, int JP, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_o4_softplus(const Params& P, int JP, int grid, size_t smem, cudaStream_t st);
+cudaError_t launch_o4_any(const Params& P, int JP, int grid, size_t smem, cudaStream_t st);
 
 // ------------------------------------------------------------------ host side
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -553,7 +30,10 @@ static Layout make_layout(const icnf_config& cfg, int& JP, int& JP3) {
     L.D = cfg.nvars + cfg.naug; L.C = cfg.ncond; L.tin = cfg.autonomous ? 0 : 1; L.act = cfg.activation;
     L.n0 = cfg.sizes[0]; L.n1 = cfg.sizes[1]; L.n2 = cfg.sizes[2];
     L.jt1 = (L.n1 + NW - 1) / NW; L.jt2 = (L.n2 + NW - 1) / NW; L.jt3 = (L.D + NW - 1) / NW;
-    JP = std::max(4, round_up(std::max(L.jt1, L.jt2), 4));
+    {
+        const int need = std::max(L.jt1, L.jt2);
+        JP = need <= 4 ? 4 : need <= 8 ? 8 : need <= 10 ? 10 : need <= 12 ? 12 : 16;
+    }
     JP3 = L.jt3 <= 2 ? 2 : 4;
     L.ld12 = NW * JP; L.ld3 = NW * JP3;
     int o = 0;
@@ -573,20 +53,6 @@ size_t smem_bytes(const icnf_config& cfg) {
     return sizeof(float) * (size_t)make_layout(cfg, JP, JP3).total;
 }
 
-template <int JP, int JP3>
-static cudaError_t launch(const Params& P, int grid, size_t smem, cudaStream_t st) {
-    static size_t attr[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (attr[dev & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(solve_kernel<JP, JP3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr[dev & 63] = smem;
-    }
-    void* args[] = {(void*)&P};
-    return cudaLaunchCooperativeKernel((const void*)solve_kernel<JP, JP3>, dim3(grid), dim3(NTHR), args, smem, st);
-}
-
 cudaError_t solve(const icnf_config& cfg, const float* amat, const SolveArgs& a, int nvars, bool adaptive, int sm_count,
                   cudaStream_t st) {
     Params P;
@@ -603,11 +69,9 @@ cudaError_t solve(const icnf_config& cfg, const float* amat, const SolveArgs& a,
     if (smem > 227 * 1024 - 1024) return cudaErrorInvalidConfiguration;   // static shared memory of the kernel: < 1 KB
     const long long ntiles = (a.B + NS - 1) / NS;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, sm_count));
-#define ICNF_NARROW_CASE(A, B3) if (JP == A && JP3 == B3) return launch<A, B3>(P, grid, smem, st);
-    ICNF_NARROW_CASE(4, 2) ICNF_NARROW_CASE(8, 2) ICNF_NARROW_CASE(12, 2) ICNF_NARROW_CASE(16, 2)
-    ICNF_NARROW_CASE(4, 4) ICNF_NARROW_CASE(8, 4) ICNF_NARROW_CASE(12, 4) ICNF_NARROW_CASE(16, 4)
-#undef ICNF_NARROW_CASE
-    return cudaErrorInvalidConfiguration;
+    const bool sp = cfg.activation == ICNF_ACT_SOFTPLUS;
+    if (JP3 == 2) return sp ? launch_o2_softplus(P, JP, grid, smem, st) : launch_o2_any(P, JP, grid, smem, st);
+    return sp ? launch_o4_softplus(P, JP, grid, smem, st) : launch_o4_any(P, JP, grid, smem, st);
 }
 
 }  // namespace narrow

@@ -1,0 +1,6 @@
+#include "narrow_kernel.cuh"
+namespace icnf {
+namespace narrow {
+ICNF_NARROW_INSTANCE(launch_o2_any, 2, -1)
+}
+}
