@@ -1,0 +1,84 @@
+"""GPU parity tests of the narrow fast path (csrc/narrow_kernel.cuh): the whole exact-trace Tsit5 solve of a narrow
+two-hidden-layer MLP in one persistent kernel, any widths at run time.  Checked against the CPU oracle over a seeded
+sweep of shapes (widths that do and do not divide by the 8 warps, conditioning inputs, autonomous fields, every
+activation), ragged batches, both time directions.  RTOL = 1e-4 (north_star)."""
+import numpy as np
+import pytest
+
+from oracle import icnf_oracle as O
+from tests.helpers import ACT_CODE, t64
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def m():
+    import cnf_b200
+    return cnf_b200
+
+
+def build(m, nvars, naug, ncond, n1, n2, act, autonomous=False):
+    D = nvars + naug
+    n0 = D + (0 if autonomous else 1) + ncond
+    nn = m.Chain(m.Dense(n0, n1, act), m.Dense(n1, n2, act), m.Dense(n2, D))
+    icnf = m.ICNF(nvariables=nvars, naugments=naug, nconditions=ncond, autonomous=autonomous, nn=nn)
+    om = O.OracleICNF(nvars=nvars, naug=naug, ncond=ncond, autonomous=autonomous, hidden=(n1, n2), activation=ACT_CODE[act],
+                      lam1=icnf.lambda1, lam2=icnf.lambda2, lam3=icnf.lambda3, tspan=icnf.tspan, steer_rate=icnf.steer_rate)
+    return icnf, om
+
+
+SWEEP = [
+    # nvars naug ncond n1  n2  act        autonomous  B
+    (3,    0,   0,    32, 32, "softplus", False,      257),    # ICNF(nvariables=3)-like, ragged batch
+    (2,    0,   0,    64, 64, "softplus", False,      1000),   # config 2's other width, 3-64-64-2
+    (16,   0,   0,    68, 68, "softplus", False,      515),    # config 3
+    (5,    2,   3,    33, 47, "tanh",     False,      130),    # widths that do not divide by 8, conditioned, augmented
+    (20,   0,   0,    100, 128, "sigmoid", True,      97),     # D' > 16 (four rows per warp), autonomous, widest layer
+    (1,    1,   0,    9,  5,  "softplus", False,      64),     # fewer units than warps
+]
+
+
+@pytest.mark.parametrize("case", SWEEP, ids=[f"{c[0]}+{c[1]}c{c[2]}-{c[3]}-{c[4]}-{c[5]}" for c in SWEEP])
+def test_single_launch_solve_matches_oracle(m, case):
+    nvars, naug, ncond, n1, n2, act, autonomous, B = case
+    icnf, om = build(m, nvars, naug, ncond, n1, n2, act, autonomous)
+    assert icnf.kernel_family == "generic"
+    rng = np.random.default_rng(5)
+    theta = O.init_params(om, 11, np.float32, bias_scale=0.3)
+    xs = rng.standard_normal((nvars, B)).astype(np.float32)
+    ys = rng.standard_normal((ncond, B)).astype(np.float32) if ncond else None
+    args = (xs,) if ys is None else (xs, ys)
+    # adaptive log p(x)
+    before = icnf.launch_count
+    logp, (E, n, A) = m.inference(icnf, m.TestMode(), *args, theta, {})
+    assert icnf.launch_count - before <= 2, "TestMode solve of a narrow network must be one launch"
+    gs = icnf.last_stats
+    st = O.SolveStats()
+    rl, (rE, rn, rA) = O.inference(om, O.TEST, t64(xs), t64(theta), None, t64(ys), stats=st)
+    assert gs.status == 0 and gs.t_final == pytest.approx(1.0)
+    assert gs.nf == 2 + 6 * (gs.naccept + gs.nreject)
+    np.testing.assert_allclose(logp, rl.numpy(), rtol=RTOL, atol=2e-5)
+    np.testing.assert_allclose(A, rA.numpy(), rtol=RTOL, atol=2e-5)
+    assert not E.any() and not n.any()
+    # fixed steps agree step for step (full state, both directions)
+    u0 = O.make_u0(om, t64(xs)).numpy().astype(np.float32)
+    for k, (t0, t1) in ((3, (0.0, 0.375)), (2, (0.25, 0.0))):
+        got = m.base_sol(icnf, m.TestMode(), u0, theta, tspan=(t0, t1), ys=ys, adaptive=False, dt=0.125)
+        ref = O.solve(om, O.TEST, t64(u0), t64(theta), None, t64(ys), t0, t1, O.SolverOpts(adaptive=False, dt=0.125)).numpy()
+        assert icnf.last_stats.naccept == k
+        np.testing.assert_allclose(got, ref, rtol=RTOL, atol=3e-5)
+
+
+def test_generate_round_trip(m):
+    """generate (t1 -> t0) from supplied base samples, then inference of the result recovers the base sample's density."""
+    icnf, om = build(m, 6, 0, 0, 40, 40, "softplus")
+    rng = np.random.default_rng(2)
+    theta = O.init_params(om, 3, np.float32, bias_scale=0.3)
+    z0 = rng.standard_normal((6, 300)).astype(np.float32)
+    xs = m.generate(icnf, m.TestMode(), theta, {}, 300, z0=z0)
+    ref = O.generate(om, O.TEST, t64(z0), t64(theta), None, None).numpy()
+    np.testing.assert_allclose(xs, ref, rtol=RTOL, atol=3e-5)
+    logp, _ = m.inference(icnf, m.TestMode(), xs, theta, {})
+    rl, _ = O.inference(om, O.TEST, t64(xs), t64(theta), None, None)
+    np.testing.assert_allclose(logp, rl.numpy(), rtol=RTOL, atol=2e-5)
