@@ -55,34 +55,36 @@ __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y
 
 // acc[jp][s] (+)= sum_k Wt[k][warp slot 2 jp, 2 jp + 1] * act[k][4 lane + s];  DUAL: the same for (Wt2, act2) -> acc2
 template <int JP, bool DUAL>
-__device__ __forceinline__ void layer_mm(const float* __restrict__ wt, const float* __restrict__ wt2, int ldw,
-                                         const float* __restrict__ act, const float* __restrict__ act2, int nin, int lane,
+__device__ __forceinline__ void layer_mm(const float* wt, const float* wt2, int ldw,
+                                         const float* act, const float* act2, int nin, int lane,
                                          float2 (&acc)[JP / 2][SPT], float2 (&acc2)[JP / 2][SPT]) {
 #pragma unroll
     for (int p = 0; p < JP / 2; ++p)
 #pragma unroll
         for (int s = 0; s < SPT; ++s) { acc[p][s] = f2(0.f, 0.f); if (DUAL) acc2[p][s] = f2(0.f, 0.f); }
     const float* ap = act + 4 * lane;
-    const float* ap2 = act2 + 4 * lane;
-#pragma unroll 2
-    for (int k = 0; k < nin; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(ap + k * NS);
+    const float* ap2 = DUAL ? act2 + 4 * lane : nullptr;
+    // pointers advance by one input per trip, so that every load of the body has a constant offset
+#pragma unroll 4
+    for (int k = 0; k < nin; ++k, wt += ldw, ap += NS) {
+        const float4 a = *reinterpret_cast<const float4*>(ap);
         const float2 as[SPT] = {f2(a.x, a.x), f2(a.y, a.y), f2(a.z, a.z), f2(a.w, a.w)};
 #pragma unroll
         for (int p = 0; p < JP / 2; ++p) {
-            const float2 wv = *reinterpret_cast<const float2*>(wt + k * ldw + 2 * p);
+            const float2 wv = *reinterpret_cast<const float2*>(wt + 2 * p);
 #pragma unroll
             for (int s = 0; s < SPT; ++s) acc[p][s] = __ffma2_rn(wv, as[s], acc[p][s]);
         }
         if constexpr (DUAL) {
-            const float4 b = *reinterpret_cast<const float4*>(ap2 + k * NS);
+            const float4 b = *reinterpret_cast<const float4*>(ap2);
             const float2 bs[SPT] = {f2(b.x, b.x), f2(b.y, b.y), f2(b.z, b.z), f2(b.w, b.w)};
 #pragma unroll
             for (int p = 0; p < JP / 2; ++p) {
-                const float2 wv = *reinterpret_cast<const float2*>(wt2 + k * ldw + 2 * p);
+                const float2 wv = *reinterpret_cast<const float2*>(wt2 + 2 * p);
 #pragma unroll
                 for (int s = 0; s < SPT; ++s) acc2[p][s] = __ffma2_rn(wv, bs[s], acc2[p][s]);
             }
+            wt2 += ldw; ap2 += NS;
         }
     }
 }
