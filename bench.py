@@ -575,6 +575,14 @@ def main():
                                            "achieved": c4["algorithmic_tflops_per_gpu"], "peak": peaks["bf16_tflops_sustained"],
                                            "unit": "TFLOP/s", "frac": c4["algorithmic_tflops_per_gpu"] / peaks["bf16_tflops_sustained"],
                                            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained, of measured"}
+            c3 = extras.get("config3_gmm16_B262144")
+            if c3:
+                # FP32 roofline of the single-launch exact-trace solve (csrc/narrow_kernel.cuh): algorithmic flop per RHS and sample
+                # = 2 P + 2 n1 n2 (closed-form trace; the reference's D' one-hot pullbacks would count 2 P (1 + D'))
+                line["roofline_fp32_config3"] = {"bound": "fp32_fma", "kernel": "narrow::solve_kernel (config 3, whole adaptive solve)",
+                                                 "achieved": c3["algorithmic_tflops"], "peak": fp32_peak, "unit": "TFLOP/s",
+                                                 "frac": c3["algorithmic_tflops"] / fp32_peak,
+                                                 "peak_source": "FFMA-chain microbenchmark in this run (icnf_measure_fp32_peak)"}
         line["extras"] = extras
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1

@@ -300,6 +300,7 @@ BT = (-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
 class SolverOpts:
     """The subset of ``sol_kwargs`` (icnf.jl:84-102) the path uses, for Tsit5."""
 
+    alg: str = "tsit5"              # "tsit5" (north_star) or "vcabm" (the reference's default alg, icnf.jl:89)
     adaptive: bool = True
     dt: float = 0.0                 # fixed step (adaptive=False) or initial dt (0 = automatic)
     reltol: float = 1e-4            # icnf.jl:87
@@ -350,9 +351,8 @@ def tsit5_step(f: Callable, u: torch.Tensor, k1: torch.Tensor, t: float, dt: flo
     return un, k7, err
 
 
-def _initial_dt(f, u0, f0, t0, tdir, opts: "SolverOpts", tend) -> float:
+def _initial_dt(f, u0, f0, t0, tdir, opts: "SolverOpts", tend, order: int = 5) -> float:
     """Hairer/Wanner starting step as OrdinaryDiffEq uses it [3P, from memory]."""
-    order = 5
     sk = opts.abstol + u0.detach().abs() * opts.reltol
     d0 = _rms(u0 / sk)
     d1 = _rms(f0 / sk)
@@ -441,6 +441,139 @@ def tsit5_solve(f: Callable, u0: torch.Tensor, t0: float, t1: float, opts: Solve
     return u
 
 
+
+# --------------------------------------------------------------------------
+# VCABM: variable-step, variable-order Adams-Bashforth-Moulton PECE, the reference's default ``alg``
+# (icnf.jl:89, third-party OrdinaryDiffEqAdamsBashforthMoulton 2 -- not vendored).  Restated from the published
+# algorithm it implements: Hairer, Norsett, Wanner, "Solving ODEs I", III.5 (variable step size Adams formulas in
+# terms of the modified divided differences Phi_j, Phi*_j and the coefficients beta_j, g_j) with Shampine-Gordon's
+# order selection (error estimates of the neighbouring orders with the constant-step coefficients gamma*_j).
+# [3P, from memory, unverifiable here]: which of these quantities OrdinaryDiffEq evaluates at the predicted and
+# which at the corrected state, its rule for the first steps (order raised by one per step up to 3) and the
+# I-controller constants.  PARITY UNPINNED, like the Tsit5 controller.
+
+GAMMA_STAR = (1.0, -1.0 / 2, -1.0 / 12, -1.0 / 24, -19.0 / 720, -3.0 / 160, -863.0 / 60480, -275.0 / 24192,
+              -33953.0 / 3628800, -8183.0 / 1036800, -3250433.0 / 479001600, -4671.0 / 788480, -13695779093.0 / 2615348736000)
+VCABM_MAX_ORDER = 12
+
+
+def vcabm_coefficients(dts: List[float], k: int, kk: int):
+    """beta_j (j < kk) and g_j (j <= k) for the step dts[0] after the earlier steps dts[1], dts[2], ...
+    HNW III.5: beta_0 = 1, beta_j = beta_{j-1} (t_{n+1} - t_{n-j+1}) / (t_n - t_{n-j});
+    c_{0,q} = 1/q, c_{1,q} = 1/(q (q+1)), c_{j,q} = c_{j-1,q} - c_{j-1,q+1} h_n / (t_{n+1} - t_{n-j+1}); g_j = c_{j,1}."""
+    h = dts[0]
+    beta = [1.0]
+    xi, xi0 = h, 0.0
+    for j in range(1, kk):
+        xi0 += dts[j]
+        beta.append(beta[-1] * xi / xi0)
+        xi += dts[j]
+    c_prev = [1.0 / q for q in range(1, k + 3)]            # c_{0,q}, q = 1 ..
+    g = [c_prev[0]]
+    if k >= 1:
+        c_cur = [1.0 / (q * (q + 1)) for q in range(1, k + 2)]
+        g.append(c_cur[0])
+        span = h
+        for j in range(2, k + 1):
+            span += dts[j - 1]                              # t_{n+1} - t_{n-j+1}
+            c_next = [c_cur[q] - c_cur[q + 1] * h / span for q in range(len(c_cur) - 1)]
+            g.append(c_next[0])
+            c_cur = c_next
+    return beta, g
+
+
+def vcabm_solve(f: Callable, u0: torch.Tensor, t0: float, t1: float, opts: SolverOpts,
+                stats: Optional[SolveStats] = None) -> torch.Tensor:
+    """Adaptive Adams PECE from t0 to t1 (t1 < t0 allowed): u(t1).  Error norm, scaling and acceptance as in
+    tsit5_solve (whole-batch RMS); step size by the I-controller q = EEst^(1/(k+1)) / gamma."""
+    stats = stats if stats is not None else SolveStats()
+    tdir = 1.0 if t1 >= t0 else -1.0
+    span = abs(t1 - t0)
+    u, t = u0, float(t0)
+    if span == 0.0:
+        return u
+    fn = f(u, t)
+    stats.nf += 1
+    if opts.dt > 0:
+        dt = min(opts.dt, span)
+    else:
+        dt = _initial_dt(f, u, fn, t, tdir, opts, t1, order=1)
+        stats.nf += 1
+    k, nstep = 1, 0
+    hist = [0.0] * (VCABM_MAX_ORDER + 2)        # hist[i] = i-th previous accepted (signed) step
+    phistar_prev: List[torch.Tensor] = []        # Phi*_j(n-1)
+    attempts = 0
+
+    def nrm(x, sk):
+        return _rms(x / sk)
+
+    while True:
+        remaining = abs(t1 - t)
+        if remaining <= 1e-12 * max(1.0, abs(t1)):
+            break
+        last = dt >= remaining * (1.0 - 1e-6)
+        h = tdir * (remaining if last else dt)
+        attempts += 1
+        if attempts > opts.max_steps:
+            raise RuntimeError("vcabm: max_steps exceeded")
+        kk = min(k + 1, nstep + 1)
+        dts = [h] + hist
+        beta, g = vcabm_coefficients(dts, k, kk)
+        phi = [fn]
+        phistar = [fn]
+        for j in range(1, kk):
+            phi.append(phi[j - 1] - phistar_prev[j - 1])
+            phistar.append(beta[j] * phi[j])
+        p = u
+        for j in range(k):
+            p = p + (h * g[j]) * phistar[j]
+        fp = f(p, t + h)
+        stats.nf += 1
+        php = [fp]
+        for j in range(1, kk + 1):
+            php.append(php[j - 1] - phistar[j - 1])
+        un = p + (h * g[k]) * php[k]
+        sk = opts.abstol + torch.maximum(u.detach().abs(), un.detach().abs()) * opts.reltol
+        eest = nrm((h * (g[k] - g[k - 1])) * php[k], sk)
+        if not math.isfinite(eest):
+            raise FloatingPointError("vcabm: non-finite error estimate")
+        if eest > 1.0:
+            stats.nreject += 1
+            q = eest ** (1.0 / (k + 1)) / opts.gamma
+            dt = abs(h) / min(1.0 / opts.qmin, max(1.0 / opts.qmax, q))
+            continue
+        # accepted: final evaluation (PECE), order for the next step
+        fnew = f(un, t1 if last else t + h)
+        stats.nf += 1
+        knew = k
+        if nstep + 1 <= 4 or k < 3:
+            knew = min(k + 1, 3, VCABM_MAX_ORDER)
+        else:
+            errm1 = nrm((h * GAMMA_STAR[k - 1]) * php[k - 1], sk)
+            errm2 = nrm((h * GAMMA_STAR[k - 2]) * php[k - 2], sk)
+            if max(errm1, errm2) <= eest:
+                knew = k - 1
+            elif k < VCABM_MAX_ORDER and kk >= k + 1:
+                errp1 = nrm((h * GAMMA_STAR[k + 1]) * php[k + 1], sk)
+                if errp1 < eest:
+                    knew = k + 1
+                    eest = errp1
+        stats.naccept += 1
+        stats.ts.append(t)
+        stats.dts.append(h)
+        t = t1 if last else t + h
+        u, fn = un, fnew
+        phistar_prev = phistar
+        hist = [h] + hist[:-1]
+        nstep += 1
+        k = knew
+        q = eest ** (1.0 / (k + 1)) / opts.gamma if eest > 0 else 0.0
+        q = max(1.0 / opts.qmax, min(1.0 / opts.qmin, q))
+        if opts.qsteady_min <= q <= opts.qsteady_max:
+            q = 1.0
+        dt = abs(h) / q
+    return u
+
 # --------------------------------------------------------------------------
 # problem build / readout / API (base_icnf.jl)
 
@@ -466,7 +599,8 @@ def solve(model: OracleICNF, mode: int, u0, theta, eps, ys=None, t0=None, t1=Non
     opts = opts or SolverOpts()
     t0 = model.tspan[0] if t0 is None else t0
     t1 = model.tspan[1] if t1 is None else t1
-    return tsit5_solve(_rhs(model, mode, theta, eps, ys, closed, create_graph), u0, t0, t1, opts, stats)
+    solver = vcabm_solve if opts.alg == "vcabm" else tsit5_solve
+    return solver(_rhs(model, mode, theta, eps, ys, closed, create_graph), u0, t0, t1, opts, stats)
 
 
 def readout(model: OracleICNF, mode: int, fsol: torch.Tensor):

@@ -10,11 +10,11 @@ ncu --set full --clock-control none --import-source on -k regex:backward_sp -s 3
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:solve_adaptive -s 3 -c 1 -o gpurun_out/prof_fwd \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-extras > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 40 -c 1 -o gpurun_out/prof_tc \
+ncu --set full --clock-control none --import-source on -k regex:tc_ -s 40 -c 1 -o gpurun_out/prof_tc \
     python scripts/time_wide.py bf16_tc > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:gemm128_kernel -s 40 -c 1 -o gpurun_out/prof_generic \
     python scripts/time_wide.py fp32 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 40 -c 1 -o gpurun_out/prof_tc_x3 \
+ncu --set full --clock-control none --import-source on -k regex:tc_ -s 40 -c 1 -o gpurun_out/prof_tc_x3 \
     python scripts/time_wide.py bf16x3_tc > /dev/null 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 150 --csv --log-file gpurun_out/launches_tc.csv \
     python scripts/time_wide.py bf16_tc > /dev/null 2>&1
@@ -23,13 +23,19 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 200 --csv --
 python scripts/time_wide.py fp32 > gpurun_out/time_wide.txt 2>&1
 python scripts/time_wide.py bf16_tc >> gpurun_out/time_wide.txt 2>&1
 python scripts/time_wide.py bf16x3_tc >> gpurun_out/time_wide.txt 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file gpurun_out/launches_c3.csv \
+ICNF_NARROW=0 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 120 --csv --log-file gpurun_out/launches_c3.csv \
     python scripts/time_config3.py fp32 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:gemm_ws -s 41 -c 1 -o gpurun_out/prof_generic_ws \
+ICNF_NARROW=0 ncu --set full --clock-control none --import-source on -k regex:gemm_ws -s 41 -c 1 -o gpurun_out/prof_generic_ws \
     python scripts/time_config3.py fp32 > /dev/null 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 700 --csv --log-file gpurun_out/launches_train4.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 120 -c 330 --csv --log-file gpurun_out/launches_train4.csv \
     python scripts/time_train4.py bf16x3_tc > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 520 -c 6 -o gpurun_out/prof_tc_train \
+ncu --set full --clock-control none --import-source on -k regex:tc_chain -s 60 -c 2 -o gpurun_out/prof_tc_train \
     python scripts/time_train4.py bf16x3_tc > /dev/null 2>&1
 python scripts/time_train4.py bf16x3_tc > gpurun_out/time_train4.txt 2>&1
 ls -la gpurun_out
+ncu --set full --clock-control none --import-source on -k regex:solve_kernel -s 1 -c 1 -o gpurun_out/prof_narrow \
+    python scripts/time_config3.py fp32 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:tc_chain -s 30 -c 1 -o gpurun_out/prof_chain \
+    python scripts/time_wide.py bf16x3_tc > /dev/null 2>&1
+python scripts/time_config3.py fp32 > gpurun_out/time_config3.txt 2>&1
+python scripts/ab_chain.py c4 8 adaptive > gpurun_out/ab_chain.txt 2>&1
