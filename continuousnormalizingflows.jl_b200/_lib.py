@@ -41,7 +41,7 @@ class Solver(C.Structure):
         ("adaptive", C.c_int32), ("dt", C.c_float), ("reltol", C.c_float), ("abstol", C.c_float),
         ("max_steps", C.c_int32), ("beta1", C.c_float), ("beta2", C.c_float), ("gamma", C.c_float),
         ("qmin", C.c_float), ("qmax", C.c_float), ("qsteady_min", C.c_float), ("qsteady_max", C.c_float),
-        ("qoldinit", C.c_float),
+        ("qoldinit", C.c_float), ("alg", C.c_int32),
     ]
 
 

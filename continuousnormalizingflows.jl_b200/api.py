@@ -36,6 +36,13 @@ except Exception:  # pragma: no cover
 
 
 # ---------------------------------------------------------------- modes (src/core/types.jl)
+
+def _alg_code(alg):
+    """``sol_kwargs.alg`` (icnf.jl:89) -> icnf_alg: 0 = Tsit5, 1 = VCABM, None = not served."""
+    name = str(alg).lower().rstrip("()")
+    return {"tsit5": 0, "vcabm": 1}.get(name)
+
+
 class Mode:
     code: int = -1
 
@@ -156,8 +163,9 @@ class ICNF:
         self.sol_kwargs = dict(DEFAULT_SOL_KWARGS)
         if sol_kwargs:
             self.sol_kwargs.update(sol_kwargs)
-        if str(self.sol_kwargs.get("alg", "Tsit5")).lower() not in ("tsit5", "tsit5()"):
-            raise ValueError("the B200 path integrates with Tsit5; pass alg='Tsit5'")
+        if _alg_code(self.sol_kwargs.get("alg", "Tsit5")) is None:
+            raise ValueError("the B200 path integrates with Tsit5 (north_star) or VCABM (the reference's default alg, served by "
+                             "the narrow-MLP family for inference / generate / loss); pass alg='Tsit5' or alg='VCABM'")
 
         sizes, acts = self._check_chain(nn, n_in, n_out)
         self.sizes = sizes
@@ -280,6 +288,10 @@ class ICNF:
         s.max_steps = int(min(mi, 2 ** 31 - 1))
         for k in ("beta1", "beta2", "gamma", "qmin", "qmax", "qsteady_min", "qsteady_max", "qoldinit"):
             setattr(s, k, float(kw.get(k, 0.0)))
+        code = _alg_code(kw.get("alg", "Tsit5"))
+        if code is None:
+            raise ValueError(f"unknown alg {kw.get('alg')!r}: 'Tsit5' or 'VCABM'")
+        s.alg = code
         return s
 
     def _set_params(self, ps):

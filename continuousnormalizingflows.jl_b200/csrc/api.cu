@@ -215,6 +215,7 @@ struct icnf_handle {
     cudaStream_t stream = nullptr;
     std::vector<float> theta_host;
     bool have_params = false;
+    DevBuf vc_hist;   // VCABM: modified divided differences of the last 13 steps
     DevBuf theta_dev, in, eps, ys, out0, out1, out2, wu0, wu1, wk0, wk1, partials, ckpt, steps, stats, gpartial,
         lossterm, scalar, dtheta, dxs;
     DevStats* stats_host = nullptr;  // pinned
@@ -370,6 +371,8 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
     if (eps_kind < ICNF_EPS_SUPPLIED || eps_kind > ICNF_EPS_RADEMACHER) return h->fail(ICNF_ERR_INVALID, "bad noise kind");
     if (c.ncond && !r.ys) return h->fail(ICNF_ERR_INVALID, "conditioned flow needs ys");
     if (!adaptive && !(r.sol && r.sol->dt > 0)) return h->fail(ICNF_ERR_INVALID, "fixed-step solve needs dt > 0");
+    if (r.sol && r.sol->alg != ICNF_ALG_TSIT5 && r.sol->alg != ICNF_ALG_VCABM) return h->fail(ICNF_ERR_INVALID, "unknown alg %d", r.sol->alg);
+    if (r.sol && r.sol->alg == ICNF_ALG_VCABM && !adaptive) return h->fail(ICNF_ERR_INVALID, "VCABM is a variable-step method: adaptive must be 1");
 
     SolveArgs a;
     memset(&a, 0, sizeof a);
@@ -409,6 +412,12 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
         h->launches++;
         return ICNF_OK;
     }
+    // VCABM (the reference's default alg): adaptive, inference-side only -- a solve that records checkpoints for the
+    // reverse sweep integrates with Tsit5 (the sweep differentiates discrete Runge-Kutta steps)
+    const bool vcabm = r.sol && r.sol->alg == ICNF_ALG_VCABM && !r.want_ckpt;
+    if (vcabm && !h->fam->solve_vcabm)
+        return h->fail(ICNF_ERR_UNSUPPORTED, "alg = VCABM is served by the tiny (narrow-MLP) kernel family; this network runs on the %s family: pass alg = Tsit5",
+                       h->fam->name);
     // adaptive: cooperative persistent kernel
     const int grid_cap = h->fam->adaptive_max_grid(mf.exact, h->sm_count);
     if (grid_cap <= 0) return h->fail(ICNF_ERR_UNSUPPORTED, "adaptive kernel cannot be made resident on this device");
@@ -442,8 +451,14 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
         a.ckpt = h->ckpt.as<float>();
         a.steps = h->steps.as<StepRec>();
     }
+    if (vcabm) {
+        CK(h, h->vc_hist.reserve(sizeof(float) * 2 * 13 * (size_t)S * r.B));
+        a.vc_hist = h->vc_hist.as<float>();
+        a.alg = ICNF_ALG_VCABM;
+    }
     h->prof_begin(0, st);
-    cudaError_t e = h->fam->solve_adaptive(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st);
+    cudaError_t e = vcabm ? h->fam->solve_vcabm(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st)
+                          : h->fam->solve_adaptive(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st);
     h->prof_end(0, st);
     if (e != cudaSuccess) return h->cuda_fail(e, "solve_adaptive launch");
     h->launches++;

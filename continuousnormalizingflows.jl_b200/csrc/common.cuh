@@ -230,6 +230,9 @@ struct SolveArgs {
     // exchanged through NVLink peer memory inside the device loop), so N shards take the steps of the unsharded solve
     NormXchg xg;
     int64_t norm_B;          // batch size in the error norm's mean (0 = B)
+    // VCABM (alg = ICNF_ALG_VCABM): history of the modified divided differences, [2][13][S][B] floats
+    float* vc_hist;
+    int alg;
 };
 
 struct RhsArgs {

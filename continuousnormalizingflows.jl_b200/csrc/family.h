@@ -47,6 +47,8 @@ struct Family {
     // (`first` has room for 34 entries; entries [0, n_blocks] are filled), null when the family has no such plan
     void (*backward_plan)(bool exact, int sm_count, long long B, int* threads, int* grid, int* first, int* n_blocks);
     int ckpt_stages;                 // training checkpoints per step and sample, in units of D' floats (tiny: 6 stage inputs)
+    // VCABM (variable-order Adams PECE, the reference's default alg); null: the family integrates with Tsit5 only
+    cudaError_t (*solve_vcabm)(void* ws, const float* theta_host, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st);
 };
 
 std::vector<const Family*>& tiny_registry();

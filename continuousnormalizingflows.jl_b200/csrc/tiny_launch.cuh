@@ -6,6 +6,7 @@
 #include "family.h"
 #include "tiny.cuh"
 #include "tiny_sp.cuh"
+#include "tiny_vcabm.cuh"
 
 namespace icnf {
 namespace tiny {
@@ -108,6 +109,20 @@ struct Launch {
         pack(theta, w);
         void* args[] = {(void*)&w, (void*)&aa, (void*)&nv};
         return cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(bs), args, smem, st);
+    }
+    static cudaError_t solve_vcabm(void*, const float* theta, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st) {
+        auto k = exact ? solve_vcabm_kernel<N, true> : solve_vcabm_kernel<N, false>;
+        const int bs = adaptive_block(a.B, sm_count);
+        const int per_sm = occupancy(k, 0, bs);
+        if (per_sm <= 0) return cudaErrorLaunchOutOfResources;
+        const long long need = (a.B + bs - 1) / bs;
+        const int grid = (int)std::max(1LL, std::min<long long>(need, (long long)per_sm * sm_count));
+        SolveArgs aa = a;
+        int nv = nvars;
+        WBlock<N> w;
+        pack(theta, w);
+        void* args[] = {(void*)&w, (void*)&aa, (void*)&nv};
+        return cudaLaunchCooperativeKernel((const void*)k, dim3(grid), dim3(bs), args, 0, st);
     }
     // networks with at least one hidden layer use the sample-parallel backward (tiny_sp.cuh); the thread-per-sample
     // backward_kernel of tiny.cuh serves networks without a hidden layer (a linear field)
@@ -228,6 +243,7 @@ struct Launch {
         f.rhs = &rhs;
         f.solve_fixed = &solve_fixed;
         f.solve_adaptive = &solve_adaptive;
+        f.solve_vcabm = &solve_vcabm;
         f.adaptive_max_grid = &adaptive_max_grid;
         f.backward = &backward;
         f.backward_grid = &backward_grid;

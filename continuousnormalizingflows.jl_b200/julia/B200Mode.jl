@@ -47,6 +47,7 @@ struct IcnfSolver
     max_steps::Int32
     beta1::Float32; beta2::Float32; gamma::Float32; qmin::Float32; qmax::Float32
     qsteady_min::Float32; qsteady_max::Float32; qoldinit::Float32
+    alg::Int32                      # 0 = Tsit5, 1 = VCABM (the reference's default, icnf.jl:89)
 end
 
 struct IcnfNoise
@@ -115,17 +116,21 @@ function set_params!(h, ps)
     GC.@preserve θ check(h, ccall((:icnf_set_params, libicnf), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int64), h, θ, length(θ)))
 end
 
-# The library integrates with Tsit5 (and nothing else): the reference's default `alg = VCABM()` (icnf.jl:89) must be
-# replaced by the caller, never silently (SURVEY D1).  Fixed-step solves pass `adaptive = false, dt = ...`.
+# The library integrates with Tsit5 or with the reference's default `alg = VCABM()` (icnf.jl:89; inference / generate /
+# loss on the narrow-MLP family -- the gradient entry point differentiates discrete Tsit5 steps whatever `alg` says, see
+# include/icnf_b200.h).  Any other `alg` is an error, never a silent substitution (SURVEY D1).  Fixed-step solves pass
+# `adaptive = false, dt = ...`.
 function tsit5_opts(icnf)
     kw = icnf.sol_kwargs
     alg = get(kw, :alg, nothing)
-    (!isnothing(alg) && nameof(typeof(alg)) === :Tsit5) ||
-        error("B200MatrixMode integrates with Tsit5: construct the ICNF with sol_kwargs = (; alg = Tsit5(), ...); got $(alg)")
+    algname = isnothing(alg) ? :none : nameof(typeof(alg))
+    (algname === :Tsit5 || algname === :VCABM) ||
+        error("B200MatrixMode integrates with Tsit5 or VCABM: construct the ICNF with sol_kwargs = (; alg = Tsit5(), ...); got $(alg)")
     adaptive = get(kw, :adaptive, true)
     maxiters = get(kw, :maxiters, 100000)
     return Ref(IcnfSolver(adaptive ? 1 : 0, Float32(get(kw, :dt, 0.0f0)), Float32(get(kw, :reltol, 1.0f-4)),
-        Float32(get(kw, :abstol, 1.0f-4)), Int32(min(maxiters, typemax(Int32))), 0, 0, 0, 0, 0, 0, 0, 0))
+        Float32(get(kw, :abstol, 1.0f-4)), Int32(min(maxiters, typemax(Int32))), 0, 0, 0, 0, 0, 0, 0, 0,
+        algname === :VCABM ? Int32(1) : Int32(0)))
 end
 
 # ---- S2: one ccall per solve (replaces base_sol, src/core/base_icnf.jl:134-140) ---

@@ -122,7 +122,13 @@ typedef struct icnf_solver {
     float reltol, abstol;       /* icnf.jl:87-88 (1e-4) */
     int32_t max_steps;          /* 0 = 100000; the reference's maxiters is typemax(Int) (icnf.jl:86) */
     float beta1, beta2, gamma, qmin, qmax, qsteady_min, qsteady_max, qoldinit;
+    int32_t alg;                /* icnf_alg: 0 = Tsit5 (BASELINE.json north_star), 1 = VCABM (the reference's default,
+                                 * src/core/icnf.jl:89): adaptive only; served for solve / inference / generate / loss by the
+                                 * single-launch narrow-MLP family.  icnf_loss_grad differentiates discrete Runge-Kutta steps
+                                 * and therefore integrates with Tsit5 whatever `alg` says (the reference's gradient is a
+                                 * continuous adjoint: neither is tied to the forward steps). */
 } icnf_solver;
+typedef enum icnf_alg { ICNF_ALG_TSIT5 = 0, ICNF_ALG_VCABM = 1 } icnf_alg;
 
 /* Hutchinson probe / base sample source.  `sample_offset` is the global column
  * index of this shard's first sample so that a sharded batch draws the same

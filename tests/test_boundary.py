@@ -43,7 +43,7 @@ def test_library_exports_every_declared_symbol(m):
 def test_struct_layouts_match_the_header(m):
     L = m._lib
     assert ctypes.sizeof(L.Config) == 4 * (6 + 9 + 1 + 3 + 3)
-    assert ctypes.sizeof(L.Solver) == 4 * 13
+    assert ctypes.sizeof(L.Solver) == 4 * 14 and L.Solver.alg.offset == 52
     assert ctypes.sizeof(L.Noise) == 24 and L.Noise.seed.offset == 8
     assert ctypes.sizeof(L.Stats) == 24
 
