@@ -163,6 +163,9 @@ struct EpiShared {
     uint32_t stage_addr;              // this warp's staging boxes: [32 rows][NC] bf16 hi, then lo
 };
 __shared__ EpiShared g_epi[4 * WQ];
+// bias of each epilogue warp's own columns (a private slice per warp, written and read by that warp only: no cross-warp
+// traffic, no double buffering, nothing for racecheck to flag)
+__shared__ float g_bias[4 * WQ][((128 / NC + WQ - 1) / WQ) * NC];
 
 struct EpiItem {          // registers (rebuilt from g_epi inside each epilogue function)
     const EpiShared* g;
@@ -382,7 +385,6 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
     uint64_t* tmem_full = empty + NSTAGE;      // [2]
     uint64_t* tmem_empty = tmem_full + 2;      // [2]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    float* sbias = reinterpret_cast<float*>(smem + NSTAGE * STAGE_BYTES + 256);   // [2][BN]
     uint8_t* sstage = smem + NSTAGE * STAGE_BYTES + 256 + 2 * 256 * 4;            // [epilogue warp][EPI_STAGE_BYTES]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -507,12 +509,10 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
             const int as = i & 1;
             const int m0 = mt * TBM, n0 = wi.nt * BN;
             const int pitch = SPLIT ? g.lo_o : g.ldo;
-            float* sb = sbias + as * BN;
+            float* sb = g_bias[warp];
             const int cbeg = chunk_begin(BN, cq) * NC, nch = chunk_begin(BN, cq + 1) - chunk_begin(BN, cq);
-            // every warp stages the bias of ITS columns itself (no CTA-wide barrier: the 12 epilogue warps run out of step).
-            // The loads are issued before the wait, the shared-memory writes after it: by then every warp has finished
-            // reading this buffer for item i - 2 (their arrivals on tmem_empty precede this item's MMAs).  The four
-            // lane quarters of a column group write identical values.
+            // every warp stages the bias of ITS columns in its own slice (no CTA-wide barrier: the 12 epilogue warps run
+            // out of step); the loads are issued before the wait on the accumulator
             float bv[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
             tc_fence_after();
 #pragma unroll
             for (int u = 0; u < 2; ++u)
-                if (lane + 32 * u < nch * NC) sb[cbeg + lane + 32 * u] = bv[u];
+                if (lane + 32 * u < nch * NC) sb[lane + 32 * u] = bv[u];
             __syncwarp();
             if (threadIdx.x == 0) trace_event(P.trace, 16384, 4000 + (i % 1000));
             const int m = m0 + q * 32 + lane;
@@ -536,7 +536,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
                 e.n_limit = g.n_limit; e.ldw = g.ldw; e.pitch = pitch;
                 e.m_base = m0 + q * 32; e.nb0 = n0 + cbeg; e.nch = nch; e.sl = sl;
                 e.trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + cbeg);
-                e.sb_addr = smem_u32(sb + cbeg);
+                e.sb_addr = smem_u32(sb);
                 e.dbg = P.dbg; e.direct = P.direct_stores;
                 e.map0 = &cg.mapO0; e.map1 = &cg.mapO1; e.stage_addr = smem_u32(sstage + warp * EPI_STAGE_BYTES);
             }
