@@ -1922,9 +1922,9 @@ static cudaError_t enqueue_stage(Workspace* w, const SolveArgs& a, StageArgs s, 
 
 // narrow MLPs, TestMode: the whole solve in one persistent kernel (narrow.cu)
 static bool narrow_route(Workspace* w, const SolveArgs& a, bool exact) {
-    return narrow::supported(w->cfg, exact, a) && narrow::smem_bytes(w->cfg) <= (size_t)226 * 1024;
+    return narrow::supported(w->cfg, exact, a) && narrow::smem_bytes(w->cfg, exact) <= (size_t)226 * 1024;
 }
-static cudaError_t narrow_solve(Workspace* w, const SolveArgs& a, int nvars, bool adaptive, cudaStream_t st) {
+static cudaError_t narrow_solve(Workspace* w, const SolveArgs& a, int nvars, bool exact, bool adaptive, cudaStream_t st) {
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1935,12 +1935,12 @@ static cudaError_t narrow_solve(Workspace* w, const SolveArgs& a, int nvars, boo
     b.wu[0] = w->U0.as<float>(); b.wu[1] = w->U1.as<float>(); b.wk[0] = w->KF0.as<float>(); b.wk[1] = w->KF1.as<float>();
     if (!b.partials) { GCK(w->TR.reserve(sizeof(double) * 4 * 32 * (size_t)sms)); b.partials = w->TR.as<double>(); }
     w->launches++;
-    return narrow::solve(w->cfg, w->amat.as<float>(), b, nvars, adaptive, sms, st);
+    return narrow::solve(w->cfg, w->amat.as<float>(), b, nvars, exact, adaptive, sms, st);
 }
 
 static cudaError_t solve_fixed(void* wsp, const float*, const SolveArgs& a, int nvars, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
-    if (narrow_route(w, a, exact)) return narrow_solve(w, a, nvars, false, st);
+    if (narrow_route(w, a, exact)) return narrow_solve(w, a, nvars, exact, false, st);
     GCK(reserve_common(w, a.B));
     GCK(load_inputs(w, a, nvars, st));
     StageArgs s = make_stage_args(w, a.B, exact, a.reg_e, a.reg_n, a.squared);
@@ -1974,7 +1974,7 @@ static cudaError_t solve_fixed(void* wsp, const float*, const SolveArgs& a, int 
 
 static cudaError_t solve_adaptive(void* wsp, const float*, const SolveArgs& a, int nvars, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
-    if (narrow_route(w, a, exact)) return narrow_solve(w, a, nvars, true, st);
+    if (narrow_route(w, a, exact)) return narrow_solve(w, a, nvars, exact, true, st);
     GCK(reserve_common(w, a.B));
     GCK(load_inputs(w, a, nvars, st));
     Ctrl* ctrl = w->ctrl.as<Ctrl>();

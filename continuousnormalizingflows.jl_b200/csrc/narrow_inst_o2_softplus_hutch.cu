@@ -1,0 +1,6 @@
+#include "narrow_kernel.cuh"
+namespace icnf {
+namespace narrow {
+ICNF_NARROW_INSTANCE(launch_o2_softplus_hutch, 2, ICNF_ACT_SOFTPLUS, false)
+}
+}

@@ -1,6 +1,6 @@
 #include "narrow_kernel.cuh"
 namespace icnf {
 namespace narrow {
-ICNF_NARROW_INSTANCE(launch_o4_any, 4, -1)
+ICNF_NARROW_INSTANCE(launch_o4_any_exact, 4, -1, true)
 }
 }

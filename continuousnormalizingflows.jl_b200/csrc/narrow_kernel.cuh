@@ -41,6 +41,10 @@ struct Layout {            // shared-memory offsets in floats
     int jt1, jt2, jt3;     // output units per warp of layers 1..3
     int ld12, ld3;         // padded row length of the transposed weights: 8 * JP / 8 * JP3
     int w1, b1, w2, at, b2, w3, b3, x, h1, d1, h2, red, total;
+    // Hutchinson modes (exact = 0): transposed-role copies of the weights for the VJP chain (W3b[i][unit of layer 2],
+    // W2b[unit of layer 2][unit of layer 1], W1b[unit of layer 1][z-row]), the probe tile, the zdot tile; no sigma' arrays
+    // (derived from h) and no trace matrix
+    int exact, w3b, w2b, w1b, eps, zdt;
 };
 
 struct Params {
@@ -96,6 +100,32 @@ __device__ __forceinline__ void act_any(int act, float a, float& h, float& d) {
     if constexpr (ACT >= 0) act_eval<ACT>(a, h, d);
     else act_eval_rt(act, a, h, d);
 }
+// sigma'(a) from h = sigma(a) (the Hutchinson path stores no sigma' arrays)
+template <int ACT>
+__device__ __forceinline__ float deriv_from_h(int act, float h) {
+    const int a = ACT >= 0 ? ACT : act;
+    if (a == ICNF_ACT_SOFTPLUS) return 1.0f - __expf(-h);
+    if (a == ICNF_ACT_TANH) return 1.0f - h * h;
+    if (a == ICNF_ACT_SIGMOID) return h * (1.0f - h);
+    return 1.0f;
+}
+// the probe of one tile (constant over the solve): supplied matrix or the in-kernel Philox draw of the other families
+static __device__ __noinline__ void fill_eps_tile(const SolveArgs& a, float* tile, long long tile0, int D) {
+    const int nblk = (D + 3) / 4;
+    for (int idx = threadIdx.x; idx < NS * nblk; idx += NTHR) {
+        const int s = idx % NS, blk = idx / NS;
+        const long long b = tile0 + s;
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        if (b < a.B) {
+            if (a.eps_kind == ICNF_EPS_SUPPLIED) {
+                for (int r = 0; r < 4; ++r) if (4 * blk + r < D) o[r] = __ldg(a.eps + b * D + 4 * blk + r);
+            } else {
+                philox_draw4(a.eps_kind, a.seed, PHILOX_STREAM_EPS, a.sample_offset + b, blk, o);
+            }
+        }
+        for (int r = 0; r < 4; ++r) if (4 * blk + r < D) tile[(4 * blk + r) * NS + s] = o[r];
+    }
+}
 // first touch of a state row (inference_prob / generate_prob): out of line, it is cold and its Gaussian draw is large
 static __device__ __noinline__ float input_value(const SolveArgs& a, long long b, int j, int D, int nvars) {
     const int S = D + 3;
@@ -105,6 +135,104 @@ static __device__ __noinline__ float input_value(const SolveArgs& a, long long b
     float o[4];
     philox_draw4(ICNF_EPS_GAUSSIAN, a.seed, PHILOX_STREAM_BASE, a.sample_offset + b, j >> 2, o);
     return o[j & 3];
+}
+
+// Hutchinson RHS (TrainMode): forward pass, then the VJP chain of the probe through transposed-role weight copies,
+//   v2 = W3' eps, g2 = v2 .* s'(a2);  v1 = W2' g2, g1 = v1 .* s'(a1);  q = W1z' g1 = eps' J,
+// and per sample l' = -q . eps, E' = |zdot|, n' = |q| (icnf.jl:517-536, :184-251).  zd = zdot rows in owner layout; the three
+// per-sample values are left in sm[L.red + {0, 1, 2} * NS + sample].  Eight CTA barriers.
+template <int JP, int JP3, int ACT>
+__device__ __forceinline__ void rhs_tile_hutch(const Layout& L, float* sm, int warp, int lane, int reg_e, int reg_n, int squared,
+                                               float (&zd)[JP3][SPT]) {
+    float2 acc[JP / 2][SPT], dummy[JP / 2][SPT];
+    // ---- forward
+    layer_mm<JP, false>(sm + L.w1 + warp * JP, nullptr, L.ld12, sm + L.x, nullptr, L.n0, lane, acc, dummy);
+#pragma unroll
+    for (int r = 0; r < JP; ++r) {
+        const int j = warp * L.jt1 + r;
+        if (r < L.jt1 && j < L.n1) {
+            const float b = sm[L.b1 + warp * JP + r];
+            float h[SPT], d[SPT];
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) act_any<ACT>(L.act, comp(acc[r >> 1][s], r & 1) + b, h[s], d[s]);
+            *reinterpret_cast<float4*>(sm + L.h1 + j * NS + 4 * lane) = make_float4(h[0], h[1], h[2], h[3]);
+        }
+    }
+    __syncthreads();
+    layer_mm<JP, false>(sm + L.w2 + warp * JP, nullptr, L.ld12, sm + L.h1, nullptr, L.n1, lane, acc, dummy);
+#pragma unroll
+    for (int r = 0; r < JP; ++r) {
+        const int j = warp * L.jt2 + r;
+        if (r < L.jt2 && j < L.n2) {
+            const float b = sm[L.b2 + warp * JP + r];
+            float h[SPT], d[SPT];
+#pragma unroll
+            for (int s = 0; s < SPT; ++s) act_any<ACT>(L.act, comp(acc[r >> 1][s], r & 1) + b, h[s], d[s]);
+            *reinterpret_cast<float4*>(sm + L.h2 + j * NS + 4 * lane) = make_float4(h[0], h[1], h[2], h[3]);
+        }
+    }
+    __syncthreads();
+    float2 acc3[JP3 / 2][SPT], dummy3[JP3 / 2][SPT];
+    layer_mm<JP3, false>(sm + L.w3 + warp * JP3, nullptr, L.ld3, sm + L.h2, nullptr, L.n2, lane, acc3, dummy3);
+#pragma unroll
+    for (int r = 0; r < JP3; ++r) {
+        const float b = sm[L.b3 + warp * JP3 + r];
+        const int j = warp * L.jt3 + r;
+#pragma unroll
+        for (int s = 0; s < SPT; ++s) zd[r][s] = comp(acc3[r >> 1][s], r & 1) + b;
+        if (r < L.jt3 && j < L.D) *reinterpret_cast<float4*>(sm + L.zdt + j * NS + 4 * lane) = make_float4(zd[r][0], zd[r][1], zd[r][2], zd[r][3]);
+    }
+    __syncthreads();            // every warp has read h2 (layer 3) before it is overwritten with g2
+    // ---- VJP chain
+    layer_mm<JP, false>(sm + L.w3b + warp * JP, nullptr, L.ld12, sm + L.eps, nullptr, L.D, lane, acc, dummy);
+#pragma unroll
+    for (int r = 0; r < JP; ++r) {
+        const int j = warp * L.jt2 + r;
+        if (r < L.jt2 && j < L.n2) {
+            float* hp = sm + L.h2 + j * NS + 4 * lane;
+            const float4 h = *reinterpret_cast<const float4*>(hp);
+            *reinterpret_cast<float4*>(hp) = make_float4(comp(acc[r >> 1][0], r & 1) * deriv_from_h<ACT>(L.act, h.x),
+                                                         comp(acc[r >> 1][1], r & 1) * deriv_from_h<ACT>(L.act, h.y),
+                                                         comp(acc[r >> 1][2], r & 1) * deriv_from_h<ACT>(L.act, h.z),
+                                                         comp(acc[r >> 1][3], r & 1) * deriv_from_h<ACT>(L.act, h.w));
+        }
+    }
+    __syncthreads();
+    layer_mm<JP, false>(sm + L.w2b + warp * JP, nullptr, L.ld12, sm + L.h2, nullptr, L.n2, lane, acc, dummy);
+#pragma unroll
+    for (int r = 0; r < JP; ++r) {
+        const int j = warp * L.jt1 + r;
+        if (r < L.jt1 && j < L.n1) {
+            float* hp = sm + L.h1 + j * NS + 4 * lane;
+            const float4 h = *reinterpret_cast<const float4*>(hp);
+            *reinterpret_cast<float4*>(hp) = make_float4(comp(acc[r >> 1][0], r & 1) * deriv_from_h<ACT>(L.act, h.x),
+                                                         comp(acc[r >> 1][1], r & 1) * deriv_from_h<ACT>(L.act, h.y),
+                                                         comp(acc[r >> 1][2], r & 1) * deriv_from_h<ACT>(L.act, h.z),
+                                                         comp(acc[r >> 1][3], r & 1) * deriv_from_h<ACT>(L.act, h.w));
+        }
+    }
+    __syncthreads();
+    layer_mm<JP3, false>(sm + L.w1b + warp * JP3, nullptr, L.ld3, sm + L.h1, nullptr, L.n1, lane, acc3, dummy3);
+#pragma unroll
+    for (int r = 0; r < JP3; ++r) {
+        const int j = warp * L.jt3 + r;     // q row j: into the (dead) stage-input rows of the x tile
+        if (r < L.jt3 && j < L.D)
+            *reinterpret_cast<float4*>(sm + L.x + j * NS + 4 * lane) =
+                make_float4(comp(acc3[r >> 1][0], r & 1), comp(acc3[r >> 1][1], r & 1), comp(acc3[r >> 1][2], r & 1), comp(acc3[r >> 1][3], r & 1));
+    }
+    __syncthreads();
+    if (threadIdx.x < NS) {      // one thread per sample: the three reductions over the D' rows, in row order
+        const int s = threadIdx.x;
+        float s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (int i = 0; i < L.D; ++i) {
+            const float q = sm[L.x + i * NS + s], e = sm[L.eps + i * NS + s], z = sm[L.zdt + i * NS + s];
+            s1 = fmaf(q, e, s1); s2 = fmaf(q, q, s2); s3 = fmaf(z, z, s3);
+        }
+        sm[L.red + s] = -s1;
+        sm[L.red + NS + s] = reg_e ? tiny::vec_norm(s3, squared) : 0.f;
+        sm[L.red + 2 * NS + s] = reg_n ? tiny::vec_norm(s2, squared) : 0.f;
+    }
+    __syncthreads();
 }
 
 // One RHS evaluation of the tile whose network input sits in sm[L.x].  zd[r][s] = derivative of z-row (warp jt3 + r) for
@@ -168,7 +296,7 @@ __device__ __forceinline__ void rhs_tile(const Layout& L, float* sm, int warp, i
     __syncthreads();
 }
 
-template <int JP, int JP3, int ACT>
+template <int JP, int JP3, int ACT, bool EXACT>
 __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ Params P) {
     extern __shared__ __align__(16) float sm[];
     __shared__ double sred[2 * NW + 2];
@@ -193,7 +321,18 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
             const int k = i / L.n2, j = i - k * L.n2;
             const int col = (j / L.jt2) * JP + (j % L.jt2);
             sm[L.w2 + k * L.ld12 + col] = th[P.woff[1] + i];
-            sm[L.at + k * L.ld12 + col] = P.amat[i];
+            if constexpr (EXACT) sm[L.at + k * L.ld12 + col] = P.amat[i];
+            else sm[L.w2b + j * L.ld12 + (k / L.jt1) * JP + (k % L.jt1)] = th[P.woff[1] + i];     // W2b[unit of layer 2][unit of layer 1]
+        }
+        if constexpr (!EXACT) {
+            for (int i = threadIdx.x; i < L.n2 * D; i += NTHR) {       // W3 (r, j) at j * D + r  ->  W3b[r][unit j of layer 2]
+                const int j = i / D, r = i - j * D;
+                sm[L.w3b + r * L.ld12 + (j / L.jt2) * JP + (j % L.jt2)] = th[P.woff[2] + i];
+            }
+            for (int i = threadIdx.x; i < D * L.n1; i += NTHR) {       // W1 (j, r) at r * n1 + j, r < D'  ->  W1b[unit j of layer 1][z-row r]
+                const int r = i / L.n1, j = i - r * L.n1;
+                sm[L.w1b + j * L.ld3 + (r / L.jt3) * JP3 + (r % L.jt3)] = th[P.woff[0] + i];
+            }
         }
         for (int i = threadIdx.x; i < L.n2 * D; i += NTHR) {
             const int k = i / D, j = i - k * D;
@@ -262,7 +401,12 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
             };
             // ---- state of the tile: z rows (owners), l (warp 0)
             float z[JP3][SPT], k1[JP3][SPT], K[4][JP3][SPT], zs[JP3][SPT], ze[JP3][SPT];
-            float lv[SPT] = {0.f, 0.f, 0.f, 0.f}, kl1[SPT] = {0.f, 0.f, 0.f, 0.f}, sl[SPT], el[SPT];
+            constexpr int NX = EXACT ? 1 : 3;     // rows l (, E, n) of the state: warp 0, lane = four samples
+            float lv[NX][SPT], kl1[NX][SPT], sl[NX][SPT], el[NX][SPT];
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) { lv[x][s] = 0.f; kl1[x][s] = 0.f; sl[x][s] = 0.f; el[x][s] = 0.f; }
             if (phase == P_INIT) {
 #pragma unroll
                 for (int r = 0; r < JP3; ++r) {
@@ -277,7 +421,9 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                 }
                 if (warp == 0 && a.in_kind == IN_U0) {
 #pragma unroll
-                    for (int s = 0; s < SPT; ++s) if (b0 + s < B) lv[s] = __ldg(a.in + (b0 + s) * S + D);
+                    for (int x = 0; x < NX; ++x)
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) if (b0 + s < B) lv[x][s] = __ldg(a.in + (b0 + s) * S + D + x);
                 }
             } else {
 #pragma unroll
@@ -289,9 +435,12 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                     k1[r][0] = k.x; k1[r][1] = k.y; k1[r][2] = k.z; k1[r][3] = k.w;
                 }
                 if (warp == 0) {
-                    const float4 u = ld4(a.wu[cur], D), k = ld4(a.wk[cur], D);
-                    lv[0] = u.x; lv[1] = u.y; lv[2] = u.z; lv[3] = u.w;
-                    kl1[0] = k.x; kl1[1] = k.y; kl1[2] = k.z; kl1[3] = k.w;
+#pragma unroll
+                    for (int x = 0; x < NX; ++x) {
+                        const float4 u = ld4(a.wu[cur], D + x), k = ld4(a.wk[cur], D + x);
+                        lv[x][0] = u.x; lv[x][1] = u.y; lv[x][2] = u.z; lv[x][3] = u.w;
+                        kl1[x][0] = k.x; kl1[x][1] = k.y; kl1[x][2] = k.z; kl1[x][3] = k.w;
+                    }
                 }
             }
             // conditioning rows of the network input are constant over the stages
@@ -300,15 +449,22 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                 const long long b = tile * NS + s;
                 sm[L.x + (D + L.tin + c) * NS + s] = b < B ? __ldg(a.ys + b * L.C + c) : 0.f;
             }
+            if constexpr (!EXACT) fill_eps_tile(a, sm + L.eps, tile * NS, D);
             if (phase == P_STEP) {
 #pragma unroll
                 for (int r = 0; r < JP3; ++r)
 #pragma unroll
                     for (int s = 0; s < SPT; ++s) { zs[r][s] = c_a[6][0] * k1[r][s]; ze[r][s] = c_bt[0] * k1[r][s]; }
 #pragma unroll
-                for (int s = 0; s < SPT; ++s) { sl[s] = c_a[6][0] * kl1[s]; el[s] = c_bt[0] * kl1[s]; }
+                for (int x = 0; x < NX; ++x)
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) { sl[x][s] = c_a[6][0] * kl1[x][s]; el[x][s] = c_bt[0] * kl1[x][s]; }
             }
-            float zd[JP3][SPT], kl[SPT] = {0.f, 0.f, 0.f, 0.f};
+            float zd[JP3][SPT], kl[NX][SPT];
+#pragma unroll
+            for (int x = 0; x < NX; ++x)
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) kl[x][s] = 0.f;
             for (int sidx = 0; sidx < nstage; ++sidx) {
                 const int i = sidx + 1;   // Tsit5 stage (1..6) when stepping
                 // ---- stage input -> shared memory
@@ -338,10 +494,21 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                 }
                 if (L.tin && warp == 1) *reinterpret_cast<float4*>(sm + L.x + D * NS + 4 * lane) = make_float4(tt, tt, tt, tt);
                 __syncthreads();
-                rhs_tile<JP, JP3, ACT>(L, sm, warp, lane, zd);
-                if (warp == 0) {
-                    const float4 tr = *reinterpret_cast<const float4*>(sm + L.red + 4 * lane);
-                    kl[0] = -tr.x; kl[1] = -tr.y; kl[2] = -tr.z; kl[3] = -tr.w;
+                if constexpr (EXACT) {
+                    rhs_tile<JP, JP3, ACT>(L, sm, warp, lane, zd);
+                    if (warp == 0) {
+                        const float4 tr = *reinterpret_cast<const float4*>(sm + L.red + 4 * lane);
+                        kl[0][0] = -tr.x; kl[0][1] = -tr.y; kl[0][2] = -tr.z; kl[0][3] = -tr.w;
+                    }
+                } else {
+                    rhs_tile_hutch<JP, JP3, ACT>(L, sm, warp, lane, a.reg_e, a.reg_n, a.squared, zd);
+                    if (warp == 0) {
+#pragma unroll
+                        for (int x = 0; x < NX; ++x) {
+                            const float4 v = *reinterpret_cast<const float4*>(sm + L.red + x * NS + 4 * lane);
+                            kl[x][0] = v.x; kl[x][1] = v.y; kl[x][2] = v.z; kl[x][3] = v.w;
+                        }
+                    }
                 }
                 // ---- stage bookkeeping (stages 1..5 of a step: k2..k6)
                 if (phase == P_STEP && i < 6) {
@@ -355,7 +522,9 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                             ze[r][s] = fmaf(bti, zd[r][s], ze[r][s]);
                         }
 #pragma unroll
-                    for (int s = 0; s < SPT; ++s) { sl[s] = fmaf(bi, kl[s], sl[s]); el[s] = fmaf(bti, kl[s], el[s]); }
+                    for (int x = 0; x < NX; ++x)
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) { sl[x][s] = fmaf(bi, kl[x][s], sl[x][s]); el[x][s] = fmaf(bti, kl[x][s], el[x][s]); }
                 }
             }
             // ---- epilogue of the phase for this tile
@@ -375,14 +544,17 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                     }
                 }
                 if (warp == 0) {
-                    st4(a.wu[0], D, make_float4(lv[0], lv[1], lv[2], lv[3]));
-                    st4(a.wk[0], D, make_float4(kl[0], kl[1], kl[2], kl[3]));
 #pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        if (b0 + s >= B) continue;
-                        const float sk = ctl.abstol + fabsf(lv[s]) * ctl.reltol;
-                        acc_a += (double)((lv[s] / sk) * (lv[s] / sk));
-                        acc_b += (double)((kl[s] / sk) * (kl[s] / sk));
+                    for (int x = 0; x < NX; ++x) {
+                        st4(a.wu[0], D + x, make_float4(lv[x][0], lv[x][1], lv[x][2], lv[x][3]));
+                        st4(a.wk[0], D + x, make_float4(kl[x][0], kl[x][1], kl[x][2], kl[x][3]));
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            if (b0 + s >= B) continue;
+                            const float sk = ctl.abstol + fabsf(lv[x][s]) * ctl.reltol;
+                            acc_a += (double)((lv[x][s] / sk) * (lv[x][s] / sk));
+                            acc_b += (double)((kl[x][s] / sk) * (kl[x][s] / sk));
+                        }
                     }
                 }
             } else if (phase == P_PROBE) {
@@ -399,12 +571,14 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                 }
                 if (warp == 0) {
 #pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        if (b0 + s >= B) continue;
-                        const float sk = ctl.abstol + fabsf(lv[s]) * ctl.reltol;
-                        const float df = (kl[s] - kl1[s]) / sk;
-                        acc_a += (double)(df * df);
-                    }
+                    for (int x = 0; x < NX; ++x)
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            if (b0 + s >= B) continue;
+                            const float sk = ctl.abstol + fabsf(lv[x][s]) * ctl.reltol;
+                            const float df = (kl[x][s] - kl1[x][s]) / sk;
+                            acc_a += (double)(df * df);
+                        }
                 }
             } else {
                 // zd / kl hold the FSAL stage k7 = f(u_new)
@@ -427,19 +601,22 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                     st4(a.wk[cur ^ 1], j, make_float4(zd[r][0], zd[r][1], zd[r][2], zd[r][3]));
                 }
                 if (warp == 0) {
-                    float ln[SPT];
 #pragma unroll
-                    for (int s = 0; s < SPT; ++s) {
-                        ln[s] = fmaf(h, sl[s], lv[s]);
-                        if (b0 + s < B) {
-                            const float e = h * fmaf(c_bt[6], kl[s], el[s]);
-                            const float sk = ctl.abstol + fmaxf(fabsf(lv[s]), fabsf(ln[s])) * ctl.reltol;
-                            const float q = e / sk;
-                            acc_a += (double)(q * q);
+                    for (int x = 0; x < NX; ++x) {
+                        float ln[SPT];
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) {
+                            ln[s] = fmaf(h, sl[x][s], lv[x][s]);
+                            if (b0 + s < B) {
+                                const float e = h * fmaf(c_bt[6], kl[x][s], el[x][s]);
+                                const float sk = ctl.abstol + fmaxf(fabsf(lv[x][s]), fabsf(ln[s])) * ctl.reltol;
+                                const float q = e / sk;
+                                acc_a += (double)(q * q);
+                            }
                         }
+                        st4(a.wu[cur ^ 1], D + x, make_float4(ln[0], ln[1], ln[2], ln[3]));
+                        st4(a.wk[cur ^ 1], D + x, make_float4(kl[x][0], kl[x][1], kl[x][2], kl[x][3]));
                     }
-                    st4(a.wu[cur ^ 1], D, make_float4(ln[0], ln[1], ln[2], ln[3]));
-                    st4(a.wk[cur ^ 1], D, make_float4(kl[0], kl[1], kl[2], kl[3]));
                 }
             }
         }
@@ -507,14 +684,19 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
             if (a.out_u) a.out_u[b * S + j] = v;
             if (a.out_x && j < P.nvars) a.out_x[b * P.nvars + j] = v;
         }
-        if (moved) l = a.wu[cur][(long long)D * B + b];
-        else if (a.in_kind == IN_U0) l = a.in[b * S + D];
-        if (a.out_u) { a.out_u[b * S + D] = l; a.out_u[b * S + D + 1] = 0.f; a.out_u[b * S + D + 2] = 0.f; }
+        float E = 0.f, n = 0.f;
+        if (moved) {
+            l = a.wu[cur][(long long)D * B + b];
+            if constexpr (!EXACT) { E = a.wu[cur][(long long)(D + 1) * B + b]; n = a.wu[cur][(long long)(D + 2) * B + b]; }
+        } else if (a.in_kind == IN_U0) {
+            l = a.in[b * S + D]; E = a.in[b * S + D + 1]; n = a.in[b * S + D + 2];
+        }
+        if (a.out_u) { a.out_u[b * S + D] = l; a.out_u[b * S + D + 1] = E; a.out_u[b * S + D + 2] = n; }
         const float logp = -0.91893853320467274178f * (float)D - 0.5f * zz - l;
         const float Aa = a.reg_a ? tiny::vec_norm(za, a.squared) : 0.0f;
         if (a.out_logp) a.out_logp[b] = logp;
-        if (a.out_regs) { a.out_regs[b * 3] = 0.f; a.out_regs[b * 3 + 1] = 0.f; a.out_regs[b * 3 + 2] = Aa; }
-        if (a.out_lossterm) a.out_lossterm[b] = -logp + a.lam3 * Aa;
+        if (a.out_regs) { a.out_regs[b * 3] = E; a.out_regs[b * 3 + 1] = n; a.out_regs[b * 3 + 2] = Aa; }
+        if (a.out_lossterm) a.out_lossterm[b] = -logp + a.lam1 * E + a.lam2 * n + a.lam3 * Aa;
     }
     if (P.adaptive && a.xg.nranks > 1 && blockIdx.x == 0 && threadIdx.x == 0)
         *reinterpret_cast<volatile unsigned*>(a.xg.peers.p[a.xg.rank]) = red.seq;
@@ -528,30 +710,28 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
     }
 }
 
-template <int JP, int JP3, int ACT>
+template <int JP, int JP3, int ACT, bool EXACT>
 static cudaError_t launch(const Params& P, int grid, size_t smem, cudaStream_t st) {
     static size_t attr[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (attr[dev & 63] < smem) {
-        cudaError_t e = cudaFuncSetAttribute(solve_kernel<JP, JP3, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(solve_kernel<JP, JP3, ACT, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr[dev & 63] = smem;
     }
     void* args[] = {(void*)&P};
-    return cudaLaunchCooperativeKernel((const void*)solve_kernel<JP, JP3, ACT>, dim3(grid), dim3(NTHR), args, smem, st);
+    return cudaLaunchCooperativeKernel((const void*)solve_kernel<JP, JP3, ACT, EXACT>, dim3(grid), dim3(NTHR), args, smem, st);
 }
 
 
-// one translation unit per (JP3, ACT): the kernel is large and ptxas takes ~15 s per instantiation
-#define ICNF_NARROW_INSTANCE(NAME, JP3V, ACTV)                                                                    \
+// one translation unit per (JP3, ACT, EXACT): the kernel is large and ptxas takes ~15 s per instantiation
+#define ICNF_NARROW_INSTANCE(NAME, JP3V, ACTV, EXACTV)                                                            \
     cudaError_t NAME(const Params& P, int JP, int grid, size_t smem, cudaStream_t st) {                           \
         switch (JP) {                                                                                             \
-            case 4: return launch<4, JP3V, ACTV>(P, grid, smem, st);                                              \
-            case 8: return launch<8, JP3V, ACTV>(P, grid, smem, st);                                              \
-            case 10: return launch<10, JP3V, ACTV>(P, grid, smem, st);                                            \
-            case 12: return launch<12, JP3V, ACTV>(P, grid, smem, st);                                            \
-            case 16: return launch<16, JP3V, ACTV>(P, grid, smem, st);                                            \
+            case 4: return launch<4, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                      \
+            case 10: return launch<10, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                    \
+            case 16: return launch<16, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                    \
             default: return cudaErrorInvalidConfiguration;                                                        \
         }                                                                                                         \
     }

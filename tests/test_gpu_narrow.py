@@ -1,4 +1,4 @@
-"""GPU parity tests of the narrow fast path (csrc/narrow_kernel.cuh): the whole exact-trace Tsit5 solve of a narrow
+"""GPU parity tests of the narrow fast path (csrc/narrow_kernel.cuh): the whole Tsit5 solve (exact trace or Hutchinson) of a narrow
 two-hidden-layer MLP in one persistent kernel, any widths at run time.  Checked against the CPU oracle over a seeded
 sweep of shapes (widths that do and do not divide by the 8 warps, conditioning inputs, autonomous fields, every
 activation), ragged batches, both time directions.  RTOL = 1e-4 (north_star)."""
@@ -61,6 +61,23 @@ def test_single_launch_solve_matches_oracle(m, case):
     np.testing.assert_allclose(logp, rl.numpy(), rtol=RTOL, atol=2e-5)
     np.testing.assert_allclose(A, rA.numpy(), rtol=RTOL, atol=2e-5)
     assert not E.any() and not n.any()
+    # Hutchinson modes (supplied probe): log p(x) estimate and the RNODE regularisers, one launch as well
+    eps = rng.standard_normal((nvars + naug, B)).astype(np.float32)
+    for mode, omode in ((m.TrainMode(True), O.TRAIN_REG), (m.TrainMode(False), O.TRAIN_NOREG)):
+        before = icnf.launch_count
+        logp, (E, n, A) = m.inference(icnf, mode, *args, theta, {}, eps=eps, tspan=icnf.tspan)
+        assert icnf.launch_count - before <= 2
+        gs = icnf.last_stats
+        rl, (rE, rn, rA) = O.inference(om, omode, t64(xs), t64(theta), t64(eps), t64(ys))
+        assert gs.status == 0 and gs.t_final == pytest.approx(1.0)
+        np.testing.assert_allclose(logp, rl.numpy(), rtol=RTOL, atol=3e-5)
+        np.testing.assert_allclose(E, rE.numpy(), rtol=RTOL, atol=3e-5)
+        np.testing.assert_allclose(A, rA.numpy(), rtol=RTOL, atol=3e-5)
+        np.testing.assert_allclose(n, rn.numpy(), rtol=RTOL, atol=2e-2 * float(rn.abs().mean()) + 1e-5)
+    got = m.base_sol(icnf, m.TrainMode(True), O.make_u0(om, t64(xs)).numpy().astype(np.float32), theta, tspan=(0.0, 0.25), eps=eps,
+                     ys=ys, adaptive=False, dt=0.125)
+    ref = O.solve(om, O.TRAIN_REG, O.make_u0(om, t64(xs)), t64(theta), t64(eps), t64(ys), 0.0, 0.25, O.SolverOpts(adaptive=False, dt=0.125)).numpy()
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=3e-5)
     # fixed steps agree step for step (full state, both directions)
     u0 = O.make_u0(om, t64(xs)).numpy().astype(np.float32)
     for k, (t0, t1) in ((3, (0.0, 0.375)), (2, (0.25, 0.0))):
