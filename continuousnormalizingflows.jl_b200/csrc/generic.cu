@@ -1930,6 +1930,10 @@ static cudaError_t narrow_solve(Workspace* w, const SolveArgs& a, int nvars, boo
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     SolveArgs b = a;
     const size_t f = sizeof(float);
+    if (a.ckpt) {   // a training solve: the reverse sweep (multi-launch, below) reads the probe and the conditions from the workspace
+        GCK(reserve_common(w, a.B));
+        GCK(load_inputs(w, a, nvars, st));
+    }
     GCK(w->U0.reserve(f * w->S * a.B)); GCK(w->U1.reserve(f * w->S * a.B));
     GCK(w->KF0.reserve(f * w->S * a.B)); GCK(w->KF1.reserve(f * w->S * a.B));
     b.wu[0] = w->U0.as<float>(); b.wu[1] = w->U1.as<float>(); b.wk[0] = w->KF0.as<float>(); b.wk[1] = w->KF1.as<float>();

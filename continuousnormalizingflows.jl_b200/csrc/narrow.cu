@@ -17,7 +17,7 @@ static int round_up(int x, int m) { return (x + m - 1) / m * m; }
 
 bool supported(const icnf_config& cfg, bool exact, const SolveArgs& a) {
     if (cfg.n_layers != 3 || cfg.precision != ICNF_FP32) return false;
-    if (a.ckpt || a.out_loss) return false;                       // training solves keep the multi-launch path (checkpoints)
+    if (a.out_loss) return false;
     if (!exact && a.mode == ICNF_TEST) return false;
     const int D = cfg.nvars + cfg.naug;
     if (D > 32 || cfg.sizes[1] > 128 || cfg.sizes[2] > 128 || cfg.sizes[0] > 160) return false;

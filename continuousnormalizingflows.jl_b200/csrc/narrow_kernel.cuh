@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                 hmag = last ? remaining : dt;
                 h = tdir * hmag;
                 if (!(hmag > 0.0f) || t + h == t) { status = ICNF_ERR_DT_UNDERFLOW; break; }
-                if (++attempts > ctl.max_steps) { status = ICNF_ERR_MAX_STEPS; break; }
+                if (++attempts > ctl.max_steps || (a.ckpt && nacc >= a.max_ckpt_steps)) { status = ICNF_ERR_MAX_STEPS; break; }
             } else {
                 if (fixed_step >= a.nsteps) break;
                 const float tb = fminf(span, fixed_step * a.dt);
@@ -450,7 +450,15 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                 sm[L.x + (D + L.tin + c) * NS + s] = b < B ? __ldg(a.ys + b * L.C + c) : 0.f;
             }
             if constexpr (!EXACT) fill_eps_tile(a, sm + L.eps, tile * NS, D);
+            // training checkpoints: the inputs of the six stages of the step, ckpt[slot][stage][D'][B] (a rejected attempt's
+            // slot is simply rewritten)
+            auto ckpt_stage = [&](int stage) { return a.ckpt + ((long long)nacc * 6 + stage) * D * B; };
             if (phase == P_STEP) {
+                if (a.ckpt) {
+#pragma unroll
+                    for (int r = 0; r < JP3; ++r)
+                        if (own[r]) st4(ckpt_stage(0), warp * L.jt3 + r, make_float4(z[r][0], z[r][1], z[r][2], z[r][3]));
+                }
 #pragma unroll
                 for (int r = 0; r < JP3; ++r)
 #pragma unroll
@@ -491,6 +499,7 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
                         xi[s] = v;
                     }
                     *reinterpret_cast<float4*>(sm + L.x + (warp * L.jt3 + r) * NS + 4 * lane) = make_float4(xi[0], xi[1], xi[2], xi[3]);
+                    if (a.ckpt && phase == P_STEP && i < 6) st4(ckpt_stage(i), warp * L.jt3 + r, make_float4(xi[0], xi[1], xi[2], xi[3]));
                 }
                 if (L.tin && warp == 1) *reinterpret_cast<float4*>(sm + L.x + D * NS + 4 * lane) = make_float4(tt, tt, tt, tt);
                 __syncthreads();
@@ -626,6 +635,7 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
             // fixed steps: a tile's state is written and read by the same threads of the same CTA (tile -> CTA is static),
             // so the steps need no grid-wide synchronisation at all
             if (phase == P_INIT) { nf = 1; phase = P_STEP; continue; }
+            if (a.steps && blockIdx.x == 0 && threadIdx.x == 0) { a.steps[nacc].t = t; a.steps[nacc].dt = h; }
             nf += 6; nacc++; dt_last = h; fixed_step++; cur ^= 1;
             t = (fixed_step >= a.nsteps) ? a.t1 : t + h;
             continue;
@@ -657,6 +667,7 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
             float q = q11 / powf(qold, ctl.beta2);
             q = fmaxf(1.0f / ctl.qmax, fminf(1.0f / ctl.qmin, q / ctl.gamma));
             if (eest <= 1.0f) {
+                if (a.steps && blockIdx.x == 0 && threadIdx.x == 0) { a.steps[nacc].t = t; a.steps[nacc].dt = h; }
                 nacc++;
                 dt_last = h;
                 t = last ? a.t1 : t + h;
@@ -683,6 +694,7 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
             if (j >= P.nvars) za = fmaf(v, v, za);
             if (a.out_u) a.out_u[b * S + j] = v;
             if (a.out_x && j < P.nvars) a.out_x[b * P.nvars + j] = v;
+            if (a.ckpt) a.ckpt[(((long long)nacc * 6) * D + j) * B + b] = v;     // slot `nacc`, stage 0 = the final state
         }
         float E = 0.f, n = 0.f;
         if (moved) {

@@ -99,3 +99,27 @@ def test_generate_round_trip(m):
     logp, _ = m.inference(icnf, m.TestMode(), xs, theta, {})
     rl, _ = O.inference(om, O.TEST, t64(xs), t64(theta), None, None)
     np.testing.assert_allclose(logp, rl.numpy(), rtol=RTOL, atol=2e-5)
+
+
+@pytest.mark.parametrize("adaptive", [False, True])
+@pytest.mark.parametrize("case", [SWEEP[0], SWEEP[3]], ids=["3-32-32-softplus", "5+2c3-33-47-tanh"])
+def test_training_gradient_from_single_launch_checkpoints(m, case, adaptive):
+    """A training step of a narrow network: the forward solve (one launch) records the stage-input checkpoints that the
+    multi-launch reverse sweep of the generic family consumes; loss, d theta and d xs against the oracle's autograd."""
+    nvars, naug, ncond, n1, n2, act, autonomous, _ = case
+    B = 200
+    icnf, om = build(m, nvars, naug, ncond, n1, n2, act, autonomous)
+    rng = np.random.default_rng(9)
+    theta = O.init_params(om, 5, np.float32, bias_scale=0.3)
+    xs = rng.standard_normal((nvars, B)).astype(np.float32)
+    ys = rng.standard_normal((ncond, B)).astype(np.float32) if ncond else None
+    eps = rng.standard_normal((nvars + naug, B)).astype(np.float32)
+    args = (xs,) if ys is None else (xs, ys)
+    sol = {} if adaptive else dict(adaptive=False, dt=0.25)
+    l, g, gx = m.loss_and_gradient(icnf, m.TrainMode(True), *args, theta, {}, eps=eps, tspan=icnf.tspan, want_dxs=True, **sol)
+    opts = O.SolverOpts() if adaptive else O.SolverOpts(adaptive=False, dt=0.25)
+    rl, rg, rgx = O.loss_grad(om, O.TRAIN_REG, t64(xs), t64(theta), t64(eps), t64(ys), opts=opts, want_dxs=True)
+    assert abs(l - float(rl)) <= 2e-4 * abs(float(rl))
+    tol = 2e-4 if not adaptive else 2e-3
+    assert np.linalg.norm(g - rg.numpy()) <= tol * np.linalg.norm(rg.numpy())
+    assert np.linalg.norm(gx - rgx.numpy()) <= tol * np.linalg.norm(rgx.numpy())
