@@ -249,6 +249,7 @@ def logp_extras(m, local, dev, flush_buf):
         ("config1_usage_B1024", dict(nvariables=1), "fp32", 1024, m.TestMode()),                        # examples/usage.jl shape, tiny
         ("config2_moons_B65536", dict(nvariables=2, naugments=0), "fp32", 65536, m.TestMode()),         # tiny
         ("config2_moons_w64_B65536", dict(nvariables=2, naugments=0, n_hidden=64), "fp32", 65536, m.TestMode()),   # 3-64-64-2
+        ("config2_moons_w64_B65536_hutch", dict(nvariables=2, naugments=0, n_hidden=64), "fp32", 65536, m.TrainMode(True)),   # same net, Hutchinson + regularisers
         ("config3_gmm16_B262144", dict(nvariables=16, naugments=0), "fp32", 262144, m.TestMode()),      # 17-68-68-16
         ("config3_gmm16_B262144_bf16x3tc", dict(nvariables=16, naugments=0), "bf16x3_tc", 262144, m.TestMode()),
         ("config5_cond64_B65536_fp32", dict(nvariables=64, naugments=0, nconditions=32), "fp32", 65536, m.TestMode()),   # 97-388-388-64
@@ -306,6 +307,23 @@ def config5_sweep(m, local, dev, flush_buf):
                                    "parity_err_subbatch": {"inference": e_inf, "generate": e_gen}, "kernel_family": icnf.kernel_family}
         del icnf
     return out
+
+
+def w64_training(m, local, dev, flush_buf):
+    """config 2's other width: 3-64-64-2 RNODE training step at batch 65 536 -- forward solve in one launch
+    (narrow kernel, checkpoints), reverse sweep on the fp32 SGEMMs of the generic family."""
+    icnf = _icnf(m, local, "fp32", nvariables=2, naugments=0, n_hidden=64, rng=4321)
+    rng = np.random.default_rng(7)
+    theta, _ = m.setup(rng, icnf)
+    err = parity_gate(m, icnf, m.TrainMode(True), theta, "train", {}, nb=128)
+    theta_d = torch.from_numpy(theta).to(dev)
+    B = 65536
+    xs = torch.from_numpy(np.ascontiguousarray(two_moons(B, seed=3).T.astype(np.float32))).to(dev)
+    ms = _timed_calls(lambda: m.loss_and_gradient(icnf, m.TrainMode(True), xs.t(), theta_d, {}, seed=3), flush_buf)
+    st = icnf.check_last()
+    return {"train_samples_per_sec": B / (ms * 1e-3), "ms_per_step": ms, "kernel_family": icnf.kernel_family,
+            "mode": "TrainMode(True) loss + gradient", "solver_steps": st.naccept, "rhs_calls": st.nf, "solver_status": st.status,
+            "parity_err_subbatch": err}
 
 
 def config4_training(m, local, dev, flush_buf, rank, world, precisions):
@@ -567,6 +585,7 @@ def main():
             extras.update(logp_extras(m, local, dev, flush_buf))
             extras["config5_generate_inference_sweep"] = config5_sweep(m, local, dev, flush_buf)
             extras["config2_train_device_adam"] = device_adam_variant(m, local, dev, flush_buf, B)
+            extras["config2_moons_w64_B65536_train"] = w64_training(m, local, dev, flush_buf)
             c4 = extras.get("config4_ffjord784_B8192_train_bf16x3_tc")
             if c4 and peaks.get("bf16_tflops_sustained"):
                 # tensor-pipe roofline of the wide path: algorithmic flop (x3 physical MMAs in split precision are

@@ -33,7 +33,7 @@ static Layout make_layout(const icnf_config& cfg, bool exact, int& JP, int& JP3)
     L.jt1 = (L.n1 + NW - 1) / NW; L.jt2 = (L.n2 + NW - 1) / NW; L.jt3 = (L.D + NW - 1) / NW;
     {
         const int need = std::max(L.jt1, L.jt2);
-        JP = need <= 4 ? 4 : need <= 10 ? 10 : 16;
+        JP = need <= 4 ? 4 : need <= 8 ? 8 : need <= 10 ? 10 : 16;
     }
     JP3 = L.jt3 <= 2 ? 2 : 4;
     L.ld12 = NW * JP; L.ld3 = NW * JP3;

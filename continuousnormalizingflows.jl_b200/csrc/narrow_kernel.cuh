@@ -742,6 +742,7 @@ static cudaError_t launch(const Params& P, int grid, size_t smem, cudaStream_t s
     cudaError_t NAME(const Params& P, int JP, int grid, size_t smem, cudaStream_t st) {                           \
         switch (JP) {                                                                                             \
             case 4: return launch<4, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                      \
+            case 8: return launch<8, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                      \
             case 10: return launch<10, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                    \
             case 16: return launch<16, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                    \
             default: return cudaErrorInvalidConfiguration;                                                        \
