@@ -8,7 +8,7 @@ CPU or PyTorch fallback for any numeric result.
 
 from ._lib import ICNFError, LIB_PATH, lib  # noqa: F401  (loads the shared library)
 from .api import (  # noqa: F401
-    B200MatrixMode, Chain, ComputeMode, Dense, ICNF, MatrixMode, Mode, SolverStats, TestMode, TrainMode,
+    B200MatrixMode, Chain, ComputeMode, Dense, ICNF, MatrixMode, Mode, PlanarLayer, SolverStats, TestMode, TrainMode,
     augmented_f, base_sol, create_group, generate, group_info, group_join_id, group_set_global_norm, group_unique_id, inference, loss,
     loss_and_gradient, measure_fp32_peak, setup,
 )
@@ -18,6 +18,6 @@ from .mlj import Adam, CondICNFModel, ICNFModel, WeightDecay, make_opt_callback 
 
 __all__ = [
     "ICNF", "inference", "generate", "loss", "loss_and_gradient", "setup", "augmented_f", "base_sol",
-    "TestMode", "TrainMode", "B200MatrixMode", "Dense", "Chain", "ICNFDist", "CondICNFDist",
+    "TestMode", "TrainMode", "B200MatrixMode", "Dense", "PlanarLayer", "Chain", "ICNFDist", "CondICNFDist",
     "ICNFModel", "CondICNFModel", "ICNFError", "SolverStats",
 ]

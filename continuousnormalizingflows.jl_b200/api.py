@@ -92,6 +92,39 @@ class Dense:
 
 
 @dataclass(frozen=True)
+class PlanarLayer:
+    """``PlanarLayer(n_in => n_out, activation; use_bias)`` (src/layers/planar_layer.jl:1-97): f(x) = u * act(w'x + b),
+    parameters ``(u [n_out], w [n_in], b [1])`` in that order.  It IS ``Dense(n_in => 1, act)`` followed by a bias-free
+    ``Dense(1 => n_out)``, which is how it reaches the kernels: the mirror (and the Julia glue) re-orders the parameters
+    into ``[w; b; u; 0]`` on the way in and the gradient back on the way out; the output bias stays zero."""
+    n_in: int
+    n_out: int
+    activation: str = "identity"
+    use_bias: bool = True
+
+    @property
+    def n_params(self) -> int:
+        return self.n_out + self.n_in + int(self.use_bias)
+
+    def to_lib(self, ps):
+        """planar (u, w[, b]) -> [W1 = w; b1 = b; W2 = u; b2 = 0] (numpy or torch, any device)."""
+        no, ni = self.n_out, self.n_in
+        if _is_torch(ps):
+            p = ps.detach().to(dtype=torch.float32).reshape(-1)
+            b = p[no + ni:no + ni + 1] if self.use_bias else p.new_zeros(1)
+            return torch.cat([p[no:no + ni], b, p[:no], p.new_zeros(no)])
+        p = np.asarray(ps, dtype=np.float32).reshape(-1)
+        b = p[no + ni:no + ni + 1] if self.use_bias else np.zeros(1, np.float32)
+        return np.concatenate([p[no:no + ni], b, p[:no], np.zeros(no, np.float32)])
+
+    def grad_from_lib(self, g):
+        """gradient w.r.t. [W1; b1; W2; b2] -> gradient w.r.t. (u, w[, b])."""
+        no, ni = self.n_out, self.n_in
+        parts = [g[ni + 1:ni + 1 + no], g[:ni]] + ([g[ni:ni + 1]] if self.use_bias else [])
+        return torch.cat(parts) if _is_torch(g) else np.concatenate(parts)
+
+
+@dataclass(frozen=True)
 class Chain:
     layers: Tuple[Dense, ...]
 
@@ -167,6 +200,15 @@ class ICNF:
             raise ValueError("the B200 path integrates with Tsit5 (north_star) or VCABM (the reference's default alg, served by "
                              "the narrow-MLP family for inference / generate / loss); pass alg='Tsit5' or alg='VCABM'")
 
+        self.planar = None
+        if isinstance(nn, PlanarLayer):
+            nn = Chain(nn)
+        if isinstance(nn, Chain) and len(nn.layers) == 1 and isinstance(nn.layers[0], PlanarLayer):
+            self.planar = nn.layers[0]
+            if (self.planar.n_in, self.planar.n_out) != (n_in, n_out):
+                raise ValueError(f"network must map {n_in} -> {n_out}")
+            self.nn = nn
+            nn = Chain(Dense(n_in, 1, self.planar.activation), Dense(1, n_out))
         sizes, acts = self._check_chain(nn, n_in, n_out)
         self.sizes = sizes
         cfg = _lib.Config()
@@ -256,6 +298,11 @@ class ICNF:
 
     @property
     def n_params(self) -> int:
+        """length of ``ps`` as the caller sees it (a PlanarLayer has fewer entries than the Dense pair that serves it)"""
+        return self.planar.n_params if self.planar is not None else int(lib.icnf_n_params(self._h))
+
+    @property
+    def n_params_lib(self) -> int:
         return int(lib.icnf_n_params(self._h))
 
     @property
@@ -296,6 +343,8 @@ class ICNF:
 
     def _set_params(self, ps):
         """``ps`` travels with every reference call; upload only when it changed."""
+        if self.planar is not None:
+            ps = self.planar.to_lib(ps)
         if _is_torch(ps):
             p = ps.detach().to(dtype=torch.float32).contiguous()
             if not p.is_cuda:
@@ -361,6 +410,11 @@ def setup(rng, icnf: ICNF):
     [vec(W1); b1; vec(W2); b2; ...] (W column-major), glorot-uniform weights and
     zero biases (Lux's Dense defaults), and an empty state."""
     g = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+    if icnf.planar is not None:      # planar_layer.jl:36-51: u, w ~ init_weight (glorot-uniform), b = 0
+        pl = icnf.planar
+        lu, lw = math.sqrt(6.0 / (pl.n_out + 1)), math.sqrt(6.0 / (pl.n_in + 1))
+        parts = [g.uniform(-lu, lu, size=pl.n_out), g.uniform(-lw, lw, size=pl.n_in)] + ([np.zeros(1)] if pl.use_bias else [])
+        return np.concatenate(parts).astype(np.float32), {}
     parts = []
     for layer in icnf.nn.layers:
         lim = math.sqrt(6.0 / (layer.n_in + layer.n_out))
@@ -566,7 +620,8 @@ def _loss_impl(icnf: ICNF, mode: Mode, xs, ys, ps, want_grad: bool, want_dxs: bo
     t0, t1 = tspan if tspan is not None else icnf.steer_tspan(mode)
     noise = icnf._noise(mode, eps, seed, sample_offset)
     solver = icnf._solver(sol)
-    npar = icnf.n_params
+    npar = icnf.n_params_lib
+    planar = icnf.planar
     if dev:
         device = xa.keep.device
         # gradient and loss share one buffer [dtheta; loss] so that a data-parallel caller can
@@ -582,6 +637,8 @@ def _loss_impl(icnf: ICNF, mode: Mode, xs, ys, ps, want_grad: bool, want_dxs: bo
                        ya.ptr, lossv.data_ptr(), dth.data_ptr() if want_grad else None,
                        dxs.data_ptr() if want_dxs else None, ds.data_ptr(), xa.B, int(global_batch), _stream(icnf)))
         icnf._pending_stats = ds
+        if planar is not None and dth is not None:
+            dth = planar.grad_from_lib(dth)
         return lossv[0], dth, (dxs.t() if want_dxs else None)
     lossv = C.c_float()
     stt = _lib.Stats()
@@ -598,6 +655,8 @@ def _loss_impl(icnf: ICNF, mode: Mode, xs, ys, ps, want_grad: bool, want_dxs: bo
                            C.byref(lossv), C.byref(stt), xa.B, int(global_batch))
     icnf.last_stats = _stats_from(stt)
     icnf._check(rc)
+    if planar is not None and dth is not None:
+        dth = planar.grad_from_lib(dth)
     return float(lossv.value), dth, dxs
 
 

@@ -79,7 +79,14 @@ function activation_code(f)
     error("B200MatrixMode: no kernel for activation $(f); use softplus, tanh, sigmoid or identity")
 end
 
+# A PlanarLayer (src/layers/planar_layer.jl: f(x) = u * act(w'x + b), parameters (u, w, b)) IS Dense(n_in => 1, act)
+# followed by a bias-free Dense(1 => n_out): it reaches the kernels as that pair, with the parameters re-ordered to
+# [w; b; u; 0] on the way in and the gradient re-ordered back on the way out (the output bias is not a parameter).
+is_planar(nn::Lux.Chain) = length(nn.layers) == 1 && nn.layers[1] isa PlanarLayer
+planar_use_bias(::PlanarLayer{USE_BIAS}) where {USE_BIAS} = USE_BIAS
+
 function dense_sizes(nn::Lux.Chain)
+    is_planar(nn) && return Int32[nn.layers[1].in_dims, 1, nn.layers[1].out_dims]
     sizes = Int32[nn.layers[1].in_dims]
     for l in nn.layers
         push!(sizes, l.out_dims)
@@ -87,16 +94,30 @@ function dense_sizes(nn::Lux.Chain)
     return sizes
 end
 
+function planar_to_lib(pl::PlanarLayer, θ::Vector{Float32})
+    no, ni = pl.out_dims, pl.in_dims
+    b = planar_use_bias(pl) ? θ[(no + ni + 1):(no + ni + 1)] : zeros(Float32, 1)
+    return vcat(θ[(no + 1):(no + ni)], b, θ[1:no], zeros(Float32, no))
+end
+
+function planar_grad_from_lib(pl::PlanarLayer, g::Vector{Float32})
+    no, ni = pl.out_dims, pl.in_dims
+    return planar_use_bias(pl) ? vcat(g[(ni + 2):(ni + 1 + no)], g[1:ni], g[(ni + 1):(ni + 1)]) :
+           vcat(g[(ni + 2):(ni + 1 + no)], g[1:ni])
+end
+
 function handle(icnf::ICNF{Float32, <:B200MatrixMode})
     get!(HANDLES, icnf) do
         sizes = dense_sizes(icnf.nn)
         padded = ntuple(i -> i <= length(sizes) ? sizes[i] : Int32(0), 9)
         length(sizes) - 1 <= 8 || error("B200MatrixMode: at most 8 Dense layers")
-        all(l -> l isa Lux.Dense, icnf.nn.layers) || error("B200MatrixMode: nn must be a Lux.Chain of Dense layers")
-        act = activation_code(length(icnf.nn.layers) > 1 ? icnf.nn.layers[1].activation : identity)
-        all(l -> activation_code(l.activation) == act, icnf.nn.layers[1:(end - 1)]) ||
+        planar = is_planar(icnf.nn)
+        planar || all(l -> l isa Lux.Dense, icnf.nn.layers) ||
+            error("B200MatrixMode: nn must be a Lux.Chain of Dense layers or of one PlanarLayer")
+        act = activation_code(planar || length(icnf.nn.layers) > 1 ? icnf.nn.layers[1].activation : identity)
+        planar || all(l -> activation_code(l.activation) == act, icnf.nn.layers[1:(end - 1)]) ||
             error("B200MatrixMode: all hidden layers must share one activation")
-        activation_code(icnf.nn.layers[end].activation) == 3 || error("B200MatrixMode: the last Dense layer must be linear")
+        planar || activation_code(icnf.nn.layers[end].activation) == 3 || error("B200MatrixMode: the last Dense layer must be linear")
         autonomous = icnf isa ICNF{Float32, <:Any, <:Any, <:Any, true}
         cfg = Ref(IcnfConfig(1, icnf.nvariables, icnf.naugments,
             first(sizes) - icnf.nvariables - icnf.naugments - !autonomous,
@@ -111,8 +132,9 @@ end
 
 check(h, rc) = rc == 0 || error(unsafe_string(ccall((:icnf_last_error, libicnf), Cstring, (Ptr{Cvoid},), h)))
 
-function set_params!(h, ps)
+function set_params!(h, ps, icnf = nothing)
     θ = ComponentArrays.getdata(ps)::Vector{Float32}
+    (!isnothing(icnf) && is_planar(icnf.nn)) && (θ = planar_to_lib(icnf.nn.layers[1], θ))
     GC.@preserve θ check(h, ccall((:icnf_set_params, libicnf), Cint, (Ptr{Cvoid}, Ptr{Float32}, Int64), h, θ, length(θ)))
 end
 
@@ -139,7 +161,7 @@ function base_sol(
     prob::SciMLBase.AbstractODEProblem{<:AbstractMatrix{<:Real}, NTuple{2, Float32}, INPLACE},
 ) where {INPLACE}
     h = handle(icnf)
-    set_params!(h, prob.p)
+    set_params!(h, prob.p, icnf)
     f = prob.f.f                      # the closure built by make_ode_func: carries mode, ϵ, ys
     u0 = Matrix{Float32}(prob.u0)
     ufinal = similar(u0)
@@ -162,12 +184,13 @@ end
 #      src/core/icnf.jl:90-99, :628-649) ------------------------------------------
 function b200_loss_grad(icnf, mode, xs, ys, ps; want_dxs = false)
     h = handle(icnf)
-    set_params!(h, ps)
+    set_params!(h, ps, icnf)
     B = size(xs, 2)
     ϵ = similar(xs, icnf.nvariables + icnf.naugments, B)
     Random.rand!(icnf.rng, icnf.epsdist, ϵ)                     # base_icnf.jl:258-259
     t0, t1 = steer_tspan(icnf, mode)                            # base_icnf.jl:23-43
-    dθ = zeros(Float32, length(ComponentArrays.getdata(ps)))
+    # the library's parameter count (a PlanarLayer is served as a Dense pair with n_out more entries: its zero output bias)
+    dθ = zeros(Float32, length(ComponentArrays.getdata(ps)) + (is_planar(icnf.nn) ? icnf.nn.layers[1].out_dims + !planar_use_bias(icnf.nn.layers[1]) : 0))
     dxs = want_dxs ? similar(xs) : nothing
     loss = Ref{Float32}(0)
     stats = IcnfStats()
@@ -179,6 +202,7 @@ function b200_loss_grad(icnf, mode, xs, ys, ps; want_dxs = false)
             h, mode_code(mode), tsit5_opts(icnf), t0, t1, xs, noise, ϵ,
             isnothing(ys) ? C_NULL : pointer(ys), loss, dθ, want_dxs ? pointer(dxs) : C_NULL, stats, B, 0))
     end
+    is_planar(icnf.nn) && (dθ = planar_grad_from_lib(icnf.nn.layers[1], dθ))
     return loss[], dθ, dxs
 end
 
