@@ -432,7 +432,7 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
         a.out_loss = r.out_loss; a.loss_scale = r.loss_scale; a.out_lossterm = nullptr;
         r.loss_fused = true;
     }
-    if (group_wants_global_norm(h) && r.global_B > 0) {
+    if (group_wants_global_norm(h) && r.global_B > 0 && h->fam->global_norm_capable(h->ws, a, mf.exact)) {
         // exact data-parallel mode: the controller's error norm is taken over the global batch
         group_fill_xchg(h, a.xg);
         a.norm_B = r.global_B;
@@ -1080,7 +1080,7 @@ struct Group {
 namespace {
 bool group_wants_global_norm(const icnf_handle* h) {
     const Group* g = h->grp;
-    return g && g->global_norm && g->peer_ok && g->nranks > 1 && std::string(h->fam->name) == "tiny";
+    return g && g->global_norm && g->peer_ok && g->nranks > 1 && h->fam->global_norm_capable;
 }
 void group_fill_xchg(const icnf_handle* h, NormXchg& x) {
     x.peers = h->grp->peers;
@@ -1248,8 +1248,8 @@ int icnf_group_info(const icnf_handle* h, int32_t* n_ranks, int32_t* rank, int32
 int icnf_group_set_global_norm(icnf_handle* h, int enabled) {
     if (!h) return ICNF_ERR_INVALID;
     if (!h->grp) return h->fail(ICNF_ERR_INVALID, "handle is not in a group");
-    if (enabled && !(h->grp->peer_ok && std::string(h->fam->name) == "tiny"))
-        return h->fail(ICNF_ERR_UNSUPPORTED, "the global error norm needs NVLink peer memory and the single-launch (tiny) solve");
+    if (enabled && !(h->grp->peer_ok && h->fam->global_norm_capable))
+        return h->fail(ICNF_ERR_UNSUPPORTED, "the global error norm needs NVLink peer memory and a single-launch solve (tiny family, narrow path)");
     h->grp->global_norm = enabled != 0;
     return ICNF_OK;
 }

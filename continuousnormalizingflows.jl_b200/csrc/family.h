@@ -49,6 +49,9 @@ struct Family {
     int ckpt_stages;                 // training checkpoints per step and sample, in units of D' floats (tiny: 6 stage inputs)
     // VCABM (variable-order Adams PECE, the reference's default alg); null: the family integrates with Tsit5 only
     cudaError_t (*solve_vcabm)(void* ws, const float* theta_host, const SolveArgs& a, int nvars, bool exact, int sm_count, cudaStream_t st);
+    // does this adaptive solve run in a persistent kernel that can exchange the error-norm sums with the other ranks of a
+    // group inside its device loop (exact data-parallel mode)?  null: no
+    bool (*global_norm_capable)(void* ws, const SolveArgs& a, bool exact);
 };
 
 std::vector<const Family*>& tiny_registry();

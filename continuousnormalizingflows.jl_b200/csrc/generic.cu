@@ -1924,6 +1924,7 @@ static cudaError_t enqueue_stage(Workspace* w, const SolveArgs& a, StageArgs s, 
 static bool narrow_route(Workspace* w, const SolveArgs& a, bool exact) {
     return narrow::supported(w->cfg, exact, a) && narrow::smem_bytes(w->cfg, exact) <= (size_t)226 * 1024;
 }
+static bool global_norm_capable(void* wsp, const SolveArgs& a, bool exact) { return narrow_route((Workspace*)wsp, a, exact); }
 static cudaError_t narrow_solve(Workspace* w, const SolveArgs& a, int nvars, bool exact, bool adaptive, cudaStream_t st) {
     int sms = 0, dev = 0;
     cudaGetDevice(&dev);
@@ -2549,6 +2550,7 @@ const Family* generic_family() {
         g.backward_partials_per_block = 1;
         g.supports_backward = 1;
         g.ckpt_stages = 6;   // the inputs of all six Tsit5 stages of every accepted step: ckpt[slot][stage][D'][B]
+        g.global_norm_capable = &generic::global_norm_capable;   // the single-launch narrow path
         return g;
     }();
     return &f;

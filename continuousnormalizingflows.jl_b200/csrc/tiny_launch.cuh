@@ -244,6 +244,7 @@ struct Launch {
         f.solve_fixed = &solve_fixed;
         f.solve_adaptive = &solve_adaptive;
         f.solve_vcabm = &solve_vcabm;
+        f.global_norm_capable = [](void*, const SolveArgs&, bool) { return true; };
         f.adaptive_max_grid = &adaptive_max_grid;
         f.backward = &backward;
         f.backward_grid = &backward_grid;

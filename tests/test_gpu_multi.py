@@ -28,6 +28,8 @@ def _free_port():
 def _case(m, which, device):
     if which == "tiny":
         return m.ICNF(nvariables=2, naugments=0, device=device), 1001
+    if which == "narrow":       # ICNF(nvariables = 3): 8-32-32-7, not in the tiny whitelist -> generic family, single-launch solves
+        return m.ICNF(nvariables=3, device=device), 1001
     nn = m.Chain(m.Dense(97, 128, "softplus"), m.Dense(128, 160, "softplus"), m.Dense(160, 128, "softplus"), m.Dense(128, 96))
     return m.ICNF(nvariables=96, naugments=0, nn=nn, device=device, precision="bf16x3_tc"), 515
 
@@ -63,7 +65,7 @@ def _worker(rank, world, port, which, out):
     lh, gh = m.loss_and_gradient(icnf, m.TrainMode(True), xs[:, lo:hi], theta, {}, eps=eps[:, lo:hi], tspan=icnf.tspan,
                                  sample_offset=lo, global_batch=B, data_parallel=True, **sol)
     exact = None
-    if which == "tiny":
+    if which in ("tiny", "narrow"):
         # exact mode: ADAPTIVE solve with the error norm of the global batch -> the unsharded solve's own steps
         m.group_set_global_norm(icnf, True)
         la, ga = m.dp_loss_and_gradient(icnf, m.TrainMode(True), xd, theta, {}, rank=rank, world=world, global_batch=B,
@@ -86,7 +88,7 @@ def _worker(rank, world, port, which, out):
 
 
 @needs2
-@pytest.mark.parametrize("which", ["tiny", "wide_tc"])
+@pytest.mark.parametrize("which", ["tiny", "narrow", "wide_tc"])
 def test_two_process_group_gradient_equals_unsharded(which):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
@@ -104,16 +106,21 @@ def test_two_process_group_gradient_equals_unsharded(which):
         assert info["peer_memory"], "NVLink peer-memory exchange should be available between two GPUs of one box"
     lw, gw = whole
     tol = 2e-6 if which == "tiny" else 2e-5       # summation order differs between 1 and 2 shards, nothing else
+    if which == "narrow":
+        assert info["peer_memory"]
     for l, g in res + [host]:
         assert abs(l - lw) <= 1e-5 * abs(lw)
         assert np.linalg.norm(g - gw) / np.linalg.norm(gw) < tol
     # the steps are identical, bit for bit (deterministic exchange)
-    assert all(np.array_equal(res[0][1], r[1]) for r in res[1:])
+    if which == "narrow":    # the fp32 weight-gradient SGEMMs of the generic family accumulate their split-K slices with atomics
+        assert all(np.linalg.norm(res[0][1] - r[1]) <= 2e-6 * np.linalg.norm(res[0][1]) for r in res[1:])
+    else:
+        assert all(np.array_equal(res[0][1], r[1]) for r in res[1:])
     if exact is not None:
         la, ga, nacc, nrej, tf, lb, gb, lwa, gwa, nacc_w, nrej_w = exact
         # global error norm: same accepted / rejected steps as the unsharded adaptive solve, same gradient to rounding
         assert (nacc, nrej) == (nacc_w, nrej_w)
-        assert abs(la - lwa) <= 1e-5 * abs(lwa) and np.linalg.norm(ga - gwa) / np.linalg.norm(gwa) < 5e-6
+        assert abs(la - lwa) <= 1e-5 * abs(lwa) and np.linalg.norm(ga - gwa) / np.linalg.norm(gwa) < (5e-6 if which == "tiny" else 2e-5)
         # shard-local norm (default): agreement to solver tolerance only
         assert abs(lb - lwa) <= 1e-3 * abs(lwa) and np.linalg.norm(gb - gwa) / np.linalg.norm(gwa) < 1e-2
 
