@@ -445,7 +445,11 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
         // ICNF_ERR_MAX_STEPS instead of exhausting the device
         const size_t per_step = sizeof(float) * (size_t)r.B * D * std::max(1, h->fam->ckpt_stages);
         const int mem_cap = (int)std::max<size_t>(8, ((size_t)16 << 30) / std::max<size_t>(per_step, 1));
-        a.max_ckpt_steps = std::min(std::min(a.ctl.max_steps, 256), mem_cap);
+        // 256 accepted steps by default; a caller that sets `max_steps` (maxiters) to something between 256 and the glue's
+        // default of 100 000 gets room for that many, up to the memory cap -- a stiff late-training flow can then be
+        // differentiated instead of failing with ICNF_ERR_MAX_STEPS
+        const bool explicit_cap = r.sol && r.sol->max_steps > 256 && r.sol->max_steps < 100000;
+        a.max_ckpt_steps = std::min(explicit_cap ? a.ctl.max_steps : std::min(a.ctl.max_steps, 256), mem_cap);
         CK(h, h->ckpt.reserve(sizeof(float) * (size_t)(a.max_ckpt_steps + 1) * r.B * D * std::max(1, h->fam->ckpt_stages)));
         CK(h, h->steps.reserve(sizeof(StepRec) * (size_t)(a.max_ckpt_steps + 1)));
         a.ckpt = h->ckpt.as<float>();

@@ -120,7 +120,8 @@ typedef struct icnf_solver {
     int32_t adaptive;           /* 1: PI-controlled steps, error norm over the whole S x B state */
     float dt;                   /* fixed step, or initial step (0 = automatic) when adaptive */
     float reltol, abstol;       /* icnf.jl:87-88 (1e-4) */
-    int32_t max_steps;          /* 0 = 100000; the reference's maxiters is typemax(Int) (icnf.jl:86) */
+    int32_t max_steps;          /* 0 = 100000; the reference's maxiters is typemax(Int) (icnf.jl:86).  Training solves keep
+                                 * checkpoints for 256 accepted steps unless 256 < max_steps < 100000 asks for more */
     float beta1, beta2, gamma, qmin, qmax, qsteady_min, qsteady_max, qoldinit;
     int32_t alg;                /* icnf_alg: 0 = Tsit5 (BASELINE.json north_star), 1 = VCABM (the reference's default,
                                  * src/core/icnf.jl:89): adaptive only; served for solve / inference / generate / loss by the
