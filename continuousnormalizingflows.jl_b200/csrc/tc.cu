@@ -133,7 +133,8 @@ cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, 
 int& knob(int which) {
     static int v[4] = {[] { const char* e = getenv("ICNF_TC_CHAIN"); return e ? atoi(e) : 1; }(),
                        [] { const char* e = getenv("ICNF_CHAIN_DIRECT"); return e ? atoi(e) : -1; }(),
-                       [] { const char* e = getenv("ICNF_CHAIN_SG"); return e ? atoi(e) : 1; }(), 0};
+                       [] { const char* e = getenv("ICNF_CHAIN_SG"); return e ? atoi(e) : 1; }(),
+                       [] { const char* e = getenv("ICNF_CHAIN_CLUSTER"); const int c = e ? atoi(e) : 1; return (c == 2 || c == 4) ? c : 1; }()};
     return v[which & 3];
 }
 
@@ -141,7 +142,7 @@ int& knob(int which) {
 struct ChainSlot {
     bool valid = false;
     int n = 0;
-    int sg_knob = -1;
+    int sg_knob = -1, cl_knob = -1;
     ChainStep steps[CHAIN_MAXG];
     ChainParams P;
 };
@@ -161,7 +162,7 @@ void chain_state_destroy(ChainState* cs) {
 }
 
 static long long* g_chain_trace = nullptr;
-static bool build_chain_gemm(const ChainStep& s, ChainGemm& o) {
+static bool build_chain_gemm(const ChainStep& s, ChainGemm& o, int cl) {
     const TcArgs& g = s.g;
     const uint64_t ka = g.split ? (uint64_t)g.lo_a + g.K : (uint64_t)g.K;
     const uint64_t kb = g.split ? (uint64_t)g.lo_b + g.K : (uint64_t)g.K;
@@ -175,6 +176,16 @@ static bool build_chain_gemm(const ChainStep& s, ChainGemm& o) {
             return false;
     } else {
         o.mapA2 = o.mapA; o.mapB2 = o.mapB;
+    }
+    o.mapAs = o.mapA; o.mapA2s = o.mapA2;
+    if (cl > 1) {
+        if (!make_map(&o.mapAs, s.A, (uint64_t)g.M, ka, (uint64_t)s.lda, TBM / cl)) return false;
+        if (g.K2 > 0) {
+            const uint64_t ka2 = g.split ? (uint64_t)g.lo_a2 + g.K2 : (uint64_t)g.K2;
+            if (!make_map(&o.mapA2s, s.A2, (uint64_t)g.M, ka2, (uint64_t)s.lda2, TBM / cl)) return false;
+        } else {
+            o.mapA2s = o.mapAs;
+        }
     }
     o.mapO0 = o.mapA; o.mapO1 = o.mapA;
     const uint64_t ocols = g.split ? 2 * (uint64_t)g.lo_o : (uint64_t)g.ldo;
@@ -199,7 +210,8 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
     }
     if (!ds.sms) cudaDeviceGetAttribute(&ds.sms, cudaDevAttrMultiProcessorCount, dev);
     ChainSlot& sl = cs->slot[slot];
-    const bool same = sl.valid && sl.n == n && sl.sg_knob == knob(2) && memcmp(sl.steps, steps, sizeof(ChainStep) * n) == 0;
+    const int cl = knob(3);
+    const bool same = sl.valid && sl.n == n && sl.sg_knob == knob(2) && sl.cl_knob == cl && memcmp(sl.steps, steps, sizeof(ChainStep) * n) == 0;
     if (!same) {
         sl.valid = false;
         memset(&sl.P, 0, sizeof sl.P);
@@ -209,11 +221,12 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
             const ChainStep& s = steps[i];
             if (s.g.split != split) return cudaErrorInvalidValue;
             ChainGemm& o = sl.P.gm[i];
-            if (!build_chain_gemm(s, o)) return cudaErrorInvalidValue;
+            if (!build_chain_gemm(s, o, cl)) return cudaErrorInvalidValue;
             const int ntm = (s.g.M + TBM - 1) / TBM;
             o.ntn = (s.g.N + 127) / 128;
             o.nsl = s.g.nslices > 1 ? s.g.nslices : 1;
-            o.nwork = ntm * o.ntn * o.nsl;
+            o.ntg = (o.ntn + cl - 1) / cl;
+            o.nwork = ntm * o.ntg * o.nsl;
             o.work_begin = work;
             work += o.nwork;
             max_rows = std::max(max_rows, ntm);
@@ -225,7 +238,10 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
                     if ((d.g.M + TBM - 1) / TBM != ntm) return cudaErrorInvalidValue;          // row tiles must correspond
                     o.row_target[k] = (unsigned)(d.ntn * d.nsl * 4 * WQ);
                 }
-                if (s.dep_all[k] >= 0) o.all_target[k] = (unsigned)(sl.P.gm[s.dep_all[k]].nwork * 4 * WQ);
+                if (s.dep_all[k] >= 0) {
+                    const ChainGemm& d = sl.P.gm[s.dep_all[k]];
+                    o.all_target[k] = (unsigned)(((d.g.M + TBM - 1) / TBM) * d.ntn * d.nsl * 4 * WQ);      // valid tiles publish, not work items
+                }
             }
         }
         sl.P.ngemm = n; sl.P.nwork = work;
@@ -239,10 +255,10 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
             for (int i = 0; i < n; ++i) {
                 const ChainGemm& o = sl.P.gm[i];
                 if ((steps[i].g.M + TBM - 1) / TBM != ntm0 || steps[i].dep_all[0] >= 0 || steps[i].dep_all[1] >= 0) uniform = false;
-                row_items += o.ntn * o.nsl;
-                max_ntn = std::max(max_ntn, o.ntn * o.nsl);
+                row_items += o.ntg * o.nsl;
+                max_ntn = std::max(max_ntn, o.ntg * o.nsl);
             }
-            const int rg = std::max(1, 3 * ds.sms / max_ntn);
+            const int rg = std::max(1, 3 * (ds.sms / cl) / max_ntn);
             const int sg_on = knob(2);
             if (uniform && sg_on && ntm0 > rg) { sl.P.rg = rg; sl.P.ntm = ntm0; sl.P.row_items = row_items; }
             else { sl.P.rg = 0; sl.P.ntm = ntm0; sl.P.row_items = row_items; }
@@ -250,6 +266,8 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
         memcpy(sl.steps, steps, sizeof(ChainStep) * n);
         sl.n = n;
         sl.sg_knob = knob(2);
+        sl.cl_knob = cl;
+        sl.P.cl = cl;
         sl.valid = true;
     }
     // counters: one allocation serves every slot (launches of a workspace are ordered on its stream)
@@ -281,9 +299,33 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
     P.direct_stores = knob(1) > 0 ? 1 : 0;
     { static const int dbg = [] { const char* e = getenv("ICNF_CHAIN_DBG"); return e ? atoi(e) : 0; }(); P.dbg = dbg; }
     cs->parity++;
-    const dim3 grid((unsigned)std::min<long long>(P.nwork, (long long)ds.sms));
-    if (steps[0].g.split) tc_chain_kernel<true><<<grid, TTHREADS, smem_bytes(true, 128), st>>>(P);
-    else tc_chain_kernel<false><<<grid, TTHREADS, smem_bytes(false, 128), st>>>(P);
+    if (P.cl <= 1) {
+        const dim3 grid((unsigned)std::min<long long>(P.nwork, (long long)ds.sms));
+        if (steps[0].g.split) tc_chain_kernel<true><<<grid, TTHREADS, smem_bytes(true, 128), st>>>(P);
+        else tc_chain_kernel<false><<<grid, TTHREADS, smem_bytes(false, 128), st>>>(P);
+        return cudaGetLastError();
+    }
+    // clusters: the whole grid must be resident at once (an item only waits on earlier items, but a cluster that is not
+    // scheduled never runs its early items), so the grid is what the device can hold of this cluster shape
+    const bool split = steps[0].g.split != 0;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(TTHREADS); cfg.dynamicSmemBytes = smem_bytes(split, 128); cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    static int max_clusters[64][2][5] = {};
+    int& mc = max_clusters[dev & 63][split ? 1 : 0][P.cl];
+    if (mc == 0) {
+        cfg.gridDim = dim3((unsigned)(ds.sms / P.cl * P.cl));
+        int n_cl = 0;
+        cudaError_t e = split ? cudaOccupancyMaxActiveClusters(&n_cl, tc_chain_kernel<true>, &cfg)
+                              : cudaOccupancyMaxActiveClusters(&n_cl, tc_chain_kernel<false>, &cfg);
+        if (e != cudaSuccess || n_cl <= 0) return e != cudaSuccess ? e : cudaErrorLaunchOutOfResources;
+        mc = n_cl;
+    }
+    cfg.gridDim = dim3((unsigned)(std::min<long long>(P.nwork, (long long)mc) * P.cl));
+    return split ? cudaLaunchKernelEx(&cfg, tc_chain_kernel<true>, P) : cudaLaunchKernelEx(&cfg, tc_chain_kernel<false>, P);
     return cudaGetLastError();
 }
 

@@ -17,9 +17,11 @@ namespace tc {
 
 struct alignas(128) ChainGemm {
     CUtensorMap mapA, mapB, mapA2, mapB2, mapO0, mapO1;
+    CUtensorMap mapAs, mapA2s;   // clusters: the A operand in slices of 128 / cl rows (each CTA loads one slice and multicasts it)
     TcArgs g;
     int work_begin, nwork;   // this GEMM's slice of the work list
     int ntn, nsl;            // unit tiles per row tile, split-K slices
+    int ntg;                 // groups of `cl` unit tiles per row tile = work items per (row tile, slice)
     int dep_row[2], dep_all[2];
     unsigned row_target[2], all_target[2];
 };
@@ -33,6 +35,9 @@ struct ChainParams {
     // L2, with ~3 rounds of work between an item and the items it waits for.  rg = row tiles per super-group (0: off),
     // ntm = row tiles in total, row_items = sum over the GEMMs of (unit tiles x slices) per row tile
     int rg, ntm, row_items;
+    // clusters of cl CTAs (1, 2 or 4) take the cl unit tiles of one group: they share the group's A tile, which every CTA loads
+    // a 1 / cl slice of and multicasts to the others -- fewer operand bytes through L2 per MAC
+    int cl;
     const int* done;
     long long* trace;
     int direct_stores;      // row-major outputs: 1 = 16-byte stores from registers (short chains: latency), 0 = bulk tensor stores (long chains: throughput)
@@ -339,6 +344,19 @@ __device__ __noinline__ float epi_item(int warp) {
     return rowsum;
 }
 
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+        : "memory");
+}
+// arrive on the barrier at this offset in every CTA of the cluster once all prior MMAs of THIS CTA have completed
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
 struct WorkItem { int gi, mt, nt, sl; };
 __device__ __forceinline__ WorkItem decode_work(const ChainParams& P, int work, int& gi_hint) {
     WorkItem w;
@@ -347,7 +365,7 @@ __device__ __forceinline__ WorkItem decode_work(const ChainParams& P, int work, 
         const ChainGemm& cg = P.gm[gi_hint];
         const int local = work - cg.work_begin;
         const int tile = local / cg.nsl;
-        w.gi = gi_hint; w.sl = local - tile * cg.nsl; w.mt = tile / cg.ntn; w.nt = tile - w.mt * cg.ntn;
+        w.gi = gi_hint; w.sl = local - tile * cg.nsl; w.mt = tile / cg.ntg; w.nt = tile - w.mt * cg.ntg;
         return w;
     }
     const int per_sg = P.rg * P.row_items;
@@ -356,15 +374,15 @@ __device__ __forceinline__ WorkItem decode_work(const ChainParams& P, int work, 
     const int rows = min(P.rg, P.ntm - sg * P.rg);
     int g = 0;
     for (; g < P.ngemm - 1; ++g) {
-        const int cnt = rows * P.gm[g].ntn * P.gm[g].nsl;
+        const int cnt = rows * P.gm[g].ntg * P.gm[g].nsl;
         if (rem < cnt) break;
         rem -= cnt;
     }
     const ChainGemm& cg = P.gm[g];
     const int tile = rem / cg.nsl;
     w.gi = g; w.sl = rem - tile * cg.nsl;
-    const int r = tile / cg.ntn;
-    w.mt = sg * P.rg + r; w.nt = tile - r * cg.ntn;
+    const int r = tile / cg.ntg;
+    w.mt = sg * P.rg + r; w.nt = tile - r * cg.ntg;
     return w;
 }
 
@@ -391,7 +409,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
     unsigned* all_flags = P.flags + CHAIN_MAXG * P.row_stride;
 
     if (warp == TMA_WARP && lane == 0) {
-        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)P.cl); }   // a slot is free when EVERY CTA of the cluster has consumed it
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4 * WQ); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -400,24 +418,30 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
-    __syncthreads();
+    if (P.cl > 1) cluster_sync_all();      // the peers' barriers are initialised before anything signals them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    const int cl = P.cl;
+    const int crank = cl > 1 ? (int)cluster_ctarank() : 0;
+    const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
+    const int work0 = blockIdx.x / cl, wstride = gridDim.x / cl;     // a cluster walks the item list together
+    const int arows = TBM / cl;                                      // rows of the A tile this CTA loads (and multicasts)
 
     if (warp == TMA_WARP) {
         // ===== TMA producer =====
         if (lane == 0) {
             int it = 0, gi = 0;
-            for (int work = blockIdx.x; work < P.nwork; work += gridDim.x) {
+            for (int work = work0; work < P.nwork; work += wstride) {
                 const WorkItem wi = decode_work(P, work, gi);
                 const ChainGemm& cg = P.gm[wi.gi];
                 const TcArgs& g = cg.g;
                 const int nsl = cg.nsl;
                 const int sl = wi.sl, mt = wi.mt;
-                const int m0 = mt * TBM, n0 = wi.nt * BN;
+                const int m0 = mt * TBM, n0 = (wi.nt * cl + crank) * BN;      // (a unit tile beyond N: zero-filled loads, no epilogue)
                 const int nkb0 = (g.K + TBK - 1) / TBK;
                 const int nkb1 = g.K2 > 0 ? (g.K2 + TBK - 1) / TBK : 0;
-                const int nseg = (nkb1 && n0 < g.N2) ? 2 : 1;
+                const int nseg = (nkb1 && wi.nt * cl * BN < g.N2) ? 2 : 1;   // cluster-uniform: the CTAs of a cluster step through the same K blocks
                 // ---- dependencies: everything this item reads has been published
                 bool waited = false;
 #pragma unroll
@@ -427,7 +451,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
                 }
                 if (waited) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
                 for (int seg = 0; seg < nseg; ++seg) {
-                    const CUtensorMap* ma = seg ? &cg.mapA2 : &cg.mapA;
+                    const CUtensorMap* ma = cl > 1 ? (seg ? &cg.mapA2s : &cg.mapAs) : (seg ? &cg.mapA2 : &cg.mapA);
                     const CUtensorMap* mb = seg ? &cg.mapB2 : &cg.mapB;
                     const int nkb = seg ? nkb1 : nkb0;
                     const int lo_a = seg ? g.lo_a2 : g.lo_a, lo_b = seg ? g.lo_b2 : g.lo_b;
@@ -439,8 +463,14 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
                         mbar_wait(&empty[s], ph ^ 1);
                         trace_event(P.trace, 0, 1000 + (it % 1000));
                         mbar_expect_tx(&full[s], STAGE_BYTES);
-                        tma_load_2d(st, ma, &full[s], kb * TBK, m0);
-                        if constexpr (SPLIT) tma_load_2d(st + A_TILE_BYTES, ma, &full[s], lo_a + kb * TBK, m0);
+                        if (cl > 1) {   // this CTA's slice of the A tile, to every CTA of the cluster
+                            const int ao = crank * arows * TBK * 2;
+                            tma_load_2d_mc(st + ao, ma, &full[s], kb * TBK, m0 + crank * arows, cmask);
+                            if constexpr (SPLIT) tma_load_2d_mc(st + A_TILE_BYTES + ao, ma, &full[s], lo_a + kb * TBK, m0 + crank * arows, cmask);
+                        } else {
+                            tma_load_2d(st, ma, &full[s], kb * TBK, m0);
+                            if constexpr (SPLIT) tma_load_2d(st + A_TILE_BYTES, ma, &full[s], lo_a + kb * TBK, m0);
+                        }
                         tma_load_2d(st + NT_A * A_TILE_BYTES, mb, &full[s], kb * TBK, n0);
                         if constexpr (SPLIT) tma_load_2d(st + NT_A * A_TILE_BYTES + BTB, mb, &full[s], lo_b + kb * TBK, n0);
                     }
@@ -452,16 +482,15 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc(TBM, BN);
             int it = 0, i = 0, gi = 0;
-            for (int work = blockIdx.x; work < P.nwork; work += gridDim.x, ++i) {
+            for (int work = work0; work < P.nwork; work += wstride, ++i) {
                 const WorkItem wi = decode_work(P, work, gi);
                 const ChainGemm& cg = P.gm[wi.gi];
                 const TcArgs& g = cg.g;
                 const int nsl = cg.nsl;
                 const int sl = wi.sl;
-                const int n0 = wi.nt * BN;
                 const int nkb0 = (g.K + TBK - 1) / TBK;
                 const int nkb1 = g.K2 > 0 ? (g.K2 + TBK - 1) / TBK : 0;
-                const int nseg = (nkb1 && n0 < g.N2) ? 2 : 1;
+                const int nseg = (nkb1 && wi.nt * cl * BN < g.N2) ? 2 : 1;
                 const int as = i & 1;
                 mbar_wait(&tmem_empty[as], ((i >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
@@ -489,7 +518,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
 #pragma unroll
                             for (int k = 0; k < TBK / 16; ++k) tc_mma_bf16(tacc, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
                         }
-                        tc_commit(&empty[s]);
+                        if (cl > 1) tc_commit_mc(&empty[s], cmask);
+                        else tc_commit(&empty[s]);
                         trace_event(P.trace, 8192, 3000 + (it % 1000));
                     }
                 }
@@ -501,13 +531,13 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
         const int q = warp & 3;
         const int cq = warp >> 2;
         int i = 0, gi = 0;
-        for (int work = blockIdx.x; work < P.nwork; work += gridDim.x, ++i) {
+        for (int work = work0; work < P.nwork; work += wstride, ++i) {
             const WorkItem wi = decode_work(P, work, gi);
             const ChainGemm& cg = P.gm[wi.gi];
             const TcArgs& g = cg.g;
             const int sl = wi.sl, mt = wi.mt;
             const int as = i & 1;
-            const int m0 = mt * TBM, n0 = wi.nt * BN;
+            const int m0 = mt * TBM, nt = wi.nt * cl + crank, n0 = nt * BN;
             const int pitch = SPLIT ? g.lo_o : g.ldo;
             float* sb = g_bias[warp];
             const int cbeg = chunk_begin(BN, cq) * NC, nch = chunk_begin(BN, cq + 1) - chunk_begin(BN, cq);
@@ -557,12 +587,13 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
-            if (g.ep == TEP_TRACE && row_ok) g.out_f32[(size_t)(wi.nt * WQ + cq) * g.M + m] = rowsum;
+            const bool tile_valid = nt < cg.ntn;      // clusters: the last group of a row tile may hold fewer than cl unit tiles
+            if (g.ep == TEP_TRACE && row_ok && tile_valid) g.out_f32[(size_t)(nt * WQ + cq) * g.M + m] = rowsum;
             // ---- publish: this warp's stores of the item are complete and visible device-wide, then count it
             // (one fence by one lane: the other lanes' stores are ordered before it by the warp barrier, and the fence is
             // cumulative; 32 lanes each running __threadfence + two releasing reductions cost a fifth of the kernel)
             __syncwarp();
-            if (lane == 0) {
+            if (lane == 0 && tile_valid) {
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // this warp's bulk stores have completed
                 asm volatile("fence.proxy.async;" ::: "memory");
                 if (!(P.dbg & 4)) asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -573,7 +604,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (cl > 1) cluster_sync_all();     // no CTA leaves while a peer may still multicast into it or arrive on its barriers
+    else __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));

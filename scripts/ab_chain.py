@@ -30,7 +30,7 @@ else:
 theta, _ = m.setup(rng, icnf)
 theta_d = torch.from_numpy(theta).cuda()
 knob = m.lib.icnf_tc_knob_set
-variants = {"unchained": [(0, 0)], "chain direct": [(0, 1), (1, 1)], "chain bulk": [(0, 1), (1, 0)]}
+variants = {"unchained": [(0, 0), (3, 1)], "chain": [(0, 1), (1, 0), (3, 1)], "chain cluster 2": [(0, 1), (1, 0), (3, 2)], "chain cluster 4": [(0, 1), (1, 0), (3, 4)]}
 def timed(fn):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); fn(); b.record(); torch.cuda.synchronize()
@@ -49,5 +49,5 @@ for r in range(rounds + 1):
         if r > 0:
             res[name]["inf"].append(ti); res[name]["train"].append(tt)
 for name in variants:
-    print(f"{what} {name:14s} inference 24 RHS: median {np.median(res[name]['inf']):7.3f} min {np.min(res[name]['inf']):7.3f} ms"
+    print(f"{what} {name:16s} inference 24 RHS: median {np.median(res[name]['inf']):7.3f} min {np.min(res[name]['inf']):7.3f} ms"
           + (f"   training step (4 fixed steps): median {np.median(res[name]['train']):7.3f} min {np.min(res[name]['train']):7.3f} ms" if what == "c4" else ""), flush=True)
