@@ -205,3 +205,24 @@ def test_tc_gradient_is_bit_reproducible(m):
     a = m.loss_and_gradient(icnf, m.TrainMode(True), xs, ys, theta, {}, eps=eps, tspan=icnf.tspan, **sol)
     b = m.loss_and_gradient(icnf, m.TrainMode(True), xs, ys, theta, {}, eps=eps, tspan=icnf.tspan, **sol)
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
+
+
+@pytest.mark.parametrize("knobs", [dict(chain=0), dict(cluster=2), dict(cluster=4), dict(direct=1), dict(sg=0)],
+                         ids=["per-layer launches", "cluster 2", "cluster 4", "direct stores", "no super-groups"])
+def test_tuning_knobs_do_not_change_results(m, knobs):
+    """The optional paths of the tensor-core family (icnf_tc_knob_set: GEMMs as per-layer launches instead of one chain,
+    clusters with TMA multicast of the activation tile, register-direct row stores, plain tile order) compute the same
+    products in the same order per output element: bit-identical gradients."""
+    idx = dict(chain=0, direct=1, sg=2, cluster=3)
+    default = dict(chain=1, direct=-1, sg=1, cluster=1)
+    icnf = _make(m, "ffjord_small", precision="bf16x3_tc")
+    om, theta, xs, eps, ys = make_inputs(icnf, 700)
+    try:
+        l0, g0 = m.loss_and_gradient(icnf, m.TrainMode(True), xs, theta, {}, eps=eps, tspan=icnf.tspan, adaptive=False, dt=0.5)
+        for k, v in knobs.items():
+            m.lib.icnf_tc_knob_set(idx[k], v)
+        l1, g1 = m.loss_and_gradient(icnf, m.TrainMode(True), xs, theta, {}, eps=eps, tspan=icnf.tspan, adaptive=False, dt=0.5)
+    finally:
+        for k, v in default.items():
+            m.lib.icnf_tc_knob_set(idx[k], v)
+    assert l0 == l1 and np.array_equal(g0, g1)
