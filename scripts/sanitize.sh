@@ -20,5 +20,7 @@ run tc memcheck tests/test_gpu_tc.py -k "selftest or training_gradient_ragged or
 run narrow racecheck tests/test_gpu_narrow.py -k "3+0c0-32-32 or generate"
 run tiny racecheck tests/test_gpu_parity.py -k "gradient and config2_moons"
 run tc racecheck tests/test_gpu_tc.py -k "bf16x3_tc_meets"
+run tc_knobs memcheck tests/test_gpu_tc.py -k "knobs"
+run planar memcheck tests/test_planar.py
 cat gpurun_out/sanitizer_summary.txt
 for f in gpurun_out/sanitizer_*.log; do tail -c 20000 $f > $f.tail; rm -f $f; done
