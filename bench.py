@@ -276,7 +276,7 @@ def logp_extras(m, local, dev, flush_buf):
         st = icnf.check_last()
         P = sum(icnf.sizes[i] * icnf.sizes[i + 1] for i in range(len(icnf.sizes) - 1))
         flop_rhs = 4 * P if not isinstance(mode, m.TestMode) else 2 * P + 2 * icnf.sizes[1] * icnf.sizes[2]
-        out[name] = {"logp_evals_per_sec": B / (ms * 1e-3), "ms_per_call": ms, "kernel_family": icnf.kernel_family,
+        out[name] = {"logp_evals_per_sec": B / (ms * 1e-3), "ms_per_call": ms, "kernel_family": icnf.solve_path(mode),
                      "mode": repr(mode), "solver_steps": st.naccept, "rhs_calls": st.nf, "parity_err_subbatch": err,
                      "algorithmic_tflops": flop_rhs * st.nf * B / (ms * 1e-3) / 1e12}
         del icnf
@@ -321,7 +321,8 @@ def w64_training(m, local, dev, flush_buf):
     xs = torch.from_numpy(np.ascontiguousarray(two_moons(B, seed=3).T.astype(np.float32))).to(dev)
     ms = _timed_calls(lambda: m.loss_and_gradient(icnf, m.TrainMode(True), xs.t(), theta_d, {}, seed=3), flush_buf)
     st = icnf.check_last()
-    return {"train_samples_per_sec": B / (ms * 1e-3), "ms_per_step": ms, "kernel_family": icnf.kernel_family,
+    return {"train_samples_per_sec": B / (ms * 1e-3), "ms_per_step": ms,
+            "kernel_family": icnf.solve_path(m.TrainMode(True)) + " forward solve, " + icnf.kernel_family + " reverse sweep",
             "mode": "TrainMode(True) loss + gradient", "solver_steps": st.naccept, "rhs_calls": st.nf, "solver_status": st.status,
             "parity_err_subbatch": err}
 

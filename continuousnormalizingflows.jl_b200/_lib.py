@@ -70,6 +70,7 @@ SYMBOLS = [
     ("icnf_n_params", C.c_int64, [_P]),
     ("icnf_n_state", C.c_int32, [_P]),
     ("icnf_kernel_family", C.c_char_p, [_P]),
+    ("icnf_solve_path", C.c_char_p, [_P, C.c_int]),
     ("icnf_set_params", C.c_int, [_P, _F, C.c_int64]),
     ("icnf_set_params_dev", C.c_int, [_P, _F, C.c_int64, _P]),
     ("icnf_rhs", C.c_int, [_P, C.c_int, C.c_float, _F, _F, _F, _F, C.c_int64]),

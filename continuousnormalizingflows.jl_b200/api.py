@@ -296,6 +296,10 @@ class ICNF:
     def kernel_family(self) -> str:
         return lib.icnf_kernel_family(self._h).decode()
 
+    def solve_path(self, mode) -> str:
+        """where a solve of ``mode`` runs: 'tiny', 'narrow' (single launch, any narrow shape), 'generic' or 'tc'"""
+        return lib.icnf_solve_path(self._h, mode.code).decode()
+
     @property
     def n_params(self) -> int:
         """length of ``ps`` as the caller sees it (a PlanarLayer has fewer entries than the Dense pair that serves it)"""

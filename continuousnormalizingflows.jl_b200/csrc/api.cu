@@ -657,6 +657,16 @@ const char* icnf_kernel_family(const icnf_handle* h) {
     if (h->cfg.precision == ICNF_BF16_TC || h->cfg.precision == ICNF_BF16X3_TC) return "tc";
     return h->fam->name;
 }
+const char* icnf_solve_path(const icnf_handle* h, int mode) {
+    if (!h || !h->fam) return "";
+    if (std::string(h->fam->name) == "generic" && h->fam->global_norm_capable) {
+        SolveArgs a;
+        memset(&a, 0, sizeof a);
+        a.mode = mode;
+        if (h->fam->global_norm_capable(h->ws, a, mode == ICNF_TEST)) return "narrow";
+    }
+    return icnf_kernel_family(h);
+}
 int64_t icnf_launch_count(const icnf_handle* h) { return h ? h->launches : 0; }
 
 int icnf_set_profiling(icnf_handle* h, int enabled) {

@@ -160,6 +160,9 @@ ICNF_API int64_t icnf_n_params(const icnf_handle* h);
 ICNF_API int32_t icnf_n_state(const icnf_handle* h);        /* S = nvars + naug + 3 (icnf.jl:143-145) */
 /* name of the kernel family that serves this config ("tiny", "generic", "tc") */
 ICNF_API const char* icnf_kernel_family(const icnf_handle* h);
+/* Where a solve of `mode` (icnf_mode) of this handle runs: "tiny", "narrow" (single-launch path of the generic family,
+ * forward solves only: its reverse sweep runs on the generic SGEMMs), "generic" or "tc". */
+ICNF_API const char* icnf_solve_path(const icnf_handle* h, int mode);
 
 /* `ps` of every reference call (ComponentArray data, host or device pointer) */
 ICNF_API int icnf_set_params(icnf_handle* h, const float* theta, int64_t n);

@@ -34,7 +34,9 @@ SWEEP = [
     (2,    0,   0,    64, 64, "softplus", False,      1000),   # config 2's other width, 3-64-64-2
     (16,   0,   0,    68, 68, "softplus", False,      515),    # config 3
     (5,    2,   3,    33, 47, "tanh",     False,      130),    # widths that do not divide by 8, conditioned, augmented
-    (20,   0,   0,    100, 128, "sigmoid", True,      97),     # D' > 16 (four rows per warp), autonomous, widest layer
+    (20,   0,   0,    40, 56, "sigmoid",  True,      97),     # D' > 16 (four rows per warp), autonomous
+    (4,    0,   0,    96, 8,  "softplus", False,      300),    # 12 units per warp in the first layer (the widest unit tile)
+    (20,   0,   0,    100, 128, "sigmoid", True,      97),     # too wide for one SM's shared memory: stays on the multi-launch path
     (1,    1,   0,    9,  5,  "softplus", False,      64),     # fewer units than warps
 ]
 
@@ -43,7 +45,9 @@ SWEEP = [
 def test_single_launch_solve_matches_oracle(m, case):
     nvars, naug, ncond, n1, n2, act, autonomous, B = case
     icnf, om = build(m, nvars, naug, ncond, n1, n2, act, autonomous)
+    fits = max(n1, n2) < 100     # weights, trace matrix and the activation tiles of 128 samples must fit one SM's shared memory
     assert icnf.kernel_family == "generic"
+    assert icnf.solve_path(m.TestMode()) == icnf.solve_path(m.TrainMode(True)) == ("narrow" if fits else "generic")
     rng = np.random.default_rng(5)
     theta = O.init_params(om, 11, np.float32, bias_scale=0.3)
     xs = rng.standard_normal((nvars, B)).astype(np.float32)
