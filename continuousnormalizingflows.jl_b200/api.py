@@ -198,7 +198,7 @@ class ICNF:
             self.sol_kwargs.update(sol_kwargs)
         if _alg_code(self.sol_kwargs.get("alg", "Tsit5")) is None:
             raise ValueError("the B200 path integrates with Tsit5 (north_star) or VCABM (the reference's default alg, served by "
-                             "the narrow-MLP family for inference / generate / loss); pass alg='Tsit5' or alg='VCABM'")
+                             "the single-launch solves for inference / generate / loss); pass alg='Tsit5' or alg='VCABM'")
 
         self.planar = None
         if isinstance(nn, PlanarLayer):

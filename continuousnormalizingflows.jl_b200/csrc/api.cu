@@ -464,6 +464,11 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
     cudaError_t e = vcabm ? h->fam->solve_vcabm(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st)
                           : h->fam->solve_adaptive(h->ws, h->theta_host.data(), a, c.nvars, mf.exact, h->sm_count, st);
     h->prof_end(0, st);
+    if (vcabm && e == cudaErrorNotSupported) {
+        (void)cudaGetLastError();
+        return h->fail(ICNF_ERR_UNSUPPORTED, "alg = VCABM is served by the single-launch solves (tiny family, narrow path); this network runs on the multi-launch %s path: pass alg = Tsit5",
+                       icnf_kernel_family(h));
+    }
     if (e != cudaSuccess) return h->cuda_fail(e, "solve_adaptive launch");
     h->launches++;
     return ICNF_OK;

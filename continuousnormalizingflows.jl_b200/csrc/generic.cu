@@ -1943,6 +1943,13 @@ static cudaError_t narrow_solve(Workspace* w, const SolveArgs& a, int nvars, boo
     return narrow::solve(w->cfg, w->amat.as<float>(), b, nvars, exact, adaptive, sms, st);
 }
 
+// VCABM (the reference's default alg): on the single-launch path only
+static cudaError_t solve_vcabm(void* wsp, const float*, const SolveArgs& a, int nvars, bool exact, int, cudaStream_t st) {
+    Workspace* w = (Workspace*)wsp;
+    if (!narrow_route(w, a, exact)) return cudaErrorNotSupported;
+    return narrow_solve(w, a, nvars, exact, true, st);
+}
+
 static cudaError_t solve_fixed(void* wsp, const float*, const SolveArgs& a, int nvars, bool exact, int, cudaStream_t st) {
     Workspace* w = (Workspace*)wsp;
     if (narrow_route(w, a, exact)) return narrow_solve(w, a, nvars, exact, false, st);
@@ -2551,6 +2558,7 @@ const Family* generic_family() {
         g.supports_backward = 1;
         g.ckpt_stages = 6;   // the inputs of all six Tsit5 stages of every accepted step: ckpt[slot][stage][D'][B]
         g.global_norm_capable = &generic::global_norm_capable;   // the single-launch narrow path
+        g.solve_vcabm = &generic::solve_vcabm;                   // likewise
         return g;
     }();
     return &f;

@@ -10,6 +10,7 @@ namespace narrow {
 #define ICNF_NARROW_DECL(N) cudaError_t N(const Params& P, int JP, int grid, size_t smem, cudaStream_t st);
 ICNF_NARROW_DECL(launch_o2_softplus_exact) ICNF_NARROW_DECL(launch_o2_any_exact) ICNF_NARROW_DECL(launch_o4_softplus_exact) ICNF_NARROW_DECL(launch_o4_any_exact)
 ICNF_NARROW_DECL(launch_o2_softplus_hutch) ICNF_NARROW_DECL(launch_o2_any_hutch) ICNF_NARROW_DECL(launch_o4_softplus_hutch) ICNF_NARROW_DECL(launch_o4_any_hutch)
+ICNF_NARROW_DECL(launch_vcabm_o2_exact) ICNF_NARROW_DECL(launch_vcabm_o2_hutch) ICNF_NARROW_DECL(launch_vcabm_o4_exact) ICNF_NARROW_DECL(launch_vcabm_o4_hutch)
 #undef ICNF_NARROW_DECL
 
 // ------------------------------------------------------------------ host side
@@ -73,6 +74,11 @@ cudaError_t solve(const icnf_config& cfg, const float* amat, const SolveArgs& a,
     if (smem > 227 * 1024 - 1024) return cudaErrorInvalidConfiguration;   // static shared memory of the kernel: < 1 KB
     const long long ntiles = (a.B + NS - 1) / NS;
     const int grid = (int)std::max<long long>(1, std::min<long long>(ntiles, sm_count));
+    if (a.alg == ICNF_ALG_VCABM) {
+        if (!adaptive || !a.vc_hist) return cudaErrorInvalidValue;
+        if (exact) return JP3 == 2 ? launch_vcabm_o2_exact(P, JP, grid, smem, st) : launch_vcabm_o4_exact(P, JP, grid, smem, st);
+        return JP3 == 2 ? launch_vcabm_o2_hutch(P, JP, grid, smem, st) : launch_vcabm_o4_hutch(P, JP, grid, smem, st);
+    }
     const bool sp = cfg.activation == ICNF_ACT_SOFTPLUS;
     if (exact) {
         if (JP3 == 2) return sp ? launch_o2_softplus_exact(P, JP, grid, smem, st) : launch_o2_any_exact(P, JP, grid, smem, st);

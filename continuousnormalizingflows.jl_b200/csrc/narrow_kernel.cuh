@@ -24,6 +24,7 @@
 
 #pragma once
 #include "tiny.cuh"
+#include "tiny_vcabm.cuh"
 #include "narrow.h"
 
 namespace icnf {
@@ -296,19 +297,12 @@ __device__ __forceinline__ void rhs_tile(const Layout& L, float* sm, int warp, i
     __syncthreads();
 }
 
-template <int JP, int JP3, int ACT, bool EXACT>
-__global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ Params P) {
-    extern __shared__ __align__(16) float sm[];
-    __shared__ double sred[2 * NW + 2];
+// weights -> shared memory (transposed, padded per warp; the padding reads as zero)
+template <int JP, int JP3, bool EXACT>
+__device__ __forceinline__ void stage_weights(const Params& P, float* sm) {
     const SolveArgs& a = P.a;
     const Layout& L = P.L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int D = L.D, S = D + 3;
-    const long long B = a.B;
-    tiny::GridReducer red{cg::this_grid(), a.partials, sred, 0, &a.xg, 0u, false};
-    if (P.adaptive && a.xg.nranks > 1) red.seq = *reinterpret_cast<const volatile unsigned*>(a.xg.peers.p[a.xg.rank]);
-
-    // ---- weights -> shared memory (transposed, padded per warp; the padding reads as zero)
+    const int D = L.D;
     for (int i = threadIdx.x; i < L.x; i += NTHR) sm[i] = 0.f;
     __syncthreads();
     {
@@ -343,6 +337,57 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
         for (int j = threadIdx.x; j < D; j += NTHR) sm[L.b3 + (j / L.jt3) * JP3 + (j % L.jt3)] = th[P.boff[2] + j];
     }
     __syncthreads();
+
+}
+
+// readout: one thread per sample (inference_sol, reg_z_aug, generate_sol); E = n = 0 in TestMode.  The caller has made the
+// final state visible grid-wide.
+template <bool EXACT>
+__device__ __forceinline__ void readout(const Params& P, int cur, float span, int nacc) {
+    const SolveArgs& a = P.a;
+    const Layout& L = P.L;
+    const int D = L.D, S = D + 3;
+    const long long B = a.B;
+    for (long long b = (long long)blockIdx.x * NTHR + threadIdx.x; b < B; b += (long long)gridDim.x * NTHR) {
+        float zz = 0.f, za = 0.f, l = 0.f;
+        const bool moved = span > 0.0f;
+        for (int j = 0; j < D; ++j) {
+            const float v = moved ? a.wu[cur][(long long)j * B + b] : input_value(a, b, j, D, P.nvars);
+            zz = fmaf(v, v, zz);
+            if (j >= P.nvars) za = fmaf(v, v, za);
+            if (a.out_u) a.out_u[b * S + j] = v;
+            if (a.out_x && j < P.nvars) a.out_x[b * P.nvars + j] = v;
+            if (a.ckpt) a.ckpt[(((long long)nacc * 6) * D + j) * B + b] = v;     // slot `nacc`, stage 0 = the final state
+        }
+        float E = 0.f, n = 0.f;
+        if (moved) {
+            l = a.wu[cur][(long long)D * B + b];
+            if constexpr (!EXACT) { E = a.wu[cur][(long long)(D + 1) * B + b]; n = a.wu[cur][(long long)(D + 2) * B + b]; }
+        } else if (a.in_kind == IN_U0) {
+            l = a.in[b * S + D]; E = a.in[b * S + D + 1]; n = a.in[b * S + D + 2];
+        }
+        if (a.out_u) { a.out_u[b * S + D] = l; a.out_u[b * S + D + 1] = E; a.out_u[b * S + D + 2] = n; }
+        const float logp = -0.91893853320467274178f * (float)D - 0.5f * zz - l;
+        const float Aa = a.reg_a ? tiny::vec_norm(za, a.squared) : 0.0f;
+        if (a.out_logp) a.out_logp[b] = logp;
+        if (a.out_regs) { a.out_regs[b * 3] = E; a.out_regs[b * 3 + 1] = n; a.out_regs[b * 3 + 2] = Aa; }
+        if (a.out_lossterm) a.out_lossterm[b] = -logp + a.lam1 * E + a.lam2 * n + a.lam3 * Aa;
+    }
+}
+
+template <int JP, int JP3, int ACT, bool EXACT>
+__global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ double sred[2 * NW + 2];
+    const SolveArgs& a = P.a;
+    const Layout& L = P.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = L.D, S = D + 3;
+    const long long B = a.B;
+    tiny::GridReducer red{cg::this_grid(), a.partials, sred, 0, &a.xg, 0u, false};
+    if (P.adaptive && a.xg.nranks > 1) red.seq = *reinterpret_cast<const volatile unsigned*>(a.xg.peers.p[a.xg.rank]);
+
+    stage_weights<JP, JP3, EXACT>(P, sm);
 
     const float tdir = (a.t1 >= a.t0) ? 1.0f : -1.0f;
     const float span = fabsf(a.t1 - a.t0);
@@ -682,34 +727,9 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
         }
     }
 
-    // ---- readout: one thread per sample (inference_sol, reg_z_aug, generate_sol); E = n = 0 in TestMode
     __threadfence();
     red.grid.sync();
-    for (long long b = (long long)blockIdx.x * NTHR + threadIdx.x; b < B; b += (long long)gridDim.x * NTHR) {
-        float zz = 0.f, za = 0.f, l = 0.f;
-        const bool moved = span > 0.0f;
-        for (int j = 0; j < D; ++j) {
-            const float v = moved ? a.wu[cur][(long long)j * B + b] : input_value(a, b, j, D, P.nvars);
-            zz = fmaf(v, v, zz);
-            if (j >= P.nvars) za = fmaf(v, v, za);
-            if (a.out_u) a.out_u[b * S + j] = v;
-            if (a.out_x && j < P.nvars) a.out_x[b * P.nvars + j] = v;
-            if (a.ckpt) a.ckpt[(((long long)nacc * 6) * D + j) * B + b] = v;     // slot `nacc`, stage 0 = the final state
-        }
-        float E = 0.f, n = 0.f;
-        if (moved) {
-            l = a.wu[cur][(long long)D * B + b];
-            if constexpr (!EXACT) { E = a.wu[cur][(long long)(D + 1) * B + b]; n = a.wu[cur][(long long)(D + 2) * B + b]; }
-        } else if (a.in_kind == IN_U0) {
-            l = a.in[b * S + D]; E = a.in[b * S + D + 1]; n = a.in[b * S + D + 2];
-        }
-        if (a.out_u) { a.out_u[b * S + D] = l; a.out_u[b * S + D + 1] = E; a.out_u[b * S + D + 2] = n; }
-        const float logp = -0.91893853320467274178f * (float)D - 0.5f * zz - l;
-        const float Aa = a.reg_a ? tiny::vec_norm(za, a.squared) : 0.0f;
-        if (a.out_logp) a.out_logp[b] = logp;
-        if (a.out_regs) { a.out_regs[b * 3] = E; a.out_regs[b * 3 + 1] = n; a.out_regs[b * 3 + 2] = Aa; }
-        if (a.out_lossterm) a.out_lossterm[b] = -logp + a.lam1 * E + a.lam2 * n + a.lam3 * Aa;
-    }
+    readout<EXACT>(P, cur, span, nacc);
     if (P.adaptive && a.xg.nranks > 1 && blockIdx.x == 0 && threadIdx.x == 0)
         *reinterpret_cast<volatile unsigned*>(a.xg.peers.p[a.xg.rank]) = red.seq;
     if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
@@ -721,6 +741,308 @@ __global__ void __launch_bounds__(NTHR, 1) solve_kernel(const __grid_constant__ 
         a.stats->dt_last = dt_last;
     }
 }
+
+// ------------------------------------------------------------------ VCABM (the reference's default alg) on the tile layout
+// Variable-order Adams PECE as in tiny_vcabm.cuh (same coefficients, controller and order selection: oracle.vcabm_solve), with
+// the RHS evaluated per 128-sample tile by the routines above.  Per attempt and tile: predictor from the stored Phi*(n-1)
+// (HBM, [2][13][S][B], double-buffered against rejections), RHS, corrector, the four error estimates, and -- speculatively --
+// the final evaluation at the corrected state.  Rows are owned as in solve_kernel (z rows by the thread that computes their
+// derivative, the l / E / n rows by warp 0).
+template <int JP, int JP3, int ACT, bool EXACT>
+__global__ void __launch_bounds__(NTHR, 1) solve_vcabm_kernel(const __grid_constant__ Params P) {
+    extern __shared__ __align__(16) float sm[];
+    __shared__ double sred[2 * NW + 2];
+    __shared__ float s_beta[tiny::VC_MAXK + 2], s_g[tiny::VC_MAXK + 2];
+    constexpr int NX = EXACT ? 1 : 3;
+    constexpr int VK = tiny::VC_MAXK;
+    const SolveArgs& a = P.a;
+    const Layout& L = P.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = L.D, S = D + 3;
+    const long long B = a.B;
+    tiny::GridReducer red{cg::this_grid(), a.partials, sred, 0, &a.xg, 0u, false};
+    if (a.xg.nranks > 1) red.seq = *reinterpret_cast<const volatile unsigned*>(a.xg.peers.p[a.xg.rank]);
+    stage_weights<JP, JP3, EXACT>(P, sm);
+
+    const float tdir = (a.t1 >= a.t0) ? 1.0f : -1.0f;
+    const float span = fabsf(a.t1 - a.t0);
+    const Controller ctl = a.ctl;
+    const double inv_count = 1.0 / ((double)(a.norm_B > 0 ? a.norm_B : B) * (double)S);
+    const long long ntiles = (B + NS - 1) / NS;
+    enum { P_INIT = 0, P_PROBE = 1, P_STEP = 2 };
+    int phase = P_INIT, cur = 0;
+    int nacc = 0, nrej = 0, nf = 0, status = ICNF_OK, attempts = 0, k = 1, nstep = 0;
+    float hist[VK + 2];
+#pragma unroll
+    for (int i = 0; i < VK + 2; ++i) hist[i] = 0.0f;
+    float t = a.t0, dt = (a.dt > 0.0f) ? fminf(a.dt, span) : 0.0f, dt0 = 0.0f, d1n = 0.0f, dt_last = 0.0f;
+    bool last = false;
+    bool own[JP3];
+#pragma unroll
+    for (int r = 0; r < JP3; ++r) own[r] = r < L.jt3 && warp * L.jt3 + r < D;
+
+    while (span > 0.0f) {
+        float h = 0.0f;
+        int kk = 1;
+        if (phase == P_STEP) {
+            const float remaining = fabsf(a.t1 - t);
+            if (remaining <= 1e-7f * fmaxf(1.0f, fabsf(a.t1))) break;
+            last = dt >= remaining * (1.0f - 1e-6f);
+            h = tdir * (last ? remaining : dt);
+            if (!(fabsf(h) > 0.0f) || t + h == t) { status = ICNF_ERR_DT_UNDERFLOW; break; }
+            if (++attempts > ctl.max_steps) { status = ICNF_ERR_MAX_STEPS; break; }
+            kk = min(k + 1, nstep + 1);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float dts[VK + 3];
+                dts[0] = h;
+                for (int i = 0; i < VK + 2; ++i) dts[i + 1] = hist[i];
+                tiny::vcabm_coefficients(dts, k, kk, s_beta, s_g);
+            }
+            __syncthreads();
+        } else if (phase == P_PROBE) {
+            h = tdir * dt0;
+        }
+        const int neval = (phase == P_STEP) ? 2 : 1;
+        double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long b0 = tile * NS + 4 * lane;
+            const bool in4 = b0 + 3 < B;
+            auto ld4 = [&](const float* base, long long row) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float* p = base + row * B + b0;
+                if (in4 && ((B & 3) == 0)) v = *reinterpret_cast<const float4*>(p);
+                else { if (b0 < B) v.x = p[0]; if (b0 + 1 < B) v.y = p[1]; if (b0 + 2 < B) v.z = p[2]; if (b0 + 3 < B) v.w = p[3]; }
+                return v;
+            };
+            auto st4 = [&](float* base, long long row, const float (&v)[SPT]) {
+                float* p = base + row * B + b0;
+                if (in4 && ((B & 3) == 0)) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+                else { if (b0 < B) p[0] = v[0]; if (b0 + 1 < B) p[1] = v[1]; if (b0 + 2 < B) p[2] = v[2]; if (b0 + 3 < B) p[3] = v[3]; }
+            };
+            auto hrow = [&](int par, int j, int row) { return ((long long)par * (VK + 1) + j) * S + row; };   // row index into vc_hist
+            auto get4 = [&](const float4& v, float (&o)[SPT]) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; };
+            // rows of this thread: slots 0 .. JP3-1 = z rows (owners), slots JP3 .. JP3+NX-1 = l (, E, n) rows (warp 0)
+            constexpr int NR = JP3 + NX;
+            bool mine[NR];
+            int grow[NR];
+#pragma unroll
+            for (int r = 0; r < JP3; ++r) { mine[r] = own[r]; grow[r] = warp * L.jt3 + r; }
+#pragma unroll
+            for (int x = 0; x < NX; ++x) { mine[JP3 + x] = warp == 0; grow[JP3 + x] = D + x; }
+            float u[NR][SPT], fn[NR][SPT], pv[NR][SPT], fo[NR][SPT];
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+#pragma unroll
+                for (int s = 0; s < SPT; ++s) { u[r][s] = 0.f; fn[r][s] = 0.f; pv[r][s] = 0.f; fo[r][s] = 0.f; }
+            if (phase == P_INIT) {
+#pragma unroll
+                for (int r = 0; r < JP3; ++r)
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s)
+                        if (mine[r] && b0 + s < B) u[r][s] = input_value(a, b0 + s, grow[r], D, P.nvars);
+                if (warp == 0 && a.in_kind == IN_U0) {
+#pragma unroll
+                    for (int x = 0; x < NX; ++x)
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) if (b0 + s < B) u[JP3 + x][s] = __ldg(a.in + (b0 + s) * S + D + x);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < NR; ++r)
+                    if (mine[r]) { get4(ld4(a.wu[cur], grow[r]), u[r]); get4(ld4(a.wk[cur], grow[r]), fn[r]); }
+            }
+            for (int i = threadIdx.x; i < L.C * NS; i += NTHR) {
+                const int c = i / NS, s = i - c * NS;
+                const long long b = tile * NS + s;
+                sm[L.x + (D + L.tin + c) * NS + s] = b < B ? __ldg(a.ys + b * L.C + c) : 0.f;
+            }
+            if constexpr (!EXACT) fill_eps_tile(a, sm + L.eps, tile * NS, D);
+            // ---- predictor (P_STEP); the evaluation point of the other phases
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                if (!mine[r]) continue;
+                if (phase == P_INIT) {
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) pv[r][s] = u[r][s];
+                } else if (phase == P_PROBE) {
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) pv[r][s] = fmaf(h, fn[r][s], u[r][s]);
+                } else {
+                    float phi[SPT];
+                    const float hg0 = h * s_g[0];
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) { phi[s] = fn[r][s]; pv[r][s] = fmaf(hg0, fn[r][s], u[r][s]); }
+                    st4(a.vc_hist, hrow(cur ^ 1, 0, grow[r]), fn[r]);
+                    for (int j = 1; j < kk; ++j) {
+                        const float bj = s_beta[j], hg = (j < k) ? h * s_g[j] : 0.0f;
+                        float hp[SPT], ps[SPT];
+                        get4(ld4(a.vc_hist, hrow(cur, j - 1, grow[r])), hp);
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) { phi[s] -= hp[s]; ps[s] = bj * phi[s]; pv[r][s] = fmaf(hg, ps[s], pv[r][s]); }
+                        st4(a.vc_hist, hrow(cur ^ 1, j, grow[r]), ps);
+                    }
+                }
+            }
+            float un[NR][SPT];
+            for (int ev = 0; ev < neval; ++ev) {
+                // ---- evaluation point -> shared memory, RHS
+                const float tt = (phase == P_INIT) ? t : (ev == 1 && last) ? a.t1 : t + h;
+#pragma unroll
+                for (int r = 0; r < JP3; ++r)
+                    if (mine[r]) {
+                        const float (&y)[SPT] = (ev == 0) ? pv[r] : un[r];
+                        *reinterpret_cast<float4*>(sm + L.x + grow[r] * NS + 4 * lane) = make_float4(y[0], y[1], y[2], y[3]);
+                    }
+                if (L.tin && warp == 1) *reinterpret_cast<float4*>(sm + L.x + D * NS + 4 * lane) = make_float4(tt, tt, tt, tt);
+                __syncthreads();
+                float zd[JP3][SPT];
+                if constexpr (EXACT) rhs_tile<JP, JP3, ACT>(L, sm, warp, lane, zd);
+                else rhs_tile_hutch<JP, JP3, ACT>(L, sm, warp, lane, a.reg_e, a.reg_n, a.squared, zd);
+#pragma unroll
+                for (int r = 0; r < JP3; ++r)
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) fo[r][s] = zd[r][s];
+                if (warp == 0) {
+#pragma unroll
+                    for (int x = 0; x < NX; ++x) {
+                        const float4 v = *reinterpret_cast<const float4*>(sm + L.red + x * NS + 4 * lane);
+                        const float sgn = EXACT ? -1.0f : 1.0f;      // rhs_tile leaves the trace, rhs_tile_hutch the derivative of l
+                        fo[JP3 + x][0] = sgn * v.x; fo[JP3 + x][1] = sgn * v.y; fo[JP3 + x][2] = sgn * v.z; fo[JP3 + x][3] = sgn * v.w;
+                    }
+                }
+                if (phase != P_STEP || ev == 1) break;
+                // ---- corrector and error estimates (fo = f at the predictor)
+                const float hgk = h * s_g[k], hdg = h * (s_g[k] - s_g[k - 1]);
+                const float hm1 = h * tiny::c_gstar[k - 1], hm2 = (k >= 2) ? h * tiny::c_gstar[k - 2] : 0.0f;
+                const bool has_p1 = (k < VK) && (kk >= k + 1);
+                const float hp1 = has_p1 ? h * tiny::c_gstar[k + 1] : 0.0f;
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    if (!mine[r]) continue;
+                    float php[SPT], pm1[SPT], pm2[SPT];
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) { php[s] = fo[r][s]; pm1[s] = 0.f; pm2[s] = 0.f; }
+                    for (int j = 1; j <= k; ++j) {
+                        float hp[SPT];
+                        get4(ld4(a.vc_hist, hrow(cur ^ 1, j - 1, grow[r])), hp);
+#pragma unroll
+                        for (int s = 0; s < SPT; ++s) { pm2[s] = pm1[s]; pm1[s] = php[s]; php[s] -= hp[s]; }
+                    }
+                    float hk[SPT] = {0.f, 0.f, 0.f, 0.f};
+                    if (has_p1) get4(ld4(a.vc_hist, hrow(cur ^ 1, k, grow[r])), hk);
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        un[r][s] = fmaf(hgk, php[s], pv[r][s]);
+                        if (b0 + s < B) {
+                            const float sk = ctl.abstol + fmaxf(fabsf(u[r][s]), fabsf(un[r][s])) * ctl.reltol;
+                            const float q0 = hdg * php[s] / sk, q1 = hm1 * pm1[s] / sk, q2 = hm2 * pm2[s] / sk;
+                            e0 += (double)(q0 * q0); e1 += (double)(q1 * q1); e2 += (double)(q2 * q2);
+                            if (has_p1) { const float q3 = hp1 * (php[s] - hk[s]) / sk; e3 += (double)(q3 * q3); }
+                        }
+                    }
+                }
+            }
+            // ---- per-phase epilogue of the tile
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                if (!mine[r]) continue;
+                if (phase == P_INIT) {
+                    st4(a.wu[0], grow[r], u[r]);
+                    st4(a.wk[0], grow[r], fo[r]);
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        if (b0 + s >= B) continue;
+                        const float sk = ctl.abstol + fabsf(u[r][s]) * ctl.reltol;
+                        e0 += (double)((u[r][s] / sk) * (u[r][s] / sk));
+                        e1 += (double)((fo[r][s] / sk) * (fo[r][s] / sk));
+                    }
+                } else if (phase == P_PROBE) {
+#pragma unroll
+                    for (int s = 0; s < SPT; ++s) {
+                        if (b0 + s >= B) continue;
+                        const float sk = ctl.abstol + fabsf(u[r][s]) * ctl.reltol;
+                        const float df = (fo[r][s] - fn[r][s]) / sk;
+                        e0 += (double)(df * df);
+                    }
+                } else {
+                    st4(a.wu[cur ^ 1], grow[r], un[r]);
+                    st4(a.wk[cur ^ 1], grow[r], fo[r]);
+                }
+            }
+        }
+        double t0s, t1s, t2s = 0.0, t3s = 0.0;
+        red.sum2(e0, e1, t0s, t1s, true);
+        if (phase == P_STEP) red.sum2(e2, e3, t2s, t3s, true);
+        // ---- control: tiny_vcabm.cuh, identical arithmetic in every thread
+        if (phase == P_INIT) {
+            nf = 1;
+            if (a.dt > 0.0f) phase = P_STEP;
+            else {
+                const float d0 = (float)sqrt(t0s * inv_count);
+                d1n = (float)sqrt(t1s * inv_count);
+                dt0 = (d0 < 1e-5f || d1n < 1e-5f) ? 1e-6f : 0.01f * d0 / d1n;
+                dt0 = fminf(dt0, span);
+                phase = P_PROBE;
+            }
+        } else if (phase == P_PROBE) {
+            nf += 1;
+            const float d2 = (float)sqrt(t0s * inv_count) / dt0;
+            const float dm = fmaxf(d1n, d2);
+            const float dt1 = (dm <= 1e-15f) ? fmaxf(1e-6f, dt0 * 1e-3f) : exp10f(-(2.0f + log10f(dm)) / 2.0f);
+            dt = fminf(fminf(100.0f * dt0, dt1), span);
+            phase = P_STEP;
+        } else {
+            float eest = (float)sqrt(t0s * inv_count);
+            if (!isfinite(eest)) { status = ICNF_ERR_NONFINITE; break; }
+            const float hmag = fabsf(h);
+            nf += 2;
+            if (eest > 1.0f) {
+                nrej++;
+                const float q = powf(eest, 1.0f / (float)(k + 1)) / ctl.gamma;
+                dt = hmag / fminf(1.0f / ctl.qmin, fmaxf(1.0f / ctl.qmax, q));
+            } else {
+                int knew = k;
+                if (nstep + 1 <= 4 || k < 3) knew = min(min(k + 1, 3), VK);
+                else {
+                    const float errm1 = (float)sqrt(t1s * inv_count), errm2 = (float)sqrt(t2s * inv_count);
+                    if (fmaxf(errm1, errm2) <= eest) knew = k - 1;
+                    else if (k < VK && kk >= k + 1) {
+                        const float errp1 = (float)sqrt(t3s * inv_count);
+                        if (errp1 < eest) { knew = k + 1; eest = errp1; }
+                    }
+                }
+                nacc++;
+                dt_last = h;
+                t = last ? a.t1 : t + h;
+                cur ^= 1;
+#pragma unroll
+                for (int i = VK + 1; i > 0; --i) hist[i] = hist[i - 1];
+                hist[0] = h;
+                nstep++;
+                k = knew;
+                float q = eest > 0.0f ? powf(eest, 1.0f / (float)(k + 1)) / ctl.gamma : 0.0f;
+                q = fmaxf(1.0f / ctl.qmax, fminf(1.0f / ctl.qmin, q));
+                if (q >= ctl.qsteady_min && q <= ctl.qsteady_max) q = 1.0f;
+                dt = hmag / q;
+            }
+        }
+    }
+    __threadfence();
+    red.grid.sync();
+    readout<EXACT>(P, cur, span, 0);
+    if (a.xg.nranks > 1 && blockIdx.x == 0 && threadIdx.x == 0)
+        *reinterpret_cast<volatile unsigned*>(a.xg.peers.p[a.xg.rank]) = red.seq;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.stats) {
+        a.stats->naccept = nacc;
+        a.stats->nreject = nrej;
+        a.stats->nf = nf;
+        a.stats->status = status;
+        a.stats->t_final = span > 0.0f ? t : a.t1;
+        a.stats->dt_last = dt_last;
+    }
+}
+
 
 template <int JP, int JP3, int ACT, bool EXACT>
 static cudaError_t launch(const Params& P, int grid, size_t smem, cudaStream_t st) {
@@ -737,6 +1059,20 @@ static cudaError_t launch(const Params& P, int grid, size_t smem, cudaStream_t s
 }
 
 
+template <int JP, int JP3, int ACT, bool EXACT>
+static cudaError_t launch_vcabm(const Params& P, int grid, size_t smem, cudaStream_t st) {
+    static size_t attr[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (attr[dev & 63] < smem) {
+        cudaError_t e = cudaFuncSetAttribute(solve_vcabm_kernel<JP, JP3, ACT, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr[dev & 63] = smem;
+    }
+    void* args[] = {(void*)&P};
+    return cudaLaunchCooperativeKernel((const void*)solve_vcabm_kernel<JP, JP3, ACT, EXACT>, dim3(grid), dim3(NTHR), args, smem, st);
+}
+
 // one translation unit per (JP3, ACT, EXACT): the kernel is large and ptxas takes ~15 s per instantiation
 #define ICNF_NARROW_INSTANCE(NAME, JP3V, ACTV, EXACTV)                                                            \
     cudaError_t NAME(const Params& P, int JP, int grid, size_t smem, cudaStream_t st) {                           \
@@ -745,6 +1081,18 @@ static cudaError_t launch(const Params& P, int grid, size_t smem, cudaStream_t s
             case 8: return launch<8, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                      \
             case 10: return launch<10, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                    \
             case 16: return launch<16, JP3V, ACTV, EXACTV>(P, grid, smem, st);                                    \
+            default: return cudaErrorInvalidConfiguration;                                                        \
+        }                                                                                                         \
+    }
+
+// VCABM: run-time activation only (it is the compatibility path for default `sol_kwargs`, not a throughput path)
+#define ICNF_NARROW_INSTANCE_VCABM(NAME, JP3V, EXACTV)                                                            \
+    cudaError_t NAME(const Params& P, int JP, int grid, size_t smem, cudaStream_t st) {                           \
+        switch (JP) {                                                                                             \
+            case 4: return launch_vcabm<4, JP3V, -1, EXACTV>(P, grid, smem, st);                                  \
+            case 8: return launch_vcabm<8, JP3V, -1, EXACTV>(P, grid, smem, st);                                  \
+            case 10: return launch_vcabm<10, JP3V, -1, EXACTV>(P, grid, smem, st);                                \
+            case 16: return launch_vcabm<16, JP3V, -1, EXACTV>(P, grid, smem, st);                                \
             default: return cudaErrorInvalidConfiguration;                                                        \
         }                                                                                                         \
     }

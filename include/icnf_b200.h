@@ -125,7 +125,7 @@ typedef struct icnf_solver {
     float beta1, beta2, gamma, qmin, qmax, qsteady_min, qsteady_max, qoldinit;
     int32_t alg;                /* icnf_alg: 0 = Tsit5 (BASELINE.json north_star), 1 = VCABM (the reference's default,
                                  * src/core/icnf.jl:89): adaptive only; served for solve / inference / generate / loss by the
-                                 * single-launch narrow-MLP family.  icnf_loss_grad differentiates discrete Runge-Kutta steps
+                                 * single-launch solves (tiny family and the narrow path: two hidden layers up to ~80 wide).  icnf_loss_grad differentiates discrete Runge-Kutta steps
                                  * and therefore integrates with Tsit5 whatever `alg` says (the reference's gradient is a
                                  * continuous adjoint: neither is tied to the forward steps). */
 } icnf_solver;

@@ -1,4 +1,5 @@
-"""GPU tests of the VCABM stepper (the reference's default ``alg``, icnf.jl:89) in the tiny family: the kernel follows
+"""GPU tests of the VCABM stepper (the reference's default ``alg``, icnf.jl:89) in the tiny family and on the narrow
+single-launch path: the kernels follow
 the oracle's restatement (oracle/icnf_oracle.py vcabm_solve: Hairer-Norsett-Wanner III.5 + Shampine-Gordon order
 selection) operation for operation; fp32 rounding may move an accept/reject or an order decision, so results are
 compared at tolerance level (as for adaptive Tsit5) and step counts within a small margin."""
@@ -18,10 +19,13 @@ def m():
     return cnf_b200
 
 
-@pytest.mark.parametrize("shape", ["config2_moons", "config1_usage", "cond"])
+@pytest.mark.parametrize("shape", ["config2_moons", "config1_usage", "cond", "nvars3_default", "cond_generic"])
 def test_vcabm_inference_matches_the_oracle(m, shape):
-    icnf = make_icnf(m, shape)
-    assert icnf.kernel_family == "tiny"
+    if shape == "nvars3_default":       # ICNF(nvariables = 3) with every default: 8-32-32-7 softplus, the narrow single-launch path
+        icnf = m.ICNF(nvariables=3)
+    else:
+        icnf = make_icnf(m, shape)
+    assert icnf.solve_path(m.TestMode()) in ("tiny", "narrow")
     om, theta, xs, eps, ys = make_inputs(icnf, 500)
     theta = (1.5 * theta).astype(np.float32)
     args = (xs,) if ys is None else (xs, ys)
@@ -57,10 +61,10 @@ def test_vcabm_generate_runs_backwards(m):
 
 
 def test_vcabm_is_refused_where_it_is_not_served_and_gradients_use_tsit5(m):
-    wide = make_icnf(m, "config3_gmm16")
+    wide = m.ICNF(nvariables=64, naugments=0, nconditions=32, n_hidden=256)     # multi-launch generic path: Tsit5 only
     om, theta, xs, eps, ys = make_inputs(wide, 64)
     with pytest.raises(m.ICNFError):
-        m.inference(wide, m.TestMode(), xs, theta, {}, alg="VCABM")
+        m.inference(wide, m.TestMode(), xs, ys, theta, {}, alg="VCABM")
     with pytest.raises(ValueError):
         m.ICNF(nvariables=2, sol_kwargs=dict(alg="Rodas5"))
     icnf = make_icnf(m, "config2_moons")
