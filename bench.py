@@ -454,7 +454,8 @@ def main():
         xd = xs_host.to(dev, non_blocking=True)
         l, g = m.dp_loss_and_gradient(icnf, mode, xd.t(), theta, {}, rank=rank, world=world, global_batch=B * world,
                                       seed=1000 + i)
-        return float(l.cpu()), g.cpu().numpy()
+        both = icnf._grad_loss_buf.cpu().numpy()       # [gradient; loss] share one device buffer: one device-to-host copy
+        return float(both[-1]), both[:-1]
 
     def timed(fn, K, W):
         for i in range(W):

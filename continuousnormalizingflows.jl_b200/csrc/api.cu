@@ -416,7 +416,7 @@ int enqueue_solve(icnf_handle* h, SolveRequest& r, cudaStream_t st) {
     // reverse sweep integrates with Tsit5 (the sweep differentiates discrete Runge-Kutta steps)
     const bool vcabm = r.sol && r.sol->alg == ICNF_ALG_VCABM && !r.want_ckpt;
     if (vcabm && !h->fam->solve_vcabm)
-        return h->fail(ICNF_ERR_UNSUPPORTED, "alg = VCABM is served by the tiny (narrow-MLP) kernel family; this network runs on the %s family: pass alg = Tsit5",
+        return h->fail(ICNF_ERR_UNSUPPORTED, "alg = VCABM is served by the single-launch solves (tiny family, narrow path); this network runs on the %s family: pass alg = Tsit5",
                        h->fam->name);
     // adaptive: cooperative persistent kernel
     const int grid_cap = h->fam->adaptive_max_grid(mf.exact, h->sm_count);
