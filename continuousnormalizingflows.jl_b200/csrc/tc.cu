@@ -299,21 +299,23 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
     P.direct_stores = knob(1) > 0 ? 1 : 0;
     { static const int dbg = [] { const char* e = getenv("ICNF_CHAIN_DBG"); return e ? atoi(e) : 0; }(); P.dbg = dbg; }
     cs->parity++;
-    if (P.cl <= 1) {
-        const dim3 grid((unsigned)std::min<long long>(P.nwork, (long long)ds.sms));
-        if (steps[0].g.split) tc_chain_kernel<true><<<grid, TTHREADS, smem_bytes(true, 128), st>>>(P);
-        else tc_chain_kernel<false><<<grid, TTHREADS, smem_bytes(false, 128), st>>>(P);
-        return cudaGetLastError();
-    }
-    // clusters: the whole grid must be resident at once (an item only waits on earlier items, but a cluster that is not
-    // scheduled never runs its early items), so the grid is what the device can hold of this cluster shape
+    // The grid must be resident as a whole: an item only waits on earlier items, but a CTA that is not scheduled never runs
+    // its early items, and two chains sharing a device from different streams could otherwise starve each other.  A
+    // cooperative launch gives that guarantee (the tiny and narrow solves rely on it as well).
     const bool split = steps[0].g.split != 0;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)P.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(TTHREADS); cfg.dynamicSmemBytes = smem_bytes(split, 128); cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = (unsigned)P.cl; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+    cfg.blockDim = dim3(TTHREADS); cfg.dynamicSmemBytes = smem_bytes(split, 128); cfg.stream = st; cfg.attrs = attr;
+    cfg.numAttrs = P.cl > 1 ? 2 : 1;
+    if (P.cl <= 1) {
+        cfg.gridDim = dim3((unsigned)std::min<long long>(P.nwork, (long long)ds.sms));
+        return split ? cudaLaunchKernelEx(&cfg, tc_chain_kernel<true>, P) : cudaLaunchKernelEx(&cfg, tc_chain_kernel<false>, P);
+    }
     static int max_clusters[64][2][5] = {};
     int& mc = max_clusters[dev & 63][split ? 1 : 0][P.cl];
     if (mc == 0) {

@@ -53,8 +53,14 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// (bounded: ~2^26 polls of >= 64 ns is several seconds, far beyond any chain; a launch that could not make progress then
+// finishes with wrong numbers instead of hanging the device)
 __device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
-    while (ld_acquire_u32(p) < target) __nanosleep(64);
+    long long spins = 0;
+    while (ld_acquire_u32(p) < target) {
+        if (++spins > (1LL << 26)) break;
+        __nanosleep(64);
+    }
 }
 
 
