@@ -131,11 +131,12 @@ cudaError_t gemm(const __nv_bfloat16* A, long long lda, const __nv_bfloat16* B, 
 }
 
 int& knob(int which) {
-    static int v[4] = {[] { const char* e = getenv("ICNF_TC_CHAIN"); return e ? atoi(e) : 1; }(),
+    static int v[8] = {[] { const char* e = getenv("ICNF_TC_CHAIN"); return e ? atoi(e) : 1; }(),
                        [] { const char* e = getenv("ICNF_CHAIN_DIRECT"); return e ? atoi(e) : -1; }(),
-                       [] { const char* e = getenv("ICNF_CHAIN_SG"); return e ? atoi(e) : 1; }(),
-                       [] { const char* e = getenv("ICNF_CHAIN_CLUSTER"); const int c = e ? atoi(e) : 1; return (c == 2 || c == 4) ? c : 1; }()};
-    return v[which & 3];
+                       [] { const char* e = getenv("ICNF_CHAIN_SG"); return e ? atoi(e) : 0; }(),
+                       [] { const char* e = getenv("ICNF_CHAIN_CLUSTER"); const int c = e ? atoi(e) : 1; return (c == 2 || c == 4) ? c : 1; }(),
+                       [] { const char* e = getenv("ICNF_CHAIN_NACC"); return (e && atoi(e) == 4) ? 4 : 2; }(), 0, 0, 0};
+    return v[which & 7];
 }
 
 // ---- GEMM chains (tc_chain.cuh) -------------------------------------------------------------------------------
@@ -258,8 +259,8 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
                 row_items += o.ntg * o.nsl;
                 max_ntn = std::max(max_ntn, o.ntg * o.nsl);
             }
-            const int rg = std::max(1, 3 * (ds.sms / cl) / max_ntn);
-            const int sg_on = knob(2);
+            const int sg_on = knob(2);   // 0 = off, 1 = on (three waves of the widest GEMM per super-group), n > 1: n waves
+            const int rg = std::max(1, (sg_on > 1 ? sg_on : 3) * (ds.sms / cl) / max_ntn);
             if (uniform && sg_on && ntm0 > rg) { sl.P.rg = rg; sl.P.ntm = ntm0; sl.P.row_items = row_items; }
             else { sl.P.rg = 0; sl.P.ntm = ntm0; sl.P.row_items = row_items; }
         }
@@ -297,6 +298,8 @@ cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, 
     // row-major outputs leave through bulk tensor stores; 16-byte stores straight from the registers (knob 1) measured
     // equal on the 8192-sample shapes and 10 % slower on the large-batch ones (scripts/ab_chain.py)
     P.direct_stores = knob(1) > 0 ? 1 : 0;
+    P.nacc = knob(4) == 4 ? 4 : 2;
+    P.nacc_log2 = P.nacc == 2 ? 1 : 2;
     { static const int dbg = [] { const char* e = getenv("ICNF_CHAIN_DBG"); return e ? atoi(e) : 0; }(); P.dbg = dbg; }
     cs->parity++;
     // The grid must be resident as a whole: an item only waits on earlier items, but a CTA that is not scheduled never runs

@@ -119,7 +119,9 @@ void chain_state_destroy(ChainState*);
 // slot: which cached parameter block to compare against / refill (one per call site, < 8)
 cudaError_t gemm_chain(ChainState* cs, int slot, const ChainStep* steps, int n, const int* done, cudaStream_t st, long long* trace = nullptr);
 // tuning knobs (environment at first use; icnf_tc_knob_set changes them at run time for A/B measurements in one process):
-// 0 = chains on/off (ICNF_TC_CHAIN), 1 = direct row stores: -1 auto / 0 / 1 (ICNF_CHAIN_DIRECT), 2 = row-tile super-groups (ICNF_CHAIN_SG)
+// 0 = chains on/off (ICNF_TC_CHAIN), 1 = direct row stores: -1 auto / 0 / 1 (ICNF_CHAIN_DIRECT), 2 = row-tile super-groups:
+// 0 off (default) / 1 = three waves per group / n = n waves (ICNF_CHAIN_SG), 3 = cluster size (ICNF_CHAIN_CLUSTER),
+// 4 = TMEM accumulators in rotation, 2 (default) or 4 (ICNF_CHAIN_NACC)
 int& knob(int which);
 inline bool chain_enabled() { return knob(0) != 0 && tile_mode(512) == 1; }   // chains run 128 x 128 tiles
 

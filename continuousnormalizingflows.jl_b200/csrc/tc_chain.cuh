@@ -41,6 +41,7 @@ struct ChainParams {
     const int* done;
     long long* trace;
     int direct_stores;      // row-major outputs: 1 = 16-byte stores from registers (short chains: latency), 0 = bulk tensor stores (long chains: throughput)
+    int nacc, nacc_log2;    // TMEM accumulators in rotation: 2 (default) or 4 (knob 4, ICNF_CHAIN_NACC)
     int dbg;                // development knob (ICNF_CHAIN_DBG): 1 = skip row stores, 2 = identity activation, 4 = skip publish fence, 8 = skip TMEM loads
     ChainGemm gm[CHAIN_MAXG];
 };
@@ -406,9 +407,13 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);
     uint64_t* empty = full + NSTAGE;
-    uint64_t* tmem_full = empty + NSTAGE;      // [2]
-    uint64_t* tmem_empty = tmem_full + 2;      // [2]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    // up to four accumulators in rotation (all 512 TMEM columns are allocated; one CTA per SM).  Two is the default: with
+    // four the MMA thread runs further ahead, which measured +0 % on the main-loop-bound config 4 and -1 % on the
+    // epilogue-bound config 5 (scripts/ab_chain.py, knob 4 / ICNF_CHAIN_NACC)
+    constexpr int NACC = 4;
+    uint64_t* tmem_full = empty + NSTAGE;         // [NACC]
+    uint64_t* tmem_empty = tmem_full + NACC;      // [NACC]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + NACC);
     uint8_t* sstage = smem + NSTAGE * STAGE_BYTES + 256 + 2 * 256 * 4;            // [epilogue warp][EPI_STAGE_BYTES]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -416,11 +421,11 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
 
     if (warp == TMA_WARP && lane == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], (uint32_t)P.cl); }   // a slot is free when EVERY CTA of the cluster has consumed it
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4 * WQ); }
+        for (int a = 0; a < NACC; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4 * WQ); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(2 * BN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(NACC * BN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -497,8 +502,8 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
                 const int nkb0 = (g.K + TBK - 1) / TBK;
                 const int nkb1 = g.K2 > 0 ? (g.K2 + TBK - 1) / TBK : 0;
                 const int nseg = (nkb1 && wi.nt * cl * BN < g.N2) ? 2 : 1;
-                const int as = i & 1;
-                mbar_wait(&tmem_empty[as], ((i >> 1) & 1) ^ 1);   // the epilogue has drained this accumulator
+                const int as = i & (P.nacc - 1);
+                mbar_wait(&tmem_empty[as], ((i >> P.nacc_log2) & 1) ^ 1);   // the epilogue has drained this accumulator
                 tc_fence_after();
                 const uint32_t tacc = tmem_base + (uint32_t)(as * BN);
                 uint32_t started = 0;
@@ -542,7 +547,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
             const ChainGemm& cg = P.gm[wi.gi];
             const TcArgs& g = cg.g;
             const int sl = wi.sl, mt = wi.mt;
-            const int as = i & 1;
+            const int as = i & (P.nacc - 1);
             const int m0 = mt * TBM, nt = wi.nt * cl + crank, n0 = nt * BN;
             const int pitch = SPLIT ? g.lo_o : g.ldo;
             float* sb = g_bias[warp];
@@ -555,7 +560,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
                 const int c = cbeg + lane + 32 * u;
                 bv[u] = (g.bias && lane + 32 * u < nch * NC && n0 + c < g.N) ? __ldg(g.bias + n0 + c) : 0.f;
             }
-            mbar_wait(&tmem_full[as], (i >> 1) & 1);
+            mbar_wait(&tmem_full[as], (i >> P.nacc_log2) & 1);
             tc_fence_after();
 #pragma unroll
             for (int u = 0; u < 2; ++u)
@@ -614,7 +619,7 @@ __global__ void __launch_bounds__(TTHREADS, 1) tc_chain_kernel(const __grid_cons
     else __syncthreads();
     if (warp == MMA_WARP) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(NACC * BN));
     }
 }
 

@@ -30,7 +30,10 @@ else:
 theta, _ = m.setup(rng, icnf)
 theta_d = torch.from_numpy(theta).cuda()
 knob = m.lib.icnf_tc_knob_set
-variants = {"unchained": [(0, 0), (3, 1)], "chain": [(0, 1), (1, 0), (3, 1)], "chain cluster 2": [(0, 1), (1, 0), (3, 2)], "chain cluster 4": [(0, 1), (1, 0), (3, 4)]}
+variants = {"unchained": [(0, 0), (2, 0), (3, 1), (4, 2)], "chain": [(0, 1), (1, 0), (2, 0), (3, 1), (4, 2)],
+            "chain, 4 accumulators": [(0, 1), (1, 0), (2, 0), (3, 1), (4, 4)],
+            "chain, super-groups (3 waves)": [(0, 1), (1, 0), (2, 1), (3, 1), (4, 2)],
+            "chain cluster 2": [(0, 1), (1, 0), (2, 0), (3, 2), (4, 2)]}
 def timed(fn):
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(); fn(); b.record(); torch.cuda.synchronize()
@@ -49,5 +52,5 @@ for r in range(rounds + 1):
         if r > 0:
             res[name]["inf"].append(ti); res[name]["train"].append(tt)
 for name in variants:
-    print(f"{what} {name:16s} inference 24 RHS: median {np.median(res[name]['inf']):7.3f} min {np.min(res[name]['inf']):7.3f} ms"
+    print(f"{what} {name:30s} inference 24 RHS: median {np.median(res[name]['inf']):7.3f} min {np.min(res[name]['inf']):7.3f} ms"
           + (f"   training step (4 fixed steps): median {np.median(res[name]['train']):7.3f} min {np.min(res[name]['train']):7.3f} ms" if what == "c4" else ""), flush=True)

@@ -207,16 +207,18 @@ def test_tc_gradient_is_bit_reproducible(m):
     assert a[0] == b[0] and np.array_equal(a[1], b[1])
 
 
-@pytest.mark.parametrize("knobs", [dict(chain=0), dict(cluster=2), dict(cluster=4), dict(direct=1), dict(sg=0)],
-                         ids=["per-layer launches", "cluster 2", "cluster 4", "direct stores", "no super-groups"])
+@pytest.mark.parametrize("knobs", [dict(chain=0), dict(cluster=2), dict(cluster=4), dict(direct=1), dict(sg=1), dict(sg=2, nacc=4), dict(nacc=4)],
+                         ids=["per-layer launches", "cluster 2", "cluster 4", "direct stores", "super-groups", "super-groups of 2 waves, 4 accumulators", "4 accumulators"])
 def test_tuning_knobs_do_not_change_results(m, knobs):
     """The optional paths of the tensor-core family (icnf_tc_knob_set: GEMMs as per-layer launches instead of one chain,
-    clusters with TMA multicast of the activation tile, register-direct row stores, plain tile order) compute the same
+    clusters with TMA multicast of the activation tile, register-direct row stores, row-tile super-groups, four
+    TMEM accumulators) compute the same
     products in the same order per output element: bit-identical gradients."""
-    idx = dict(chain=0, direct=1, sg=2, cluster=3)
-    default = dict(chain=1, direct=-1, sg=1, cluster=1)
+    idx = dict(chain=0, direct=1, sg=2, cluster=3, nacc=4)
+    default = dict(chain=1, direct=-1, sg=0, cluster=1, nacc=2)
     icnf = _make(m, "ffjord_small", precision="bf16x3_tc")
-    om, theta, xs, eps, ys = make_inputs(icnf, 700)
+    # super-groups only form when the batch has more row tiles than a group holds (74 per wave for this net)
+    om, theta, xs, eps, ys = make_inputs(icnf, 40000 if "sg" in knobs else 700)
     try:
         l0, g0 = m.loss_and_gradient(icnf, m.TrainMode(True), xs, theta, {}, eps=eps, tspan=icnf.tspan, adaptive=False, dt=0.5)
         for k, v in knobs.items():
