@@ -7,7 +7,7 @@ cd "$(dirname "$0")/.."
 for n in bwd fwd tc tc_x3 generic generic_ws narrow chain tc_train; do
     [ -f gpurun_out/prof_$n.txt ] && cp gpurun_out/prof_$n.txt profiles/${R}_ncu_prof_$n.txt
 done
-for f in launches_train4.csv time_train4.txt time_config3.txt ab_chain.txt; do [ -f gpurun_out/$f ] && cp gpurun_out/$f profiles/${R}_$f; done
+for f in launches_train4.csv time_train4.txt time_config3.txt ab_chain_round.txt; do [ -f gpurun_out/$f ] && cp gpurun_out/$f profiles/${R}_$f; done
 cp gpurun_out/bench_full.json profiles/${R}_bench.json
 cp gpurun_out/bench_reference.json profiles/${R}_bench_reference.json
 cp gpurun_out/launches_bench.csv profiles/${R}_launches_bench.csv

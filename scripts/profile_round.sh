@@ -47,4 +47,4 @@ ncu --set full --clock-control none --import-source on -k regex:tc_chain -s 30 -
     python scripts/time_wide.py bf16x3_tc > /dev/null 2>&1
 python scripts/ncu_summary.py gpurun_out/prof_chain.ncu-rep > gpurun_out/prof_chain.txt 2>&1; rm -f gpurun_out/prof_chain.ncu-rep
 python scripts/time_config3.py fp32 > gpurun_out/time_config3.txt 2>&1
-python scripts/ab_chain.py c4 8 adaptive > gpurun_out/ab_chain.txt 2>&1
+python scripts/ab_chain.py c4 8 adaptive > gpurun_out/ab_chain_round.txt 2>&1
